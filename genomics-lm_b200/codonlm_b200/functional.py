@@ -1,0 +1,304 @@
+"""Autograd glue: each Function's forward/backward is a short sequence of C-ABI kernel launches.
+
+Activations between Functions are 2-D [M=B*T, features]; the residual stream is fp32, GEMM operands
+are bf16, weight gradients are fp32.  No arithmetic is done by PyTorch here except trivial scalar
+bookkeeping (loss = sum / count) — torch provides memory, streams and the autograd graph.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+from torch.autograd import Function
+
+from . import ops
+from .ops import EPI_GELU, EPI_GELU_GRAD, EPI_NONE, bf16, f32
+
+_SMS = 148
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, n_out: int, k_in: int, dy_ld=None, x_ld=None, dy_off=0):
+    """dW[n_out, k_in] = dy[:, dy_off:dy_off+n_out]ᵀ · x[:, :k_in]  (fp32, split-K over the tokens)."""
+    Mtok = x.shape[0]
+    dw = torch.zeros((n_out, k_in), dtype=f32, device=x.device)
+    a = dy if dy_off == 0 else dy[:, dy_off:]
+    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    split = ops.pick_split_k(tiles, (Mtok + 63) // 64, _SMS)
+    ops.gemm(a, x, dw, M=n_out, N=k_in, K=Mtok, a_mn=True, b_mn=True, lda=dy_ld or dy.stride(0),
+             ldb=x_ld or x.stride(0), ldc=k_in, accumulate=True, split_k=split)
+    return dw
+
+
+def _colsum(dy: torch.Tensor, n: int) -> torch.Tensor:
+    out = torch.zeros((n,), dtype=f32, device=dy.device)
+    ops.colsum_bf16(dy, out, N=n)
+    return out
+
+
+class EmbedFn(Function):
+    """x = tok_emb[idx] (+ pos_emb[:T])  — model_tiny_gpt.py:306-309."""
+
+    @staticmethod
+    def forward(ctx, idx, tok_w, pos_w):
+        ctx.save_for_backward(idx)
+        ctx.shapes = (tok_w.shape, None if pos_w is None else pos_w.shape)
+        return ops.embed_fwd(idx, tok_w, pos_w)
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        ts, ps = ctx.shapes
+        g = g.contiguous()
+        dtok = torch.zeros(ts, dtype=f32, device=g.device)
+        dpos = torch.zeros(ps, dtype=f32, device=g.device) if ps is not None else None
+        ops.embed_bwd(idx, g, dtok, dpos)
+        return None, dtok, dpos
+
+
+class ResidualLayerNormFn(Function):
+    """(x, y) = (x, LN(x)): returning the residual stream through the Function lets backward fuse
+    dx = d_residual + LN'(dy) into one kernel (model_tiny_gpt.py:151-152 pre-norm pattern)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, want_f32):
+        M, d = x.shape
+        yb, yf, mean, rstd = ops.layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=want_f32)
+        ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.want_f32 = want_f32
+        if want_f32:
+            return x.view_as(x), yb, yf
+        return x.view_as(x), yb
+
+    @staticmethod
+    def backward(ctx, gx, gyb, gyf=None):
+        x, gamma, mean, rstd = ctx.saved_tensors
+        dgamma = torch.zeros_like(gamma)
+        dbeta = torch.zeros_like(gamma)
+        if gyf is not None and gyb is not None:
+            dy = gyf + gyb.float()
+        elif gyf is not None:
+            dy = gyf
+        elif gyb is not None:
+            dy = gyb
+        else:
+            return gx, None, None, None
+        dx, _ = ops.layernorm_bwd(dy.contiguous(), x, gamma, mean, rstd, None if gx is None else gx.contiguous(),
+                                  dgamma, dbeta)
+        return dx, dgamma, dbeta, None
+
+
+class PackedLinearFn(Function):
+    """y = x·W_packedᵀ + b_packed (+ residual): one GEMM for several nn.Linear that share the input
+    (query|key|value, model_tiny_gpt.py:85-93; w_gate|w_up, :57) or for a single one (proj :132).
+
+    `masters` are the fp32 Parameters in packed row order: weights first, then biases (may be empty);
+    `rows` lists (row_offset_in_packed, n_rows) per weight."""
+
+    @staticmethod
+    def forward(ctx, x, w_sh, b_sh, residual, rows, out_f32, *masters):
+        M, K = x.shape
+        N = w_sh.shape[0]
+        out = torch.empty((M, N), dtype=f32 if (out_f32 or residual is not None) else bf16, device=x.device)
+        ops.gemm(x, w_sh, out, M=M, N=N, K=K, bias=b_sh, residual=residual)
+        ctx.save_for_backward(x, w_sh)
+        ctx.rows = rows
+        ctx.has_res = residual is not None
+        ctx.n_w = len(rows)
+        ctx.has_bias = b_sh is not None
+        ctx.k_in = [m.shape[1] for m in masters[: len(rows)]]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w_sh = ctx.saved_tensors
+        M, K = x.shape
+        N = w_sh.shape[0]
+        g = g.contiguous()
+        gb = ops.cast_bf16(g) if g.dtype == f32 else g
+        dx = dw_list = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty((M, K), dtype=bf16, device=x.device)
+            ops.gemm(gb, w_sh, dx, M=M, N=K, K=N, b_mn=True)
+        grads: List[Optional[torch.Tensor]] = []
+        for (r0, n), k_in in zip(ctx.rows, ctx.k_in):
+            grads.append(_wgrad(gb, x, n, k_in, dy_off=r0))
+        if ctx.has_bias:
+            db = _colsum(gb, N)
+            for (r0, n) in ctx.rows:
+                grads.append(db[r0:r0 + n])
+        return (dx, None, None, g if ctx.has_res else None, None, None, *grads)
+
+
+class MlpGeluFn(Function):
+    """x + fc2(gelu(fc1(h)))  — model_tiny_gpt.py:143-148,152 with bias+GELU and bias+residual fused into
+    the GEMM epilogues and GELU' fused into the fc2 dgrad epilogue."""
+
+    @staticmethod
+    def forward(ctx, h, x_res, w1_sh, b1, w2_sh, b2, w1, w2):
+        M, d = h.shape
+        F = w1_sh.shape[0]
+        pre = torch.empty((M, F), dtype=bf16, device=h.device)
+        act = torch.empty((M, F), dtype=bf16, device=h.device)
+        ops.gemm(h, w1_sh, act, M=M, N=F, K=d, bias=b1, epilogue=EPI_GELU, aux_out=pre, ldaux=F)
+        n_out = w2_sh.shape[0]
+        out = torch.empty((M, n_out), dtype=f32, device=h.device)
+        ops.gemm(act, w2_sh, out, M=M, N=n_out, K=F, bias=b2, residual=x_res)
+        ctx.save_for_backward(h, pre, act, w1_sh, w2_sh)
+        ctx.has_res = x_res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, pre, act, w1_sh, w2_sh = ctx.saved_tensors
+        M, d = h.shape
+        F = w1_sh.shape[0]
+        n_out = w2_sh.shape[0]
+        g = g.contiguous()
+        gb = ops.cast_bf16(g)
+        dw2 = _wgrad(gb, act, n_out, F)
+        db2 = _colsum(gb, n_out)
+        dpre = torch.empty((M, F), dtype=bf16, device=h.device)
+        ops.gemm(gb, w2_sh, dpre, M=M, N=F, K=n_out, b_mn=True, epilogue=EPI_GELU_GRAD, aux=pre, ldaux=F)
+        dw1 = _wgrad(dpre, h, F, d)
+        db1 = _colsum(dpre, F)
+        dh = torch.empty((M, d), dtype=bf16, device=h.device)
+        ops.gemm(dpre, w1_sh, dh, M=M, N=d, K=F, b_mn=True)
+        return dh, (g if ctx.has_res else None), None, db1, None, db2, dw1, dw2
+
+
+class MlpSwiGLUFn(Function):
+    """x + w_down(silu(w_gate h) * w_up h)  — model_tiny_gpt.py:47-57,152.  Hidden width h=int(8d/3) is
+    padded to hp (multiple of 8) in the bf16 shadows; the padding columns are exact zeros."""
+
+    @staticmethod
+    def forward(ctx, hin, x_res, wgu_sh, wd_sh, w_gate, w_up, w_down):
+        M, d = hin.shape
+        hp = wgu_sh.shape[0] // 2
+        gu = torch.empty((M, 2 * hp), dtype=bf16, device=hin.device)
+        ops.gemm(hin, wgu_sh, gu, M=M, N=2 * hp, K=d)
+        act = ops.swiglu_fwd(gu, hp)
+        n_out = wd_sh.shape[0]
+        out = torch.empty((M, n_out), dtype=f32, device=hin.device)
+        ops.gemm(act, wd_sh, out, M=M, N=n_out, K=hp, residual=x_res)
+        ctx.save_for_backward(hin, gu, act, wgu_sh, wd_sh)
+        ctx.hidden = w_gate.shape[0]
+        ctx.has_res = x_res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        hin, gu, act, wgu_sh, wd_sh = ctx.saved_tensors
+        M, d = hin.shape
+        hp = wgu_sh.shape[0] // 2
+        hid = ctx.hidden
+        n_out = wd_sh.shape[0]
+        g = g.contiguous()
+        gb = ops.cast_bf16(g)
+        dwd = _wgrad(gb, act, n_out, hid)                       # [d, hid] (unpadded, odd pitch allowed)
+        dact = torch.empty((M, hp), dtype=bf16, device=hin.device)
+        ops.gemm(gb, wd_sh, dact, M=M, N=hp, K=n_out, b_mn=True)
+        dgu = ops.swiglu_bwd(gu, dact, hp)
+        dwg = _wgrad(dgu, hin, hid, d, dy_off=0)
+        dwu = _wgrad(dgu, hin, hid, d, dy_off=hp)
+        dh = torch.empty((M, d), dtype=bf16, device=hin.device)
+        ops.gemm(dgu, wgu_sh, dh, M=M, N=d, K=2 * hp, b_mn=True)
+        return dh, (g if ctx.has_res else None), None, None, dwg, dwu, dwd
+
+
+class OffsetHeadFn(Function):
+    """h_o = W2·gelu(W1·x + b1) + b2 on the post-ln_f hidden state — model_tiny_gpt.py:235-239,335.
+    Input bf16, output fp32 (it feeds the fp32 LM head)."""
+
+    @staticmethod
+    def forward(ctx, xb, w1_sh, b1, w2_sh, b2, w1, w2):
+        M, d = xb.shape
+        pre = torch.empty((M, d), dtype=bf16, device=xb.device)
+        act = torch.empty((M, d), dtype=bf16, device=xb.device)
+        ops.gemm(xb, w1_sh, act, M=M, N=d, K=d, bias=b1, epilogue=EPI_GELU, aux_out=pre, ldaux=d)
+        out = torch.empty((M, d), dtype=f32, device=xb.device)
+        ops.gemm(act, w2_sh, out, M=M, N=d, K=d, bias=b2)
+        ctx.save_for_backward(xb, pre, act, w1_sh, w2_sh)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, pre, act, w1_sh, w2_sh = ctx.saved_tensors
+        M, d = xb.shape
+        gb = ops.cast_bf16(g.contiguous())
+        dw2 = _wgrad(gb, act, d, d)
+        db2 = _colsum(gb, d)
+        dpre = torch.empty((M, d), dtype=bf16, device=xb.device)
+        ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_GELU_GRAD, aux=pre, ldaux=d)
+        dw1 = _wgrad(dpre, xb, d, d)
+        db1 = _colsum(dpre, d)
+        dx = torch.empty((M, d), dtype=bf16, device=xb.device)
+        ops.gemm(dpre, w1_sh, dx, M=M, N=d, K=d, b_mn=True)
+        return dx, None, db1, None, db2, dw1, dw2
+
+
+class AttentionFn(Function):
+    """softmax(QKᵀ/sqrt(hd) + mask)V on packed qkv with optional RoPE — model_tiny_gpt.py:94-131."""
+
+    @staticmethod
+    def forward(ctx, qkv, seg_start, rope, B, T, H, Hk, hd, window):
+        if rope is not None:
+            ops.rope_qk(qkv, rope[0], rope[1], B, T, H, Hk, hd)  # in place: the QKV GEMM output has no other reader
+        out, lse = ops.attn_fwd(qkv, seg_start, B, T, H, Hk, hd, window=window)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.aux = (seg_start, rope, B, T, H, Hk, hd, window)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        qkv, out, lse = ctx.saved_tensors
+        seg_start, rope, B, T, H, Hk, hd, window = ctx.aux
+        dqkv = ops.attn_bwd(qkv, seg_start, out, g.contiguous(), lse, B, T, H, Hk, hd, window=window)
+        if rope is not None:
+            ops.rope_qk(dqkv, rope[0], rope[1], B, T, H, Hk, hd, inverse=True)
+        return dqkv, None, None, None, None, None, None, None, None
+
+
+class SkinnyLinearFn(Function):
+    """fp32 x·wᵀ (+b) for N <= 128 outputs: LM head (:327,336) and termination head (:330)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        ctx.save_for_backward(x, w)
+        ctx.has_bias = bias is not None
+        return ops.skinny_linear_fwd(x, w, bias)
+
+    @staticmethod
+    def backward(ctx, g):
+        x, w = ctx.saved_tensors
+        g = g.contiguous()
+        dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        dw = torch.zeros_like(w)
+        db = torch.zeros((w.shape[0],), dtype=f32, device=w.device) if ctx.has_bias else None
+        ops.skinny_linear_bwd(g, x, w, dx, False, dw, db)
+        return dx, dw, db
+
+
+class CrossEntropyFn(Function):
+    """Mean CE with ignore_index / label smoothing / class weights / offset validity, no host sync
+    (model_tiny_gpt.py:343-349; objectives.py:39-57, 94-105).  Returns (loss, kept_weight)."""
+
+    @staticmethod
+    def forward(ctx, logits2d, targets, next_boundary, class_w, B, T, shift, smoothing, ignore_index, zero_if_empty):
+        sums, row_lse = ops.ce_fwd(logits2d, targets, B, T, shift=shift, next_boundary=next_boundary, class_w=class_w,
+                                   smoothing=smoothing, ignore_index=ignore_index)
+        ctx.save_for_backward(logits2d, row_lse, targets, sums)
+        ctx.aux = (next_boundary, class_w, B, T, shift, smoothing, ignore_index)
+        loss = sums[0] / sums[1]
+        if zero_if_empty:
+            loss = torch.where(sums[1] > 0, loss, torch.zeros_like(loss))
+        ctx.mark_non_differentiable(sums)
+        return loss, sums
+
+    @staticmethod
+    def backward(ctx, g, _gs):
+        logits2d, row_lse, targets, sums = ctx.saved_tensors
+        next_boundary, class_w, B, T, shift, smoothing, ignore_index = ctx.aux
+        gs = g.reshape(1).to(f32).contiguous()
+        dl = ops.ce_bwd(logits2d, row_lse, targets, sums, gs, B, T, shift=shift, next_boundary=next_boundary,
+                        class_w=class_w, smoothing=smoothing, ignore_index=ignore_index)
+        return dl, None, None, None, None, None, None, None, None, None

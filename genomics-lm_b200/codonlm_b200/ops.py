@@ -1,0 +1,263 @@
+"""Tensor-level wrappers over the C ABI: torch is used for device memory and streams only."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import EPI_GELU, EPI_GELU_GRAD, EPI_NONE, GemmArgs, check  # noqa: F401
+
+bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
+
+
+def _L():
+    return _lib.load()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _dev(t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.CgptError("cgpt_b200 ops need CUDA tensors: this path has no CPU implementation")
+    _lib.ensure_device(t.device.index if t.device.index is not None else torch.cuda.current_device())
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _req(t, dtype, name):
+    if t.dtype != dtype or not t.is_contiguous():
+        raise _lib.CgptError(f"{name}: expected contiguous {dtype}, got {t.dtype} contiguous={t.is_contiguous()}")
+    return t
+
+
+# ------------------------------------------------------------------ integer scans
+def segment_ids(idx: torch.Tensor, sep_id: int) -> torch.Tensor:
+    _dev(idx)
+    _req(idx, i64, "idx")
+    B, T = idx.shape
+    out = torch.empty((B, T), dtype=i32, device=idx.device)
+    check(_L().cgpt_segment_ids(idx.data_ptr(), out.data_ptr(), B, T, int(sep_id), _stream()))
+    return out
+
+
+def segment_starts(idx: torch.Tensor, sep_id: int) -> torch.Tensor:
+    _dev(idx)
+    _req(idx, i64, "idx")
+    B, T = idx.shape
+    out = torch.empty((B, T), dtype=i32, device=idx.device)
+    check(_L().cgpt_segment_starts(idx.data_ptr(), out.data_ptr(), B, T, int(sep_id), _stream()))
+    return out
+
+
+def next_in_set(yb: torch.Tensor, ids: Sequence[int]) -> torch.Tensor:
+    _dev(yb)
+    _req(yb, i64, "yb")
+    B, T = yb.shape
+    out = torch.empty((B, T), dtype=i32, device=yb.device)
+    arr = (C.c_int64 * max(1, len(ids)))(*[int(v) for v in ids])
+    check(_L().cgpt_next_in_set(yb.data_ptr(), out.data_ptr(), B, T, arr, len(ids), _stream()))
+    return out
+
+
+def termination_labels(yb: torch.Tensor, next_stop: torch.Tensor, edges: Sequence[int], ignore_index: int = -100):
+    _dev(yb)
+    B, T = yb.shape
+    out = torch.empty((B, T), dtype=i64, device=yb.device)
+    arr = (C.c_int64 * max(1, len(edges)))(*[int(v) for v in edges])
+    check(_L().cgpt_termination_labels(yb.data_ptr(), next_stop.data_ptr(), out.data_ptr(), B, T, arr, len(edges),
+                                       int(ignore_index), _stream()))
+    return out
+
+
+# ------------------------------------------------------------------ embedding
+def embed_fwd(idx, tok_w, pos_w):
+    _dev(idx)
+    B, T = idx.shape
+    V, d = tok_w.shape
+    x = torch.empty((B, T, d), dtype=f32, device=idx.device)
+    check(_L().cgpt_embed_fwd(idx.data_ptr(), tok_w.data_ptr(), _p(pos_w), x.data_ptr(), B, T, d, V, _stream()))
+    return x
+
+
+def embed_bwd(idx, dx, dtok_w, dpos_w):
+    B, T = idx.shape
+    V, d = dtok_w.shape
+    check(_L().cgpt_embed_bwd(idx.data_ptr(), dx.data_ptr(), dtok_w.data_ptr(), _p(dpos_w), B, T, d, V, _stream()))
+
+
+# ------------------------------------------------------------------ layernorm
+def layernorm_fwd(x2d, gamma, beta, want_bf16=True, want_f32=False, eps=1e-5):
+    _dev(x2d)
+    M, d = x2d.shape
+    yb = torch.empty((M, d), dtype=bf16, device=x2d.device) if want_bf16 else None
+    yf = torch.empty((M, d), dtype=f32, device=x2d.device) if want_f32 else None
+    mean = torch.empty((M,), dtype=f32, device=x2d.device)
+    rstd = torch.empty((M,), dtype=f32, device=x2d.device)
+    check(_L().cgpt_layernorm_fwd(x2d.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(yb), _p(yf), mean.data_ptr(),
+                                  rstd.data_ptr(), M, d, float(eps), _stream()))
+    return yb, yf, mean, rstd
+
+
+def layernorm_bwd(dy, x2d, gamma, mean, rstd, dres, dgamma, dbeta, want_bf16=False):
+    M, d = x2d.shape
+    dx = torch.empty((M, d), dtype=f32, device=x2d.device)
+    dxb = torch.empty((M, d), dtype=bf16, device=x2d.device) if want_bf16 else None
+    check(_L().cgpt_layernorm_bwd(dy.data_ptr(), 1 if dy.dtype == f32 else 0, x2d.data_ptr(), gamma.data_ptr(),
+                                  mean.data_ptr(), rstd.data_ptr(), _p(dres), dx.data_ptr(), _p(dxb),
+                                  dgamma.data_ptr(), dbeta.data_ptr(), M, d, _stream()))
+    return dx, dxb
+
+
+# ------------------------------------------------------------------ GEMM
+def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, bias=None, epilogue=EPI_NONE,
+         aux=None, aux_out=None, ldaux=0, residual=None, accumulate=False, split_k=1):
+    """out[M,N] (+)= A·Bᵀ (+bias, epilogue).  a/b bf16; out bf16 or fp32 (by dtype)."""
+    g = GemmArgs()
+    g.a, g.b = a.data_ptr(), b.data_ptr()
+    g.a_mn_major, g.b_mn_major = int(a_mn), int(b_mn)
+    g.lda = int(lda if lda is not None else a.stride(0))
+    g.ldb = int(ldb if ldb is not None else b.stride(0))
+    g.M, g.N, g.K = int(M), int(N), int(K)
+    g.split_k = int(split_k)
+    g.bias = _p(bias)
+    g.epilogue = int(epilogue)
+    g.aux, g.aux_out, g.ldaux = _p(aux), _p(aux_out), int(ldaux)
+    g.residual = _p(residual)
+    g.out = out.data_ptr()
+    g.out_f32 = 1 if out.dtype == f32 else 0
+    g.accumulate = int(accumulate)
+    g.ldc = int(ldc if ldc is not None else out.stride(0))
+    check(_L().cgpt_gemm_bf16(C.byref(g), _stream()))
+    return out
+
+
+def pick_split_k(tiles: int, kblocks: int, sms: int = 148) -> int:
+    """Split the reduction so that a weight-gradient GEMM fills the machine."""
+    if tiles >= sms or kblocks <= 8:
+        return 1
+    s = max(1, (2 * sms) // max(1, tiles))
+    return int(min(s, max(1, kblocks // 4)))
+
+
+# ------------------------------------------------------------------ elementwise
+def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None, ld_out: Optional[int] = None):
+    """fp32 [rows, cols] -> bf16 [rows, ld_out] (pad columns zeroed)."""
+    _dev(src)
+    s2 = src if src.dim() == 2 else src.reshape(1, -1)
+    rows, cols = s2.shape
+    ld_out = cols if ld_out is None else ld_out
+    if out is None:
+        out = torch.empty((rows, ld_out), dtype=bf16, device=src.device)
+    check(_L().cgpt_cast_f32_bf16(s2.data_ptr(), s2.stride(0), out.data_ptr(), ld_out, rows, cols, _stream()))
+    return out
+
+
+def colsum_bf16(x2d, out, N=None, ld=None):
+    M = x2d.shape[0]
+    check(_L().cgpt_colsum_bf16(x2d.data_ptr(), int(ld if ld is not None else x2d.stride(0)), out.data_ptr(), M,
+                                int(N if N is not None else x2d.shape[1]), _stream()))
+
+
+def rope_qk(qkv, cos_t, sin_t, B, T, H, Hk, hd, inverse=False):
+    check(_L().cgpt_rope_qk(qkv.data_ptr(), cos_t.data_ptr(), sin_t.data_ptr(), B, T, H, Hk, hd, int(inverse), _stream()))
+
+
+def swiglu_fwd(gu, hp):
+    M = gu.shape[0]
+    act = torch.empty((M, hp), dtype=bf16, device=gu.device)
+    check(_L().cgpt_swiglu_fwd(gu.data_ptr(), gu.stride(0), act.data_ptr(), hp, M, hp, _stream()))
+    return act
+
+
+def swiglu_bwd(gu, dact, hp):
+    M = gu.shape[0]
+    dgu = torch.empty_like(gu)
+    check(_L().cgpt_swiglu_bwd(gu.data_ptr(), gu.stride(0), dact.data_ptr(), dact.stride(0), dgu.data_ptr(), M, hp,
+                               _stream()))
+    return dgu
+
+
+# ------------------------------------------------------------------ attention
+def attn_fwd(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None):
+    _dev(qkv)
+    scale = 1.0 / math.sqrt(hd) if scale is None else scale
+    out = torch.empty((B * T, H * hd), dtype=bf16, device=qkv.device)
+    lse = torch.empty((B, H, T), dtype=f32, device=qkv.device)
+    check(_L().cgpt_attn_fwd(qkv.data_ptr(), _p(seg_start), out.data_ptr(), lse.data_ptr(), B, T, H, Hk, hd,
+                             int(window or 0), float(scale), _stream()))
+    return out, lse
+
+
+def attn_bwd(qkv, seg_start, out, dout, lse, B, T, H, Hk, hd, window=0, scale=None):
+    scale = 1.0 / math.sqrt(hd) if scale is None else scale
+    dqkv = torch.empty_like(qkv)
+    nbytes = _L().cgpt_attn_bwd_workspace(B, T, H, Hk, hd)
+    ws = torch.empty((nbytes // 4,), dtype=f32, device=qkv.device)
+    check(_L().cgpt_attn_bwd(qkv.data_ptr(), _p(seg_start), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                             dqkv.data_ptr(), ws.data_ptr(), B, T, H, Hk, hd, int(window or 0), float(scale), _stream()))
+    return dqkv
+
+
+def attn_probs(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None):
+    scale = 1.0 / math.sqrt(hd) if scale is None else scale
+    att = torch.empty((B, H, T, T), dtype=f32, device=qkv.device)
+    check(_L().cgpt_attn_probs(qkv.data_ptr(), _p(seg_start), att.data_ptr(), B, T, H, Hk, hd, int(window or 0),
+                               float(scale), _stream()))
+    return att
+
+
+# ------------------------------------------------------------------ heads / loss
+def skinny_linear_fwd(x2d, w, bias=None):
+    _dev(x2d)
+    M, d = x2d.shape
+    N = w.shape[0]
+    out = torch.empty((M, N), dtype=f32, device=x2d.device)
+    check(_L().cgpt_skinny_linear_fwd(x2d.data_ptr(), w.data_ptr(), _p(bias), out.data_ptr(), M, N, d, _stream()))
+    return out
+
+
+def skinny_linear_bwd(dout, x2d, w, dx, dx_accumulate, dw, dbias):
+    M, d = x2d.shape
+    N = w.shape[0]
+    check(_L().cgpt_skinny_linear_bwd(dout.data_ptr(), x2d.data_ptr(), w.data_ptr(), _p(dx), int(dx_accumulate),
+                                      _p(dw), _p(dbias), M, N, d, _stream()))
+
+
+def ce_fwd(logits2d, targets, B, T, *, shift=0, next_boundary=None, class_w=None, smoothing=0.0, ignore_index=0):
+    """Returns (sums[2] = (loss_sum, weight_sum), row_lse[M])."""
+    _dev(logits2d)
+    M, V = logits2d.shape
+    sums = torch.zeros((2,), dtype=f32, device=logits2d.device)
+    row_lse = torch.empty((M,), dtype=f32, device=logits2d.device)
+    row_ws = torch.empty((2 * M,), dtype=f32, device=logits2d.device)
+    check(_L().cgpt_ce_fwd(logits2d.data_ptr(), targets.data_ptr(), _p(next_boundary), _p(class_w), sums.data_ptr(),
+                           row_lse.data_ptr(), row_ws.data_ptr(), B, T, V, int(shift), float(smoothing),
+                           int(ignore_index), _stream()))
+    return sums, row_lse
+
+
+def ce_bwd(logits2d, row_lse, targets, sums, gscale, B, T, *, coef=1.0, shift=0, next_boundary=None, class_w=None,
+           smoothing=0.0, ignore_index=0):
+    M, V = logits2d.shape
+    dlogits = torch.empty((M, V), dtype=f32, device=logits2d.device)
+    check(_L().cgpt_ce_bwd(logits2d.data_ptr(), row_lse.data_ptr(), targets.data_ptr(), _p(next_boundary), _p(class_w),
+                           sums.data_ptr(), _p(gscale), float(coef), dlogits.data_ptr(), B, T, V, int(shift),
+                           float(smoothing), int(ignore_index), _stream()))
+    return dlogits
+
+
+# ------------------------------------------------------------------ optimiser
+def adamw(p, g, m, v, shadow, lr, beta1, beta2, eps, wd, step, grad_scale=1.0):
+    check(_L().cgpt_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow), p.numel(), float(lr),
+                          float(beta1), float(beta2), float(eps), float(wd), int(step), float(grad_scale), _stream()))
+
+
+def launch_count() -> int:
+    return int(_L().cgpt_launch_count())

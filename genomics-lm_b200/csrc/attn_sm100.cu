@@ -1,0 +1,794 @@
+// Causal / segment / window masked multi-head attention for sm_100a, forward and backward, on
+// tcgen05 tensor cores with TMEM accumulators and TMA-fed, swizzled shared-memory tiles.
+//
+// Replaces model_tiny_gpt.py:103-131 (both the SDPA and the manual branch) together with the mask
+// of :273-295, which is never materialised: the kernels take per-token segment STARTS (int32) and a
+// window, turn the mask into a per-row interval jlo(i) <= j <= i, and skip whole KV tiles that the
+// causal / window / segment structure rules out.  GQA reads kv head h/(H/Hk) directly (:94-96).
+//
+// Layout: packed qkv bf16 [B*T, W], W=(H+2Hk)*hd, column blocks q | k | v.  One 3-D TMA map
+// {W, T, B} with box {AW, 128, 1} serves Q, K, V, dO ... (AW = swizzle-atom width in elements).
+// Every tile lives in smem as rows of 2*AW bytes with the TMA swizzle; the same bytes are read as a
+// K-major operand (reduction over hd) or an MN-major operand (reduction over rows) by choosing the
+// UMMA descriptor, so no transposes are ever made.
+//
+// TMEM lane == query row, so softmax statistics are per-thread scalars (no shuffles); 256 threads
+// split each row's columns in two halves.
+#include "common.cuh"
+
+namespace cgpt {
+namespace {
+
+constexpr int BQ = 128;   // query rows per tile
+constexpr int BKV = 128;  // kv rows per tile
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+template <int HD>
+struct HeadCfg {
+  static_assert(HD % 16 == 0 && HD <= 128, "head_dim must be a multiple of 16, <= 128");
+  static constexpr int AW = (HD % 64 == 0) ? 64 : ((HD % 32 == 0) ? 32 : 16);  // atom width (elements)
+  static constexpr int NA = HD / AW;                                            // atoms per row
+  static constexpr int ROWB = AW * 2;                                           // bytes per smem row
+  static constexpr int SBO = 8 * ROWB;                                          // 8-row group pitch
+  static constexpr uint32_t LAYOUT = AW == 64 ? kLayoutSW128 : (AW == 32 ? kLayoutSW64 : kLayoutSW32);
+  static constexpr int SWZ = ROWB;                                              // TMA swizzle bytes
+  static constexpr int ATOM_BYTES = 128 * ROWB;                                 // one atom of a 128-row tile
+  static constexpr int TILE_BYTES = NA * ATOM_BYTES;                            // 128 x HD bf16
+  // K-major view of a [128 x HD] tile, k-step ks (16 elements of hd)
+  __device__ static uint64_t kmajor(uint32_t base, int ks) {
+    const int e = ks * 16;
+    return umma_smem_desc(base + (e / AW) * ATOM_BYTES + (e % AW) * 2, 16, SBO, LAYOUT);
+  }
+  // MN-major view (hd is the M/N dim, rows are the reduction), k-step ks = 16 rows
+  __device__ static uint64_t mnmajor(uint32_t base, int ks) {
+    return umma_smem_desc(base + ks * 16 * ROWB, ATOM_BYTES, SBO, LAYOUT);
+  }
+};
+
+// P / dS tile: [128 rows x 128 cols] bf16, two SW128 atoms of 64 columns (16 KB each).
+constexpr int kPTileBytes = 2 * 128 * 128;
+__device__ __forceinline__ uint64_t ptile_kmajor(uint32_t base, int ks) {  // reduction over the 128 columns
+  return umma_smem_desc(base + (ks >> 2) * 16384 + (ks & 3) * 32, 16, 1024, kLayoutSW128);
+}
+__device__ __forceinline__ uint64_t ptile_mnmajor(uint32_t base, int ks) {  // reduction over the 128 rows
+  return umma_smem_desc(base + ks * 2048, 16384, 1024, kLayoutSW128);
+}
+// thread `row` stores 8 consecutive bf16 (one 16-byte chunk `chunk` in 0..15) of its row
+__device__ __forceinline__ void ptile_store(uint8_t* base, int row, int chunk, uint4 v) {
+  const int atom = chunk >> 3, c = chunk & 7;
+  *reinterpret_cast<uint4*>(base + atom * 16384 + row * 128 + ((c ^ (row & 7)) << 4)) = v;
+}
+
+template <int HD>
+__device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int col, int row, int b) {
+  using C = HeadCfg<HD>;
+#pragma unroll
+  for (int a = 0; a < C::NA; ++a) tma_load_3d(dst + a * C::ATOM_BYTES, tm, bar, col + a * C::AW, row, b);
+}
+
+// first position p in [0,T) with a[p] > key (a non-decreasing); T if none
+__device__ __forceinline__ int upper_bound_i32(const int32_t* a, int T, int key) {
+  int lo = 0, hi = T;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (a[mid] <= key) lo = mid + 1; else hi = mid;
+  }
+  return lo;
+}
+
+// The mask of model_tiny_gpt.py:273-295 as a per-row interval: because segment ids are non-decreasing,
+//   j<=i && i-j<window && seg[i]==seg[j]   <=>   jlo(i) <= j <= i,
+//   jlo(i) = max(seg_start[i], i-window+1), seg_start[i] = last position <= i holding <SEP> (or 0).
+__device__ __forceinline__ int row_jlo(const int32_t* seg_start_b, int i, int T, int window) {
+  if (i >= T) return 0x3fffffff;  // rows past the end see nothing
+  int lo = seg_start_b ? seg_start_b[i] : 0;
+  if (window > 0) lo = max(lo, i - window + 1);
+  return lo;
+}
+
+// ===================================================================================== forward
+template <int HD>
+struct FwdSmem {
+  using C = HeadCfg<HD>;
+  static constexpr int kQ = 0;
+  static constexpr int kK = kQ + C::TILE_BYTES;         // 2 buffers
+  static constexpr int kV = kK + 2 * C::TILE_BYTES;     // 2 buffers
+  static constexpr int kP = kV + 2 * C::TILE_BYTES;
+  static constexpr int kBar = kP + kPTileBytes;
+  static constexpr int kTotal = kBar + 64;
+  static constexpr int kMaxPerCta2 = 115712;            // (228 KB - 2 x 1 KB reserved) / 2
+  static constexpr bool kTwoCtas = kTotal <= kMaxPerCta2;
+  // slack for aligning the base up to 1024 B; trimmed when it would cost the second resident CTA
+  static constexpr int kDynamic = kTwoCtas ? (kTotal + 1024 <= kMaxPerCta2 ? kTotal + 1024 : kMaxPerCta2) : kTotal + 1024;
+};
+
+// 256 threads: thread t owns query row (t & 127) and the column half (t >> 7) of every tile, so the
+// softmax work per thread is 64 scores per KV tile.  Thread 0 also drives TMA and the MMAs.
+template <int HD>
+__global__ void __launch_bounds__(256, FwdSmem<HD>::kTwoCtas ? 2 : 1)
+attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restrict__ seg_start,
+                __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int Hk, int window,
+                float scale_log2, int smem_bytes) {
+  using C = HeadCfg<HD>;
+  using S = FwdSmem<HD>;
+  constexpr int TMEM_COLS = 256;
+  constexpr int HH = HD / 2;  // output columns per thread
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(smem - smem_raw) + S::kTotal > smem_bytes) __trap();
+  uint8_t* sQ = smem + S::kQ;
+  uint8_t* sP = smem + S::kP;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
+  uint64_t* q_bar = bars;
+  uint64_t* kv_bar = bars + 1;  // [2]
+  uint64_t* mma_bar = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;
+  const int qb = gridDim.x - 1 - blockIdx.x;  // heaviest (most KV tiles) first
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int kvh = h / (H / Hk);
+  const int q0 = qb * BQ;
+  const int qcol = h * HD, kcol = (H + kvh) * HD, vcol = (H + Hk + kvh) * HD;
+  const int32_t* ssb = seg_start ? seg_start + (size_t)b * T : nullptr;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(q_bar, 1);
+    mbar_init(&kv_bar[0], 1);
+    mbar_init(&kv_bar[1], 1);
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;          // 128 columns: scores
+  const uint32_t tO = tmem_base + 128;    // HD columns: P·V of the current tile
+  const int kv_lo = row_jlo(ssb, q0, T, window) / BKV;  // jlo is non-decreasing in i
+  const int kv_hi = qb;
+  const int nblk = kv_hi - kv_lo + 1;
+
+  if (tid == 0) {
+    mbar_expect_tx(q_bar, C::TILE_BYTES);
+    tma_tile<HD>(sQ, &tm, q_bar, qcol, q0, b);
+    mbar_expect_tx(&kv_bar[0], 2 * C::TILE_BYTES);
+    tma_tile<HD>(smem + S::kK, &tm, &kv_bar[0], kcol, kv_lo * BKV, b);
+    tma_tile<HD>(smem + S::kV, &tm, &kv_bar[0], vcol, kv_lo * BKV, b);
+  }
+
+  const int i = q0 + row;  // my query row
+  const int jlo = row_jlo(ssb, i, T, window);
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  // exchange slot: written by (row, half), read by (row, 1-half); lives in the part of the P tile that
+  // only the READER overwrites later (atom 1-half, row `row`), see the sync structure below.
+  float* xchg_wr = reinterpret_cast<float*>(sP + (1 - half) * 16384 + row * 128);
+  float* xchg_rd = reinterpret_cast<float*>(sP + half * 16384 + row * 128);
+  float m_run = -INFINITY, l_run = 0.f;
+  float o_acc[HH];
+#pragma unroll
+  for (int c = 0; c < HH; ++c) o_acc[c] = 0.f;
+  uint32_t mma_phase = 0;
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+  constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
+
+  for (int it = 0; it < nblk; ++it) {
+    const int buf = it & 1;
+    const int kv0 = (kv_lo + it) * BKV;
+    uint8_t* sK = smem + S::kK + buf * C::TILE_BYTES;
+    uint8_t* sV = smem + S::kV + buf * C::TILE_BYTES;
+    if (tid == 0) {
+      if (it + 1 < nblk) {  // prefetch next KV tile (its buffer was released by the last PV wait)
+        const int nb = buf ^ 1;
+        mbar_expect_tx(&kv_bar[nb], 2 * C::TILE_BYTES);
+        tma_tile<HD>(smem + S::kK + nb * C::TILE_BYTES, &tm, &kv_bar[nb], kcol, kv0 + BKV, b);
+        tma_tile<HD>(smem + S::kV + nb * C::TILE_BYTES, &tm, &kv_bar[nb], vcol, kv0 + BKV, b);
+      }
+      if (it == 0) mbar_wait(q_bar, 0);
+      mbar_wait(&kv_bar[buf], (it >> 1) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+        umma_bf16(tS, C::kmajor(smem_u32(sQ), ks), C::kmajor(smem_u32(sK), ks), idesc_s, ks > 0);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+
+    // a tile strictly below the diagonal and at/after every row's jlo needs no per-score test
+    const bool need_mask = (kv0 + BKV - 1 > q0) || (kv0 < row_jlo(ssb, min(q0 + BQ - 1, T - 1), T, window));
+    // pass 1: row maximum over my 64 columns
+    float mloc = -INFINITY;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c4 = half * 2 + cc;
+      uint32_t r[32];
+      tmem_ld32(tS + lane_base + c4 * 32, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float s = __uint_as_float(r[j]) * scale_log2;
+        if (need_mask) {
+          const int jj = kv0 + c4 * 32 + j;
+          if (jj < jlo || jj > i) s = -INFINITY;
+        }
+        mloc = fmaxf(mloc, s);
+      }
+    }
+    *xchg_wr = mloc;
+    __syncthreads();
+    const float m_new = fmaxf(m_run, fmaxf(mloc, *xchg_rd));
+    const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+    const float alpha = exp2f(m_run - m_safe);
+    // pass 2: probabilities -> bf16 P tile in smem
+    float lsum = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c4 = half * 2 + cc;
+      uint32_t r[32];
+      tmem_ld32(tS + lane_base + c4 * 32, r);
+      tmem_ld_wait();
+      float p[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        float pv = exp2f(__uint_as_float(r[j]) * scale_log2 - m_safe);
+        if (need_mask) {
+          const int jj = kv0 + c4 * 32 + j;
+          if (jj < jlo || jj > i) pv = 0.f;
+        }
+        p[j] = pv;
+        lsum += pv;
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 v;
+        v.x = pack_bf16(p[q * 8 + 0], p[q * 8 + 1]);
+        v.y = pack_bf16(p[q * 8 + 2], p[q * 8 + 3]);
+        v.z = pack_bf16(p[q * 8 + 4], p[q * 8 + 5]);
+        v.w = pack_bf16(p[q * 8 + 6], p[q * 8 + 7]);
+        ptile_store(sP, row, c4 * 4 + q, v);
+      }
+    }
+    l_run = l_run * alpha + lsum;
+    m_run = m_new;
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < BKV / 16; ++ks)
+        umma_bf16(tO, ptile_kmajor(smem_u32(sP), ks), C::mnmajor(smem_u32(sV), ks), idesc_o, ks > 0);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int c0 = 0; c0 < HH; c0 += 8) {
+      uint32_t r[8];
+      tmem_ld8(tO + lane_base + half * HH + c0, r);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) o_acc[c0 + j] = o_acc[c0 + j] * alpha + __uint_as_float(r[j]);
+    }
+    tc_fence_before();
+    __syncthreads();  // nobody may lag a full mbarrier phase behind thread 0
+  }
+
+  // combine the two halves' row sums (the P tile is free: the last PV MMA has completed)
+  *xchg_wr = l_run;
+  __syncthreads();
+  const float l_tot = l_run + *xchg_rd;
+  if (i < T) {
+    const float inv = 1.f / l_tot;
+    __nv_bfloat16* o = out + ((size_t)b * T + i) * (size_t)(H * HD) + h * HD + half * HH;
+#pragma unroll
+    for (int c = 0; c < HH; c += 8) {
+      uint4 v;
+      v.x = pack_bf16(o_acc[c + 0] * inv, o_acc[c + 1] * inv);
+      v.y = pack_bf16(o_acc[c + 2] * inv, o_acc[c + 3] * inv);
+      v.z = pack_bf16(o_acc[c + 4] * inv, o_acc[c + 5] * inv);
+      v.w = pack_bf16(o_acc[c + 6] * inv, o_acc[c + 7] * inv);
+      *reinterpret_cast<uint4*>(o + c) = v;
+    }
+    if (half == 0) lse[((size_t)b * H + h) * T + i] = (m_run + log2f(l_tot)) * kLn2;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ===================================================================================== backward
+// delta[b,h,i] = sum_c dO[i,c] * O[i,c]   (one warp per (token, head))
+__global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                  float* __restrict__ delta, int B, int T, int H, int hd) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)B * T * H) return;
+  const long long tok = w / H;
+  const int h = (int)(w - tok * H);
+  const __nv_bfloat16* po = o + tok * (long long)(H * hd) + h * hd;
+  const __nv_bfloat16* pd = dout + tok * (long long)(H * hd) + h * hd;
+  float s = 0.f;
+  for (int c = lane * 2; c < hd; c += 64) {
+    const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(po + c));
+    const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(pd + c));
+    s += a.x * g.x + a.y * g.y;
+  }
+  s = warp_sum(s);
+  if (lane == 0) {
+    const long long bb = tok / T, t = tok - bb * T;
+    delta[(bb * H + h) * T + t] = s;
+  }
+}
+
+template <int HD>
+struct BwdSmem {
+  using C = HeadCfg<HD>;
+  static constexpr int NQB = HD > 96 ? 1 : 2;          // (Q, dO) buffers
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + C::TILE_BYTES;
+  static constexpr int kQ = kV + C::TILE_BYTES;
+  static constexpr int kdO = kQ + NQB * C::TILE_BYTES;
+  static constexpr int kP = kdO + NQB * C::TILE_BYTES;
+  static constexpr int kdS = kP + kPTileBytes;
+  static constexpr int kBar = kdS + kPTileBytes;
+  static constexpr int kTotal = kBar + 64;
+  static constexpr int kDynamic = kTotal + 1024;
+  // the dQ staging (128 rows) aliases the P + dS tiles once they are consumed
+  static constexpr int kdQRow = HD * 4 + (HD <= 96 ? 16 : 0);
+  static_assert(128 * kdQRow <= 2 * kPTileBytes, "dQ staging must fit in the P+dS region");
+};
+
+// One CTA per (kv tile, kv head, batch).  Loops over the query heads of the GQA group and over the
+// query tiles that can see the kv tile; dK/dV accumulate in TMEM over the whole loop; each dQ tile is
+// added to an fp32 workspace [B,H,T,hd] with bulk reduce-adds (rows are contiguous there).
+// 256 threads: thread t owns query row (t & 127) and the column half (t >> 7).
+template <int HD>
+__global__ void __launch_bounds__(256, 1)
+attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                const int32_t* __restrict__ seg_start, const float* __restrict__ lse,
+                const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_ws, int T,
+                int H, int Hk, int window, float scale) {
+  using C = HeadCfg<HD>;
+  using S = BwdSmem<HD>;
+  constexpr int TMEM_COLS = 512;
+  constexpr int HH = HD / 2;
+  constexpr int NQB = S::NQB;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sK = smem + S::kK;
+  uint8_t* sV = smem + S::kV;
+  uint8_t* sP = smem + S::kP;
+  uint8_t* sdS = smem + S::kdS;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
+  uint64_t* kv_bar = bars;
+  uint64_t* q_bar = bars + 1;  // [2]
+  uint64_t* mma_bar = bars + 3;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  int* s_qhi = reinterpret_cast<int*>(bars + 5);
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int row = tid & 127, half = tid >> 7;
+  const int kvb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int rep = H / Hk;
+  const int kv0 = kvb * BKV;
+  const int W = (H + 2 * Hk) * HD;
+  const int kcol = (H + kvh) * HD, vcol = (H + Hk + kvh) * HD;
+  const int32_t* ssb = seg_start ? seg_start + (size_t)b * T : nullptr;
+  const int nqb_total = (T + BQ - 1) / BQ;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    mbar_init(kv_bar, 1);
+    mbar_init(&q_bar[0], 1);
+    mbar_init(&q_bar[1], 1);
+    mbar_init(mma_bar, 1);
+    fence_mbar_init();
+    int hi_pos = T - 1;  // last query position that can see this kv tile
+    const int kv_last = min(T - 1, kv0 + BKV - 1);
+    if (window > 0) hi_pos = min(hi_pos, kv_last + window - 1);
+    if (ssb) hi_pos = min(hi_pos, upper_bound_i32(ssb, T, kv_last) - 1);  // seg_start[i] <= kv_last
+    *s_qhi = hi_pos / BQ;
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;              // 128 cols: scores, later reused for the dQ tile
+  const uint32_t tdP = tmem_base + 128;       // 128 cols
+  const uint32_t tdV = tmem_base + 256;       // HD cols, accumulates over the loop
+  const uint32_t tdK = tmem_base + 256 + HD;  // HD cols, accumulates over the loop
+  const uint32_t tdQ = tS;
+  const int qb_lo = kvb, qb_hi = min(*s_qhi, nqb_total - 1);
+  const int nq = qb_hi - qb_lo + 1;
+  const int niter = nq > 0 ? nq * rep : 0;
+
+  auto load_q = [&](int it2) {
+    const int nb = it2 % NQB;
+    const int nh = kvh * rep + it2 / nq, nq0 = (qb_lo + it2 % nq) * BQ;
+    mbar_expect_tx(&q_bar[nb], 2 * C::TILE_BYTES);
+    tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], nh * HD, nq0, b);
+    tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], nh * HD, nq0, b);
+  };
+  if (tid == 0) {
+    mbar_expect_tx(kv_bar, 2 * C::TILE_BYTES);
+    tma_tile<HD>(sK, &tm_qkv, kv_bar, kcol, kv0, b);
+    tma_tile<HD>(sV, &tm_qkv, kv_bar, vcol, kv0, b);
+    if (niter > 0) load_q(0);
+  }
+
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const float scale_log2 = scale * kLog2e;
+  uint32_t mma_phase = 0;
+  constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);   // S = Q Kᵀ, dP = dO Vᵀ
+  constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD, true, true);     // dV = Pᵀ dO, dK = dSᵀ Q
+  constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, false, true);     // dQ = dS K
+
+  for (int it = 0; it < niter; ++it) {
+    const int buf = it % NQB;
+    const int hq = kvh * rep + it / nq;     // query head
+    const int qb = qb_lo + it % nq;
+    const int q0 = qb * BQ;
+    uint8_t* sQ = smem + S::kQ + buf * C::TILE_BYTES;
+    uint8_t* sdO = smem + S::kdO + buf * C::TILE_BYTES;
+    if (tid == 0) {
+      // prefetch the next (Q, dO): with two buffers the other one was released by the previous MMA wait
+      if (NQB == 2 && it + 1 < niter) load_q(it + 1);
+      if (it == 0) mbar_wait(kv_bar, 0);
+      mbar_wait(&q_bar[buf], (it / NQB) & 1);
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+        umma_bf16(tS, C::kmajor(smem_u32(sQ), ks), C::kmajor(smem_u32(sK), ks), idesc_s, ks > 0);
+#pragma unroll
+      for (int ks = 0; ks < HD / 16; ++ks)
+        umma_bf16(tdP, C::kmajor(smem_u32(sdO), ks), C::kmajor(smem_u32(sV), ks), idesc_s, ks > 0);
+      umma_commit(mma_bar);
+    }
+    const int i = q0 + row;
+    const bool row_ok = i < T;
+    const size_t stat = ((size_t)b * H + hq) * T + (row_ok ? i : 0);
+    const float lse2 = row_ok ? lse[stat] * kLog2e : 0.f;
+    const float dl = row_ok ? delta[stat] : 0.f;
+    const int jlo = row_jlo(ssb, i, T, window);
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+
+#pragma unroll 1
+    for (int cc = 0; cc < 2; ++cc) {
+      const int c4 = half * 2 + cc;
+      uint32_t rs[32], rp[32];
+      tmem_ld32(tS + lane_base + c4 * 32, rs);
+      tmem_ld32(tdP + lane_base + c4 * 32, rp);
+      tmem_ld_wait();
+      float p[32], ds[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int jj = kv0 + c4 * 32 + j;
+        const bool ok = (jj >= jlo) && (jj <= i);
+        const float pv = ok ? exp2f(__uint_as_float(rs[j]) * scale_log2 - lse2) : 0.f;
+        p[j] = pv;
+        ds[j] = pv * (__uint_as_float(rp[j]) - dl);
+      }
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 v, w;
+        v.x = pack_bf16(p[q * 8 + 0], p[q * 8 + 1]);
+        v.y = pack_bf16(p[q * 8 + 2], p[q * 8 + 3]);
+        v.z = pack_bf16(p[q * 8 + 4], p[q * 8 + 5]);
+        v.w = pack_bf16(p[q * 8 + 6], p[q * 8 + 7]);
+        w.x = pack_bf16(ds[q * 8 + 0], ds[q * 8 + 1]);
+        w.y = pack_bf16(ds[q * 8 + 2], ds[q * 8 + 3]);
+        w.z = pack_bf16(ds[q * 8 + 4], ds[q * 8 + 5]);
+        w.w = pack_bf16(ds[q * 8 + 6], ds[q * 8 + 7]);
+        ptile_store(sP, row, c4 * 4 + q, v);
+        ptile_store(sdS, row, c4 * 4 + q, w);
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll
+      for (int ks = 0; ks < BQ / 16; ++ks)  // dV[kv,hd] += Pᵀ[kv,q] dO[q,hd]
+        umma_bf16(tdV, ptile_mnmajor(smem_u32(sP), ks), C::mnmajor(smem_u32(sdO), ks), idesc_kv, (it > 0) || (ks > 0));
+#pragma unroll
+      for (int ks = 0; ks < BQ / 16; ++ks)  // dK[kv,hd] += dSᵀ[kv,q] Q[q,hd]
+        umma_bf16(tdK, ptile_mnmajor(smem_u32(sdS), ks), C::mnmajor(smem_u32(sQ), ks), idesc_kv, (it > 0) || (ks > 0));
+#pragma unroll
+      for (int ks = 0; ks < BKV / 16; ++ks)  // dQ[q,hd] = dS[q,kv] K[kv,hd]
+        umma_bf16(tdQ, ptile_kmajor(smem_u32(sdS), ks), C::mnmajor(smem_u32(sK), ks), idesc_q, ks > 0);
+      umma_commit(mma_bar);
+    }
+    mbar_wait(mma_bar, mma_phase);
+    mma_phase ^= 1;
+    tc_fence_after();
+    if (NQB == 1 && tid == 0 && it + 1 < niter) load_q(it + 1);  // single buffer: free only now
+    // dQ tile -> smem row (aliases the consumed P/dS tiles) -> bulk reduce-add into the fp32 workspace
+    {
+      uint8_t* myrow = sP + row * S::kdQRow + half * (HH * 4);
+#pragma unroll
+      for (int c0 = 0; c0 < HH; c0 += 8) {
+        uint32_t r[8];
+        tmem_ld8(tdQ + lane_base + half * HH + c0, r);
+        tmem_ld_wait();
+        *reinterpret_cast<uint4*>(myrow + c0 * 4) = make_uint4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<uint4*>(myrow + c0 * 4 + 16) = make_uint4(r[4], r[5], r[6], r[7]);
+      }
+      fence_proxy_async_smem();
+      if (row_ok) {
+        float* g = dq_ws + (((size_t)b * H + hq) * T + i) * HD + half * HH;
+        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
+                     "r"(smem_u32(myrow)), "r"(HH * 4)
+                     : "memory");
+      }
+      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();  // P/dS region and the S/dQ TMEM columns are free again
+  }
+
+  // dK (scaled) and dV -> bf16 into the k / v column blocks of dqkv (TMEM lane = kv row)
+  {
+    const int j = kv0 + row;
+    __nv_bfloat16* gk = dqkv + ((size_t)b * T + min(j, T - 1)) * W + kcol + half * HH;
+    __nv_bfloat16* gv = dqkv + ((size_t)b * T + min(j, T - 1)) * W + vcol + half * HH;
+#pragma unroll
+    for (int c0 = 0; c0 < HH; c0 += 8) {
+      uint32_t rk[8], rv[8];
+      if (niter > 0) {  // CTA-uniform
+        tmem_ld8(tdK + lane_base + half * HH + c0, rk);
+        tmem_ld8(tdV + lane_base + half * HH + c0, rv);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rk[q] = rv[q] = 0u;
+      }
+      if (j < T) {
+        uint4 a, c;
+        a.x = pack_bf16(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale);
+        a.y = pack_bf16(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale);
+        a.z = pack_bf16(__uint_as_float(rk[4]) * scale, __uint_as_float(rk[5]) * scale);
+        a.w = pack_bf16(__uint_as_float(rk[6]) * scale, __uint_as_float(rk[7]) * scale);
+        c.x = pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]));
+        c.y = pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
+        c.z = pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]));
+        c.w = pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
+        *reinterpret_cast<uint4*>(gk + c0) = a;
+        *reinterpret_cast<uint4*>(gv + c0) = c;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// dq (fp32 [B,H,T,hd]) * scale -> bf16 into the q column block of dqkv
+__global__ void attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfloat16* __restrict__ dqkv, int B, int T,
+                                       int H, int hd, int W, float scale) {
+  const int hd4 = hd >> 2;
+  const long long total = (long long)B * H * T * hd4;
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
+       e += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(e % hd4);
+    long long r = e / hd4;
+    const int t = (int)(r % T);
+    r /= T;
+    const int h = (int)(r % H);
+    const int b = (int)(r / H);
+    const float4 v = reinterpret_cast<const float4*>(dq_ws)[e];
+    uint2 o = make_uint2(pack_bf16(v.x * scale, v.y * scale), pack_bf16(v.z * scale, v.w * scale));
+    *reinterpret_cast<uint2*>(dqkv + ((size_t)b * T + t) * W + h * hd + c4 * 4) = o;
+  }
+}
+
+// ===================================================================================== dense probabilities
+// Introspection path only (use_sdpa=False stores last_attn, model_tiny_gpt.py:116-128): one warp per
+// (b, h, i) row, SIMT dot products.  O(T^2 hd) and not tuned: never on the training path.
+__global__ void attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ seg,
+                                  float* __restrict__ att, int B, int T, int H, int Hk, int hd, int window,
+                                  float scale) {
+  const int lane = threadIdx.x & 31;
+  const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (w >= (long long)B * H * T) return;
+  const int i = (int)(w % T);
+  const int h = (int)((w / T) % H);
+  const int b = (int)(w / ((long long)T * H));
+  const int W = (H + 2 * Hk) * hd;
+  const int kvh = h / (H / Hk);
+  const __nv_bfloat16* q = qkv + ((size_t)b * T + i) * W + h * hd;
+  const int jlo = row_jlo(seg ? seg + (size_t)b * T : nullptr, i, T, window);
+  float* row = att + (size_t)w * T;
+  float mx = -INFINITY;
+  for (int j = lane; j < T; j += 32) {
+    float s = -INFINITY;
+    if (j >= jlo && j <= i) {
+      const __nv_bfloat16* k = qkv + ((size_t)b * T + j) * W + (H + kvh) * hd;
+      float acc = 0.f;
+      for (int c = 0; c < hd; c += 2) {
+        const float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(q + c));
+        const float2 kk = unpack_bf16(*reinterpret_cast<const uint32_t*>(k + c));
+        acc += a.x * kk.x + a.y * kk.y;
+      }
+      s = acc * scale;
+    }
+    row[j] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  float se = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    const float s = row[j];
+    const float p = (s == -INFINITY) ? 0.f : expf(s - mx);
+    row[j] = p;
+    se += p;
+  }
+  se = warp_sum(se);
+  const float inv = 1.f / se;
+  for (int j = lane; j < T; j += 32) row[j] *= inv;
+}
+
+int make_qkv_tmap(CUtensorMap* tm, const void* base, int B, int T, int W, int aw) {
+  const uint64_t dims[3] = {(uint64_t)W, (uint64_t)T, (uint64_t)B};
+  const uint64_t str[2] = {(uint64_t)W * 2, (uint64_t)T * W * 2};
+  const uint32_t box[3] = {(uint32_t)aw, 128u, 1u};
+  return make_tmap_bf16(tm, base, 3, dims, str, box, aw * 2);
+}
+
+template <int HD>
+int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B, int T, int H, int Hk, int window,
+               float scale, cudaStream_t st) {
+  using S = FwdSmem<HD>;
+  CUtensorMap tm;
+  int rc = make_qkv_tmap(&tm, qkv, B, T, (H + 2 * Hk) * HD, HeadCfg<HD>::AW);
+  if (rc) return rc;
+  auto kern = attn_fwd_kernel<HD>;
+  static bool configured = false;
+  if (!configured) {
+    CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
+    configured = true;
+  }
+  dim3 grid((T + BQ - 1) / BQ, H, B);
+  kern<<<grid, 256, S::kDynamic, st>>>(tm, seg, reinterpret_cast<__nv_bfloat16*>(out), lse, T, H, Hk, window,
+                                       scale * kLog2e, S::kDynamic);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int HD>
+int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse, void* dqkv,
+               void* ws, int B, int T, int H, int Hk, int window, float scale, cudaStream_t st) {
+  using S = BwdSmem<HD>;
+  const int W = (H + 2 * Hk) * HD;
+  CUtensorMap tq, td;
+  int rc = make_qkv_tmap(&tq, qkv, B, T, W, HeadCfg<HD>::AW);
+  if (rc) return rc;
+  rc = make_qkv_tmap(&td, dout, B, T, H * HD, HeadCfg<HD>::AW);
+  if (rc) return rc;
+  float* delta = reinterpret_cast<float*>(ws);
+  float* dq_ws = delta + (size_t)B * H * T;
+  CGPT_CHECK(cudaMemsetAsync(dq_ws, 0, (size_t)B * H * T * HD * sizeof(float), st));
+  {
+    const long long warps = (long long)B * T * H;
+    attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out),
+                                                                   reinterpret_cast<const __nv_bfloat16*>(dout), delta, B,
+                                                                   T, H, HD);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+  }
+  auto kern = attn_bwd_kernel<HD>;
+  static bool configured = false;
+  if (!configured) {
+    CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
+    configured = true;
+  }
+  dim3 grid((T + BKV - 1) / BKV, Hk, B);
+  kern<<<grid, 256, S::kDynamic, st>>>(tq, td, seg, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, T, H, Hk,
+                                       window, scale);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  {
+    const long long n = (long long)B * H * T * (HD / 4);
+    long long g = (n + 255) / 256;
+    if (g > (long long)num_sms() * 8) g = (long long)num_sms() * 8;
+    attn_dq_convert_kernel<<<(unsigned)g, 256, 0, st>>>(dq_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), B, T, H, HD, W,
+                                                        scale);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int check_attn_args(const char* who, int B, int T, int H, int Hk, int hd) {
+  CGPT_REQUIRE(B > 0 && T > 0 && H > 0 && Hk > 0, "%s: bad sizes B=%d T=%d H=%d Hk=%d", who, B, T, H, Hk);
+  CGPT_REQUIRE(H % Hk == 0, "%s: n_head=%d must be divisible by n_kv_head=%d", who, H, Hk);
+  CGPT_REQUIRE(hd == 16 || hd == 32 || hd == 48 || hd == 64 || hd == 96 || hd == 128,
+               "%s: head_dim=%d not supported (16, 32, 48, 64, 96, 128)", who, hd);
+  return 0;
+}
+
+}  // namespace
+}  // namespace cgpt
+
+using namespace cgpt;
+
+#define DISPATCH_HD(hd, CALL)        \
+  switch (hd) {                      \
+    case 16: return CALL(16);        \
+    case 32: return CALL(32);        \
+    case 48: return CALL(48);        \
+    case 64: return CALL(64);        \
+    case 96: return CALL(96);        \
+    default: return CALL(128);       \
+  }
+
+extern "C" {
+
+int cgpt_attn_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B, int T, int H, int Hk, int hd,
+                  int window, float scale, cgpt_stream_t stream) {
+  CGPT_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
+  int rc = check_attn_args("attn_fwd", B, T, H, Hk, hd);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define CALL(HD) launch_fwd<HD>(qkv, seg, out, lse, B, T, H, Hk, window, scale, st)
+  DISPATCH_HD(hd, CALL)
+#undef CALL
+}
+
+int64_t cgpt_attn_bwd_workspace(int B, int T, int H, int Hk, int hd) {
+  (void)Hk;
+  return (int64_t)sizeof(float) * ((int64_t)B * H * T + (int64_t)B * H * T * hd);
+}
+
+int cgpt_attn_bwd(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse, void* dqkv,
+                  void* ws, int B, int T, int H, int Hk, int hd, int window, float scale, cgpt_stream_t stream) {
+  CGPT_REQUIRE(qkv && out && dout && lse && dqkv && ws, "attn_bwd: null pointer");
+  int rc = check_attn_args("attn_bwd", B, T, H, Hk, hd);
+  if (rc) return rc;
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+#define CALL(HD) launch_bwd<HD>(qkv, seg, out, dout, lse, dqkv, ws, B, T, H, Hk, window, scale, st)
+  DISPATCH_HD(hd, CALL)
+#undef CALL
+}
+
+int cgpt_attn_probs(const void* qkv, const int32_t* seg, float* att, int B, int T, int H, int Hk, int hd, int window,
+                    float scale, cgpt_stream_t stream) {
+  CGPT_REQUIRE(qkv && att, "attn_probs: null pointer");
+  CGPT_REQUIRE(B > 0 && T > 0 && H > 0 && Hk > 0 && H % Hk == 0 && hd % 2 == 0, "attn_probs: bad sizes");
+  const long long warps = (long long)B * H * T;
+  attn_probs_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv), seg, att, B, T, H, Hk, hd, window, scale);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,675 @@
+// Memory-bound kernels of the codon-GPT step: integer scans, embedding gather / scatter-add,
+// LayerNorm fwd/bwd, casts, column sums, RoPE, SwiGLU gate, AdamW.  All HBM-bound: vectorised,
+// coalesced accesses, warp-shuffle reductions, grids sized in multiples of the SM count.
+#include "common.cuh"
+
+namespace cgpt {
+namespace {
+
+// ============================================================ integer scans (one warp per row)
+__global__ void segment_ids_kernel(const int64_t* __restrict__ idx, int32_t* __restrict__ seg, int B, int T,
+                                   int sep_id) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int64_t* r = idx + (size_t)row * T;
+  int32_t* o = seg + (size_t)row * T;
+  int running = 0;
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool f = (t < T) && (r[t] == (int64_t)sep_id);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    const int incl = __popc(m & (0xffffffffu >> (31 - lane)));
+    if (t < T) o[t] = running + incl;
+    running += __popc(m);
+  }
+}
+
+__global__ void segment_starts_kernel(const int64_t* __restrict__ idx, int32_t* __restrict__ start, int B, int T,
+                                      int sep_id) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int64_t* r = idx + (size_t)row * T;
+  int32_t* o = start + (size_t)row * T;
+  int carry = 0;  // no separator yet: the segment starts at 0
+  for (int t0 = 0; t0 < T; t0 += 32) {
+    const int t = t0 + lane;
+    const bool f = (t < T) && (r[t] == (int64_t)sep_id);
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    const unsigned at_or_before = m & (0xffffffffu >> (31 - lane));
+    const int mine = at_or_before ? (t0 + 31 - __clz(at_or_before)) : carry;
+    if (t < T) o[t] = mine;
+    if (m) carry = t0 + 31 - __clz(m);
+  }
+}
+
+struct IdSet {
+  int64_t v[8];
+  int n;
+};
+
+__global__ void next_in_set_kernel(const int64_t* __restrict__ yb, int32_t* __restrict__ next, int B, int T,
+                                   IdSet ids) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= B) return;
+  const int64_t* r = yb + (size_t)row * T;
+  int32_t* o = next + (size_t)row * T;
+  int carry = T;  // sentinel: nothing at or after
+  for (int t0 = ((T - 1) / 32) * 32; t0 >= 0; t0 -= 32) {
+    const int t = t0 + lane;
+    bool f = false;
+    if (t < T) {
+      const int64_t tok = r[t];
+      for (int i = 0; i < ids.n; ++i) f |= (tok == ids.v[i]);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, f);
+    const unsigned at_or_after = m >> lane;
+    const int mine = at_or_after ? (t + __ffs(at_or_after) - 1) : carry;
+    if (t < T) o[t] = mine;
+    if (m) carry = t0 + __ffs(m) - 1;
+  }
+}
+
+struct EdgeSet {
+  int64_t v[8];
+  int n;
+};
+
+__global__ void termination_labels_kernel(const int64_t* __restrict__ yb, const int32_t* __restrict__ next_stop,
+                                          int64_t* __restrict__ labels, int B, int T, EdgeSet e, int64_t ignore) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)B * T) return;
+  const int t = (int)(i % T);
+  int64_t lab;
+  if (yb[i] == 0) {
+    lab = ignore;
+  } else if (next_stop[i] >= T) {
+    lab = e.n;
+  } else {
+    const int64_t dist = next_stop[i] - t;
+    int c = 0;
+    for (int k = 0; k < e.n; ++k) c += (dist > e.v[k]);
+    lab = c;
+  }
+  labels[i] = lab;
+}
+
+// ============================================================ embedding
+__global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float4* __restrict__ tok,
+                                 const float4* __restrict__ pos, float4* __restrict__ x, size_t n4, int T, int d4,
+                                 int vocab) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t m = i / d4;
+    const int c = (int)(i - m * d4);
+    int64_t v = idx[m];
+    v = v < 0 ? 0 : (v >= vocab ? vocab - 1 : v);
+    float4 a = __ldg(tok + (size_t)v * d4 + c);
+    if (pos) {
+      const float4 p = __ldg(pos + (size_t)(m % T) * d4 + c);
+      a.x += p.x;
+      a.y += p.y;
+      a.z += p.z;
+      a.w += p.w;
+    }
+    x[i] = a;
+  }
+}
+
+// Token-embedding gradient: V (~68) rows receive M updates.  Each CTA owns a token range and a
+// column slice, accumulates a private [V, cols] table in shared memory with plain adds (threads own
+// columns, tokens are walked serially -> no atomics, no contention), then flushes with one atomic per
+// table element.
+__global__ void embed_bwd_tok_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dx,
+                                     float* __restrict__ dtok, int M, int d, int vocab, int cols_per_cta,
+                                     int toks_per_cta) {
+  extern __shared__ float table[];  // [vocab][cols_per_cta]
+  const int c0 = blockIdx.y * cols_per_cta;
+  const int ncols = min(cols_per_cta, d - c0);
+  const int m0 = blockIdx.x * toks_per_cta;
+  const int m1 = min(M, m0 + toks_per_cta);
+  for (int i = threadIdx.x; i < vocab * cols_per_cta; i += blockDim.x) table[i] = 0.f;
+  __syncthreads();
+  for (int m = m0; m < m1; ++m) {
+    int64_t v = idx[m];
+    v = v < 0 ? 0 : (v >= vocab ? vocab - 1 : v);
+    const float* src = dx + (size_t)m * d + c0;
+    float* dst = table + (size_t)v * cols_per_cta;
+    for (int c = threadIdx.x; c < ncols; c += blockDim.x) dst[c] += src[c];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < vocab * cols_per_cta; i += blockDim.x) {
+    const int v = i / cols_per_cta, c = i - v * cols_per_cta;
+    const float val = table[i];
+    if (c < ncols && val != 0.f) atomicAdd(dtok + (size_t)v * d + c0 + c, val);
+  }
+}
+
+__global__ void embed_bwd_pos_kernel(const float4* __restrict__ dx, float4* __restrict__ dpos, int B, int T,
+                                     int d4) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)T * d4) return;
+  float4 acc = dpos[i];
+  for (int b = 0; b < B; ++b) {
+    const float4 v = __ldg(dx + (size_t)b * T * d4 + i);
+    acc.x += v.x;
+    acc.y += v.y;
+    acc.z += v.z;
+    acc.w += v.w;
+  }
+  dpos[i] = acc;
+}
+
+// ============================================================ LayerNorm (one warp per row, d <= 1024, d % 4 == 0)
+constexpr int kLnMaxVec = 8;  // float4 per lane
+
+__global__ void __launch_bounds__(256)
+layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     __nv_bfloat16* __restrict__ yb, float* __restrict__ yf, float* __restrict__ mean,
+                     float* __restrict__ rstd, int M, int d, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = d >> 2;
+  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
+    float4 v[kLnMaxVec];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nvec) {
+        v[k] = xr[c];
+        s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+      }
+    }
+    const float mu = warp_sum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nvec) {
+        const float a = v[k].x - mu, b = v[k].y - mu, e = v[k].z - mu, f = v[k].w - mu;
+        q += (a * a + b * b) + (e * e + f * f);
+      }
+    }
+    const float rs = rsqrtf(warp_sum(q) / d + eps);
+    if (lane == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        float4 o;
+        o.x = (v[k].x - mu) * rs * g.x + b.x;
+        o.y = (v[k].y - mu) * rs * g.y + b.y;
+        o.z = (v[k].z - mu) * rs * g.z + b.z;
+        o.w = (v[k].w - mu) * rs * g.w + b.w;
+        if (yf) reinterpret_cast<float4*>(yf + (size_t)row * d)[c] = o;
+        if (yb) reinterpret_cast<uint2*>(yb + (size_t)row * d)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+}
+
+template <bool DY_F32>
+__global__ void __launch_bounds__(256)
+layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
+                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
+                     float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dgamma,
+                     float* __restrict__ dbeta, int M, int d) {
+  __shared__ float red[8][32 * 4 + 4];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  const int wpb = blockDim.x >> 5;
+  const int nvec = d >> 2;
+  float4 ag[kLnMaxVec], ab[kLnMaxVec];
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
+    const float mu = mean[row], rs = rstd[row];
+    const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
+    float4 xh[kLnMaxVec], g[kLnMaxVec];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nvec) {
+        float4 dyv;
+        if constexpr (DY_F32) {
+          dyv = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * d)[c];
+        } else {
+          const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + (size_t)row * d)[c];
+          const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+          dyv = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
+        const float4 xv = xr[c];
+        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+        g[k] = make_float4(dyv.x * gm.x, dyv.y * gm.y, dyv.z * gm.z, dyv.w * gm.w);
+        s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
+        s2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
+        ag[k].x += dyv.x * xh[k].x;
+        ag[k].y += dyv.y * xh[k].y;
+        ag[k].z += dyv.z * xh[k].z;
+        ag[k].w += dyv.w * xh[k].w;
+        ab[k].x += dyv.x;
+        ab[k].y += dyv.y;
+        ab[k].z += dyv.z;
+        ab[k].w += dyv.w;
+      }
+    }
+    const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
+#pragma unroll
+    for (int k = 0; k < kLnMaxVec; ++k) {
+      const int c = lane + 32 * k;
+      if (c < nvec) {
+        float4 o;
+        o.x = rs * (g[k].x - m1 - xh[k].x * m2);
+        o.y = rs * (g[k].y - m1 - xh[k].y * m2);
+        o.z = rs * (g[k].z - m1 - xh[k].z * m2);
+        o.w = rs * (g[k].w - m1 - xh[k].w * m2);
+        if (dres) {
+          const float4 r = reinterpret_cast<const float4*>(dres + (size_t)row * d)[c];
+          o.x += r.x;
+          o.y += r.y;
+          o.z += r.z;
+          o.w += r.w;
+        }
+        reinterpret_cast<float4*>(dx + (size_t)row * d)[c] = o;
+        if (dxb)
+          reinterpret_cast<uint2*>(dxb + (size_t)row * d)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      }
+    }
+  }
+  // cross-warp reduction of the per-column partials, then one atomic per column per CTA
+#pragma unroll
+  for (int k = 0; k < kLnMaxVec; ++k) {
+    const int c = lane + 32 * k;
+    if (32 * k >= nvec) break;
+    for (int pass = 0; pass < 2; ++pass) {
+      const float4 val = pass == 0 ? ag[k] : ab[k];
+      __syncthreads();
+      red[warp][lane * 4 + 0] = val.x;
+      red[warp][lane * 4 + 1] = val.y;
+      red[warp][lane * 4 + 2] = val.z;
+      red[warp][lane * 4 + 3] = val.w;
+      __syncthreads();
+      if (warp == 0 && c < nvec) {
+        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int w2 = 0; w2 < wpb; ++w2) {
+          t.x += red[w2][lane * 4 + 0];
+          t.y += red[w2][lane * 4 + 1];
+          t.z += red[w2][lane * 4 + 2];
+          t.w += red[w2][lane * 4 + 3];
+        }
+        float* dst = (pass == 0 ? dgamma : dbeta) + c * 4;
+        atomicAdd(dst + 0, t.x);
+        atomicAdd(dst + 1, t.y);
+        atomicAdd(dst + 2, t.z);
+        atomicAdd(dst + 3, t.w);
+      }
+    }
+  }
+}
+
+// ============================================================ casts / column sums
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
+                                     long long ld_out, long long rows, long long cols) {
+  const long long total = rows * ld_out;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / ld_out, c = i - r * ld_out;
+    out[i] = __float2bfloat16_rn(c < cols ? in[r * ld_in + c] : 0.f);
+  }
+}
+
+__global__ void cast_f32_bf16_vec_kernel(const float4* __restrict__ in, uint2* __restrict__ out, long long n4) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = in[i];
+    out[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+  }
+}
+
+// out[n] += sum_m x[m,n]; CTA = 64 columns x a row range; 8 warps stride rows, lanes own column pairs.
+__global__ void __launch_bounds__(256)
+colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
+                   int rows_per_cta) {
+  __shared__ float2 red[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 64 + 2 * lane;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float2 acc = make_float2(0.f, 0.f);
+  if (col + 1 < N) {
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const float2 v = unpack_bf16(*reinterpret_cast<const uint32_t*>(x + (size_t)r * ld + col));
+      acc.x += v.x;
+      acc.y += v.y;
+    }
+  } else if (col < N) {
+    for (int r = r0 + warp; r < r1; r += 8) acc.x += __bfloat162float(x[(size_t)r * ld + col]);
+  }
+  red[warp][lane] = acc;
+  __syncthreads();
+  if (warp == 0) {
+    float2 t = make_float2(0.f, 0.f);
+    for (int w2 = 0; w2 < 8; ++w2) {
+      t.x += red[w2][lane].x;
+      t.y += red[w2][lane].y;
+    }
+    if (col < N) atomicAdd(out + col, t.x);
+    if (col + 1 < N) atomicAdd(out + col + 1, t.y);
+  }
+}
+
+// ============================================================ RoPE on the q|k blocks of packed qkv (in place)
+__global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_t,
+                               const float* __restrict__ sin_t, int M, int T, int nheads, int hd, long long ld,
+                               int inverse) {
+  const int half = hd >> 1;
+  const int pairs_per_row = nheads * (half >> 1);  // each thread rotates 2 adjacent (i, i+half) pairs
+  const long long total = (long long)M * pairs_per_row;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / pairs_per_row;
+    const int r = (int)(i - m * pairs_per_row);
+    const int h = r / (half >> 1);
+    const int j = (r - h * (half >> 1)) * 2;
+    const int t = (int)(m % T);
+    __nv_bfloat16* base = qkv + m * ld + (long long)h * hd;
+    const float2 x1 = unpack_bf16(*reinterpret_cast<uint32_t*>(base + j));
+    const float2 x2 = unpack_bf16(*reinterpret_cast<uint32_t*>(base + half + j));
+    const float2 c = *reinterpret_cast<const float2*>(cos_t + (size_t)t * half + j);
+    float2 s = *reinterpret_cast<const float2*>(sin_t + (size_t)t * half + j);
+    if (inverse) {
+      s.x = -s.x;
+      s.y = -s.y;
+    }
+    const float o1x = x1.x * c.x - x2.x * s.x, o1y = x1.y * c.y - x2.y * s.y;
+    const float o2x = x2.x * c.x + x1.x * s.x, o2y = x2.y * c.y + x1.y * s.y;
+    *reinterpret_cast<uint32_t*>(base + j) = pack_bf16(o1x, o1y);
+    *reinterpret_cast<uint32_t*>(base + half + j) = pack_bf16(o2x, o2y);
+  }
+}
+
+// ============================================================ SwiGLU gate (gu = [g | u], each h wide, h % 2 == 0)
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+
+__global__ void swiglu_fwd_kernel(const __nv_bfloat16* __restrict__ gu, long long ldgu, __nv_bfloat16* __restrict__ act,
+                                  long long ldact, int M, int h) {
+  const int h2 = h >> 1;
+  const long long total = (long long)M * h2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / h2;
+    const int j = (int)(i - m * h2) * 2;
+    const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(gu + m * ldgu + j));
+    const float2 u = unpack_bf16(*reinterpret_cast<const uint32_t*>(gu + m * ldgu + h + j));
+    *reinterpret_cast<uint32_t*>(act + m * ldact + j) =
+        pack_bf16(g.x * sigmoidf_(g.x) * u.x, g.y * sigmoidf_(g.y) * u.y);
+  }
+}
+
+__global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, long long ldgu,
+                                  const __nv_bfloat16* __restrict__ dact, long long ldact,
+                                  __nv_bfloat16* __restrict__ dgu, int M, int h) {
+  const int h2 = h >> 1;
+  const long long total = (long long)M * h2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / h2;
+    const int j = (int)(i - m * h2) * 2;
+    const float2 g = unpack_bf16(*reinterpret_cast<const uint32_t*>(gu + m * ldgu + j));
+    const float2 u = unpack_bf16(*reinterpret_cast<const uint32_t*>(gu + m * ldgu + h + j));
+    const float2 da = unpack_bf16(*reinterpret_cast<const uint32_t*>(dact + m * ldact + j));
+    const float sx = sigmoidf_(g.x), sy = sigmoidf_(g.y);
+    const float dgx = da.x * u.x * sx * (1.f + g.x * (1.f - sx));
+    const float dgy = da.y * u.y * sy * (1.f + g.y * (1.f - sy));
+    const float dux = da.x * g.x * sx, duy = da.y * g.y * sy;
+    *reinterpret_cast<uint32_t*>(dgu + m * ldgu + j) = pack_bf16(dgx, dgy);
+    *reinterpret_cast<uint32_t*>(dgu + m * ldgu + h + j) = pack_bf16(dux, duy);
+  }
+}
+
+// ============================================================ AdamW (torch.optim.AdamW semantics)
+__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                             float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float lr,
+                             float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float gr = g[i] * gscale;
+    float pv = p[i] * (1.f - lr * wd);
+    const float mv = b1 * m[i] + (1.f - b1) * gr;
+    const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / bc2_sqrt + eps;
+    pv -= (lr / bc1) * (mv / denom);
+    p[i] = pv;
+    if (shadow) shadow[i] = __float2bfloat16_rn(pv);
+  }
+}
+
+inline int grid_for(long long work_items, int threads, int max_waves = 8) {
+  long long g = (work_items + threads - 1) / threads;
+  const long long cap = (long long)num_sms() * max_waves;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+}  // namespace
+}  // namespace cgpt
+
+using namespace cgpt;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int cgpt_segment_ids(const int64_t* idx, int32_t* seg, int B, int T, int sep_id, cgpt_stream_t stream) {
+  CGPT_REQUIRE(idx && seg && B > 0 && T > 0, "segment_ids: bad arguments");
+  segment_ids_kernel<<<(B + 3) / 4, 128, 0, ST(stream)>>>(idx, seg, B, T, sep_id);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_segment_starts(const int64_t* idx, int32_t* start, int B, int T, int sep_id, cgpt_stream_t stream) {
+  CGPT_REQUIRE(idx && start && B > 0 && T > 0, "segment_starts: bad arguments");
+  segment_starts_kernel<<<(B + 3) / 4, 128, 0, ST(stream)>>>(idx, start, B, T, sep_id);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_next_in_set(const int64_t* yb, int32_t* next, int B, int T, const int64_t* ids_host, int n_ids,
+                     cgpt_stream_t stream) {
+  CGPT_REQUIRE(yb && next && B > 0 && T > 0, "next_in_set: bad arguments");
+  CGPT_REQUIRE(n_ids >= 0 && n_ids <= 8, "next_in_set: at most 8 ids (got %d)", n_ids);
+  IdSet ids;
+  ids.n = n_ids;
+  for (int i = 0; i < n_ids; ++i) ids.v[i] = ids_host[i];
+  next_in_set_kernel<<<(B + 3) / 4, 128, 0, ST(stream)>>>(yb, next, B, T, ids);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_termination_labels(const int64_t* yb, const int32_t* next_stop, int64_t* labels, int B, int T,
+                            const int64_t* edges_host, int n_edges, int64_t ignore_index, cgpt_stream_t stream) {
+  CGPT_REQUIRE(yb && next_stop && labels && B > 0 && T > 0, "termination_labels: bad arguments");
+  CGPT_REQUIRE(n_edges >= 0 && n_edges <= 8, "termination_labels: at most 8 bucket edges (got %d)", n_edges);
+  EdgeSet e;
+  e.n = n_edges;
+  for (int i = 0; i < n_edges; ++i) e.v[i] = edges_host[i];
+  const size_t n = (size_t)B * T;
+  termination_labels_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ST(stream)>>>(yb, next_stop, labels, B, T, e,
+                                                                                 ignore_index);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_embed_fwd(const int64_t* idx, const float* tok_w, const float* pos_w, float* x, int B, int T, int d,
+                   int vocab, cgpt_stream_t stream) {
+  CGPT_REQUIRE(idx && tok_w && x && B > 0 && T > 0, "embed_fwd: bad arguments");
+  CGPT_REQUIRE(d % 4 == 0, "embed_fwd: d=%d must be a multiple of 4", d);
+  const size_t n4 = (size_t)B * T * (d / 4);
+  embed_fwd_kernel<<<grid_for((long long)n4, 256), 256, 0, ST(stream)>>>(
+      idx, reinterpret_cast<const float4*>(tok_w), reinterpret_cast<const float4*>(pos_w),
+      reinterpret_cast<float4*>(x), n4, T, d / 4, vocab);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok_w, float* dpos_w, int B, int T, int d,
+                   int vocab, cgpt_stream_t stream) {
+  CGPT_REQUIRE(idx && dx && dtok_w && B > 0 && T > 0, "embed_bwd: bad arguments");
+  CGPT_REQUIRE(d % 4 == 0, "embed_bwd: d=%d must be a multiple of 4", d);
+  const int M = B * T;
+  const int max_smem = 200 * 1024;
+  int cols = d;
+  while ((size_t)vocab * cols * 4 > (size_t)max_smem) cols = (cols + 1) / 2;
+  cols = (cols + 3) / 4 * 4;
+  const int col_tiles = (d + cols - 1) / cols;
+  int tok_ctas = (2 * num_sms()) / col_tiles;
+  if (tok_ctas < 1) tok_ctas = 1;
+  if (tok_ctas > M) tok_ctas = M;
+  const int toks = (M + tok_ctas - 1) / tok_ctas;
+  tok_ctas = (M + toks - 1) / toks;
+  const size_t smem = (size_t)vocab * cols * 4;
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    CGPT_CHECK(cudaFuncSetAttribute(embed_bwd_tok_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  embed_bwd_tok_kernel<<<dim3(tok_ctas, col_tiles), 256, smem, ST(stream)>>>(idx, dx, dtok_w, M, d, vocab, cols,
+                                                                            toks);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  if (dpos_w) {
+    const size_t n = (size_t)T * (d / 4);
+    embed_bwd_pos_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ST(stream)>>>(
+        reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dpos_w), B, T, d / 4);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int cgpt_layernorm_fwd(const float* x, const float* gamma, const float* beta, void* y_bf16, float* y_f32,
+                       float* mean, float* rstd, int M, int d, float eps, cgpt_stream_t stream) {
+  CGPT_REQUIRE(x && gamma && beta && mean && rstd && (y_bf16 || y_f32) && M > 0, "layernorm_fwd: bad arguments");
+  CGPT_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
+               128 * kLnMaxVec);
+  const int grid = grid_for((long long)M * 32, 256, 4);
+  layernorm_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32,
+                                                     mean, rstd, M, d, eps);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float* gamma, const float* mean,
+                       const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
+                       int M, int d, cgpt_stream_t stream) {
+  CGPT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "layernorm_bwd: bad arguments");
+  CGPT_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
+               128 * kLnMaxVec);
+  const int grid = grid_for((long long)M * 32, 256, 2);
+  if (dy_is_f32)
+    layernorm_bwd_kernel<true><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx,
+                                                             reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, M, d);
+  else
+    layernorm_bwd_kernel<false><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx,
+                                                              reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, M, d);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_cast_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t ld_out, int64_t rows, int64_t cols,
+                       cgpt_stream_t stream) {
+  CGPT_REQUIRE(in && out && rows > 0 && cols > 0 && ld_in >= cols && ld_out >= cols, "cast: bad arguments");
+  const bool dense = (ld_in == cols) && (ld_out == cols) && ((rows * cols) % 4 == 0) &&
+                     ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+  if (dense) {
+    const long long n4 = rows * cols / 4;
+    cast_f32_bf16_vec_kernel<<<grid_for(n4, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(in),
+                                                                        reinterpret_cast<uint2*>(out), n4);
+  } else {
+    cast_f32_bf16_kernel<<<grid_for(rows * ld_out, 256), 256, 0, ST(stream)>>>(
+        in, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
+  }
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, cgpt_stream_t stream) {
+  CGPT_REQUIRE(x && out && M > 0 && N > 0 && ld >= N && ld % 2 == 0, "colsum: bad arguments");
+  const int col_tiles = (N + 63) / 64;
+  int row_ctas = (4 * num_sms() + col_tiles - 1) / col_tiles;
+  int rows = (M + row_ctas - 1) / row_ctas;
+  if (rows < 64) rows = 64;
+  row_ctas = (M + rows - 1) / rows;
+  colsum_bf16_kernel<<<dim3(col_tiles, row_ctas), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld,
+                                                                       out, M, N, rows);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_rope_qk(void* qkv, const float* cos_t, const float* sin_t, int B, int T, int H, int Hk, int hd,
+                 int inverse, cgpt_stream_t stream) {
+  CGPT_REQUIRE(qkv && cos_t && sin_t && B > 0 && T > 0, "rope: bad arguments");
+  CGPT_REQUIRE(hd % 4 == 0, "rope: head_dim=%d must be a multiple of 4", hd);
+  const long long ld = (long long)(H + 2 * Hk) * hd;
+  const long long total = (long long)B * T * (H + Hk) * (hd / 4);
+  rope_qk_kernel<<<grid_for(total, 256), 256, 0, ST(stream)>>>(reinterpret_cast<__nv_bfloat16*>(qkv), cos_t, sin_t,
+                                                               B * T, T, H + Hk, hd, ld, inverse);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_swiglu_fwd(const void* gu, int64_t ldgu, void* act, int64_t ldact, int M, int h, cgpt_stream_t stream) {
+  CGPT_REQUIRE(gu && act && M > 0 && h > 0 && h % 2 == 0 && ldgu % 2 == 0 && ldact % 2 == 0, "swiglu_fwd: bad arguments");
+  swiglu_fwd_kernel<<<grid_for((long long)M * h / 2, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gu), ldgu, reinterpret_cast<__nv_bfloat16*>(act), ldact, M, h);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_swiglu_bwd(const void* gu, int64_t ldgu, const void* dact, int64_t ldact, void* dgu, int M, int h,
+                    cgpt_stream_t stream) {
+  CGPT_REQUIRE(gu && dact && dgu && M > 0 && h > 0 && h % 2 == 0 && ldgu % 2 == 0 && ldact % 2 == 0,
+               "swiglu_bwd: bad arguments");
+  swiglu_bwd_kernel<<<grid_for((long long)M * h / 2, 256), 256, 0, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(gu), ldgu, reinterpret_cast<const __nv_bfloat16*>(dact), ldact,
+      reinterpret_cast<__nv_bfloat16*>(dgu), M, h);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
+               float beta2, float eps, float weight_decay, int step, float grad_scale, cgpt_stream_t stream) {
+  CGPT_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adamw_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n,
+                                                         lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,399 @@
+// Small-vocabulary heads: out = x·wᵀ (+b) with N <= 128 output columns (the ~68-codon LM head and
+// the 5-class termination head), their backward, and the softmax cross-entropy (ignore_index,
+// label smoothing, class weights, offset-validity mask).  Kept in fp32 FMA: 2·d·V FLOP/token is
+// < 0.1 % of the step and the reference's argmax must be reproduced (SURVEY §7 hard part 1).
+// Replaces model_tiny_gpt.py:327,330,336,343-349 and objectives.py:39-57,100-105.
+#include "common.cuh"
+
+namespace cgpt {
+namespace {
+
+constexpr int kKC = 32;       // k-chunk
+constexpr int kPitch = 36;    // smem row pitch in floats (16-byte aligned, conflict-free float4 reads)
+
+// ------------------------------------------------------------------ forward: 64 rows x (16*J) cols per CTA
+template <int J>
+__global__ void __launch_bounds__(256)
+skinny_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ bias,
+                  float* __restrict__ out, int M, int N, int d) {
+  __shared__ __align__(16) float xs[64 * kPitch];
+  __shared__ __align__(16) float ws[16 * J * kPitch];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.x * 64;
+  float acc[4][J];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[i][j] = 0.f;
+
+  for (int k0 = 0; k0 < d; k0 += kKC) {
+    __syncthreads();
+    for (int i = tid; i < 64 * (kKC / 4); i += 256) {
+      const int r = i / (kKC / 4), c4 = i % (kKC / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (row0 + r < M && k0 + c4 * 4 < d) v = *reinterpret_cast<const float4*>(x + (size_t)(row0 + r) * d + k0 + c4 * 4);
+      *reinterpret_cast<float4*>(&xs[r * kPitch + c4 * 4]) = v;
+    }
+    for (int i = tid; i < 16 * J * (kKC / 4); i += 256) {
+      const int r = i / (kKC / 4), c4 = i % (kKC / 4);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r < N && k0 + c4 * 4 < d) v = __ldg(reinterpret_cast<const float4*>(w + (size_t)r * d + k0 + c4 * 4));
+      *reinterpret_cast<float4*>(&ws[r * kPitch + c4 * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kKC; kk += 4) {
+      float4 xv[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xv[i] = *reinterpret_cast<const float4*>(&xs[(ty * 4 + i) * kPitch + kk]);
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const float4 wv = *reinterpret_cast<const float4*>(&ws[(tx + 16 * j) * kPitch + kk]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          acc[i][j] += (xv[i].x * wv.x + xv[i].y * wv.y) + (xv[i].z * wv.z + xv[i].w * wv.w);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r >= M) continue;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int c = tx + 16 * j;
+      if (c < N) out[(size_t)r * N + c] = acc[i][j] + (bias ? __ldg(bias + c) : 0.f);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ dx (+)= dout·w : 64 rows x 64 d-cols per CTA
+__global__ void __launch_bounds__(256)
+skinny_dx_kernel(const float* __restrict__ dout, const float* __restrict__ w, float* __restrict__ dx, int M, int N,
+                 int d, int accumulate) {
+  extern __shared__ __align__(16) float sm[];
+  const int np = N + 1;
+  float* ds = sm;                 // [64][np]
+  float* ws = sm + 64 * np + ((4 - (64 * np) % 4) % 4);  // [N][64], 16-byte aligned
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int row0 = blockIdx.x * 64, c0 = blockIdx.y * 64;
+  for (int i = tid; i < 64 * N; i += 256) {
+    const int r = i / N, n = i - r * N;
+    ds[r * np + n] = (row0 + r < M) ? dout[(size_t)(row0 + r) * N + n] : 0.f;
+  }
+  for (int i = tid; i < N * 16; i += 256) {
+    const int n = i >> 4, c4 = i & 15;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (c0 + c4 * 4 < d) v = __ldg(reinterpret_cast<const float4*>(w + (size_t)n * d + c0 + c4 * 4));
+    *reinterpret_cast<float4*>(&ws[n * 64 + c4 * 4]) = v;
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (int n = 0; n < N; ++n) {
+    const float4 b = *reinterpret_cast<const float4*>(&ws[n * 64 + tx * 4]);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float a = ds[(ty * 4 + i) * np + n];
+      acc[i][0] += a * b.x;
+      acc[i][1] += a * b.y;
+      acc[i][2] += a * b.z;
+      acc[i][3] += a * b.w;
+    }
+  }
+  const int c = c0 + tx * 4;
+  if (c >= d) return;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = row0 + ty * 4 + i;
+    if (r >= M) continue;
+    float4* o = reinterpret_cast<float4*>(dx + (size_t)r * d + c);
+    float4 v = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    if (accumulate) {
+      const float4 p = *o;
+      v.x += p.x;
+      v.y += p.y;
+      v.z += p.z;
+      v.w += p.w;
+    }
+    *o = v;
+  }
+}
+
+// ------------------------------------------------------------------ dw += doutᵀ·x ; dbias += colsum(dout)
+template <int J>
+__global__ void __launch_bounds__(256)
+skinny_dw_kernel(const float* __restrict__ dout, const float* __restrict__ x, float* __restrict__ dw,
+                 float* __restrict__ dbias, int M, int N, int d, int rows_per_cta) {
+  __shared__ __align__(16) float ds[32 * 16 * J];
+  __shared__ __align__(16) float xs[32 * 64];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int c0 = blockIdx.x * 64;
+  const int r_begin = blockIdx.y * rows_per_cta;
+  const int r_end = min(M, r_begin + rows_per_cta);
+  float acc[J][4];
+  float bacc[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    bacc[j] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[j][i] = 0.f;
+  }
+  for (int r0 = r_begin; r0 < r_end; r0 += 32) {
+    __syncthreads();
+    for (int i = tid; i < 32 * 16 * J; i += 256) {
+      const int r = i / (16 * J), n = i - r * (16 * J);
+      ds[i] = (r0 + r < r_end && n < N) ? dout[(size_t)(r0 + r) * N + n] : 0.f;
+    }
+    for (int i = tid; i < 32 * 16; i += 256) {
+      const int r = i >> 4, c4 = i & 15;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + r < r_end && c0 + c4 * 4 < d) v = *reinterpret_cast<const float4*>(x + (size_t)(r0 + r) * d + c0 + c4 * 4);
+      *reinterpret_cast<float4*>(&xs[r * 64 + c4 * 4]) = v;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int r = 0; r < 32; ++r) {
+      const float4 b = *reinterpret_cast<const float4*>(&xs[r * 64 + tx * 4]);
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        const float a = ds[r * 16 * J + ty + 16 * j];
+        acc[j][0] += a * b.x;
+        acc[j][1] += a * b.y;
+        acc[j][2] += a * b.z;
+        acc[j][3] += a * b.w;
+        bacc[j] += a;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int n = ty + 16 * j;
+    if (n >= N) continue;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int c = c0 + tx * 4 + i;
+      if (c < d) atomicAdd(dw + (size_t)n * d + c, acc[j][i]);
+    }
+    if (dbias && blockIdx.x == 0 && tx == 0) atomicAdd(dbias + n, bacc[j]);
+  }
+}
+
+// ------------------------------------------------------------------ cross entropy (one warp per row, V <= 128)
+struct RowInfo {
+  bool keep;
+  int64_t target;
+};
+
+__device__ __forceinline__ RowInfo ce_row_info(const int64_t* targets, const int32_t* next_boundary, int row, int T,
+                                               int shift, int64_t ignore_index) {
+  RowInfo ri;
+  const int b = row / T, t = row - b * T;
+  ri.keep = false;
+  ri.target = 0;
+  if (t + shift < T) {
+    const int64_t tg = targets[(size_t)b * T + t + shift];
+    ri.target = tg;
+    ri.keep = (tg != ignore_index) && (next_boundary == nullptr || next_boundary[row] >= t + shift);
+  }
+  return ri;
+}
+
+__global__ void __launch_bounds__(256)
+ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
+              const int32_t* __restrict__ next_boundary, const float* __restrict__ class_w, float* __restrict__ row_ws,
+              float* __restrict__ row_lse, int M, int T, int V, int shift, float smoothing, int64_t ignore_index) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const float* z = logits + (size_t)row * V;
+  float v[4];
+  float mx = -INFINITY;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    v[k] = c < V ? z[c] : -INFINITY;
+    mx = fmaxf(mx, v[k]);
+  }
+  mx = warp_max(mx);
+  float se = 0.f, swz = 0.f, sw = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    if (c < V) {
+      se += expf(v[k] - mx);
+      const float wc = class_w ? __ldg(class_w + c) : 1.f;
+      swz += wc * v[k];
+      sw += wc;
+    }
+  }
+  se = warp_sum(se);
+  const float lse = mx + logf(se);
+  const RowInfo ri = ce_row_info(targets, next_boundary, row, T, shift, ignore_index);
+  float loss = 0.f, wt = 0.f;
+  if (ri.keep) {
+    swz = warp_sum(swz);
+    sw = warp_sum(sw);
+    const int tg = (int)ri.target;
+    const float wy = class_w ? __ldg(class_w + tg) : 1.f;
+    loss = (1.f - smoothing) * wy * (lse - z[tg]);
+    if (smoothing > 0.f) loss += (smoothing / V) * (sw * lse - swz);
+    wt = wy;
+  }
+  if (lane == 0) {
+    row_lse[row] = lse;
+    row_ws[row] = loss;
+    row_ws[M + row] = wt;
+  }
+}
+
+// deterministic (fixed-order) reduction of the per-row terms into sums[0..1]
+__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_ws, float* __restrict__ sums, int M) {
+  __shared__ float red[2][32];
+  float a = 0.f, b = 0.f;
+  for (int i = threadIdx.x; i < M; i += 1024) {
+    a += row_ws[i];
+    b += row_ws[M + i];
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if ((threadIdx.x & 31) == 0) {
+    red[0][threadIdx.x >> 5] = a;
+    red[1][threadIdx.x >> 5] = b;
+  }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    a = warp_sum(red[0][threadIdx.x]);
+    b = warp_sum(red[1][threadIdx.x]);
+    if (threadIdx.x == 0) {
+      sums[0] += a;
+      sums[1] += b;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ row_lse, const int64_t* __restrict__ targets,
+              const int32_t* __restrict__ next_boundary, const float* __restrict__ class_w,
+              const float* __restrict__ sums, const float* __restrict__ gscale, float coef, float* __restrict__ dlogits,
+              int M, int T, int V, int shift, float smoothing, int64_t ignore_index) {
+  const int lane = threadIdx.x & 31;
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const RowInfo ri = ce_row_info(targets, next_boundary, row, T, shift, ignore_index);
+  float* o = dlogits + (size_t)row * V;
+  if (!ri.keep) {
+    for (int c = lane; c < V; c += 32) o[c] = 0.f;
+    return;
+  }
+  const float* z = logits + (size_t)row * V;
+  const float lse = row_lse[row];
+  const float scale = coef * (gscale ? *gscale : 1.f) / sums[1];
+  float sw = 0.f;
+  for (int c = lane; c < V; c += 32) sw += class_w ? __ldg(class_w + c) : 1.f;
+  sw = warp_sum(sw);
+  const int tg = (int)ri.target;
+  const float wy = class_w ? __ldg(class_w + tg) : 1.f;
+  for (int c = lane; c < V; c += 32) {
+    const float p = expf(z[c] - lse);
+    const float wc = class_w ? __ldg(class_w + c) : 1.f;
+    float g = (1.f - smoothing) * wy * (p - (c == tg ? 1.f : 0.f));
+    if (smoothing > 0.f) g += (smoothing / V) * (p * sw - wc);
+    o[c] = g * scale;
+  }
+}
+
+}  // namespace
+}  // namespace cgpt
+
+using namespace cgpt;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" {
+
+int cgpt_skinny_linear_fwd(const float* x, const float* w, const float* bias, float* out, int M, int N, int d,
+                           cgpt_stream_t stream) {
+  CGPT_REQUIRE(x && w && out && M > 0 && N > 0 && d > 0, "skinny_linear_fwd: bad arguments");
+  CGPT_REQUIRE(N <= 128, "skinny_linear: N=%d > 128 (use cgpt_gemm_bf16)", N);
+  CGPT_REQUIRE(d % 4 == 0, "skinny_linear: d=%d must be a multiple of 4", d);
+  const int grid = (M + 63) / 64;
+  if (N <= 16)
+    skinny_fwd_kernel<1><<<grid, 256, 0, ST(stream)>>>(x, w, bias, out, M, N, d);
+  else if (N <= 80)
+    skinny_fwd_kernel<5><<<grid, 256, 0, ST(stream)>>>(x, w, bias, out, M, N, d);
+  else
+    skinny_fwd_kernel<8><<<grid, 256, 0, ST(stream)>>>(x, w, bias, out, M, N, d);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_skinny_linear_bwd(const float* dout, const float* x, const float* w, float* dx, int dx_accumulate, float* dw,
+                           float* dbias, int M, int N, int d, cgpt_stream_t stream) {
+  CGPT_REQUIRE(dout && x && w && M > 0 && N > 0 && d > 0, "skinny_linear_bwd: bad arguments");
+  CGPT_REQUIRE(N <= 128, "skinny_linear: N=%d > 128", N);
+  CGPT_REQUIRE(d % 4 == 0, "skinny_linear: d=%d must be a multiple of 4", d);
+  const int col_tiles = (d + 63) / 64;
+  if (dx) {
+    const size_t smem = (size_t)(64 * (N + 1) + 4 + N * 64) * 4;
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      CGPT_CHECK(cudaFuncSetAttribute(skinny_dx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    skinny_dx_kernel<<<dim3((M + 63) / 64, col_tiles), 256, smem, ST(stream)>>>(dout, w, dx, M, N, d, dx_accumulate);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+  }
+  if (dw) {
+    int row_ctas = (3 * num_sms() + col_tiles - 1) / col_tiles;
+    int rows = (M + row_ctas - 1) / row_ctas;
+    rows = (rows + 31) / 32 * 32;
+    row_ctas = (M + rows - 1) / rows;
+    dim3 grid(col_tiles, row_ctas);
+    if (N <= 16)
+      skinny_dw_kernel<1><<<grid, 256, 0, ST(stream)>>>(dout, x, dw, dbias, M, N, d, rows);
+    else if (N <= 80)
+      skinny_dw_kernel<5><<<grid, 256, 0, ST(stream)>>>(dout, x, dw, dbias, M, N, d, rows);
+    else
+      skinny_dw_kernel<8><<<grid, 256, 0, ST(stream)>>>(dout, x, dw, dbias, M, N, d, rows);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int cgpt_ce_fwd(const float* logits, const int64_t* targets, const int32_t* next_boundary, const float* class_w,
+                float* sums, float* row_lse, float* row_ws, int B, int T, int V, int shift, float smoothing,
+                int64_t ignore_index, cgpt_stream_t stream) {
+  CGPT_REQUIRE(logits && targets && sums && row_lse && row_ws && B > 0 && T > 0, "ce_fwd: bad arguments");
+  CGPT_REQUIRE(V >= 1 && V <= 128, "ce: V=%d must be in [1,128]", V);
+  CGPT_REQUIRE(shift >= 0, "ce: shift must be >= 0");
+  const int M = B * T;
+  ce_fwd_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, targets, next_boundary, class_w, row_ws, row_lse, M, T, V,
+                                                     shift, smoothing, ignore_index);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  ce_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_ws, sums, M);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_ce_bwd(const float* logits, const float* row_lse, const int64_t* targets, const int32_t* next_boundary,
+                const float* class_w, const float* sums, const float* gscale, float coef, float* dlogits, int B, int T,
+                int V, int shift, float smoothing, int64_t ignore_index, cgpt_stream_t stream) {
+  CGPT_REQUIRE(logits && row_lse && targets && sums && dlogits && B > 0 && T > 0, "ce_bwd: bad arguments");
+  CGPT_REQUIRE(V >= 1 && V <= 128, "ce: V=%d must be in [1,128]", V);
+  const int M = B * T;
+  ce_bwd_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, row_lse, targets, next_boundary, class_w, sums, gscale,
+                                                     coef, dlogits, M, T, V, shift, smoothing, ignore_index);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
