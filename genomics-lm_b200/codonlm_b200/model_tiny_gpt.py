@@ -1,0 +1,605 @@
+"""Drop-in for the reference's ``src/codonlm/model_tiny_gpt.py`` running on libcgpt_b200 (sm_100a).
+
+Same classes, constructor arguments, attribute / submodule names, ``state_dict`` keys and shapes,
+``forward(idx, targets, return_aux, shape_embeddings, attention_window)`` contract and error
+behaviour as the reference (model_tiny_gpt.py:9-389); submodules are created in the reference's order
+so ``torch.manual_seed(s); TinyGPT(...)`` yields bit-identical initial weights.
+
+What differs is where the arithmetic happens: every op runs in a hand-written CUDA kernel behind the
+C ABI of include/cgpt.h (fp32 residual stream and LayerNorm statistics, bf16 tensor-core GEMMs and
+attention with fp32 accumulation, fp32 LM head and cross-entropy).  There is no CPU path: calling the
+model with parameters that are not on a B200 raises.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from . import functional as Fn
+from .ops import bf16, f32
+
+
+# ----------------------------------------------------------------------------------------------
+# helpers
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class MaskSpec:
+    """The reference's boolean (B,1,T,T) mask (model_tiny_gpt.py:273-295) in the form the kernels use:
+    allowed[i,j] = seg_start[b,i] <= j <= i and i-j < window."""
+    seg_start: Optional[torch.Tensor]  # int32 [B,T] or None (pure causal)
+    window: int = 0                    # 0 = unlimited
+
+
+class _CastBf16(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return ops.cast_bf16(x.reshape(-1, x.shape[-1]).contiguous()).view(x.shape)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g.float()
+
+
+def _has_hooks(m: nn.Module) -> bool:
+    return bool(m._forward_hooks or m._forward_pre_hooks or m._backward_hooks)
+
+
+def _require_cuda(t: torch.Tensor, what: str):
+    if not t.is_cuda:
+        raise _lib.CgptError(
+            f"{what} is on '{t.device}': codonlm_b200 has no CPU implementation — move the model and its "
+            "inputs to a B200 (model.to('cuda'))")
+
+
+def rotate_half(x):
+    x1 = x[..., : x.shape[-1] // 2]
+    x2 = x[..., x.shape[-1] // 2:]
+    return torch.cat((-x2, x1), dim=-1)
+
+
+# ----------------------------------------------------------------------------------------------
+# leaf modules (same parameters / keys as nn.LayerNorm, nn.Embedding, nn.Linear)
+# ----------------------------------------------------------------------------------------------
+class LayerNorm(nn.LayerNorm):
+    def forward(self, x):  # public path: fp32 in -> fp32 out (hooks on ln_f see what the reference shows)
+        _require_cuda(self.weight, "LayerNorm.weight")
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).float().contiguous()
+        _, _, yf = Fn.ResidualLayerNormFn.apply(x2, self.weight, self.bias, True)
+        return yf.view(shp)
+
+    def fused(self, x2d):
+        """(residual alias, bf16 normalised) for the pre-norm residual pattern."""
+        return Fn.ResidualLayerNormFn.apply(x2d, self.weight, self.bias, False)
+
+
+class Embedding(nn.Embedding):
+    def forward(self, idx):
+        _require_cuda(self.weight, "Embedding.weight")
+        flat = idx.to(self.weight.device).long().reshape(1, -1).contiguous()
+        return Fn.EmbedFn.apply(flat, self.weight, None).view(*idx.shape, -1)
+
+
+class Linear(nn.Linear):
+    """nn.Linear whose forward is the tcgen05 GEMM (bf16 operands, fp32 accumulate, fp32 output)."""
+
+    def forward(self, x):
+        _require_cuda(self.weight, "Linear.weight")
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
+        n, k = self.weight.shape
+        if k % 8 != 0:
+            raise _lib.CgptError(f"Linear in_features={k} must be a multiple of 8 for the TMA path")
+        w_sh = ops.cast_bf16(self.weight.detach())
+        masters = (self.weight,) if self.bias is None else (self.weight, self.bias)
+        out = Fn.PackedLinearFn.apply(xb.contiguous(), w_sh, None if self.bias is None else self.bias.detach(), None,
+                                      ((0, n),), True, *masters)
+        return out.view(*shp[:-1], n)
+
+
+class SkinnyLinear(nn.Linear):
+    """fp32 head with <= 128 outputs (LM head, termination head)."""
+
+    def forward(self, x):
+        _require_cuda(self.weight, "head.weight")
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1]).float().contiguous()
+        if self.out_features > 128:
+            raise _lib.CgptError(f"head with {self.out_features} outputs > 128 is not supported by the fp32 head kernel")
+        out = Fn.SkinnyLinearFn.apply(x2, self.weight, self.bias)
+        return out.view(*shp[:-1], self.out_features)
+
+
+class RotaryEmbedding(nn.Module):
+    """cos/sin tables exactly as the reference builds them (model_tiny_gpt.py:9-33)."""
+
+    def __init__(self, dim, max_position_embeddings=512, base=10000, device=None):
+        super().__init__()
+        self.dim = dim
+        self.max_position_embeddings = max_position_embeddings
+        self.base = base
+        inv_freq = 1.0 / (self.base ** (torch.arange(0, self.dim, 2, dtype=torch.float32) / self.dim))
+        self.register_buffer("inv_freq", inv_freq, persistent=False)
+        self._set_cos_sin_cache(seq_len=max_position_embeddings, device=device, dtype=torch.get_default_dtype())
+
+    def _set_cos_sin_cache(self, seq_len, device, dtype):
+        self.max_seq_len_cached = seq_len
+        t = torch.arange(self.max_seq_len_cached, device=device, dtype=self.inv_freq.dtype)
+        freqs = torch.outer(t, self.inv_freq.to(t.device))
+        emb = torch.cat((freqs, freqs), dim=-1)
+        self.register_buffer("cos_cached", emb.cos().to(dtype), persistent=False)
+        self.register_buffer("sin_cached", emb.sin().to(dtype), persistent=False)
+        self._half = None
+
+    def forward(self, x, seq_len=None):
+        if seq_len > self.max_seq_len_cached:
+            self._set_cos_sin_cache(seq_len=seq_len, device=x.device, dtype=torch.float32)
+        return self.cos_cached[:seq_len].to(x.device), self.sin_cached[:seq_len].to(x.device)
+
+    def half_tables(self, T, device):
+        """fp32 [T, dim/2] cos / sin (the two halves of the reference tables are identical)."""
+        if T > self.max_seq_len_cached:
+            self._set_cos_sin_cache(seq_len=T, device=device, dtype=torch.float32)
+        if self._half is None or self._half[0].device != device or self._half[0].shape[0] < T:
+            h = self.dim // 2
+            self._half = (self.cos_cached[:, :h].to(device=device, dtype=f32).contiguous(),
+                          self.sin_cached[:, :h].to(device=device, dtype=f32).contiguous())
+        return self._half
+
+
+def apply_rotary_pos_emb(q, k, cos, sin):
+    cos = cos.unsqueeze(0).unsqueeze(1)
+    sin = sin.unsqueeze(0).unsqueeze(1)
+    return (q * cos) + (rotate_half(q) * sin), (k * cos) + (rotate_half(k) * sin)
+
+
+# ----------------------------------------------------------------------------------------------
+# blocks
+# ----------------------------------------------------------------------------------------------
+_SHADOW_GEN = [0]
+
+
+def bump_shadow_generation():
+    """Call after writing master weights outside autograd's view (e.g. the fused AdamW kernel)."""
+    _SHADOW_GEN[0] += 1
+
+
+class _ShadowMixin:
+    """bf16 (and packed) copies of the fp32 master parameters, rebuilt when a master changes."""
+
+    def _shadow_key(self, params):
+        return (_SHADOW_GEN[0],) + tuple((p.data_ptr(), p._version) for p in params)
+
+    def _get_shadow(self, name, params, builder):
+        cache = self.__dict__.setdefault("_shadow_cache", {})
+        key = self._shadow_key(params)
+        hit = cache.get(name)
+        if hit is None or hit[0] != key:
+            with torch.no_grad():
+                hit = (key, builder())
+            cache[name] = hit
+        return hit[1]
+
+
+class SwiGLU(nn.Module, _ShadowMixin):
+    def __init__(self, n_embd, dropout):
+        super().__init__()
+        hidden_dim = int(8 * n_embd // 3)
+        self.w_gate = nn.Linear(n_embd, hidden_dim, bias=False)
+        self.w_up = nn.Linear(n_embd, hidden_dim, bias=False)
+        self.w_down = nn.Linear(hidden_dim, n_embd, bias=False)
+        self.dropout = nn.Dropout(dropout)
+
+    def _shadows(self):
+        h, d = self.w_gate.weight.shape
+        hp = (h + 7) // 8 * 8
+
+        def build():
+            wgu = torch.zeros((2 * hp, d), dtype=bf16, device=self.w_gate.weight.device)
+            ops.cast_bf16(self.w_gate.weight, out=wgu[:h])
+            ops.cast_bf16(self.w_up.weight, out=wgu[hp:hp + h])
+            wd = ops.cast_bf16(self.w_down.weight, ld_out=hp)
+            return wgu, wd
+        return self._get_shadow("swiglu", (self.w_gate.weight, self.w_up.weight, self.w_down.weight), build)
+
+    def forward(self, x, residual=None):
+        _require_cuda(self.w_gate.weight, "SwiGLU weights")
+        _check_dropout(self, self.dropout.p)
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
+        wgu, wd = self._shadows()
+        r2 = None if residual is None else residual.reshape(-1, shp[-1])
+        out = Fn.MlpSwiGLUFn.apply(xb.contiguous(), r2, wgu, wd, self.w_gate.weight, self.w_up.weight,
+                                   self.w_down.weight)
+        return out.view(shp[:-1] + (out.shape[-1],))
+
+
+class GeluMLP(nn.Sequential, _ShadowMixin):
+    """nn.Sequential(Linear(d,4d), GELU(), Linear(4d,d), Dropout) with the reference's child indices
+    (state_dict keys mlp.0.*, mlp.2.*), evaluated as two fused GEMMs."""
+
+    def __init__(self, n_embd, dropout):
+        super().__init__(nn.Linear(n_embd, 4 * n_embd), nn.GELU(), nn.Linear(4 * n_embd, n_embd), nn.Dropout(dropout))
+
+    def forward(self, x, residual=None):
+        fc1, fc2 = self[0], self[2]
+        _require_cuda(fc1.weight, "MLP weights")
+        _check_dropout(self, self[3].p)
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
+        w1, w2 = self._get_shadow("mlp", (fc1.weight, fc2.weight),
+                                  lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
+        r2 = None if residual is None else residual.reshape(-1, shp[-1])
+        out = Fn.MlpGeluFn.apply(xb.contiguous(), r2, w1, fc1.bias, w2, fc2.bias, fc1.weight, fc2.weight)
+        return out.view(shp[:-1] + (out.shape[-1],))
+
+
+def _check_dropout(module: nn.Module, p: float):
+    if module.training and p > 0.0:
+        raise NotImplementedError(
+            "codonlm_b200: dropout > 0 in training mode is not implemented yet; build the model with dropout=0.0 "
+            "(eval mode ignores dropout exactly like the reference)")
+
+
+class CausalSelfAttention(nn.Module, _ShadowMixin):
+    def __init__(self, n_embd, n_head, dropout, block_size, n_kv_head: int | None = None, use_sdpa: bool = False,
+                 use_rope: bool = False):
+        super().__init__()
+        assert n_embd % n_head == 0
+        self.n_head = n_head
+        self.n_kv_head = n_kv_head if (n_kv_head is not None and n_kv_head > 0 and n_kv_head <= n_head) else None
+        self.use_sdpa = bool(use_sdpa)
+        head_dim = n_embd // n_head
+        kv_dim = (self.n_kv_head * head_dim) if self.n_kv_head is not None else n_embd
+        self.key = nn.Linear(n_embd, kv_dim)
+        self.query = nn.Linear(n_embd, n_embd)
+        self.value = nn.Linear(n_embd, kv_dim)
+        self.proj = nn.Linear(n_embd, n_embd)
+        self.dropout = nn.Dropout(dropout)
+        self.register_buffer("mask", torch.tril(torch.ones(block_size, block_size)).unsqueeze(0).unsqueeze(0))
+        self.rotary_emb = RotaryEmbedding(dim=head_dim, max_position_embeddings=block_size) if use_rope else None
+        self.last_attn = None
+
+    def _shadows(self):
+        q, k, v = self.query, self.key, self.value
+
+        def build():
+            d = q.weight.shape[1]
+            nq, nk = q.weight.shape[0], k.weight.shape[0]
+            w = torch.empty((nq + 2 * nk, d), dtype=bf16, device=q.weight.device)
+            ops.cast_bf16(q.weight, out=w[:nq])
+            ops.cast_bf16(k.weight, out=w[nq:nq + nk])
+            ops.cast_bf16(v.weight, out=w[nq + nk:])
+            b = torch.cat((q.bias, k.bias, v.bias)).float().contiguous()
+            return w, b, ops.cast_bf16(self.proj.weight)
+        return self._get_shadow("attn", (q.weight, k.weight, v.weight, q.bias, k.bias, v.bias, self.proj.weight), build)
+
+    def forward(self, x, attn_mask=None, residual=None):
+        _require_cuda(self.query.weight, "attention weights")
+        _check_dropout(self, self.dropout.p)
+        B, T, Cdim = x.size()
+        H = self.n_head
+        hd = Cdim // H
+        Hk = self.n_kv_head if self.n_kv_head is not None else H
+        if H % Hk != 0:
+            raise ValueError("n_head must be divisible by n_kv_head for GQA")
+        if isinstance(attn_mask, torch.Tensor):
+            raise NotImplementedError(
+                "codonlm_b200 attention takes the mask as a MaskSpec (segment starts + window), see "
+                "TinyGPT.mask_spec(); arbitrary boolean mask tensors are not supported")
+        spec: MaskSpec = attn_mask if attn_mask is not None else MaskSpec(None, 0)
+        x2 = x.reshape(B * T, Cdim)
+        xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
+        w_qkv, b_qkv, w_proj = self._shadows()
+        nq, nk = self.query.weight.shape[0], self.key.weight.shape[0]
+        qkv = Fn.PackedLinearFn.apply(xb.contiguous(), w_qkv, b_qkv, None, ((0, nq), (nq, nk), (nq + nk, nk)), False,
+                                      self.query.weight, self.key.weight, self.value.weight,
+                                      self.query.bias, self.key.bias, self.value.bias)
+        rope = self.rotary_emb.half_tables(T, x.device) if self.rotary_emb is not None else None
+        y = Fn.AttentionFn.apply(qkv, spec.seg_start, rope, B, T, H, Hk, hd, int(spec.window or 0))
+        if not self.use_sdpa:
+            # the reference's manual branch keeps the probabilities for introspection (:128)
+            with torch.no_grad():
+                self.last_attn = ops.attn_probs(qkv.detach(), spec.seg_start, B, T, H, Hk, hd, int(spec.window or 0))
+        r2 = None if residual is None else residual.reshape(B * T, Cdim)
+        out = Fn.PackedLinearFn.apply(y, w_proj, self.proj.bias.detach(), r2, ((0, Cdim),), True, self.proj.weight,
+                                      self.proj.bias)
+        return out.view(B, T, Cdim)
+
+
+class Block(nn.Module):
+    def __init__(self, n_embd, n_head, dropout, block_size, n_kv_head: int | None = None, use_sdpa: bool = False,
+                 use_swiglu: bool = False, use_rope: bool = False):
+        super().__init__()
+        self.ln1 = LayerNorm(n_embd)
+        self.attn = CausalSelfAttention(n_embd, n_head, dropout, block_size, n_kv_head=n_kv_head, use_sdpa=use_sdpa,
+                                        use_rope=use_rope)
+        self.ln2 = LayerNorm(n_embd)
+        self.mlp = SwiGLU(n_embd, dropout) if use_swiglu else GeluMLP(n_embd, dropout)
+
+    def forward(self, x, attn_mask=None):
+        B, T, d = x.shape
+        x2 = x.reshape(B * T, d)
+        if x2.dtype != f32:
+            x2 = x2.float()
+        # x = x + attn(ln1(x)): LN returns the residual stream so that backward fuses the two gradient paths;
+        # the residual add itself happens in the epilogue of the proj / fc2 GEMM.
+        if _has_hooks(self.ln1):
+            h = _CastBf16.apply(self.ln1(x2))
+        else:
+            x2, h = self.ln1.fused(x2.contiguous())
+        if _has_hooks(self.attn):
+            x2 = x2 + self.attn(h.view(B, T, d), attn_mask=attn_mask).reshape(B * T, d)
+        else:
+            x2 = self.attn(h.view(B, T, d), attn_mask=attn_mask, residual=x2).reshape(B * T, d)
+        if _has_hooks(self.ln2):
+            h = _CastBf16.apply(self.ln2(x2))
+        else:
+            x2, h = self.ln2.fused(x2.contiguous())
+        if _has_hooks(self.mlp):
+            x2 = x2 + self.mlp(h.view(B, T, d)).reshape(B * T, d)
+        else:
+            x2 = self.mlp(h.view(B, T, d), residual=x2).reshape(B * T, d)
+        return x2.view(B, T, d)
+
+
+class _OffsetMLP(nn.Sequential, _ShadowMixin):
+    """nn.Sequential(Linear(d,d), GELU(), Linear(d,d)) per offset (model_tiny_gpt.py:235-239)."""
+
+    def forward(self, x):
+        fc1, fc2 = self[0], self[2]
+        _require_cuda(fc1.weight, "offset head weights")
+        shp = x.shape
+        x2 = x.reshape(-1, shp[-1])
+        xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
+        w1, w2 = self._get_shadow("off", (fc1.weight, fc2.weight),
+                                  lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
+        out = Fn.OffsetHeadFn.apply(xb.contiguous(), w1, fc1.bias, w2, fc2.bias, fc1.weight, fc2.weight)
+        return out.view(shp)
+
+
+# ----------------------------------------------------------------------------------------------
+# the model
+# ----------------------------------------------------------------------------------------------
+class TinyGPT(nn.Module):
+    def __init__(
+        self,
+        vocab_size,
+        block_size,
+        n_layer=3,
+        n_head=4,
+        n_embd=256,
+        dropout=0.1,
+        use_checkpoint=False,
+        label_smoothing: float = 0.0,
+        sep_id: int | None = 3,
+        tie_embeddings: bool = True,
+        n_kv_head: int | None = None,
+        use_sdpa: bool = False,
+        loss_weights: list[float] | None = None,
+        termination_aux: bool = False,
+        termination_n_classes: int = 5,
+        multi_offset_targets: list[int] | None = None,
+        use_swiglu: bool = False,
+        use_rope: bool = False,
+        use_shape_guidance: bool = False,
+    ):
+        super().__init__()
+        self.block_size = block_size
+        self.vocab_size = vocab_size
+        self.n_layer = n_layer
+        self.n_head = n_head
+        self.n_embd = n_embd
+        self.dropout_p = float(dropout)
+        self.use_checkpoint = use_checkpoint  # accepted for config parity; activations fit in 180 GB, no recompute
+        self.label_smoothing = float(label_smoothing)
+        self.sep_id = sep_id
+        self.tie_embeddings = bool(tie_embeddings)
+        self.n_kv_head = n_kv_head if (n_kv_head is not None and n_kv_head > 0) else None
+        self.use_sdpa = bool(use_sdpa)
+        self.termination_aux = bool(termination_aux)
+        self.termination_n_classes = int(termination_n_classes)
+        self.use_swiglu = bool(use_swiglu)
+        self.use_rope = bool(use_rope)
+        self.use_shape_guidance = bool(use_shape_guidance)
+
+        self.tok_emb = Embedding(vocab_size, n_embd)
+        self.pos_emb = Embedding(block_size, n_embd) if not self.use_rope else None
+        self.drop = nn.Dropout(dropout)
+        self.blocks = nn.ModuleList([
+            Block(n_embd, n_head, dropout, block_size, n_kv_head=self.n_kv_head, use_sdpa=self.use_sdpa,
+                  use_swiglu=self.use_swiglu, use_rope=self.use_rope)
+            for _ in range(n_layer)
+        ])
+        self.ln_f = LayerNorm(n_embd)
+        self.head = SkinnyLinear(n_embd, vocab_size, bias=False)
+        if self.tie_embeddings:
+            self.head.weight = self.tok_emb.weight
+        self.termination_head = SkinnyLinear(n_embd, self.termination_n_classes) if self.termination_aux else None
+
+        if self.use_shape_guidance:
+            self.shape_proj = nn.Linear(3, n_embd)
+            nn.init.zeros_(self.shape_proj.weight)
+            nn.init.zeros_(self.shape_proj.bias)
+
+        self.multi_offset_targets = sorted(list(set([int(t) for t in multi_offset_targets]))) if multi_offset_targets else []
+        self.offset_projs = nn.ModuleDict()
+        for offset in self.multi_offset_targets:
+            mlp = _OffsetMLP(nn.Linear(n_embd, n_embd), nn.GELU(), nn.Linear(n_embd, n_embd))
+            nn.init.eye_(mlp[0].weight)
+            nn.init.zeros_(mlp[0].bias)
+            nn.init.eye_(mlp[2].weight)
+            nn.init.zeros_(mlp[2].bias)
+            self.offset_projs[str(offset)] = mlp
+
+        if loss_weights is not None:
+            self.register_buffer("loss_weights", torch.tensor(loss_weights, dtype=torch.float32))
+        else:
+            self.register_buffer("loss_weights", torch.ones(vocab_size, dtype=torch.float32))
+        self._lw_cache = None
+
+    # ------------------------------------------------------------------ reference API
+    def to_dict(self) -> dict:
+        return {
+            "vocab_size": int(self.vocab_size),
+            "block_size": int(self.block_size),
+            "n_layer": int(self.n_layer),
+            "n_head": int(self.n_head),
+            "n_embd": int(self.n_embd),
+            "dropout": float(self.dropout_p),
+            "sep_mask_enabled": self.sep_id is not None,
+            "tie_embeddings": bool(self.tie_embeddings),
+            "n_kv_head": self.n_kv_head,
+            "use_sdpa": bool(self.use_sdpa),
+            "termination_aux": bool(self.termination_aux),
+            "termination_n_classes": int(self.termination_n_classes),
+            "multi_offset_targets": self.multi_offset_targets,
+            "use_swiglu": bool(self.use_swiglu),
+            "use_rope": bool(self.use_rope),
+            "use_shape_guidance": bool(self.use_shape_guidance),
+        }
+
+    def build_attention_mask(self, idx: torch.Tensor, attention_window: int | None = None) -> torch.Tensor | None:
+        """The boolean (B,1,T,T) mask of the reference (:273-295), for introspection only: the kernels use
+        mask_spec() and never materialise it.  Index arithmetic only, any device."""
+        _, length = idx.shape
+        if attention_window is not None and int(attention_window) < 1:
+            raise ValueError("attention_window must be at least 1")
+        if self.sep_id is None and attention_window is None:
+            return None
+        pos = torch.arange(length, device=idx.device)
+        dist = pos.unsqueeze(1) - pos.unsqueeze(0)
+        allowed = dist >= 0
+        if attention_window is not None:
+            allowed = allowed & (dist < int(attention_window))
+        allowed = allowed.unsqueeze(0).unsqueeze(0)
+        if self.sep_id is not None:
+            seg = (ops.segment_ids(idx.contiguous(), int(self.sep_id)).long() if idx.is_cuda
+                   else torch.cumsum(idx == int(self.sep_id), dim=1))
+            allowed = allowed & (seg.unsqueeze(-1) == seg.unsqueeze(-2)).unsqueeze(1)
+        return allowed
+
+    def mask_spec(self, idx: torch.Tensor, attention_window: int | None = None) -> MaskSpec:
+        if attention_window is not None and int(attention_window) < 1:
+            raise ValueError("attention_window must be at least 1")
+        seg_start = ops.segment_starts(idx, int(self.sep_id)) if self.sep_id is not None else None
+        return MaskSpec(seg_start, int(attention_window) if attention_window is not None else 0)
+
+    # ------------------------------------------------------------------ internals
+    def _prep_idx(self, idx):
+        dev = self.tok_emb.weight.device
+        _require_cuda(self.tok_emb.weight, "TinyGPT parameters")
+        if idx.device != dev:
+            idx = idx.to(dev)
+        if idx.dtype != torch.int64:
+            idx = idx.long()
+        B, T = idx.shape
+        if not self.use_rope and T > self.block_size:
+            raise IndexError(f"sequence length {T} exceeds block_size {self.block_size}")
+        return idx.contiguous()
+
+    def _embed(self, idx, shape_embeddings):
+        if shape_embeddings is not None and self.use_shape_guidance:
+            raise NotImplementedError("use_shape_guidance is outside the scope of codonlm_b200 (SURVEY §2.2)")
+        B, T = idx.shape
+        if _has_hooks(self.tok_emb) or (self.pos_emb is not None and _has_hooks(self.pos_emb)):
+            x = self.tok_emb(idx)
+            if self.pos_emb is not None:
+                x = x + self.pos_emb(torch.arange(0, T, device=idx.device).unsqueeze(0))
+        else:
+            x = Fn.EmbedFn.apply(idx, self.tok_emb.weight, None if self.pos_emb is None else self.pos_emb.weight)
+        _check_dropout(self, self.drop.p)
+        return x
+
+    def class_weights(self):
+        """loss_weights, or None when they are all 1 (the reference checks this with a host sync on every
+        forward, :341; here once per buffer version)."""
+        lw = self.loss_weights
+        key = (lw.data_ptr(), lw._version)
+        if self._lw_cache is None or self._lw_cache[0] != key:
+            self._lw_cache = (key, bool(torch.all(lw == 1.0).item()))
+        return None if self._lw_cache[1] else lw
+
+    def _heads(self, x, B, T):
+        """x: (B,T,d) fp32 after ln_f -> logits, aux dict."""
+        logits = self.head(x)
+        aux = {}
+        if self.termination_head is not None:
+            aux["termination_logits"] = self.termination_head(x)
+        if len(self.offset_projs) > 0:
+            xb = _CastBf16.apply(x)
+            offset_logits = {}
+            for offset in self.multi_offset_targets:
+                proj_x = self.offset_projs[str(offset)](xb)
+                offset_logits[offset] = self.head(proj_x)
+            aux["offset_logits"] = offset_logits
+        return logits, aux
+
+    def forward(self, idx, targets=None, return_aux: bool = False, shape_embeddings=None,
+                attention_window: int | None = None):
+        in_dev = idx.device
+        idx = self._prep_idx(idx)
+        B, T = idx.shape
+        x = self._embed(idx, shape_embeddings)
+        spec = self.mask_spec(idx, attention_window)
+        for blk in self.blocks:
+            x = blk(x, attn_mask=spec)
+        x = self.ln_f(x)
+        logits, aux = self._heads(x, B, T)
+        loss = None
+        if targets is not None:
+            tg = targets.to(idx.device).long().contiguous()
+            loss, _ = Fn.CrossEntropyFn.apply(logits.view(B * T, -1), tg, None, self.class_weights(), B, T, 0,
+                                              self.label_smoothing, 0, False)
+        if in_dev != idx.device:  # callers that keep their tensors on the host get host results back
+            logits = logits.to(in_dev)
+        if return_aux:
+            return logits, loss, aux
+        return logits, loss
+
+    def forward_hidden(self, idx, shape_embeddings=None, attention_window: int | None = None):
+        final = None
+        for _, hidden in self.iter_hidden_states(idx, shape_embeddings=shape_embeddings,
+                                                 attention_window=attention_window):
+            final = hidden
+        if final is None:
+            raise RuntimeError("hidden-state iterator produced no states")
+        return final
+
+    def iter_hidden_states(self, idx, shape_embeddings=None, attention_window: int | None = None):
+        """Yield canonical causal states at embedding, block, and final-norm stages (:368-389)."""
+        idx = self._prep_idx(idx)
+        x = self._embed(idx, shape_embeddings)
+        spec = self.mask_spec(idx, attention_window)
+        yield 0, x
+        for layer, blk in enumerate(self.blocks, start=1):
+            x = blk(x, attn_mask=spec)
+            yield layer, x
+        x = self.ln_f(x)
+        yield "final", x
+
+
+class _OutOfScope(nn.Module):
+    def __init__(self, *a, **k):
+        raise NotImplementedError(
+            "NoProp variants (model_tiny_gpt.py:391-459) are a different training algorithm and outside the "
+            "hot path this package accelerates (SURVEY §2, §8f-4)")
+
+
+class NoPropBlock(_OutOfScope):
+    pass
+
+
+class NoPropTinyGPT(_OutOfScope):
+    pass
+
+
+__all__ = ["TinyGPT", "NoPropBlock", "NoPropTinyGPT"]

@@ -1,0 +1,198 @@
+"""The training step around the model: flat fp32 parameter / gradient buffers, fused AdamW, and the
+data-parallel gradient exchange (bucketed bf16 all-reduce over NCCL, overlapped with backward).
+
+Host-side mirror of what the reference trainer does per optimiser step
+(src/codonlm/training/loop.py: fwd() :1067-1143, step_optimizer :1145-1182,
+_average_accumulated_gradients :145-150, AdamW param groups :681-731) minus its four host syncs per
+micro-batch: losses stay on the device and are read back only when the caller asks.
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Iterable, List, Optional, Sequence
+
+import torch
+import torch.distributed as dist
+
+from . import ops
+from .model_tiny_gpt import bump_shadow_generation
+from .objectives import training_loss
+
+HEAD_GROUP_MARKERS = ("shape_proj", "offset_projs", "termination_head")  # loop.py:660-667,689
+
+
+def split_param_groups(model) -> Dict[str, List[tuple]]:
+    """The reference's two AdamW groups (loop.py:681-731): the aux heads get lr_embedding and no weight decay,
+    everything else (tok_emb, LayerNorms and biases included — the "transformer.wte" test at :689 never
+    matches) is decayed.  Order inside a group = reverse execution order, so that gradient buckets fill from
+    the front while backward runs."""
+    seen = set()
+    named = []
+    for name, p in model.named_parameters():
+        if id(p) in seen or not p.requires_grad:
+            continue
+        seen.add(id(p))
+        named.append((name, p))
+    named.reverse()
+    groups = {"head": [], "backbone": []}
+    for name, p in named:
+        groups["head" if any(m in name for m in HEAD_GROUP_MARKERS) else "backbone"].append((name, p))
+    return groups
+
+
+class FlatGroup:
+    """Parameters of one optimiser group re-homed into a flat fp32 buffer, with flat grad / m / v."""
+
+    def __init__(self, named_params: Sequence[tuple], lr: float, weight_decay: float):
+        self.names = [n for n, _ in named_params]
+        self.params = [p for _, p in named_params]
+        self.lr, self.weight_decay = lr, weight_decay
+        dev = self.params[0].device
+        sizes = [p.numel() for p in self.params]
+        self.offsets, off = [], 0
+        for s in sizes:
+            self.offsets.append(off)
+            off += (s + 63) // 64 * 64  # keep every parameter 256-byte aligned
+        self.numel = off
+        self.flat = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.m = torch.zeros(off, dtype=torch.float32, device=dev)
+        self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        with torch.no_grad():
+            for p, o in zip(self.params, self.offsets):
+                view = self.flat[o:o + p.numel()].view_as(p)
+                view.copy_(p.data)
+                p.data = view
+                p.grad = self.grad[o:o + p.numel()].view_as(p)
+
+
+class GradBuckets:
+    """Bucketed bf16 all-reduce of a flat gradient buffer, launched on a side stream as soon as every
+    parameter of a bucket has received its gradient."""
+
+    def __init__(self, group: FlatGroup, process_group, bucket_bytes: int = 25 << 20):
+        self.g = group
+        self.pg = process_group
+        self.world = dist.get_world_size(process_group)
+        self.on_gpu = group.grad.is_cuda  # CPU tensors only in the gloo tests of this host logic
+        self.comm_stream = torch.cuda.Stream() if self.on_gpu else None
+        elems = max(1, bucket_bytes // 2)
+        self.bounds = []     # (start, end) element ranges of the flat buffer, in backward-completion order
+        self.bucket_of = {}  # param index -> bucket index
+        self.need = []       # params per bucket
+        start, count = 0, 0
+        for i, (p, o) in enumerate(zip(group.params, group.offsets)):
+            end = o + (p.numel() + 63) // 64 * 64
+            self.bucket_of[i] = len(self.bounds)
+            count += 1
+            if end - start >= elems or i == len(group.params) - 1:
+                self.bounds.append((start, end))
+                self.need.append(count)
+                start, count = end, 0
+        self.left = list(self.need)
+        self.staging = [torch.empty(e - s, dtype=torch.bfloat16, device=group.grad.device) for s, e in self.bounds]
+        self.enabled = True
+        self.pending = []
+        for i, p in enumerate(group.params):
+            p.register_post_accumulate_grad_hook(self._make_hook(i))
+
+    def _make_hook(self, i):
+        def hook(_p):
+            if not self.enabled:
+                return
+            b = self.bucket_of[i]
+            self.left[b] -= 1
+            if self.left[b] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        s, e = self.bounds[b]
+        if not self.on_gpu:
+            self.staging[b].copy_(self.g.grad[s:e])
+            work = dist.all_reduce(self.staging[b], op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self.pending.append((b, work))
+            return
+        ready = torch.cuda.Event()
+        ready.record()
+        with torch.cuda.stream(self.comm_stream):
+            self.comm_stream.wait_event(ready)
+            stg = self.staging[b]
+            ops.cast_bf16(self.g.grad[s:e].view(1, -1), out=stg.view(1, -1))
+            work = dist.all_reduce(stg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            self.pending.append((b, work))
+
+    def finish(self):
+        """Wait for all buckets and write the reduced gradients (sum over ranks) back as fp32."""
+        for b, work in self.pending:
+            work.wait()  # the compute stream now waits for that bucket's all-reduce
+            s, e = self.bounds[b]
+            self.g.grad[s:e].copy_(self.staging[b])
+        self.pending.clear()
+        self.left = list(self.need)
+
+
+class TrainStep:
+    """One optimiser step = forward + backward (+ all-reduce) + AdamW on a (B,T) batch of codon ids."""
+
+    def __init__(self, model, lr=3e-4, lr_embedding=None, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
+                 offset_weights: Optional[Dict[int, float]] = None, termination_loss_weight: float = 0.0,
+                 process_group=None, bucket_mb: int = 25):
+        self.model = model
+        self.offset_weights = offset_weights
+        self.termination_loss_weight = termination_loss_weight
+        self.betas, self.eps = betas, eps
+        groups = split_param_groups(model)
+        self.groups: List[FlatGroup] = []
+        if groups["head"]:
+            self.groups.append(FlatGroup(groups["head"], lr_embedding if lr_embedding is not None else lr, 0.0))
+        self.groups.append(FlatGroup(groups["backbone"], lr, weight_decay))
+        self.step_count = 0
+        self.world = 1
+        self.buckets: List[GradBuckets] = []
+        if process_group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            pg = process_group if process_group is not None else dist.group.WORLD
+            self.world = dist.get_world_size(pg)
+            self.buckets = [GradBuckets(g, pg, bucket_mb << 20) for g in self.groups]
+        dev = self.groups[0].flat.device
+        self._xb = self._yb = None
+        self._dev = dev
+
+    # ------------------------------------------------------------------ pieces
+    def zero_grad(self):
+        for g in self.groups:
+            g.grad.zero_()
+
+    def forward_backward(self, xb, yb):
+        total, parts, _ = training_loss(self.model, xb, yb, offset_weights=self.offset_weights,
+                                        termination_loss_weight=self.termination_loss_weight)
+        total.backward()
+        return total.detach(), parts
+
+    def optimizer_step(self, lr_scale: float = 1.0, micro_batches: int = 1):
+        self.step_count += 1
+        gscale = 1.0 / (micro_batches * self.world)  # mean over micro-batches and ranks (loop.py:145-150)
+        for bk in self.buckets:
+            bk.finish()
+        for g in self.groups:
+            ops.adamw(g.flat, g.grad, g.m, g.v, None, g.lr * lr_scale, self.betas[0], self.betas[1], self.eps,
+                      g.weight_decay, self.step_count, gscale)
+        # the kernel wrote the masters behind autograd's back: invalidate the bf16 shadow caches
+        bump_shadow_generation()
+
+    # ------------------------------------------------------------------ the step
+    def step(self, xb, yb, lr_scale: float = 1.0):
+        """Device-resident inputs; returns the total loss as a 0-dim device tensor (no host sync)."""
+        self.zero_grad()
+        loss, _ = self.forward_backward(xb, yb)
+        self.optimizer_step(lr_scale)
+        return loss
+
+    def step_host(self, xb_pinned, yb_pinned, lr_scale: float = 1.0) -> float:
+        """Host buffers in, host scalar out: H2D of the batch and D2H of the loss are part of the call."""
+        if self._xb is None or self._xb.shape != xb_pinned.shape:
+            self._xb = torch.empty(xb_pinned.shape, dtype=torch.int64, device=self._dev)
+            self._yb = torch.empty(yb_pinned.shape, dtype=torch.int64, device=self._dev)
+        self._xb.copy_(xb_pinned, non_blocking=True)
+        self._yb.copy_(yb_pinned, non_blocking=True)
+        return float(self.step(self._xb, self._yb, lr_scale).item())

@@ -655,6 +655,8 @@ __global__ void attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const i
   for (int j = lane; j < T; j += 32) row[j] *= inv;
 }
 
+inline size_t delta_floats(int B, int T, int H) { return ((size_t)B * H * T + 63) / 64 * 64; }
+
 int make_qkv_tmap(CUtensorMap* tm, const void* base, int B, int T, int W, int aw) {
   const uint64_t dims[3] = {(uint64_t)W, (uint64_t)T, (uint64_t)B};
   const uint64_t str[2] = {(uint64_t)W * 2, (uint64_t)T * W * 2};
@@ -694,7 +696,7 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   rc = make_qkv_tmap(&td, dout, B, T, H * HD, HeadCfg<HD>::AW);
   if (rc) return rc;
   float* delta = reinterpret_cast<float*>(ws);
-  float* dq_ws = delta + (size_t)B * H * T;
+  float* dq_ws = delta + delta_floats(B, T, H);  // 256-byte aligned: bulk reduce-adds and float4 reads need 16
   CGPT_CHECK(cudaMemsetAsync(dq_ws, 0, (size_t)B * H * T * HD * sizeof(float), st));
   {
     const long long warps = (long long)B * T * H;
@@ -765,12 +767,13 @@ int cgpt_attn_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, in
 
 int64_t cgpt_attn_bwd_workspace(int B, int T, int H, int Hk, int hd) {
   (void)Hk;
-  return (int64_t)sizeof(float) * ((int64_t)B * H * T + (int64_t)B * H * T * hd);
+  return (int64_t)sizeof(float) * ((int64_t)cgpt::delta_floats(B, T, H) + (int64_t)B * H * T * hd);
 }
 
 int cgpt_attn_bwd(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse, void* dqkv,
                   void* ws, int B, int T, int H, int Hk, int hd, int window, float scale, cgpt_stream_t stream) {
   CGPT_REQUIRE(qkv && out && dout && lse && dqkv && ws, "attn_bwd: null pointer");
+  CGPT_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "attn_bwd: workspace must be 256-byte aligned");
   int rc = check_attn_args("attn_bwd", B, T, H, Hk, hd);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

@@ -59,10 +59,20 @@ CASES = {
 }
 
 
+def state_sha256(model):
+    import hashlib
+    h = hashlib.sha256()
+    for k, v in model.state_dict().items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
 def build(case):
     spec = CASES[case]
     torch.manual_seed(1337)
     m = TinyGPT(**spec["ctor"])
+    spec["init_sha256"] = state_sha256(m)  # weights straight after construction under manual_seed(1337)
     g = torch.Generator().manual_seed(7)
     with torch.no_grad():
         m.tok_emb.weight.mul_(spec["emb_scale"])
@@ -126,7 +136,7 @@ def main():
                 out["grad." + k] = p.grad.detach().numpy()
         meta = dict(ctor=spec["ctor"], parts=parts, attention_window=win,
                     offset_weights={str(k): v for k, v in (ow or {}).items()},
-                    termination_loss_weight=tw, torch=torch.__version__)
+                    termination_loss_weight=tw, torch=torch.__version__, init_sha256=spec["init_sha256"])
         out["meta"] = np.array(json.dumps(meta))
         path = os.path.join(HERE, f"{case}.npz")
         np.savez_compressed(path, **out)

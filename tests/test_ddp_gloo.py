@@ -1,0 +1,70 @@
+"""World-size-2 gloo test (CPU) of the data-parallel host logic: flat parameter groups, bucket
+partitioning, gradient-ready hooks and the bucketed bf16 all-reduce.  The reduced gradient must equal the
+sum of the two ranks' gradients (to bf16 rounding) and both ranks must end up with identical buffers."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import PKG
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, PKG)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from codonlm_b200.trainer import FlatGroup, GradBuckets
+    torch.manual_seed(0)  # same weights on both ranks
+    net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.GELU(), torch.nn.Linear(64, 64), torch.nn.GELU(),
+                              torch.nn.Linear(64, 8))
+    named = list(net.named_parameters())
+    named.reverse()  # reverse execution order, as split_param_groups does
+    group = FlatGroup(named, lr=1e-3, weight_decay=0.0)
+    buckets = GradBuckets(group, dist.group.WORLD, bucket_bytes=1024)  # several buckets
+    assert len(buckets.bounds) >= 3 and buckets.bounds[0][0] == 0 and buckets.bounds[-1][1] == group.numel
+    assert all(a[1] == b[0] for a, b in zip(buckets.bounds, buckets.bounds[1:]))
+    assert sum(buckets.need) == len(group.params)
+    results = []
+    for it in range(2):  # two steps: the ready-counters must re-arm
+        group.grad.zero_()
+        torch.manual_seed(100 + rank + 10 * it)  # different data per rank
+        x = torch.randn(32, 16)
+        net(x).square().mean().backward()
+        local = group.grad.clone()
+        assert len(buckets.pending) == len(buckets.bounds)  # every bucket was launched from the hooks
+        buckets.finish()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        expect = sum(g.to(torch.bfloat16).float() for g in gathered)
+        err = (group.grad - expect).abs().max().item()
+        results.append((err, expect.abs().max().item()))
+        both = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(both, group.grad)
+        assert torch.equal(both[0], both[1])
+    if rank == 0:
+        torch.save(results, out)
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_world2(tmp_path):
+    out = str(tmp_path / "res.pt")
+    port = 29500 + (os.getpid() % 500)
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    for err, scale in torch.load(out):
+        assert err <= 2 ** -7 * scale  # bf16 all-reduce: two roundings
+
+
+def test_param_groups_follow_reference_rule():
+    from codonlm_b200 import TinyGPT
+    from codonlm_b200.trainer import split_param_groups
+    m = TinyGPT(68, 16, n_layer=2, n_head=2, n_embd=32, dropout=0.0, termination_aux=True, multi_offset_targets=[2, 4])
+    g = split_param_groups(m)
+    head_names = [n for n, _ in g["head"]]
+    assert head_names and all(("offset_projs" in n) or ("termination_head" in n) for n in head_names)
+    back = [n for n, _ in g["backbone"]]
+    assert "tok_emb.weight" in back and "ln_f.bias" in back and "head.weight" not in back  # tied: listed once
+    assert back[-1] == "tok_emb.weight" and back[0].startswith("ln_f")  # reverse execution order
+    n_total = sum(p.numel() for p in m.parameters())
+    assert sum(p.numel() for _, p in g["head"] + g["backbone"]) == n_total

@@ -315,6 +315,9 @@ ATTN_CASES = [
     (2, 300, 2, 2, 64, 37, 3),
     (1, 40, 1, 1, 16, None, 3),
     (1, 1024, 8, 8, 64, None, 3),
+    (3, 333, 2, 2, 64, None, 3),   # B*H*T not a multiple of 4: workspace alignment
+    (1, 1, 1, 1, 32, None, 3),
+    (2, 129, 2, 1, 64, 1, None),   # window 1 = identity attention
 ]
 
 
@@ -342,5 +345,6 @@ def test_attention_fwd_bwd(ops, case):
     W = (H + 2 * Hk) * hd
     for name, sl in (("dq", slice(0, H * hd)), ("dk", slice(H * hd, (H + Hk) * hd)), ("dv", slice((H + Hk) * hd, W))):
         a, r = dqkv.float()[:, sl], q32.grad[:, sl]
-        rel = ((a - r).norm() / r.norm()).item()
+        # identity attention (T=1 or window=1) has dq = dk = 0 exactly: gate on the dO scale there
+        rel = ((a - r).norm() / max(r.norm().item(), 1e-3 * dout.float().norm().item())).item()
         assert rel <= 2e-2, f"{name} rel-norm err {rel}"

@@ -1,0 +1,70 @@
+"""CPU checks of the drop-in boundary: constructor, state_dict keys/shapes and
+bit-identical initial weights against what the reference produced (tests/golden meta), errors."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden
+
+
+def _sha(model):
+    h = hashlib.sha256()
+    for k, v in model.state_dict().items():
+        h.update(k.encode())
+        h.update(v.detach().cpu().contiguous().numpy().tobytes())
+    return h.hexdigest()
+
+
+@pytest.mark.parametrize("case", GOLDEN_CASES)
+def test_state_dict_layout_and_init_bits_match_reference(case):
+    from codonlm_b200 import TinyGPT
+    z, meta, sd, grads = load_golden(case)
+    torch.manual_seed(1337)
+    m = TinyGPT(**meta["ctor"])
+    mine = {k: v for k, v in m.state_dict().items() if not k.endswith("attn.mask")}
+    assert list(mine) == list(sd), "state_dict key order differs from the reference"
+    for k in sd:
+        assert tuple(mine[k].shape) == tuple(sd[k].shape), k
+    # same construction order => same RNG stream => same bits as the reference constructor
+    assert _sha(m) == meta["init_sha256"]
+    # strict load of a reference checkpoint (loop.py:882 resumes strictly)
+    full = dict(sd)
+    for l in range(meta["ctor"]["n_layer"]):
+        bs = meta["ctor"]["block_size"]
+        full[f"blocks.{l}.attn.mask"] = torch.tril(torch.ones(bs, bs)).view(1, 1, bs, bs)
+    m.load_state_dict(full, strict=True)
+    assert set(n for n, _ in m.named_parameters()) == set(grads) | ({"head.weight"} - set(grads)) - (
+        {"head.weight"} if meta["ctor"].get("tie_embeddings", True) else set())
+
+
+def test_constructor_contract():
+    from codonlm_b200 import TinyGPT
+    m = TinyGPT(69, 16, n_layer=1, n_head=4, n_embd=32, n_kv_head=0)
+    assert m.n_kv_head is None and m.blocks[0].attn.n_kv_head is None
+    with pytest.raises(AssertionError):
+        TinyGPT(69, 16, n_layer=1, n_head=3, n_embd=32)
+    d = TinyGPT(68, 8, n_layer=1, n_head=1, n_embd=16, multi_offset_targets=[4, 2, 2], termination_aux=True).to_dict()
+    assert d["multi_offset_targets"] == [2, 4] and d["termination_aux"] and d["sep_mask_enabled"]
+    assert m.head.weight is m.tok_emb.weight
+    assert TinyGPT(68, 8, n_layer=1, n_head=1, n_embd=16, use_rope=True).pos_emb is None
+
+
+def test_mask_truth_table_on_module():  # reference tests/test_models.py:29-51
+    from codonlm_b200 import TinyGPT
+    model = TinyGPT(vocab_size=8, block_size=5, n_layer=1, n_head=1, n_embd=8, dropout=0.0, sep_id=3)
+    tokens = torch.tensor([[1, 4, 3, 5, 6]])
+    full = model.build_attention_mask(tokens)[0, 0]
+    assert full[1, 0] and not full[3, 1] and full[3, 2] and full[4, 2]
+    local = model.build_attention_mask(tokens, attention_window=1)[0, 0]
+    assert torch.equal(local, torch.eye(5, dtype=torch.bool))
+    with pytest.raises(ValueError, match="at least 1"):
+        model.build_attention_mask(tokens, attention_window=0)
+
+
+def test_cpu_forward_fails_loudly():
+    from codonlm_b200 import TinyGPT, _lib
+    m = TinyGPT(68, 8, n_layer=1, n_head=1, n_embd=16, dropout=0.0)
+    with pytest.raises(_lib.CgptError, match="no CPU implementation"):
+        m(torch.zeros((1, 4), dtype=torch.long))
