@@ -267,6 +267,9 @@ def run_ours(args):
         dist.all_reduce(ems, op=dist.ReduceOp.MAX)
     e2e_ms = float(ems.item())
 
+    if args.breakdown and rank == 0:
+        step_breakdown(step, resident[0], args.breakdown, ms_total / args.steps)
+
     if rank == 0:
         peaks, peak_src = measured_peaks()
         toks_step = B * T * world
@@ -303,6 +306,63 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def step_breakdown(step, batch, path, ms_step):
+    """Extra (untimed) steps with every C-ABI wrapper bracketed by CUDA events: per-op, per-shape device time.
+    Diagnostic only: the numbers bench.py reports never come from here."""
+    from codonlm_b200 import ops
+    names = ["segment_starts", "next_in_set", "termination_labels", "embed_fwd", "embed_bwd", "layernorm_fwd",
+             "layernorm_bwd", "gemm", "cast_bf16", "colsum_bf16", "rope_qk", "swiglu_fwd", "swiglu_bwd", "attn_fwd",
+             "attn_bwd", "skinny_linear_fwd", "skinny_linear_bwd", "ce_fwd", "ce_bwd", "adamw"]
+    rec, orig = [], {}
+
+    def wrap(name, fn):
+        def w(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **k)
+            e.record()
+            if name == "gemm":
+                sig = f"M{k['M']} N{k['N']} K{k['K']} a_mn{int(k.get('a_mn', False))} b_mn{int(k.get('b_mn', False))} " \
+                      f"split{k.get('split_k', 1)} epi{k.get('epilogue', 0)} res{int(k.get('residual') is not None)} " \
+                      f"{'f32' if a[2].dtype == torch.float32 else 'bf16'}"
+                fl = 2.0 * k["M"] * k["N"] * k["K"]
+            else:
+                t0 = next((x for x in a if isinstance(x, torch.Tensor)), None)
+                sig = "x".join(str(d) for d in t0.shape) if t0 is not None else ""
+                fl = 0.0
+            rec.append((name, sig, s, e, fl))
+            return r
+        return w
+    for n in names:
+        orig[n] = getattr(ops, n)
+        setattr(ops, n, wrap(n, orig[n]))
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    nsteps = 2
+    torch.cuda.synchronize()
+    t0.record()
+    for _ in range(nsteps):
+        step.step(*batch)
+    t1.record()
+    torch.cuda.synchronize()
+    for n in names:
+        setattr(ops, n, orig[n])
+    agg = {}
+    for name, sig, s, e, fl in rec:
+        a = agg.setdefault((name, sig), [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += s.elapsed_time(e)
+        a[2] += fl
+    total = t0.elapsed_time(t1) / nsteps
+    rows = sorted(((k, v) for k, v in agg.items()), key=lambda kv: -kv[1][1])
+    covered = sum(v[1] for _, v in rows) / nsteps
+    with open(path, "w") as f:
+        f.write(f"# one training step: {total:.2f} ms with per-op events ({ms_step:.2f} ms in the timed region); "
+                f"ops below cover {covered:.2f} ms\n# op | shape | launches/step | ms/step | share | TFLOP/s\n")
+        for (name, sig), (cnt, ms, fl) in rows:
+            tf = f"{fl / (ms / 1e3) / 1e12:8.1f}" if fl > 0 and ms > 0 else "       -"
+            f.write(f"{name:18s} | {sig:70s} | {cnt / nsteps:6.1f} | {ms / nsteps:8.3f} | {ms / nsteps / total:6.1%} | {tf}\n")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -313,6 +373,7 @@ def main():
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=12)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--breakdown", default=None, help="write a per-op CUDA-event breakdown of one step to this file")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

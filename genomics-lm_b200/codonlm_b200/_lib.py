@@ -12,7 +12,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcgpt_b200.so")
 
-EPI_NONE, EPI_GELU, EPI_GELU_GRAD = 0, 1, 2
+EPI_NONE, EPI_GELU, EPI_MUL_AUX = 0, 1, 2
 
 _vp, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
 

@@ -12,7 +12,7 @@ import torch
 from torch.autograd import Function
 
 from . import ops
-from .ops import EPI_GELU, EPI_GELU_GRAD, EPI_NONE, bf16, f32
+from .ops import EPI_GELU, EPI_MUL_AUX, EPI_NONE, bf16, f32
 
 _SMS = 148
 
@@ -131,25 +131,25 @@ class PackedLinearFn(Function):
 
 class MlpGeluFn(Function):
     """x + fc2(gelu(fc1(h)))  — model_tiny_gpt.py:143-148,152 with bias+GELU and bias+residual fused into
-    the GEMM epilogues and GELU' fused into the fc2 dgrad epilogue."""
+    the GEMM epilogues; the fc1 epilogue also emits gelu'(pre), which the fc2 dgrad epilogue multiplies in."""
 
     @staticmethod
     def forward(ctx, h, x_res, w1_sh, b1, w2_sh, b2, w1, w2):
         M, d = h.shape
         F = w1_sh.shape[0]
-        pre = torch.empty((M, F), dtype=bf16, device=h.device)
+        dact = torch.empty((M, F), dtype=bf16, device=h.device)  # gelu'(pre), written by the same epilogue
         act = torch.empty((M, F), dtype=bf16, device=h.device)
-        ops.gemm(h, w1_sh, act, M=M, N=F, K=d, bias=b1, epilogue=EPI_GELU, aux_out=pre, ldaux=F)
+        ops.gemm(h, w1_sh, act, M=M, N=F, K=d, bias=b1, epilogue=EPI_GELU, aux_out=dact, ldaux=F)
         n_out = w2_sh.shape[0]
         out = torch.empty((M, n_out), dtype=f32, device=h.device)
         ops.gemm(act, w2_sh, out, M=M, N=n_out, K=F, bias=b2, residual=x_res)
-        ctx.save_for_backward(h, pre, act, w1_sh, w2_sh)
+        ctx.save_for_backward(h, dact, act, w1_sh, w2_sh)
         ctx.has_res = x_res is not None
         return out
 
     @staticmethod
     def backward(ctx, g):
-        h, pre, act, w1_sh, w2_sh = ctx.saved_tensors
+        h, dact, act, w1_sh, w2_sh = ctx.saved_tensors
         M, d = h.shape
         F = w1_sh.shape[0]
         n_out = w2_sh.shape[0]
@@ -158,7 +158,7 @@ class MlpGeluFn(Function):
         dw2 = _wgrad(gb, act, n_out, F)
         db2 = _colsum(gb, n_out)
         dpre = torch.empty((M, F), dtype=bf16, device=h.device)
-        ops.gemm(gb, w2_sh, dpre, M=M, N=F, K=n_out, b_mn=True, epilogue=EPI_GELU_GRAD, aux=pre, ldaux=F)
+        ops.gemm(gb, w2_sh, dpre, M=M, N=F, K=n_out, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=F)
         dw1 = _wgrad(dpre, h, F, d)
         db1 = _colsum(dpre, F)
         dh = torch.empty((M, d), dtype=bf16, device=h.device)
@@ -212,23 +212,23 @@ class OffsetHeadFn(Function):
     @staticmethod
     def forward(ctx, xb, w1_sh, b1, w2_sh, b2, w1, w2):
         M, d = xb.shape
-        pre = torch.empty((M, d), dtype=bf16, device=xb.device)
+        dact = torch.empty((M, d), dtype=bf16, device=xb.device)
         act = torch.empty((M, d), dtype=bf16, device=xb.device)
-        ops.gemm(xb, w1_sh, act, M=M, N=d, K=d, bias=b1, epilogue=EPI_GELU, aux_out=pre, ldaux=d)
+        ops.gemm(xb, w1_sh, act, M=M, N=d, K=d, bias=b1, epilogue=EPI_GELU, aux_out=dact, ldaux=d)
         out = torch.empty((M, d), dtype=f32, device=xb.device)
         ops.gemm(act, w2_sh, out, M=M, N=d, K=d, bias=b2)
-        ctx.save_for_backward(xb, pre, act, w1_sh, w2_sh)
+        ctx.save_for_backward(xb, dact, act, w1_sh, w2_sh)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        xb, pre, act, w1_sh, w2_sh = ctx.saved_tensors
+        xb, dact, act, w1_sh, w2_sh = ctx.saved_tensors
         M, d = xb.shape
         gb = ops.cast_bf16(g.contiguous())
         dw2 = _wgrad(gb, act, d, d)
         db2 = _colsum(gb, d)
         dpre = torch.empty((M, d), dtype=bf16, device=xb.device)
-        ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_GELU_GRAD, aux=pre, ldaux=d)
+        ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=d)
         dw1 = _wgrad(dpre, xb, d, d)
         db1 = _colsum(dpre, d)
         dx = torch.empty((M, d), dtype=bf16, device=xb.device)

@@ -8,7 +8,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import EPI_GELU, EPI_GELU_GRAD, EPI_NONE, GemmArgs, check  # noqa: F401
+from ._lib import EPI_GELU, EPI_MUL_AUX, EPI_NONE, GemmArgs, check  # noqa: F401
 
 bf16, f32, i32, i64 = torch.bfloat16, torch.float32, torch.int32, torch.int64
 
@@ -138,12 +138,18 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=
     return out
 
 
-def pick_split_k(tiles: int, kblocks: int, sms: int = 148) -> int:
-    """Split the reduction so that a weight-gradient GEMM fills the machine."""
-    if tiles >= sms or kblocks <= 8:
+def pick_split_k(tiles: int, kblocks: int, sms: int = 148, max_split: int = 24) -> int:
+    """Split the reduction of a weight-gradient GEMM so that (tiles x split) fills whole waves of the
+    persistent grid: maximise wave efficiency, prefer fewer splits (less atomic traffic) on ties."""
+    if tiles >= 2 * sms or kblocks <= 8:
         return 1
-    s = max(1, (2 * sms) // max(1, tiles))
-    return int(min(s, max(1, kblocks // 4)))
+    best, best_eff = 1, 0.0
+    for s in range(1, max(1, min(max_split, kblocks // 8)) + 1):
+        work = tiles * s
+        eff = work / (-(-work // sms) * sms)
+        if eff > best_eff + 0.02:
+            best, best_eff = s, eff
+    return best
 
 
 # ------------------------------------------------------------------ elementwise

@@ -162,8 +162,11 @@ __global__ void embed_bwd_pos_kernel(const float4* __restrict__ dx, float4* __re
 }
 
 // ============================================================ LayerNorm (one warp per row, d <= 1024, d % 4 == 0)
-constexpr int kLnMaxVec = 8;  // float4 per lane
+// VPT = float4 per lane (compile time): lane l owns columns 4*(l + 32k), k < VPT, for every row it visits,
+// so gamma/beta and the dgamma/dbeta partial sums live in registers across the whole row loop.
+constexpr int kLnMaxVec = 8;
 
+template <int VPT>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ yb, float* __restrict__ yf, float* __restrict__ mean,
@@ -171,44 +174,47 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = d >> 2;
+  float4 g[VPT], bt[VPT];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int c = lane + 32 * k;
+    g[k] = c < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    bt[k] = c < nvec ? __ldg(reinterpret_cast<const float4*>(beta) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float inv_d = 1.f / d;
   for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
-    float4 v[kLnMaxVec];
+    float4 v[VPT];
     float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < VPT; ++k) {
       const int c = lane + 32 * k;
-      if (c < nvec) {
-        v[k] = xr[c];
-        s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
-      }
+      v[k] = c < nvec ? xr[c] : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
     }
-    const float mu = warp_sum(s) / d;
+    const float mu = warp_sum(s) * inv_d;
     float q = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
-      const int c = lane + 32 * k;
-      if (c < nvec) {
+    for (int k = 0; k < VPT; ++k) {
+      if (lane + 32 * k < nvec) {
         const float a = v[k].x - mu, b = v[k].y - mu, e = v[k].z - mu, f = v[k].w - mu;
         q += (a * a + b * b) + (e * e + f * f);
       }
     }
-    const float rs = rsqrtf(warp_sum(q) / d + eps);
+    const float rs = rsqrtf(warp_sum(q) * inv_d + eps);
     if (lane == 0) {
       mean[row] = mu;
       rstd[row] = rs;
     }
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < VPT; ++k) {
       const int c = lane + 32 * k;
       if (c < nvec) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
         float4 o;
-        o.x = (v[k].x - mu) * rs * g.x + b.x;
-        o.y = (v[k].y - mu) * rs * g.y + b.y;
-        o.z = (v[k].z - mu) * rs * g.z + b.z;
-        o.w = (v[k].w - mu) * rs * g.w + b.w;
+        o.x = (v[k].x - mu) * rs * g[k].x + bt[k].x;
+        o.y = (v[k].y - mu) * rs * g[k].y + bt[k].y;
+        o.z = (v[k].z - mu) * rs * g[k].z + bt[k].z;
+        o.w = (v[k].w - mu) * rs * g[k].w + bt[k].w;
         if (yf) reinterpret_cast<float4*>(yf + (size_t)row * d)[c] = o;
         if (yb) reinterpret_cast<uint2*>(yb + (size_t)row * d)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
       }
@@ -216,64 +222,71 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
   }
 }
 
-template <bool DY_F32>
-__global__ void __launch_bounds__(256)
+template <int VPT, bool DY_F32>
+__global__ void __launch_bounds__(256, (VPT <= 4) ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, int M, int d) {
-  __shared__ float red[8][32 * 4 + 4];
+  __shared__ float red[8][VPT * 128];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int nvec = d >> 2;
-  float4 ag[kLnMaxVec], ab[kLnMaxVec];
+  const float inv_d = 1.f / d;
+  float4 gm[VPT], ag[VPT], ab[VPT];
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-
+  for (int k = 0; k < VPT; ++k) {
+    const int c = lane + 32 * k;
+    gm[k] = c < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
-    float4 xh[kLnMaxVec], g[kLnMaxVec];
+    float4 xh[VPT], dyv[VPT];
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < VPT; ++k) {
       const int c = lane + 32 * k;
       if (c < nvec) {
-        float4 dyv;
         if constexpr (DY_F32) {
-          dyv = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * d)[c];
+          dyv[k] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(dy_) + (size_t)row * d)[c];
         } else {
           const uint2 u = reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(dy_) + (size_t)row * d)[c];
           const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
-          dyv = make_float4(lo.x, lo.y, hi.x, hi.y);
+          dyv[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
         }
         const float4 xv = xr[c];
-        const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma) + c);
         xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
-        g[k] = make_float4(dyv.x * gm.x, dyv.y * gm.y, dyv.z * gm.z, dyv.w * gm.w);
-        s1 += (g[k].x + g[k].y) + (g[k].z + g[k].w);
-        s2 += (g[k].x * xh[k].x + g[k].y * xh[k].y) + (g[k].z * xh[k].z + g[k].w * xh[k].w);
-        ag[k].x += dyv.x * xh[k].x;
-        ag[k].y += dyv.y * xh[k].y;
-        ag[k].z += dyv.z * xh[k].z;
-        ag[k].w += dyv.w * xh[k].w;
-        ab[k].x += dyv.x;
-        ab[k].y += dyv.y;
-        ab[k].z += dyv.z;
-        ab[k].w += dyv.w;
+      } else {
+        dyv[k] = xh[k] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    const float m1 = warp_sum(s1) / d, m2 = warp_sum(s2) / d;
 #pragma unroll
-    for (int k = 0; k < kLnMaxVec; ++k) {
+    for (int k = 0; k < VPT; ++k) {
+      const float gx = dyv[k].x * gm[k].x, gy = dyv[k].y * gm[k].y, gz = dyv[k].z * gm[k].z, gw = dyv[k].w * gm[k].w;
+      s1 += (gx + gy) + (gz + gw);
+      s2 += (gx * xh[k].x + gy * xh[k].y) + (gz * xh[k].z + gw * xh[k].w);
+      ag[k].x += dyv[k].x * xh[k].x;
+      ag[k].y += dyv[k].y * xh[k].y;
+      ag[k].z += dyv[k].z * xh[k].z;
+      ag[k].w += dyv[k].w * xh[k].w;
+      ab[k].x += dyv[k].x;
+      ab[k].y += dyv[k].y;
+      ab[k].z += dyv[k].z;
+      ab[k].w += dyv[k].w;
+    }
+    const float m1 = warp_sum(s1) * inv_d, m2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
       const int c = lane + 32 * k;
       if (c < nvec) {
         float4 o;
-        o.x = rs * (g[k].x - m1 - xh[k].x * m2);
-        o.y = rs * (g[k].y - m1 - xh[k].y * m2);
-        o.z = rs * (g[k].z - m1 - xh[k].z * m2);
-        o.w = rs * (g[k].w - m1 - xh[k].w * m2);
+        o.x = rs * (dyv[k].x * gm[k].x - m1 - xh[k].x * m2);
+        o.y = rs * (dyv[k].y * gm[k].y - m1 - xh[k].y * m2);
+        o.z = rs * (dyv[k].z * gm[k].z - m1 - xh[k].z * m2);
+        o.w = rs * (dyv[k].w * gm[k].w - m1 - xh[k].w * m2);
         if (dres) {
           const float4 r = reinterpret_cast<const float4*>(dres + (size_t)row * d)[c];
           o.x += r.x;
@@ -287,33 +300,22 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
       }
     }
   }
-  // cross-warp reduction of the per-column partials, then one atomic per column per CTA
+  // per-CTA reduction of the column partials over its 8 warps, then one atomic per column
 #pragma unroll
-  for (int k = 0; k < kLnMaxVec; ++k) {
-    const int c = lane + 32 * k;
-    if (32 * k >= nvec) break;
-    for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 2; ++pass) {
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
       const float4 val = pass == 0 ? ag[k] : ab[k];
-      __syncthreads();
-      red[warp][lane * 4 + 0] = val.x;
-      red[warp][lane * 4 + 1] = val.y;
-      red[warp][lane * 4 + 2] = val.z;
-      red[warp][lane * 4 + 3] = val.w;
-      __syncthreads();
-      if (warp == 0 && c < nvec) {
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int w2 = 0; w2 < wpb; ++w2) {
-          t.x += red[w2][lane * 4 + 0];
-          t.y += red[w2][lane * 4 + 1];
-          t.z += red[w2][lane * 4 + 2];
-          t.w += red[w2][lane * 4 + 3];
-        }
-        float* dst = (pass == 0 ? dgamma : dbeta) + c * 4;
-        atomicAdd(dst + 0, t.x);
-        atomicAdd(dst + 1, t.y);
-        atomicAdd(dst + 2, t.z);
-        atomicAdd(dst + 3, t.w);
-      }
+      *reinterpret_cast<float4*>(&red[warp][(lane + 32 * k) * 4]) = val;
+    }
+    __syncthreads();
+    float* dst = pass == 0 ? dgamma : dbeta;
+    for (int c = threadIdx.x; c < d; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < 8; ++w2) t += red[w2][c];
+      atomicAdd(dst + c, t);
     }
   }
 }
@@ -569,8 +571,11 @@ int cgpt_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
   CGPT_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
                128 * kLnMaxVec);
   const int grid = grid_for((long long)M * 32, 256, 4);
-  layernorm_fwd_kernel<<<grid, 256, 0, ST(stream)>>>(x, gamma, beta, reinterpret_cast<__nv_bfloat16*>(y_bf16), y_f32,
-                                                     mean, rstd, M, d, eps);
+  const int vpt = (d / 4 + 31) / 32;
+  __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
+#define LN_FWD(V) layernorm_fwd_kernel<V><<<grid, 256, 0, ST(stream)>>>(x, gamma, beta, yb, y_f32, mean, rstd, M, d, eps)
+  if (vpt <= 1) LN_FWD(1); else if (vpt <= 2) LN_FWD(2); else if (vpt <= 4) LN_FWD(4); else LN_FWD(8);
+#undef LN_FWD
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;
@@ -582,13 +587,16 @@ int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const floa
   CGPT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "layernorm_bwd: bad arguments");
   CGPT_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
                128 * kLnMaxVec);
-  const int grid = grid_for((long long)M * 32, 256, 2);
-  if (dy_is_f32)
-    layernorm_bwd_kernel<true><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx,
-                                                             reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, M, d);
-  else
-    layernorm_bwd_kernel<false><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx,
-                                                              reinterpret_cast<__nv_bfloat16*>(dx_bf16), dgamma, dbeta, M, d);
+  const int vpt = (d / 4 + 31) / 32;
+  const int grid = grid_for((long long)M * 32, 256, vpt <= 4 ? 2 : 1);
+  __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
+#define LN_BWD(V, F) layernorm_bwd_kernel<V, F><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, M, d)
+  if (dy_is_f32) {
+    if (vpt <= 1) LN_BWD(1, true); else if (vpt <= 2) LN_BWD(2, true); else if (vpt <= 4) LN_BWD(4, true); else LN_BWD(8, true);
+  } else {
+    if (vpt <= 1) LN_BWD(1, false); else if (vpt <= 2) LN_BWD(2, false); else if (vpt <= 4) LN_BWD(4, false); else LN_BWD(8, false);
+  }
+#undef LN_BWD
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

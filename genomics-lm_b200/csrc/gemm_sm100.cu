@@ -2,7 +2,7 @@
 // TMEM, double-buffered) -> fused epilogue.  Persistent, warp-specialised:
 //   warp 0      TMA producer            (one elected lane)
 //   warp 1      TMEM owner + MMA issuer (one elected lane)
-//   warps 2..5  epilogue: tcgen05.ld -> smem transpose -> bias/GELU/GELU'/residual -> coalesced stores
+//   warps 2..9  epilogue: tcgen05.ld -> swizzled smem transpose -> bias/GELU/aux/residual -> coalesced 16-B stores
 // Tile 128 x BN x 64, BN in {64,128,256}.  Operands are K-major ([rows,K]) or MN-major ([K,rows]),
 // which covers forward (x·Wᵀ), dgrad (dy·W) and wgrad (dyᵀ·x, split-K with fp32 atomics) without any
 // transposed copies.  Replaces the nn.Linear calls of model_tiny_gpt.py:85-93,132,143-147,51-57,235-239.
@@ -14,10 +14,10 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kThreads = 192;
-constexpr int kEpiWarps = 4;
-constexpr int kStgStride = 66;                                // floats per staged row (64 + 2 pad)
-constexpr int kStgBytesPerWarp = 32 * kStgStride * 4;         // 8448
+constexpr int kEpiWarps = 8;                       // two per TMEM lane quadrant; they split the column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
+constexpr int kChunk = 32;                         // accumulator columns staged per step
+constexpr int kStgBytesPerWarp = 32 * kChunk * 4;  // 32 rows x 128 B, XOR-swizzled 16-byte cells
 
 struct GemmParams {
   int M, N, K;
@@ -34,6 +34,27 @@ struct GemmParams {
   long long ldc;
 };
 
+// gelu(x) = x*Phi(x) and gelu'(x) = Phi(x) + x*phi(x) from one exp and one reciprocal
+// (Abramowitz-Stegun 7.1.26 for erfc, |error| < 1.5e-7: far below the bf16 output rounding).
+__device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, fabsf(x), 1.0f)));  // 0.3275911/sqrt(2)
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752f * x * x));               // exp(-x^2/2)
+  float p = fmaf(t, 0.5307027145f, -0.7265760135f);
+  p = fmaf(p, t, 0.7107068705f);
+  p = fmaf(p, t, -0.142248368f);
+  p = fmaf(p, t, 0.127414796f);
+  const float h = p * t * e;  // Phi(-|x|)
+  const float cdf = x >= 0.f ? 1.f - h : h;
+  y = x * cdf;
+  dy = fmaf(x, 0.3989422804f * e, cdf);
+}
+
+__device__ __forceinline__ void red_add_v4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
@@ -43,6 +64,7 @@ struct SmemLayout {
   static constexpr int kBarOff = kStgOff + kEpiWarps * kStgBytesPerWarp;
   static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16;
   static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024-B alignment
+  static_assert(kDynamic <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
 template <int BN, bool A_MN, bool B_MN, int STAGES>
@@ -161,9 +183,21 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
-    const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    float* stg = reinterpret_cast<float*>(smem + L::kStgOff + (warp - 2) * kStgBytesPerWarp);
-    const bool vec_ok = ((p.ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 7) == 0);
+    // TMEM lane = output row, so a thread first holds one row x 32 columns.  The chunk goes through a
+    // swizzled smem transpose so that global traffic is coalesced: afterwards lane l owns 4 consecutive
+    // columns (l&7) of row 4*it + (l>>3); all bias / activation / aux / residual work happens there, with the
+    // global loads of all 8 row groups issued before the first use.
+    const int ew = warp - 2;
+    const int q = warp & 3;   // TMEM lane quadrant this warp may access
+    const int grp = ew >> 2;  // which half of the column chunks
+    uint8_t* stg = smem + L::kStgOff + ew * kStgBytesPerWarp;
+    const int r_in = lane >> 3, cq = lane & 7;
+    const bool out16 = !p.out_f32;
+    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                        (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
+                        ((p.aux == nullptr && p.aux_out == nullptr) ||
+                         (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 7) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(p.aux_out) & 7) == 0)));
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int n_blk = w % p.tiles_n;
@@ -175,85 +209,120 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m_blk * BM + q * 32;
       const bool add_bias = (p.bias != nullptr) && (ks == 0);
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; ++c) {
-        const int col = n_blk * BN + c * 64 + 2 * lane;
-        if (n_blk * BN + c * 64 >= p.N) break;  // warp-uniform
-        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * 64;
-        uint32_t r0[32], r1[32];
-        tmem_ld32(taddr, r0);
-        tmem_ld32(taddr + 32, r1);
+      for (int c = grp; c < BN / kChunk; c += 2) {
+        const int n0 = n_blk * BN + c * kChunk;
+        if (n0 >= p.N) break;  // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * kChunk, r);
         tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          *reinterpret_cast<uint2*>(&stg[lane * kStgStride + j]) = make_uint2(r0[j], r0[j + 1]);
-          *reinterpret_cast<uint2*>(&stg[lane * kStgStride + 32 + j]) = make_uint2(r1[j], r1[j + 1]);
-        }
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
         __syncwarp();
-        const bool c0ok = col < p.N, c1ok = col + 1 < p.N;
-        float b0 = 0.f, b1 = 0.f;
+        const int col = n0 + cq * 4;
+        const bool full = vec_ok && (col + 3 < p.N);
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (add_bias) {
-          if (c0ok) b0 = __ldg(p.bias + col);
-          if (c1ok) b1 = __ldg(p.bias + col + 1);
-        }
-        const int rmax = min(32, p.M - row0);
-        for (int rr = 0; rr < rmax; ++rr) {
-          const long long row = row0 + rr;
-          float2 v = *reinterpret_cast<const float2*>(&stg[rr * kStgStride + 2 * lane]);
-          v.x += b0;
-          v.y += b1;
-          if (!c0ok) continue;
-          if (p.epilogue == CGPT_EPI_GELU) {
-            if (p.aux_out) {
-              __nv_bfloat16* ao = p.aux_out + row * p.ldaux + col;
-              if (c1ok)
-                *reinterpret_cast<uint32_t*>(ao) = pack_bf16(v.x, v.y);
-              else
-                ao[0] = __float2bfloat16_rn(v.x);
-            }
-            v.x = gelu_erf(v.x);
-            v.y = gelu_erf(v.y);
-          } else if (p.epilogue == CGPT_EPI_GELU_GRAD) {
-            const __nv_bfloat16* ai = p.aux + row * p.ldaux + col;
-            float a0, a1 = 0.f;
-            if (c1ok) {
-              float2 a = unpack_bf16(*reinterpret_cast<const uint32_t*>(ai));
-              a0 = a.x;
-              a1 = a.y;
-            } else {
-              a0 = __bfloat162float(ai[0]);
-            }
-            v.x *= gelu_erf_grad(a0);
-            v.y *= gelu_erf_grad(a1);
-          }
-          if (p.out_f32) {
-            float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col;
-            if (p.residual) {
-              const float* rs = p.residual + row * p.ldc + col;
-              if (c1ok && vec_ok) {
-                float2 r = *reinterpret_cast<const float2*>(rs);
-                v.x += r.x;
-                v.y += r.y;
-              } else {
-                v.x += rs[0];
-                if (c1ok) v.y += rs[1];
-              }
-            }
-            if (p.accumulate) {
-              atomicAdd(o, v.x);
-              if (c1ok) atomicAdd(o + 1, v.y);
-            } else if (c1ok && vec_ok) {
-              *reinterpret_cast<float2*>(o) = v;
-            } else {
-              o[0] = v.x;
-              if (c1ok) o[1] = v.y;
-            }
+          if (col + 3 < p.N) {
+            b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
           } else {
-            __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col;
-            if (c1ok && vec_ok)
-              *reinterpret_cast<uint32_t*>(o) = pack_bf16(v.x, v.y);
-            else {
-              o[0] = __float2bfloat16_rn(v.x);
-              if (c1ok) o[1] = __float2bfloat16_rn(v.y);
+            if (col < p.N) b4.x = __ldg(p.bias + col);
+            if (col + 1 < p.N) b4.y = __ldg(p.bias + col + 1);
+            if (col + 2 < p.N) b4.z = __ldg(p.bias + col + 2);
+          }
+        }
+        if (full) {
+          // ---------------- vector path
+          uint2 aux8[8];
+          float4 res8[8];
+          if (p.epilogue == CGPT_EPI_MUL_AUX) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const long long row = row0 + g * 4 + r_in;
+              aux8[g] = row < p.M ? *reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col) : make_uint2(0u, 0u);
+            }
+          }
+          if (p.residual) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) {
+              const long long row = row0 + g * 4 + r_in;
+              res8[g] = row < p.M ? *reinterpret_cast<const float4*>(p.residual + row * p.ldc + col)
+                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < 8; ++g) {
+            const int rl = g * 4 + r_in;
+            const long long row = row0 + rl;
+            float4 v = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cq ^ (rl & 7)) << 4));
+            v.x += b4.x;
+            v.y += b4.y;
+            v.z += b4.z;
+            v.w += b4.w;
+            if (row >= p.M) continue;
+            if (p.epilogue == CGPT_EPI_GELU) {
+              float4 d;
+              gelu_and_grad(v.x, v.x, d.x);
+              gelu_and_grad(v.y, v.y, d.y);
+              gelu_and_grad(v.z, v.z, d.z);
+              gelu_and_grad(v.w, v.w, d.w);
+              if (p.aux_out)
+                *reinterpret_cast<uint2*>(p.aux_out + row * p.ldaux + col) =
+                    make_uint2(pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
+            } else if (p.epilogue == CGPT_EPI_MUL_AUX) {
+              const float2 a0 = unpack_bf16(aux8[g].x), a1 = unpack_bf16(aux8[g].y);
+              v.x *= a0.x;
+              v.y *= a0.y;
+              v.z *= a1.x;
+              v.w *= a1.y;
+            }
+            if (out16) {
+              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col) =
+                  make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+            } else {
+              float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col;
+              if (p.residual) {
+                v.x += res8[g].x;
+                v.y += res8[g].y;
+                v.z += res8[g].z;
+                v.w += res8[g].w;
+              }
+              if (p.accumulate)
+                red_add_v4(o, v);
+              else
+                *reinterpret_cast<float4*>(o) = v;
+            }
+          }
+        } else {
+          // ---------------- scalar path: column tails and pitches that are not multiples of 4
+          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
+          for (int g = 0; g < 8; ++g) {
+            const int rl = g * 4 + r_in;
+            const long long row = row0 + rl;
+            if (row >= p.M) continue;
+            const float4 v4 = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cq ^ (rl & 7)) << 4));
+            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
+            for (int e = 0; e < 4; ++e) {
+              if (col + e >= p.N) break;
+              float v = vv[e] + bb[e];
+              if (p.epilogue == CGPT_EPI_GELU) {
+                float d;
+                gelu_and_grad(v, v, d);
+                if (p.aux_out) p.aux_out[row * p.ldaux + col + e] = __float2bfloat16_rn(d);
+              } else if (p.epilogue == CGPT_EPI_MUL_AUX) {
+                v *= __bfloat162float(p.aux[row * p.ldaux + col + e]);
+              }
+              if (out16) {
+                reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldc + col + e] = __float2bfloat16_rn(v);
+              } else {
+                float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col + e;
+                if (p.residual) v += p.residual[row * p.ldc + col + e];
+                if (p.accumulate)
+                  atomicAdd(o, v);
+                else
+                  *o = v;
+              }
             }
           }
         }
@@ -311,7 +380,7 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
   CGPT_REQUIRE(!(a->accumulate && !a->out_f32), "gemm: accumulate needs an fp32 output");
   CGPT_REQUIRE(!(a->residual && !a->out_f32), "gemm: residual epilogue needs an fp32 output");
   CGPT_REQUIRE(a->epilogue == CGPT_EPI_NONE || a->split_k == 1, "gemm: activation epilogue with split_k");
-  CGPT_REQUIRE(a->epilogue != CGPT_EPI_GELU_GRAD || a->aux, "gemm: GELU_GRAD needs aux");
+  CGPT_REQUIRE(a->epilogue != CGPT_EPI_MUL_AUX || a->aux, "gemm: MUL_AUX needs aux");
 
   const int BN = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
   CUtensorMap ta, tb;

@@ -89,8 +89,8 @@ int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const floa
  * wgrad    dW = dyᵀ·x    : A=dy[Mtok,N'] as [K,M]  B=x[Mtok,K'] as [K,N]  (1,1), split_k>1
  */
 #define CGPT_EPI_NONE 0
-#define CGPT_EPI_GELU 1      /* out = gelu_erf(v); aux_out (nullable) = v   (nn.GELU(), :145)     */
-#define CGPT_EPI_GELU_GRAD 2 /* out = v * gelu_erf'(aux)                                          */
+#define CGPT_EPI_GELU 1    /* out = gelu_erf(v); aux_out (nullable) = gelu_erf'(v)   (nn.GELU(), :145)   */
+#define CGPT_EPI_MUL_AUX 2 /* out = v * aux          (backward through GELU: aux = gelu_erf'(pre))      */
 typedef struct {
   const void* a;
   const void* b;
@@ -100,7 +100,7 @@ typedef struct {
   int split_k;           /* >= 1; > 1 requires out_f32 && accumulate */
   const float* bias;     /* [N] fp32, nullable */
   int epilogue;          /* CGPT_EPI_* */
-  const void* aux;       /* bf16 [M,N] pitch ldaux (GELU_GRAD) */
+  const void* aux;       /* bf16 [M,N] pitch ldaux (MUL_AUX) */
   void* aux_out;         /* bf16 [M,N] pitch ldaux (GELU, nullable) */
   int64_t ldaux;
   const float* residual; /* fp32 [M,N] pitch ldc, nullable: v += residual */

@@ -153,18 +153,39 @@ def test_gemm_epilogues(ops):
     W = (torch.randn(N, K, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
     bias = torch.randn(N, generator=g).to(DEV)
     ref = A.float() @ W.float().t() + bias
-    # bias + GELU, pre-activation side output
+    # bias + GELU; the side output is gelu'(pre) for the backward epilogue
     out = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
-    pre = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
-    ops.gemm(A, W, out, M=M, N=N, K=K, bias=bias, epilogue=ops.EPI_GELU, aux_out=pre, ldaux=N)
-    assert torch.allclose(pre.float(), ref, rtol=1e-2, atol=1e-2)
-    assert torch.allclose(out.float(), torch.nn.functional.gelu(ref), rtol=1e-2, atol=1e-2)
-    # GELU'
+    dact = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W, out, M=M, N=N, K=K, bias=bias, epilogue=ops.EPI_GELU, aux_out=dact, ldaux=N)
+    p32 = ref.clone().requires_grad_(True)
+    gel = torch.nn.functional.gelu(p32)
+    gel.sum().backward()
+    assert torch.allclose(out.float(), gel.detach(), rtol=1e-2, atol=1e-2)
+    assert torch.allclose(dact.float(), p32.grad, rtol=1e-2, atol=1e-2)
+    # fast erf: check the fused activation at fp32 precision through an fp32-representable path
+    xs = torch.linspace(-8, 8, 4096, device=DEV)
+    eye = torch.zeros((4096, 8), dtype=torch.bfloat16, device=DEV)
+    eye[:, 0] = 1
+    wx = torch.zeros((8, 8), dtype=torch.bfloat16, device=DEV)
+    wx[0, 0] = 1
+    bvec = torch.zeros(8, device=DEV)
+    for shift in (0.0, 0.00390625):  # exact bf16-representable grid points as bias, value through the GEMM
+        col = torch.zeros((4096, 8), dtype=torch.bfloat16, device=DEV)
+        col[:, 0] = xs.to(torch.bfloat16)
+        o2 = torch.empty((4096, 8), dtype=torch.bfloat16, device=DEV)
+        d2 = torch.empty((4096, 8), dtype=torch.bfloat16, device=DEV)
+        bvec[0] = shift
+        ops.gemm(col, wx, o2, M=4096, N=8, K=8, bias=bvec, epilogue=ops.EPI_GELU, aux_out=d2, ldaux=8)
+        xv = (col[:, 0].float() + shift).requires_grad_(True)
+        gv = torch.nn.functional.gelu(xv)
+        gv.sum().backward()
+        assert torch.equal(o2[:, 0], gv.detach().to(torch.bfloat16)) or \
+            (o2[:, 0].float() - gv.detach()).abs().max().item() <= 2 ** -8 * gv.detach().abs().max().item()
+        assert (d2[:, 0].float() - xv.grad).abs().max().item() <= 2 ** -7
+    # multiply-by-aux epilogue (backward through GELU)
     dz = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
-    ops.gemm(A, W, dz, M=M, N=N, K=K, epilogue=ops.EPI_GELU_GRAD, aux=pre, ldaux=N)
-    p32 = pre.float().requires_grad_(True)
-    torch.nn.functional.gelu(p32).sum().backward()
-    assert torch.allclose(dz.float(), (A.float() @ W.float().t()) * p32.grad, rtol=2e-2, atol=2e-2)
+    ops.gemm(A, W, dz, M=M, N=N, K=K, epilogue=ops.EPI_MUL_AUX, aux=dact, ldaux=N)
+    assert torch.allclose(dz.float(), (A.float() @ W.float().t()) * dact.float(), rtol=2e-2, atol=2e-2)
     # bias + residual -> fp32
     res = torch.randn(M, N, generator=g).to(DEV)
     o32 = torch.empty((M, N), dtype=torch.float32, device=DEV)
