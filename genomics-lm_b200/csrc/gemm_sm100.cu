@@ -2,10 +2,13 @@
 // TMEM, double-buffered) -> fused epilogue.  Persistent, warp-specialised:
 //   warp 0      TMA producer            (one elected lane)
 //   warp 1      TMEM owner + MMA issuer (one elected lane)
-//   warps 2..9  epilogue: tcgen05.ld -> swizzled smem transpose -> bias/GELU/aux/residual -> coalesced 16-B stores
+//   warps 2..17 epilogue: tcgen05.ld -> swizzled smem transpose -> bias/GELU/aux/residual -> coalesced 16-B stores
 // Tile 128 x BN x 64, BN in {64,128,256}.  Operands are K-major ([rows,K]) or MN-major ([K,rows]),
 // which covers forward (x·Wᵀ), dgrad (dy·W) and wgrad (dyᵀ·x, split-K with fp32 atomics) without any
 // transposed copies.  Replaces the nn.Linear calls of model_tiny_gpt.py:85-93,132,143-147,51-57,235-239.
+#include <stdlib.h>
+#include <string.h>
+
 #include "common.cuh"
 
 namespace cgpt {
@@ -14,10 +17,9 @@ namespace {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int kEpiWarps = 8;                       // two per TMEM lane quadrant; they split the column chunks
-constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp0 TMA, warp1 MMA, warps 2..9 epilogue
-constexpr int kChunk = 32;                         // accumulator columns staged per step
-constexpr int kStgBytesPerWarp = 32 * kChunk * 4;  // 32 rows x 128 B, XOR-swizzled 16-byte cells
+constexpr int kEpiWarps = 16;                      // four per TMEM lane quadrant; they split the column chunks
+constexpr int kThreads = 64 + 32 * kEpiWarps;      // warp0 TMA, warp1 MMA, warps 2..17 epilogue
+constexpr int kStgBytesPerWarp = 32 * 64;          // 32 rows x 64 B (32 bf16 or 16 fp32), swizzled 16-byte cells
 
 struct GemmParams {
   int M, N, K;
@@ -32,27 +34,245 @@ struct GemmParams {
   int out_f32;
   int accumulate;
   long long ldc;
+  int tma_out;  // 1: out (and aux_out) are written through the TMA maps tmC / tmX
+  int debug;  // bit0: skip global stores, bit1: skip TMEM loads, bit2: skip the whole epilogue body (probe only)
 };
 
-// gelu(x) = x*Phi(x) and gelu'(x) = Phi(x) + x*phi(x) from one exp and one reciprocal
-// (Abramowitz-Stegun 7.1.26 for erfc, |error| < 1.5e-7: far below the bf16 output rounding).
+// gelu(x) = x*Phi(x) and gelu'(x) = Phi(x) + x*phi(x) with ONE special-function op (the exp of phi):
+// Phi(-|x|) = mills(|x|) * phi(x), mills(t) = (1-Phi(t))/phi(t) as a degree-9 polynomial on [0, 5.5]
+// fitted for relative error (1.5e-4 in fp32 Horner form, i.e. 30x below the bf16 rounding of the outputs and
+// uniform in the tails); beyond 5.5 phi underflows the result anyway.  The reciprocal of the classic
+// Abramowitz-Stegun form would double the load on the 16-lane XU pipe, which bounds this epilogue.
 __device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.23164189f, fabsf(x), 1.0f)));  // 0.3275911/sqrt(2)
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752f * x * x));               // exp(-x^2/2)
-  float p = fmaf(t, 0.5307027145f, -0.7265760135f);
-  p = fmaf(p, t, 0.7107068705f);
-  p = fmaf(p, t, -0.142248368f);
-  p = fmaf(p, t, 0.127414796f);
-  const float h = p * t * e;  // Phi(-|x|)
+  const float t = fminf(fabsf(x), 5.5f);
+  float m = fmaf(t, -1.94302522e-06f, 5.95369164e-05f);
+  m = fmaf(m, t, -0.000801238087f);
+  m = fmaf(m, t, 0.0062706394f);
+  m = fmaf(m, t, -0.0319994484f);
+  m = fmaf(m, t, 0.114027142f);
+  m = fmaf(m, t, -0.299928687f);
+  m = fmaf(m, t, 0.612206331f);
+  m = fmaf(m, t, -0.997367484f);
+  m = fmaf(m, t, 1.25322612f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752f * x * x));  // exp(-x^2/2)
+  const float phi = 0.3989422804f * e;
+  const float h = m * phi;  // Phi(-|x|)
   const float cdf = x >= 0.f ? 1.f - h : h;
   y = x * cdf;
-  dy = fmaf(x, 0.3989422804f * e, cdf);
+  dy = fmaf(x, phi, cdf);
 }
 
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
                : "memory");
+}
+
+__device__ __forceinline__ void sts128(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 ldg_nc_f4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.nc.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
+  return v;
+}
+// staging cell (16 bytes) of row `row` (64-byte rows), logical cell 0..3.  Swizzled so that both access
+// patterns are conflict-free: "lane = row" 16-byte writes and "4 lanes per row, 8 rows" 16-byte reads.
+__device__ __forceinline__ uint32_t stg_cell(uint32_t base, int row, int cell) {
+  return base + row * 64 + ((cell ^ ((row >> 1) & 3)) << 4);
+}
+
+// bf16 outputs, 32 accumulator columns per step: bias / GELU in the accumulator's row layout (thread = row),
+// pack to bf16, transpose 32 x 32 through 2 KB of smem, 16-byte coalesced stores (4 lanes per 64-byte segment).
+template <bool GELU>
+__device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
+                                               uint32_t taddr, uint32_t stg, int lane, int row0, int n0,
+                                               uint32_t bias_s /* smem address of this chunk's 32 bias floats */) {
+  uint32_t r[32];
+  if (!(p.debug & 2)) {
+    tmem_ld32(taddr, r);
+  } else {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = 0x3f800000u + lane + i;
+  }
+  const bool vec_ok = (n0 + 32 <= p.N) && ((p.ldc & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                      (!GELU || p.aux_out == nullptr ||
+                       (((p.ldaux & 7) == 0) && ((reinterpret_cast<uintptr_t>(p.aux_out) & 15) == 0)));
+  tmem_ld_wait();
+  uint32_t act[16], dact[GELU ? 16 : 1];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const uint4 bu = lds128(bias_s + j * 16);  // broadcast read
+    float v0 = __uint_as_float(r[4 * j]) + __uint_as_float(bu.x), v1 = __uint_as_float(r[4 * j + 1]) + __uint_as_float(bu.y);
+    float v2 = __uint_as_float(r[4 * j + 2]) + __uint_as_float(bu.z), v3 = __uint_as_float(r[4 * j + 3]) + __uint_as_float(bu.w);
+    if constexpr (GELU) {
+      float d0, d1, d2, d3;
+      gelu_and_grad(v0, v0, d0);
+      gelu_and_grad(v1, v1, d1);
+      gelu_and_grad(v2, v2, d2);
+      gelu_and_grad(v3, v3, d3);
+      dact[2 * j] = pack_bf16(d0, d1);
+      dact[2 * j + 1] = pack_bf16(d2, d3);
+    }
+    act[2 * j] = pack_bf16(v0, v1);
+    act[2 * j + 1] = pack_bf16(v2, v3);
+  }
+  const int rl_in = lane >> 2, cell = lane & 3;
+#pragma unroll
+  for (int pass = 0; pass < (GELU ? 2 : 1); ++pass) {
+    const uint32_t* src = (GELU && pass == 1) ? dact : act;
+    __nv_bfloat16* dst = (GELU && pass == 1) ? p.aux_out : reinterpret_cast<__nv_bfloat16*>(p.out);
+    const long long ld = (GELU && pass == 1) ? p.ldaux : p.ldc;
+    if (dst == nullptr) break;
+    if (p.tma_out) {  // the staging buffer may still be feeding the previous bulk store
+      if (lane == 0) bulk_wait_read0();
+      __syncwarp();
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      sts128(stg_cell(stg, lane, j), make_uint4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]));
+    if (p.tma_out) {
+      // staging layout == CU_TENSOR_MAP_SWIZZLE_64B of a {32 col, 32 row} bf16 box: one asynchronous bulk store,
+      // clipped by the hardware at the M / N edges; the warp moves on immediately
+      fence_proxy_async_smem();
+      __syncwarp();
+      if (lane == 0 && !(p.debug & 1)) {
+        tma_store_2d((GELU && pass == 1) ? tmX : tmC, stg, n0, row0);
+        bulk_commit();
+      }
+      continue;
+    }
+    __syncwarp();
+    if (vec_ok) {
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int rl = g * 8 + rl_in;
+        const long long row = row0 + rl;
+        const uint4 v = lds128(stg_cell(stg, rl, cell));
+        if (row < p.M && !(p.debug & 1)) *reinterpret_cast<uint4*>(dst + row * ld + n0 + cell * 8) = v;
+      }
+    } else {
+      for (int g = 0; g < 4; ++g) {
+        const int rl = g * 8 + rl_in;
+        const long long row = row0 + rl;
+        const uint4 v = lds128(stg_cell(stg, rl, cell));
+        if (row >= p.M) continue;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int col = n0 + cell * 8 + e;
+          const uint32_t w = e < 2 ? v.x : (e < 4 ? v.y : (e < 6 ? v.z : v.w));
+          const float2 f = unpack_bf16(w);
+          if (col < p.N) dst[row * ld + col] = __float2bfloat16_rn((e & 1) ? f.y : f.x);
+        }
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// fp32 outputs (residual add, plain store, split-K atomics) and the multiply-by-aux epilogue: 16 accumulator
+// columns per step staged as fp32; afterwards lane l owns 4 consecutive columns of rows (l>>2) + 8g, and the
+// per-element global loads (residual / aux) of all 4 row groups are issued before the accumulator is read.
+__device__ __forceinline__ void epi_chunk_f32(const GemmParams& p, uint32_t taddr, uint32_t stg, int lane, int row0,
+                                              int n0, uint32_t bias_s /* smem address of this chunk's 16 bias floats */) {
+  uint32_t r[16];
+  tmem_ld16(taddr, r);
+  const int r_in = lane >> 2, cq = lane & 3;
+  const int col = n0 + cq * 4;
+  const bool out16 = !p.out_f32;
+  const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
+                      (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
+                      (p.aux == nullptr || (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 7) == 0)));
+  const bool full = vec_ok && (col + 3 < p.N);
+  uint2 aux4[4];
+  float4 res4[4];
+  if (full && p.epilogue == CGPT_EPI_MUL_AUX) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const long long row = row0 + g * 8 + r_in;
+      aux4[g] = row < p.M ? *reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col) : make_uint2(0u, 0u);
+    }
+  }
+  if (full && p.residual) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const long long row = row0 + g * 8 + r_in;
+      res4[g] = row < p.M ? *reinterpret_cast<const float4*>(p.residual + row * p.ldc + col)
+                          : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  const uint4 bu = lds128(bias_s + cq * 16);
+  const float4 b4 = make_float4(__uint_as_float(bu.x), __uint_as_float(bu.y), __uint_as_float(bu.z),
+                                __uint_as_float(bu.w));
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) sts128(stg_cell(stg, lane, j), make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]));
+  __syncwarp();
+  if (full) {
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      const int rl = g * 8 + r_in;
+      const long long row = row0 + rl;
+      const uint4 u = lds128(stg_cell(stg, rl, cq));
+      float4 v = make_float4(__uint_as_float(u.x) + b4.x, __uint_as_float(u.y) + b4.y, __uint_as_float(u.z) + b4.z,
+                             __uint_as_float(u.w) + b4.w);
+      if (row >= p.M) continue;
+      if (p.epilogue == CGPT_EPI_MUL_AUX) {
+        const float2 a0 = unpack_bf16(aux4[g].x), a1 = unpack_bf16(aux4[g].y);
+        v.x *= a0.x;
+        v.y *= a0.y;
+        v.z *= a1.x;
+        v.w *= a1.y;
+      }
+      if (out16) {
+        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col) =
+            make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+      } else {
+        float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col;
+        if (p.residual) {
+          v.x += res4[g].x;
+          v.y += res4[g].y;
+          v.z += res4[g].z;
+          v.w += res4[g].w;
+        }
+        if (p.accumulate)
+          red_add_v4(o, v);
+        else
+          *reinterpret_cast<float4*>(o) = v;
+      }
+    }
+  } else {
+    // scalar path: column tails and pitches that are not multiples of 4
+    for (int g = 0; g < 4; ++g) {
+      const int rl = g * 8 + r_in;
+      const long long row = row0 + rl;
+      const uint4 u = lds128(stg_cell(stg, rl, cq));
+      if (row >= p.M) continue;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (col + e >= p.N) continue;
+        float v = __uint_as_float(e == 0 ? u.x : (e == 1 ? u.y : (e == 2 ? u.z : u.w))) +
+                  (e == 0 ? b4.x : (e == 1 ? b4.y : (e == 2 ? b4.z : b4.w)));
+        if (p.epilogue == CGPT_EPI_MUL_AUX) v *= __bfloat162float(p.aux[row * p.ldaux + col + e]);
+        if (out16) {
+          reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldc + col + e] = __float2bfloat16_rn(v);
+        } else {
+          float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col + e;
+          if (p.residual) v += p.residual[row * p.ldc + col + e];
+          if (p.accumulate)
+            atomicAdd(o, v);
+          else
+            *o = v;
+        }
+      }
+    }
+  }
+  __syncwarp();
 }
 
 template <int BN, int STAGES>
@@ -61,19 +281,23 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStgOff = STAGES * kStageBytes;
-  static constexpr int kBarOff = kStgOff + kEpiWarps * kStgBytesPerWarp;
+  static constexpr int kBiasOff = kStgOff + kEpiWarps * kStgBytesPerWarp;  // 2 x BN floats (per accumulator buffer)
+  static constexpr int kBarOff = kBiasOff + 2 * BN * 4;
   static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16;
-  static constexpr int kDynamic = kTotal + 1024;  // slack for manual 1024-B alignment
-  static_assert(kDynamic <= 232448, "exceeds the 227 KB of shared memory per CTA");
+  // slack for aligning the base up to 1024 B (the kernel traps if it does not fit; in practice the dynamic
+  // window starts 1 KB into the CTA's shared memory and is already aligned)
+  static constexpr int kDynamic = (kTotal + 1024 <= 232448) ? kTotal + 1024 : 232448;
+  static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
 template <int BN, bool A_MN, bool B_MN, int STAGES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const GemmParams p) {
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
   using L = SmemLayout<BN, STAGES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(smem - smem_raw) + L::kTotal > L::kDynamic) __trap();
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOff);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -87,6 +311,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.tma_out) {
+      tma_prefetch_desc(&tmC);
+      tma_prefetch_desc(&tmX);
+    }
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -183,155 +411,57 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
   } else {
     // ------------------------------------------------------------ epilogue warps
-    // TMEM lane = output row, so a thread first holds one row x 32 columns.  The chunk goes through a
-    // swizzled smem transpose so that global traffic is coalesced: afterwards lane l owns 4 consecutive
-    // columns (l&7) of row 4*it + (l>>3); all bias / activation / aux / residual work happens there, with the
-    // global loads of all 8 row groups issued before the first use.
+    // TMEM lane = output row, so a thread first holds one row of the accumulator.  Every chunk goes through a
+    // swizzled 4 KB smem transpose (explicit st/ld.shared) so that global traffic is coalesced 16-byte accesses.
     const int ew = warp - 2;
     const int q = warp & 3;   // TMEM lane quadrant this warp may access
-    const int grp = ew >> 2;  // which half of the column chunks
-    uint8_t* stg = smem + L::kStgOff + ew * kStgBytesPerWarp;
-    const int r_in = lane >> 3, cq = lane & 7;
-    const bool out16 = !p.out_f32;
-    const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.out) & 15) == 0) &&
-                        (p.residual == nullptr || (reinterpret_cast<uintptr_t>(p.residual) & 15) == 0) &&
-                        ((p.aux == nullptr && p.aux_out == nullptr) ||
-                         (((p.ldaux & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.aux) & 7) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(p.aux_out) & 7) == 0)));
+    const int grp = ew >> 2;  // 0..3: which quarter of the column chunks
+    const uint32_t stg = smem_u32(smem + L::kStgOff + ew * kStgBytesPerWarp);
+    const bool bf16_rowmath = !p.out_f32 && p.epilogue != CGPT_EPI_MUL_AUX;
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int n_blk = w % p.tiles_n;
       const int m_blk = (w / p.tiles_n) % p.tiles_m;
       const int ks = w / (p.tiles_n * p.tiles_m);
       const int acc = it & 1;
+      // this tile's bias slice -> smem (zeros when there is none), before the accumulator is even ready.
+      // Double-buffered by accumulator parity; the barrier below also orders the reuse two tiles later.
+      const uint32_t bias_tile = smem_u32(smem + L::kBiasOff) + acc * BN * 4;
+      if (ew * 32 < BN) {
+        const int cb = n_blk * BN + ew * 32 + lane;
+        float bv = 0.f;
+        if (p.bias != nullptr && ks == 0 && cb < p.N) bv = __ldg(p.bias + cb);
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_tile + (ew * 32 + lane) * 4), "f"(bv) : "memory");
+      }
+      named_bar_sync(1, kEpiWarps * 32);
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
       const int row0 = m_blk * BM + q * 32;
-      const bool add_bias = (p.bias != nullptr) && (ks == 0);
+      const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
+      if (p.debug & 4) {
+      } else if (bf16_rowmath) {
 #pragma unroll 1
-      for (int c = grp; c < BN / kChunk; c += 2) {
-        const int n0 = n_blk * BN + c * kChunk;
-        if (n0 >= p.N) break;  // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN + c * kChunk, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-              make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
-        __syncwarp();
-        const int col = n0 + cq * 4;
-        const bool full = vec_ok && (col + 3 < p.N);
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (add_bias) {
-          if (col + 3 < p.N) {
-            b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-          } else {
-            if (col < p.N) b4.x = __ldg(p.bias + col);
-            if (col + 1 < p.N) b4.y = __ldg(p.bias + col + 1);
-            if (col + 2 < p.N) b4.z = __ldg(p.bias + col + 2);
-          }
+        for (int c = grp; c < BN / 32; c += 4) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= p.N) break;  // warp-uniform
+          if (p.epilogue == CGPT_EPI_GELU)
+            epi_chunk_bf16<true>(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128);
+          else
+            epi_chunk_bf16<false>(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128);
         }
-        if (full) {
-          // ---------------- vector path
-          uint2 aux8[8];
-          float4 res8[8];
-          if (p.epilogue == CGPT_EPI_MUL_AUX) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const long long row = row0 + g * 4 + r_in;
-              aux8[g] = row < p.M ? *reinterpret_cast<const uint2*>(p.aux + row * p.ldaux + col) : make_uint2(0u, 0u);
-            }
-          }
-          if (p.residual) {
-#pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              const long long row = row0 + g * 4 + r_in;
-              res8[g] = row < p.M ? *reinterpret_cast<const float4*>(p.residual + row * p.ldc + col)
-                                  : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-          }
-#pragma unroll
-          for (int g = 0; g < 8; ++g) {
-            const int rl = g * 4 + r_in;
-            const long long row = row0 + rl;
-            float4 v = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cq ^ (rl & 7)) << 4));
-            v.x += b4.x;
-            v.y += b4.y;
-            v.z += b4.z;
-            v.w += b4.w;
-            if (row >= p.M) continue;
-            if (p.epilogue == CGPT_EPI_GELU) {
-              float4 d;
-              gelu_and_grad(v.x, v.x, d.x);
-              gelu_and_grad(v.y, v.y, d.y);
-              gelu_and_grad(v.z, v.z, d.z);
-              gelu_and_grad(v.w, v.w, d.w);
-              if (p.aux_out)
-                *reinterpret_cast<uint2*>(p.aux_out + row * p.ldaux + col) =
-                    make_uint2(pack_bf16(d.x, d.y), pack_bf16(d.z, d.w));
-            } else if (p.epilogue == CGPT_EPI_MUL_AUX) {
-              const float2 a0 = unpack_bf16(aux8[g].x), a1 = unpack_bf16(aux8[g].y);
-              v.x *= a0.x;
-              v.y *= a0.y;
-              v.z *= a1.x;
-              v.w *= a1.y;
-            }
-            if (out16) {
-              *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + row * p.ldc + col) =
-                  make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
-            } else {
-              float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col;
-              if (p.residual) {
-                v.x += res8[g].x;
-                v.y += res8[g].y;
-                v.z += res8[g].z;
-                v.w += res8[g].w;
-              }
-              if (p.accumulate)
-                red_add_v4(o, v);
-              else
-                *reinterpret_cast<float4*>(o) = v;
-            }
-          }
-        } else {
-          // ---------------- scalar path: column tails and pitches that are not multiples of 4
-          const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
-          for (int g = 0; g < 8; ++g) {
-            const int rl = g * 4 + r_in;
-            const long long row = row0 + rl;
-            if (row >= p.M) continue;
-            const float4 v4 = *reinterpret_cast<const float4*>(stg + rl * 128 + ((cq ^ (rl & 7)) << 4));
-            const float vv[4] = {v4.x, v4.y, v4.z, v4.w};
-            for (int e = 0; e < 4; ++e) {
-              if (col + e >= p.N) break;
-              float v = vv[e] + bb[e];
-              if (p.epilogue == CGPT_EPI_GELU) {
-                float d;
-                gelu_and_grad(v, v, d);
-                if (p.aux_out) p.aux_out[row * p.ldaux + col + e] = __float2bfloat16_rn(d);
-              } else if (p.epilogue == CGPT_EPI_MUL_AUX) {
-                v *= __bfloat162float(p.aux[row * p.ldaux + col + e]);
-              }
-              if (out16) {
-                reinterpret_cast<__nv_bfloat16*>(p.out)[row * p.ldc + col + e] = __float2bfloat16_rn(v);
-              } else {
-                float* o = reinterpret_cast<float*>(p.out) + row * p.ldc + col + e;
-                if (p.residual) v += p.residual[row * p.ldc + col + e];
-                if (p.accumulate)
-                  atomicAdd(o, v);
-                else
-                  *o = v;
-              }
-            }
-          }
+      } else {
+#pragma unroll 1
+        for (int c = grp; c < BN / 16; c += 4) {
+          const int n0 = n_blk * BN + c * 16;
+          if (n0 >= p.N) break;  // warp-uniform
+          epi_chunk_f32(p, tbase + c * 16, stg, lane, row0, n0, bias_tile + c * 64);
         }
-        __syncwarp();
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
+    if (p.tma_out && lane == 0) bulk_wait0();  // smem must outlive the bulk stores that read it
   }
 
   tc_fence_before();
@@ -343,7 +473,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, bool A_MN, bool B_MN, int STAGES>
-int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx,
+           const GemmParams& p, cudaStream_t st) {
   using L = SmemLayout<BN, STAGES>;
   auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
   static bool configured = false;
@@ -353,19 +484,19 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cu
   }
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kThreads, L::kDynamic, st>>>(ta, tb, p);
+  kern<<<grid, kThreads, L::kDynamic, st>>>(ta, tb, tc, tx, p);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;
 }
 
 template <int BN, int STAGES>
-int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p,
-                   cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BN, false, false, STAGES>(ta, tb, p, st);
-  if (!a_mn && b_mn) return launch<BN, false, true, STAGES>(ta, tb, p, st);
-  if (a_mn && b_mn) return launch<BN, true, true, STAGES>(ta, tb, p, st);
-  return launch<BN, true, false, STAGES>(ta, tb, p, st);
+int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
+                   const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BN, false, false, STAGES>(ta, tb, tc, tx, p, st);
+  if (!a_mn && b_mn) return launch<BN, false, true, STAGES>(ta, tb, tc, tx, p, st);
+  if (a_mn && b_mn) return launch<BN, true, true, STAGES>(ta, tb, tc, tx, p, st);
+  return launch<BN, true, false, STAGES>(ta, tb, tc, tx, p, st);
 }
 
 }  // namespace
@@ -425,9 +556,39 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
   p.out_f32 = a->out_f32;
   p.accumulate = a->accumulate;
   p.ldc = a->ldc;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("CGPT_GEMM_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
+  // bf16 outputs that satisfy the TMA alignment rules leave through asynchronous bulk tensor stores
+  CUtensorMap tc, tx;
+  memset(&tc, 0, sizeof(tc));
+  memset(&tx, 0, sizeof(tx));
+  p.tma_out = 0;
+  const bool bf16_rowmath = !a->out_f32 && a->epilogue != CGPT_EPI_MUL_AUX;
+  const bool c_ok = ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0) && ((a->ldc * 2) % 16 == 0);
+  const bool x_ok = a->aux_out == nullptr ||
+                    (((reinterpret_cast<uintptr_t>(a->aux_out) & 15) == 0) && ((a->ldaux * 2) % 16 == 0));
+  if (bf16_rowmath && c_ok && x_ok) {
+    const uint64_t dimsC[2] = {(uint64_t)a->N, (uint64_t)a->M};
+    const uint32_t boxC[2] = {32, 32};
+    const uint64_t strC[1] = {(uint64_t)a->ldc * 2};
+    rc = make_tmap_bf16(&tc, a->out, 2, dimsC, strC, boxC, 64);
+    if (rc) return rc;
+    if (a->aux_out) {
+      const uint64_t strX[1] = {(uint64_t)a->ldaux * 2};
+      rc = make_tmap_bf16(&tx, a->aux_out, 2, dimsC, strX, boxC, 64);
+      if (rc) return rc;
+    }
+    p.tma_out = 1;
+  }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
-  if (BN == 256) return dispatch_major<256, 4>(amn, bmn, ta, tb, p, st);
-  if (BN == 128) return dispatch_major<128, 6>(amn, bmn, ta, tb, p, st);
-  return dispatch_major<64, 8>(amn, bmn, ta, tb, p, st);
+  if (BN == 256) return dispatch_major<256, 4>(amn, bmn, ta, tb, tc, tx, p, st);
+  if (BN == 128) return dispatch_major<128, 6>(amn, bmn, ta, tb, tc, tx, p, st);
+  return dispatch_major<64, 8>(amn, bmn, ta, tb, tc, tx, p, st);
 }

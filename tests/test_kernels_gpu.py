@@ -182,6 +182,14 @@ def test_gemm_epilogues(ops):
         assert torch.equal(o2[:, 0], gv.detach().to(torch.bfloat16)) or \
             (o2[:, 0].float() - gv.detach()).abs().max().item() <= 2 ** -8 * gv.detach().abs().max().item()
         assert (d2[:, 0].float() - xv.grad).abs().max().item() <= 2 ** -7
+    # ragged GELU tile: N not a multiple of 8, odd aux pitch -> scalar tail path
+    Nr = 100
+    outr = torch.empty((M, Nr), dtype=torch.bfloat16, device=DEV)
+    dr = torch.empty((M, Nr), dtype=torch.bfloat16, device=DEV)
+    ops.gemm(A, W[:Nr].contiguous(), outr, M=M, N=Nr, K=K, bias=bias[:Nr].contiguous(), epilogue=ops.EPI_GELU,
+             aux_out=dr, ldaux=Nr)
+    assert torch.allclose(outr.float(), gel.detach()[:, :Nr], rtol=1e-2, atol=1e-2)
+    assert torch.allclose(dr.float(), p32.grad[:, :Nr], rtol=1e-2, atol=1e-2)
     # multiply-by-aux epilogue (backward through GELU)
     dz = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
     ops.gemm(A, W, dz, M=M, N=N, K=K, epilogue=ops.EPI_MUL_AUX, aux=dact, ldaux=N)
