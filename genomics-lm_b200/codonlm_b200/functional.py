@@ -16,22 +16,54 @@ from .ops import EPI_GELU, EPI_MUL_AUX, EPI_NONE, bf16, f32
 
 _SMS = 148
 
+# bf16 copies of fp32 gradient tensors, produced by the kernel that wrote the fp32 one (LayerNorm backward)
+# and consumed by the next Function's backward instead of a separate cast pass.  Keyed by data_ptr.
+_BF16_SIDE = {}
 
-def _wgrad(dy: torch.Tensor, x: torch.Tensor, n_out: int, k_in: int, dy_ld=None, x_ld=None, dy_off=0):
-    """dW[n_out, k_in] = dy[:, dy_off:dy_off+n_out]ᵀ · x[:, :k_in]  (fp32, split-K over the tokens)."""
+
+def _bf16_of(g: torch.Tensor) -> torch.Tensor:
+    hit = _BF16_SIDE.pop(g.data_ptr(), None)
+    if hit is not None and hit.shape == g.shape:
+        return hit
+    return ops.cast_bf16(g)
+
+
+def _main_grad(p):
+    """Flat-buffer gradient slot installed by trainer.TrainStep (None when the model is used with a plain
+    torch optimiser): kernels accumulate into it directly and autograd gets no gradient tensor."""
+    return getattr(p, "main_grad", None) if p is not None else None
+
+
+def _done(p):
+    cb = getattr(p, "_cgpt_grad_ready", None)
+    if cb is not None:
+        cb()
+
+
+def _wgrad(dy: torch.Tensor, x: torch.Tensor, n_out: int, k_in: int, dy_ld=None, x_ld=None, dy_off=0, master=None):
+    """dW[n_out, k_in] (+)= dy[:, dy_off:dy_off+n_out]ᵀ · x[:, :k_in]  (fp32, split-K over the tokens).
+    Accumulates into master.main_grad when present (returns None), else returns a fresh tensor."""
     Mtok = x.shape[0]
-    dw = torch.zeros((n_out, k_in), dtype=f32, device=x.device)
+    mg = _main_grad(master)
+    dw = mg if mg is not None else torch.zeros((n_out, k_in), dtype=f32, device=x.device)
     a = dy if dy_off == 0 else dy[:, dy_off:]
     tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
     split = ops.pick_split_k(tiles, (Mtok + 63) // 64, _SMS)
     ops.gemm(a, x, dw, M=n_out, N=k_in, K=Mtok, a_mn=True, b_mn=True, lda=dy_ld or dy.stride(0),
              ldb=x_ld or x.stride(0), ldc=k_in, accumulate=True, split_k=split)
+    if mg is not None:
+        _done(master)
+        return None
     return dw
 
 
-def _colsum(dy: torch.Tensor, n: int) -> torch.Tensor:
-    out = torch.zeros((n,), dtype=f32, device=dy.device)
-    ops.colsum_bf16(dy, out, N=n)
+def _colsum(dy: torch.Tensor, n: int, master=None, off: int = 0):
+    mg = _main_grad(master)
+    out = mg if mg is not None else torch.zeros((n,), dtype=f32, device=dy.device)
+    ops.colsum_bf16(dy if off == 0 else dy[:, off:], out, N=n, ld=dy.stride(0))
+    if mg is not None:
+        _done(master)
+        return None
     return out
 
 
@@ -41,18 +73,25 @@ class EmbedFn(Function):
     @staticmethod
     def forward(ctx, idx, tok_w, pos_w):
         ctx.save_for_backward(idx)
-        ctx.shapes = (tok_w.shape, None if pos_w is None else pos_w.shape)
+        ctx.masters = (tok_w, pos_w)
         return ops.embed_fwd(idx, tok_w, pos_w)
 
     @staticmethod
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
-        ts, ps = ctx.shapes
+        tok_w, pos_w = ctx.masters
         g = g.contiguous()
-        dtok = torch.zeros(ts, dtype=f32, device=g.device)
-        dpos = torch.zeros(ps, dtype=f32, device=g.device) if ps is not None else None
+        mt, mp = _main_grad(tok_w), _main_grad(pos_w)
+        dtok = mt if mt is not None else torch.zeros(tok_w.shape, dtype=f32, device=g.device)
+        dpos = None
+        if pos_w is not None:
+            dpos = mp if mp is not None else torch.zeros(pos_w.shape, dtype=f32, device=g.device)
         ops.embed_bwd(idx, g, dtok, dpos)
-        return None, dtok, dpos
+        if mt is not None:
+            _done(tok_w)
+        if mp is not None:
+            _done(pos_w)
+        return None, (None if mt is not None else dtok), (None if mp is not None else dpos)
 
 
 class ResidualLayerNormFn(Function):
@@ -64,6 +103,7 @@ class ResidualLayerNormFn(Function):
         M, d = x.shape
         yb, yf, mean, rstd = ops.layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=want_f32)
         ctx.save_for_backward(x, gamma, mean, rstd)
+        ctx.masters = (gamma, beta)
         ctx.want_f32 = want_f32
         if want_f32:
             return x.view_as(x), yb, yf
@@ -72,8 +112,10 @@ class ResidualLayerNormFn(Function):
     @staticmethod
     def backward(ctx, gx, gyb, gyf=None):
         x, gamma, mean, rstd = ctx.saved_tensors
-        dgamma = torch.zeros_like(gamma)
-        dbeta = torch.zeros_like(gamma)
+        gam_p, bet_p = ctx.masters
+        mg, mb = _main_grad(gam_p), _main_grad(bet_p)
+        dgamma = mg if mg is not None else torch.zeros_like(gamma)
+        dbeta = mb if mb is not None else torch.zeros_like(gamma)
         if gyf is not None and gyb is not None:
             dy = gyf + gyb.float()
         elif gyf is not None:
@@ -82,8 +124,13 @@ class ResidualLayerNormFn(Function):
             dy = gyb
         else:
             return gx, None, None, None
-        dx, _ = ops.layernorm_bwd(dy.contiguous(), x, gamma, mean, rstd, None if gx is None else gx.contiguous(),
-                                  dgamma, dbeta)
+        dx, dxb = ops.layernorm_bwd(dy.contiguous(), x, gamma, mean, rstd, None if gx is None else gx.contiguous(),
+                                    dgamma, dbeta, want_bf16=True)
+        _BF16_SIDE[dx.data_ptr()] = dxb  # the upstream residual GEMM's backward wants dx as a bf16 operand
+        if mg is not None:
+            _done(gam_p)
+            _done(bet_p)
+            return dx, None, None, None
         return dx, dgamma, dbeta, None
 
 
@@ -106,6 +153,7 @@ class PackedLinearFn(Function):
         ctx.n_w = len(rows)
         ctx.has_bias = b_sh is not None
         ctx.k_in = [m.shape[1] for m in masters[: len(rows)]]
+        ctx.masters = masters
         return out
 
     @staticmethod
@@ -114,18 +162,18 @@ class PackedLinearFn(Function):
         M, K = x.shape
         N = w_sh.shape[0]
         g = g.contiguous()
-        gb = ops.cast_bf16(g) if g.dtype == f32 else g
-        dx = dw_list = None
+        gb = _bf16_of(g) if g.dtype == f32 else g
+        dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=bf16, device=x.device)
             ops.gemm(gb, w_sh, dx, M=M, N=K, K=N, b_mn=True)
+        nw = len(ctx.rows)
         grads: List[Optional[torch.Tensor]] = []
-        for (r0, n), k_in in zip(ctx.rows, ctx.k_in):
-            grads.append(_wgrad(gb, x, n, k_in, dy_off=r0))
+        for i, ((r0, n), k_in) in enumerate(zip(ctx.rows, ctx.k_in)):
+            grads.append(_wgrad(gb, x, n, k_in, dy_off=r0, master=ctx.masters[i]))
         if ctx.has_bias:
-            db = _colsum(gb, N)
-            for (r0, n) in ctx.rows:
-                grads.append(db[r0:r0 + n])
+            for i, (r0, n) in enumerate(ctx.rows):
+                grads.append(_colsum(gb, n, master=ctx.masters[nw + i], off=r0))
         return (dx, None, None, g if ctx.has_res else None, None, None, *grads)
 
 
@@ -145,6 +193,7 @@ class MlpGeluFn(Function):
         ops.gemm(act, w2_sh, out, M=M, N=n_out, K=F, bias=b2, residual=x_res)
         ctx.save_for_backward(h, dact, act, w1_sh, w2_sh)
         ctx.has_res = x_res is not None
+        ctx.masters = (b1, b2, w1, w2)
         return out
 
     @staticmethod
@@ -154,13 +203,14 @@ class MlpGeluFn(Function):
         F = w1_sh.shape[0]
         n_out = w2_sh.shape[0]
         g = g.contiguous()
-        gb = ops.cast_bf16(g)
-        dw2 = _wgrad(gb, act, n_out, F)
-        db2 = _colsum(gb, n_out)
+        b1, b2, w1, w2 = ctx.masters
+        gb = _bf16_of(g)
+        dw2 = _wgrad(gb, act, n_out, F, master=w2)
+        db2 = _colsum(gb, n_out, master=b2)
         dpre = torch.empty((M, F), dtype=bf16, device=h.device)
         ops.gemm(gb, w2_sh, dpre, M=M, N=F, K=n_out, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=F)
-        dw1 = _wgrad(dpre, h, F, d)
-        db1 = _colsum(dpre, F)
+        dw1 = _wgrad(dpre, h, F, d, master=w1)
+        db1 = _colsum(dpre, F, master=b1)
         dh = torch.empty((M, d), dtype=bf16, device=h.device)
         ops.gemm(dpre, w1_sh, dh, M=M, N=d, K=F, b_mn=True)
         return dh, (g if ctx.has_res else None), None, db1, None, db2, dw1, dw2
@@ -183,6 +233,7 @@ class MlpSwiGLUFn(Function):
         ctx.save_for_backward(hin, gu, act, wgu_sh, wd_sh)
         ctx.hidden = w_gate.shape[0]
         ctx.has_res = x_res is not None
+        ctx.masters = (w_gate, w_up, w_down)
         return out
 
     @staticmethod
@@ -193,13 +244,14 @@ class MlpSwiGLUFn(Function):
         hid = ctx.hidden
         n_out = wd_sh.shape[0]
         g = g.contiguous()
-        gb = ops.cast_bf16(g)
-        dwd = _wgrad(gb, act, n_out, hid)                       # [d, hid] (unpadded, odd pitch allowed)
+        w_gate, w_up, w_down = ctx.masters
+        gb = _bf16_of(g)
+        dwd = _wgrad(gb, act, n_out, hid, master=w_down)        # [d, hid] (unpadded, odd pitch allowed)
         dact = torch.empty((M, hp), dtype=bf16, device=hin.device)
         ops.gemm(gb, wd_sh, dact, M=M, N=hp, K=n_out, b_mn=True)
         dgu = ops.swiglu_bwd(gu, dact, hp)
-        dwg = _wgrad(dgu, hin, hid, d, dy_off=0)
-        dwu = _wgrad(dgu, hin, hid, d, dy_off=hp)
+        dwg = _wgrad(dgu, hin, hid, d, dy_off=0, master=w_gate)
+        dwu = _wgrad(dgu, hin, hid, d, dy_off=hp, master=w_up)
         dh = torch.empty((M, d), dtype=bf16, device=hin.device)
         ops.gemm(dgu, wgu_sh, dh, M=M, N=d, K=2 * hp, b_mn=True)
         return dh, (g if ctx.has_res else None), None, None, dwg, dwu, dwd
@@ -218,19 +270,21 @@ class OffsetHeadFn(Function):
         out = torch.empty((M, d), dtype=f32, device=xb.device)
         ops.gemm(act, w2_sh, out, M=M, N=d, K=d, bias=b2)
         ctx.save_for_backward(xb, dact, act, w1_sh, w2_sh)
+        ctx.masters = (b1, b2, w1, w2)
         return out
 
     @staticmethod
     def backward(ctx, g):
         xb, dact, act, w1_sh, w2_sh = ctx.saved_tensors
         M, d = xb.shape
+        b1, b2, w1, w2 = ctx.masters
         gb = ops.cast_bf16(g.contiguous())
-        dw2 = _wgrad(gb, act, d, d)
-        db2 = _colsum(gb, d)
+        dw2 = _wgrad(gb, act, d, d, master=w2)
+        db2 = _colsum(gb, d, master=b2)
         dpre = torch.empty((M, d), dtype=bf16, device=xb.device)
         ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=d)
-        dw1 = _wgrad(dpre, xb, d, d)
-        db1 = _colsum(dpre, d)
+        dw1 = _wgrad(dpre, xb, d, d, master=w1)
+        db1 = _colsum(dpre, d, master=b1)
         dx = torch.empty((M, d), dtype=bf16, device=xb.device)
         ops.gemm(dpre, w1_sh, dx, M=M, N=d, K=d, b_mn=True)
         return dx, None, db1, None, db2, dw1, dw2
@@ -265,16 +319,26 @@ class SkinnyLinearFn(Function):
     def forward(ctx, x, w, bias):
         ctx.save_for_backward(x, w)
         ctx.has_bias = bias is not None
+        ctx.masters = (w, bias)
         return ops.skinny_linear_fwd(x, w, bias)
 
     @staticmethod
     def backward(ctx, g):
         x, w = ctx.saved_tensors
+        wm, bm = ctx.masters
         g = g.contiguous()
         dx = torch.empty_like(x) if ctx.needs_input_grad[0] else None
-        dw = torch.zeros_like(w)
-        db = torch.zeros((w.shape[0],), dtype=f32, device=w.device) if ctx.has_bias else None
+        mw, mb = _main_grad(wm), _main_grad(bm)
+        dw = mw if mw is not None else torch.zeros_like(w)
+        db = None
+        if ctx.has_bias:
+            db = mb if mb is not None else torch.zeros((w.shape[0],), dtype=f32, device=w.device)
         ops.skinny_linear_bwd(g, x, w, dx, False, dw, db)
+        if mw is not None:
+            _done(wm)
+            if bm is not None:
+                _done(bm)
+            return dx, None, None
         return dx, dw, db
 
 

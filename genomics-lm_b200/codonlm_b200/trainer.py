@@ -63,7 +63,9 @@ class FlatGroup:
                 view = self.flat[o:o + p.numel()].view_as(p)
                 view.copy_(p.data)
                 p.data = view
-                p.grad = self.grad[o:o + p.numel()].view_as(p)
+                p.grad = None
+                # kernels accumulate straight into this slot (functional._main_grad); autograd never sees a grad
+                p.main_grad = self.grad[o:o + p.numel()].view_as(p)
 
 
 class GradBuckets:
@@ -91,19 +93,26 @@ class GradBuckets:
                 start, count = end, 0
         self.left = list(self.need)
         self.staging = [torch.empty(e - s, dtype=torch.bfloat16, device=group.grad.device) for s, e in self.bounds]
-        self.enabled = True
         self.pending = []
+        # A parameter can receive several contributions per backward (tied head/tok_emb, offset heads sharing
+        # the head).  The first step counts them (no overlap: everything is reduced in finish()); later steps
+        # launch a bucket as soon as all contributions of all its parameters have arrived.
+        self.contrib_seen = [0] * len(group.params)
+        self.contrib_need = None
         for i, p in enumerate(group.params):
-            p.register_post_accumulate_grad_hook(self._make_hook(i))
+            p._cgpt_grad_ready = self._make_hook(i)
+            p.register_post_accumulate_grad_hook(lambda _p, i=i: self._make_hook(i)())  # plain-autograd path
 
     def _make_hook(self, i):
-        def hook(_p):
-            if not self.enabled:
+        def hook():
+            self.contrib_seen[i] += 1
+            if self.contrib_need is None:
                 return
-            b = self.bucket_of[i]
-            self.left[b] -= 1
-            if self.left[b] == 0:
-                self._launch(b)
+            if self.contrib_seen[i] == self.contrib_need[i]:
+                b = self.bucket_of[i]
+                self.left[b] -= 1
+                if self.left[b] == 0:
+                    self._launch(b)
         return hook
 
     def _launch(self, b):
@@ -124,6 +133,13 @@ class GradBuckets:
 
     def finish(self):
         """Wait for all buckets and write the reduced gradients (sum over ranks) back as fp32."""
+        launched = {b for b, _ in self.pending}
+        for b in range(len(self.bounds)):  # first step, or parameters that got no gradient this step
+            if b not in launched:
+                self._launch(b)
+        if self.contrib_need is None:
+            self.contrib_need = [max(1, c) for c in self.contrib_seen]
+        self.contrib_seen = [0] * len(self.contrib_seen)
         for b, work in self.pending:
             work.wait()  # the compute stream now waits for that bucket's all-reduce
             s, e = self.bounds[b]

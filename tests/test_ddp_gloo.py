@@ -29,11 +29,14 @@ def _worker(rank, world, port, out):
     results = []
     for it in range(2):  # two steps: the ready-counters must re-arm
         group.grad.zero_()
+        for p_ in group.params:  # plain autograd (no main_grad-aware kernels here): accumulate into the flat views
+            p_.grad = p_.main_grad
         torch.manual_seed(100 + rank + 10 * it)  # different data per rank
         x = torch.randn(32, 16)
         net(x).square().mean().backward()
         local = group.grad.clone()
-        assert len(buckets.pending) == len(buckets.bounds)  # every bucket was launched from the hooks
+        if it > 0:  # after the counting step every bucket is launched from the hooks, before finish()
+            assert len(buckets.pending) == len(buckets.bounds)
         buckets.finish()
         gathered = [torch.zeros_like(local) for _ in range(world)]
         dist.all_gather(gathered, local)
