@@ -312,6 +312,62 @@ class AttentionFn(Function):
         return dqkv, None, None, None, None, None, None, None, None
 
 
+TC_HEAD_MIN_ROWS = 4096  # below this the fp32 FMA head kernels are used (launch-bound sizes, tests)
+
+
+class SplitHeadFn(Function):
+    """The same fp32-accurate head, on tensor cores: x·wᵀ with both operands split into bf16 hi + lo parts and
+    the reduction dimension tripled ([hi|lo|hi]·[hi|hi|lo]ᵀ = hi·hi + lo·hi + hi·lo, ~16 mantissa bits), so one
+    tcgen05 GEMM replaces the FMA kernel.  Backward uses the same trick for dx (one GEMM) and dW (three
+    split-K GEMMs accumulating in fp32).  LM head :327,336 and termination head :330."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        M, d = x.shape
+        V = w.shape[0]
+        x3 = ops.split3(x)                       # [M, 3d]  hi|lo|hi
+        w3 = ops.split3(w.detach(), partner=True)  # [V, 3d]  hi|hi|lo
+        out = torch.empty((M, V), dtype=f32, device=x.device)
+        ops.gemm(x3, w3, out, M=M, N=V, K=3 * d, bias=bias)
+        ctx.save_for_backward(x3, w3)
+        ctx.masters = (w, bias)
+        ctx.dims = (M, d, V)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x3, w3 = ctx.saved_tensors
+        wm, bm = ctx.masters
+        M, d, V = ctx.dims
+        Vp = (V + 7) // 8 * 8
+        g3 = ops.split3(g.contiguous(), cols_pad=Vp)  # [M, 3Vp]  hi|lo|hi
+        dx = None
+        if ctx.needs_input_grad[0]:
+            # dx = g·w: reduction over the (tripled, padded) vocabulary; w as [hi; hi; lo] stacked along K
+            wk = torch.zeros((3 * Vp, d), dtype=bf16, device=g.device)
+            wk[0:V], wk[Vp:Vp + V], wk[2 * Vp:2 * Vp + V] = w3[:, 0:d], w3[:, d:2 * d], w3[:, 2 * d:3 * d]
+            dx = torch.empty((M, d), dtype=f32, device=g.device)
+            ops.gemm(g3, wk, dx, M=M, N=d, K=3 * Vp, b_mn=True)
+        mw, mb = _main_grad(wm), _main_grad(bm)
+        dw = mw if mw is not None else torch.zeros((V, d), dtype=f32, device=g.device)
+        tiles = ((V + 127) // 128) * ((d + 255) // 256)
+        split = ops.pick_split_k(tiles, (M + 63) // 64, _SMS)
+        for goff, xoff in ((0, 0), (Vp, 0), (0, d)):  # hi·hi + lo·hi + hi·lo
+            ops.gemm(g3[:, goff:], x3[:, xoff:], dw, M=V, N=d, K=M, a_mn=True, b_mn=True, lda=3 * Vp, ldb=3 * d,
+                     ldc=d, accumulate=True, split_k=split)
+        db = None
+        if bm is not None:
+            db = mb if mb is not None else torch.zeros((V,), dtype=f32, device=g.device)
+            ops.colsum_bf16(g3, db, N=V, ld=3 * Vp)
+            ops.colsum_bf16(g3[:, Vp:], db, N=V, ld=3 * Vp)
+        if mw is not None:
+            _done(wm)
+            if bm is not None:
+                _done(bm)
+            return dx, None, None
+        return dx, dw, db
+
+
 class SkinnyLinearFn(Function):
     """fp32 x·wᵀ (+b) for N <= 128 outputs: LM head (:327,336) and termination head (:330)."""
 

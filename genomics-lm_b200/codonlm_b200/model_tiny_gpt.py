@@ -112,7 +112,9 @@ class SkinnyLinear(nn.Linear):
         x2 = x.reshape(-1, shp[-1]).float().contiguous()
         if self.out_features > 128:
             raise _lib.CgptError(f"head with {self.out_features} outputs > 128 is not supported by the fp32 head kernel")
-        out = Fn.SkinnyLinearFn.apply(x2, self.weight, self.bias)
+        use_tc = (x2.shape[0] >= Fn.TC_HEAD_MIN_ROWS and shp[-1] % 8 == 0 and self.out_features % 4 == 0)
+        fn = Fn.SplitHeadFn if use_tc else Fn.SkinnyLinearFn
+        out = fn.apply(x2, self.weight, self.bias)
         return out.view(*shp[:-1], self.out_features)
 
 

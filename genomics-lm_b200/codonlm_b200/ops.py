@@ -165,6 +165,17 @@ def cast_bf16(src: torch.Tensor, out: Optional[torch.Tensor] = None, ld_out: Opt
     return out
 
 
+def split3(src: torch.Tensor, partner: bool = False, cols_pad: Optional[int] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> bf16 [rows, 3*cols_pad]: [hi|lo|hi] (or [hi|hi|lo] for the partner operand)."""
+    _dev(src)
+    rows, cols = src.shape
+    cols_pad = (cols + 7) // 8 * 8 if cols_pad is None else cols_pad
+    out = torch.empty((rows, 3 * cols_pad), dtype=bf16, device=src.device)
+    check(_L().cgpt_split3_f32_bf16(src.data_ptr(), src.stride(0), out.data_ptr(), rows, cols, cols_pad, int(partner),
+                                    _stream()))
+    return out
+
+
 def colsum_bf16(x2d, out, N=None, ld=None):
     M = x2d.shape[0]
     check(_L().cgpt_colsum_bf16(x2d.data_ptr(), int(ld if ld is not None else x2d.stride(0)), out.data_ptr(), M,

@@ -338,6 +338,23 @@ __global__ void cast_f32_bf16_vec_kernel(const float4* __restrict__ in, uint2* _
   }
 }
 
+__global__ void split3_kernel(const float* __restrict__ in, long long ld_in, __nv_bfloat16* __restrict__ out,
+                              long long rows, long long cols, long long cols_pad, int partner) {
+  const long long total = rows * cols_pad;
+  const long long ld_out = 3 * cols_pad;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_pad, c = i - r * cols_pad;
+    const float v = c < cols ? in[r * ld_in + c] : 0.f;
+    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+    const __nv_bfloat16 lo = __float2bfloat16_rn(v - __bfloat162float(hi));
+    __nv_bfloat16* o = out + r * ld_out + c;
+    o[0] = hi;
+    o[cols_pad] = partner ? hi : lo;
+    o[2 * cols_pad] = partner ? lo : hi;
+  }
+}
+
 // out[n] += sum_m x[m,n]; CTA = 64 columns x a row range; 8 warps stride rows, lanes own column pairs.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
@@ -615,6 +632,16 @@ int cgpt_cast_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t ld_out
     cast_f32_bf16_kernel<<<grid_for(rows * ld_out, 256), 256, 0, ST(stream)>>>(
         in, ld_in, reinterpret_cast<__nv_bfloat16*>(out), ld_out, rows, cols);
   }
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_split3_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t rows, int64_t cols, int64_t cols_pad,
+                         int partner, cgpt_stream_t stream) {
+  CGPT_REQUIRE(in && out && rows > 0 && cols > 0 && cols_pad >= cols && ld_in >= cols, "split3: bad arguments");
+  split3_kernel<<<grid_for(rows * cols_pad, 256), 256, 0, ST(stream)>>>(in, ld_in, reinterpret_cast<__nv_bfloat16*>(out),
+                                                                        rows, cols, cols_pad, partner);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

@@ -114,6 +114,12 @@ int cgpt_gemm_bf16(const cgpt_gemm_args* args_host, cgpt_stream_t stream);
 /* ---------------------------------------------------------------- small elementwise ------ */
 int cgpt_cast_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t ld_out, int64_t rows, int64_t cols,
                        cgpt_stream_t stream); /* pad columns [cols, ld_out) are zeroed */
+/* fp32 [rows, cols] -> bf16 [rows, 3*cols_pad] = [hi | lo | hi] with hi = bf16(x), lo = bf16(x - hi)
+ * (zero padding up to cols_pad).  Against a partner laid out [hi | hi | lo] one bf16 GEMM over the tripled
+ * reduction dimension yields hi*hi + lo*hi + hi*lo, i.e. ~16 mantissa bits: the fp32-accurate LM head on
+ * tensor cores (model_tiny_gpt.py:327,336).  partner=1 writes the [hi | hi | lo] form. */
+int cgpt_split3_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t rows, int64_t cols, int64_t cols_pad,
+                         int partner, cgpt_stream_t stream);
 /* out[n] += sum_m x[m,n]   (bias gradients) */
 int cgpt_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, cgpt_stream_t stream);
 /* RoPE, half-split pairing i <-> i+hd/2            model_tiny_gpt.py:35-45, applied in place to the

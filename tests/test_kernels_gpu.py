@@ -377,3 +377,26 @@ def test_attention_fwd_bwd(ops, case):
         # identity attention (T=1 or window=1) has dq = dk = 0 exactly: gate on the dO scale there
         rel = ((a - r).norm() / max(r.norm().item(), 1e-3 * dout.float().norm().item())).item()
         assert rel <= 2e-2, f"{name} rel-norm err {rel}"
+
+
+def test_split_head_on_tensor_cores_is_fp32_accurate(ops):
+    """hi/lo bf16 split head (tcgen05) vs float64: forward, dx, dW, db — errors must sit at the 1e-5 level,
+    two orders below a plain bf16 GEMM."""
+    from codonlm_b200 import functional as Fn
+    g = torch.Generator().manual_seed(11)
+    for (M, d, V, has_b) in [(4096, 512, 68, False), (4100, 128, 8, True)]:
+        x = torch.randn(M, d, generator=g).to(DEV).requires_grad_(True)
+        w = (torch.randn(V, d, generator=g) * 0.05).to(DEV).requires_grad_(True)
+        b = torch.randn(V, generator=g).to(DEV).requires_grad_(True) if has_b else None
+        out = Fn.SplitHeadFn.apply(x, w, b)
+        ref = x.double() @ w.double().t() + (b.double() if has_b else 0)
+        scale = ref.abs().max().item()
+        assert (out.double() - ref).abs().max().item() <= 3e-5 * scale
+        go = torch.randn(M, V, generator=g).to(DEV)
+        out.backward(go)
+        rdx = go.double() @ w.double()
+        rdw = go.double().t() @ x.double()
+        assert (x.grad.double() - rdx).abs().max().item() <= 3e-5 * rdx.abs().max().item()
+        assert (w.grad.double() - rdw).abs().max().item() <= 3e-5 * rdw.abs().max().item()
+        if has_b:
+            assert (b.grad.double() - go.double().sum(0)).abs().max().item() <= 3e-5 * go.double().sum(0).abs().max().item()
