@@ -14,6 +14,8 @@
 //
 // TMEM lane == query row, so softmax statistics are per-thread scalars (no shuffles); 256 threads
 // split each row's columns in two halves.
+#include <string.h>
+
 #include "common.cuh"
 
 namespace cgpt {
@@ -66,6 +68,14 @@ __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* tm, ui
 #pragma unroll
   for (int a = 0; a < C::NA; ++a) tma_load_3d(dst + a * C::ATOM_BYTES, tm, bar, col + a * C::AW, row, b);
 }
+
+__device__ __forceinline__ float fast_exp2(float x) {  // ex2.approx: 1 MUFU, flushes denormal results to 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// column j (absolute) is visible from row i iff jlo <= j <= i  <=>  (unsigned)(j - jlo) <= (unsigned)(i - jlo)
+__device__ __forceinline__ bool visible(int j, int jlo, unsigned span) { return static_cast<unsigned>(j - jlo) <= span; }
 
 // first position p in [0,T) with a[p] > key (a non-decreasing); T if none
 __device__ __forceinline__ int upper_bound_i32(const int32_t* a, int T, int key) {
@@ -206,31 +216,36 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
 
     // a tile strictly below the diagonal and at/after every row's jlo needs no per-score test
     const bool need_mask = (kv0 + BKV - 1 > q0) || (kv0 < row_jlo(ssb, min(q0 + BQ - 1, T - 1), T, window));
-    // pass 1: row maximum over my 64 columns
-    float mloc = -INFINITY;
+    // pass 1: row maximum over my 64 columns (raw scores: the scale is positive).  Rows past the end
+    // (jlo > i) have span = 0xffffffff... guarded by row_valid below.
+    const unsigned span = static_cast<unsigned>(i - jlo);
+    const bool row_valid = (i < T);
+    float mraw = -INFINITY;
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c4 = half * 2 + cc;
       uint32_t r[32];
       tmem_ld32(tS + lane_base + c4 * 32, r);
       tmem_ld_wait();
+      if (need_mask) {
+        const int jb = kv0 + c4 * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float s = __uint_as_float(r[j]) * scale_log2;
-        if (need_mask) {
-          const int jj = kv0 + c4 * 32 + j;
-          if (jj < jlo || jj > i) s = -INFINITY;
-        }
-        mloc = fmaxf(mloc, s);
+        for (int j = 0; j < 32; ++j)
+          mraw = fmaxf(mraw, (row_valid && visible(jb + j, jlo, span)) ? __uint_as_float(r[j]) : -INFINITY);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, __uint_as_float(r[j]));
       }
     }
+    const float mloc = mraw * scale_log2;
     *xchg_wr = mloc;
     __syncthreads();
     const float m_new = fmaxf(m_run, fmaxf(mloc, *xchg_rd));
     const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-    const float alpha = exp2f(m_run - m_safe);
+    const float alpha = fast_exp2(m_run - m_safe);
     // pass 2: probabilities -> bf16 P tile in smem
     float lsum = 0.f;
+    const float neg_m = -m_safe;
 #pragma unroll 1
     for (int cc = 0; cc < 2; ++cc) {
       const int c4 = half * 2 + cc;
@@ -238,15 +253,20 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
       tmem_ld32(tS + lane_base + c4 * 32, r);
       tmem_ld_wait();
       float p[32];
+      if (need_mask) {
+        const int jb = kv0 + c4 * 32;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        float pv = exp2f(__uint_as_float(r[j]) * scale_log2 - m_safe);
-        if (need_mask) {
-          const int jj = kv0 + c4 * 32 + j;
-          if (jj < jlo || jj > i) pv = 0.f;
+        for (int j = 0; j < 32; ++j) {
+          const float pv = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2, neg_m));
+          p[j] = (row_valid && visible(jb + j, jlo, span)) ? pv : 0.f;
+          lsum += p[j];
         }
-        p[j] = pv;
-        lsum += pv;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          p[j] = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2, neg_m));
+          lsum += p[j];
+        }
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -339,71 +359,81 @@ template <int HD>
 struct BwdSmem {
   using C = HeadCfg<HD>;
   static constexpr int NQB = HD > 96 ? 1 : 2;          // (Q, dO) buffers
+  // HD <= 64: dQ has its own TMEM columns and smem staging, so the S/dP MMAs of the next query tile are issued
+  // right behind the gradient MMAs of the current one and overlap with the dQ write-out.
+  static constexpr bool kPipelined = HD <= 64;
   static constexpr int kK = 0;
   static constexpr int kV = kK + C::TILE_BYTES;
   static constexpr int kQ = kV + C::TILE_BYTES;
   static constexpr int kdO = kQ + NQB * C::TILE_BYTES;
   static constexpr int kP = kdO + NQB * C::TILE_BYTES;
   static constexpr int kdS = kP + kPTileBytes;
-  static constexpr int kBar = kdS + kPTileBytes;
+  // dQ leaves through TMA tensor reduce-adds when a half row (HD/2 floats) is 64 or 128 bytes (or 2 x 128):
+  // each warp stages its 32 rows as swizzled {HD/2 or 32 floats, 32 rows} boxes; otherwise one small bulk
+  // reduce per thread from padded rows.
+  static constexpr bool kTmaDq = (HD == 32 || HD == 64 || HD == 128);
+  static constexpr int kdQBoxCols = HD == 32 ? 16 : 32;         // floats per box row
+  static constexpr int kdQBoxes = (HD / 2) / kdQBoxCols;        // boxes per half row (1, or 2 for HD = 128)
+  static constexpr int kdQRow = kTmaDq ? HD * 4 : HD * 4 + (HD <= 96 ? 16 : 0);
+  static constexpr int kdQ = kdS + kPTileBytes;                 // dedicated staging when pipelined, else aliases P+dS
+  static constexpr int kBar = kdQ + (kPipelined ? 128 * kdQRow : 0);
   static constexpr int kTotal = kBar + 64;
   static constexpr int kDynamic = kTotal + 1024;
-  // the dQ staging (128 rows) aliases the P + dS tiles once they are consumed
-  static constexpr int kdQRow = HD * 4 + (HD <= 96 ? 16 : 0);
-  static_assert(128 * kdQRow <= 2 * kPTileBytes, "dQ staging must fit in the P+dS region");
+  static_assert(kPipelined || 128 * kdQRow <= 2 * kPTileBytes, "dQ staging must fit in the P+dS region");
+  static_assert(kDynamic <= 232448, "exceeds the shared memory of one CTA");
 };
 
-// One CTA per (kv tile, kv head, batch).  Loops over the query heads of the GQA group and over the
-// query tiles that can see the kv tile; dK/dV accumulate in TMEM over the whole loop; each dQ tile is
-// added to an fp32 workspace [B,H,T,hd] with bulk reduce-adds (rows are contiguous there).
-// 256 threads: thread t owns query row (t & 127) and the column half (t >> 7).
+// Persistent: one CTA per SM walks work items (kv tile, kv head, batch), heaviest first.  Per item it loops
+// over the query heads of the GQA group and the query tiles that can see the kv tile; dK/dV accumulate in TMEM
+// over that loop; each dQ tile is reduce-added into an fp32 workspace [B*H, T, hd] by TMA.  The K/V and first
+// (Q, dO) tiles of the NEXT item are requested as soon as the last MMAs of the current one retire, so their
+// latency hides behind the dK/dV write-out.  TMEM is allocated and the barriers are initialised once.
+// 256 threads: thread t owns row (t & 127) of every tile and the column half (t >> 7).
 template <int HD>
 __global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                const int32_t* __restrict__ seg_start, const float* __restrict__ lse,
-                const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_ws, int T,
-                int H, int Hk, int window, float scale) {
+                const __grid_constant__ CUtensorMap tm_dq, const int32_t* __restrict__ seg_start,
+                const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                float* __restrict__ dq_ws, int Bsz, int T, int H, int Hk, int window, float scale) {
   using C = HeadCfg<HD>;
   using S = BwdSmem<HD>;
   constexpr int TMEM_COLS = 512;
   constexpr int HH = HD / 2;
   constexpr int NQB = S::NQB;
+  constexpr bool kPipe = S::kPipelined;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sK = smem + S::kK;
   uint8_t* sV = smem + S::kV;
   uint8_t* sP = smem + S::kP;
   uint8_t* sdS = smem + S::kdS;
+  uint8_t* sdQ = kPipe ? smem + S::kdQ : sP;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
   uint64_t* kv_bar = bars;
   uint64_t* q_bar = bars + 1;  // [2]
-  uint64_t* mma_bar = bars + 3;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
-  int* s_qhi = reinterpret_cast<int*>(bars + 5);
+  uint64_t* s_bar = bars + 3;  // S and dP of a query tile are in TMEM
+  uint64_t* g_bar = bars + 4;  // dV, dK, dQ MMAs of a query tile have retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 5);
+  int* s_qhi = reinterpret_cast<int*>(bars + 6);  // [2]: query-tile upper bound of the current / next item
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & 127, half = tid >> 7;
-  const int kvb = blockIdx.x, kvh = blockIdx.y, b = blockIdx.z;
   const int rep = H / Hk;
-  const int kv0 = kvb * BKV;
   const int W = (H + 2 * Hk) * HD;
-  const int kcol = (H + kvh) * HD, vcol = (H + Hk + kvh) * HD;
-  const int32_t* ssb = seg_start ? seg_start + (size_t)b * T : nullptr;
   const int nqb_total = (T + BQ - 1) / BQ;
+  const int per_kvb = Hk * Bsz;
+  const int n_items = nqb_total * per_kvb;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dq);
     mbar_init(kv_bar, 1);
     mbar_init(&q_bar[0], 1);
     mbar_init(&q_bar[1], 1);
-    mbar_init(mma_bar, 1);
+    mbar_init(s_bar, 1);
+    mbar_init(g_bar, 1);
     fence_mbar_init();
-    int hi_pos = T - 1;  // last query position that can see this kv tile
-    const int kv_last = min(T - 1, kv0 + BKV - 1);
-    if (window > 0) hi_pos = min(hi_pos, kv_last + window - 1);
-    if (ssb) hi_pos = min(hi_pos, upper_bound_i32(ssb, T, kv_last) - 1);  // seg_start[i] <= kv_last
-    *s_qhi = hi_pos / BQ;
   }
   if (warp == 0) {
     __syncwarp();
@@ -414,174 +444,303 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base;              // 128 cols: scores, later reused for the dQ tile
+  const uint32_t tS = tmem_base;              // 128 cols: scores
   const uint32_t tdP = tmem_base + 128;       // 128 cols
-  const uint32_t tdV = tmem_base + 256;       // HD cols, accumulates over the loop
-  const uint32_t tdK = tmem_base + 256 + HD;  // HD cols, accumulates over the loop
-  const uint32_t tdQ = tS;
-  const int qb_lo = kvb, qb_hi = min(*s_qhi, nqb_total - 1);
-  const int nq = qb_hi - qb_lo + 1;
-  const int niter = nq > 0 ? nq * rep : 0;
+  const uint32_t tdV = tmem_base + 256;       // HD cols, accumulates over an item
+  const uint32_t tdK = tmem_base + 256 + HD;  // HD cols, accumulates over an item
+  const uint32_t tdQ = kPipe ? tmem_base + 256 + 2 * HD : tS;
 
-  auto load_q = [&](int it2) {
-    const int nb = it2 % NQB;
-    const int nh = kvh * rep + it2 / nq, nq0 = (qb_lo + it2 % nq) * BQ;
-    mbar_expect_tx(&q_bar[nb], 2 * C::TILE_BYTES);
-    tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], nh * HD, nq0, b);
-    tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], nh * HD, nq0, b);
-  };
-  if (tid == 0) {
-    mbar_expect_tx(kv_bar, 2 * C::TILE_BYTES);
-    tma_tile<HD>(sK, &tm_qkv, kv_bar, kcol, kv0, b);
-    tma_tile<HD>(sV, &tm_qkv, kv_bar, vcol, kv0, b);
-    if (niter > 0) load_q(0);
-  }
-
-  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-  const float scale_log2 = scale * kLog2e;
-  uint32_t mma_phase = 0;
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);   // S = Q Kᵀ, dP = dO Vᵀ
   constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD, true, true);     // dV = Pᵀ dO, dK = dSᵀ Q
   constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, false, true);     // dQ = dS K
+  const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+  const float scale_log2 = scale * kLog2e;
 
-  for (int it = 0; it < niter; ++it) {
-    const int buf = it % NQB;
-    const int hq = kvh * rep + it / nq;     // query head
-    const int qb = qb_lo + it % nq;
-    const int q0 = qb * BQ;
-    uint8_t* sQ = smem + S::kQ + buf * C::TILE_BYTES;
-    uint8_t* sdO = smem + S::kdO + buf * C::TILE_BYTES;
-    if (tid == 0) {
-      // prefetch the next (Q, dO): with two buffers the other one was released by the previous MMA wait
-      if (NQB == 2 && it + 1 < niter) load_q(it + 1);
-      if (it == 0) mbar_wait(kv_bar, 0);
-      mbar_wait(&q_bar[buf], (it / NQB) & 1);
+  // item -> (kv tile, kv head, batch); kv tile 0 sees the most query tiles, so items are ordered heaviest first
+  auto decode = [&](int item, int& kvb, int& kvh, int& b) {
+    kvb = item / per_kvb;
+    const int r = item - kvb * per_kvb;
+    kvh = r % Hk;
+    b = r / Hk;
+  };
+  // last query tile that can see kv tile kvb of batch b (thread 0: binary search over the segment starts)
+  auto last_q_tile = [&](int kvb, int b) {
+    int hi_pos = T - 1;
+    const int kv_last = min(T - 1, kvb * BKV + BKV - 1);
+    if (window > 0) hi_pos = min(hi_pos, kv_last + window - 1);
+    if (seg_start) hi_pos = min(hi_pos, upper_bound_i32(seg_start + (size_t)b * T, T, kv_last) - 1);
+    return min(hi_pos / BQ, nqb_total - 1);
+  };
+  // thread 0: request K, V and the first (Q, dO) of an item.  `gq` = running count of (Q, dO) tile loads.
+  auto request_item = [&](int kvb, int kvh, int b, int gq) {
+    mbar_expect_tx(kv_bar, 2 * C::TILE_BYTES);
+    tma_tile<HD>(sK, &tm_qkv, kv_bar, (H + kvh) * HD, kvb * BKV, b);
+    tma_tile<HD>(sV, &tm_qkv, kv_bar, (H + Hk + kvh) * HD, kvb * BKV, b);
+    const int nb = gq % NQB;
+    mbar_expect_tx(&q_bar[nb], 2 * C::TILE_BYTES);
+    tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], (kvh * rep) * HD, kvb * BQ, b);
+    tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], (kvh * rep) * HD, kvb * BQ, b);
+  };
+
+  uint32_t s_phase = 0, g_phase = 0, kv_phase = 0;
+  int gq0 = 0;   // (Q, dO) tiles consumed before the current item
+  int slot = 0;  // which s_qhi entry belongs to the current item
+  if (tid == 0 && (int)blockIdx.x < n_items) {
+    int kvb, kvh, b;
+    decode(blockIdx.x, kvb, kvh, b);
+    s_qhi[0] = last_q_tile(kvb, b);
+    request_item(kvb, kvh, b, 0);
+  }
+  __syncthreads();
+
+  for (int item = blockIdx.x; item < n_items; item += gridDim.x, slot ^= 1) {
+    int kvb, kvh, b;
+    decode(item, kvb, kvh, b);
+    const int kv0 = kvb * BKV;
+    const int kcol = (H + kvh) * HD, vcol = (H + Hk + kvh) * HD;
+    const int32_t* ssb = seg_start ? seg_start + (size_t)b * T : nullptr;
+    const int qb_lo = kvb, qb_hi = s_qhi[slot];
+    const int nq = qb_hi - qb_lo + 1;
+    const int niter = nq * rep;  // >= 1: a kv tile always sees its own diagonal query tile
+    const int next_item = item + gridDim.x;
+
+    auto load_q = [&](int it2) {
+      const int nb = (gq0 + it2) % NQB;
+      const int nh = kvh * rep + it2 / nq, nq0 = (qb_lo + it2 % nq) * BQ;
+      mbar_expect_tx(&q_bar[nb], 2 * C::TILE_BYTES);
+      tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], nh * HD, nq0, b);
+      tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], nh * HD, nq0, b);
+    };
+    // S and dP of query tile it2 (thread 0 only)
+    auto issue_scores = [&](int it2) {
+      const int g = gq0 + it2, nb = g % NQB;
+      const uint32_t q_s = smem_u32(smem + S::kQ + nb * C::TILE_BYTES), do_s = smem_u32(smem + S::kdO + nb * C::TILE_BYTES);
+      mbar_wait(&q_bar[nb], (g / NQB) & 1);
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks)
-        umma_bf16(tS, C::kmajor(smem_u32(sQ), ks), C::kmajor(smem_u32(sK), ks), idesc_s, ks > 0);
+        umma_bf16(tS, C::kmajor(q_s, ks), C::kmajor(smem_u32(sK), ks), idesc_s, ks > 0);
 #pragma unroll
       for (int ks = 0; ks < HD / 16; ++ks)
-        umma_bf16(tdP, C::kmajor(smem_u32(sdO), ks), C::kmajor(smem_u32(sV), ks), idesc_s, ks > 0);
-      umma_commit(mma_bar);
+        umma_bf16(tdP, C::kmajor(do_s, ks), C::kmajor(smem_u32(sV), ks), idesc_s, ks > 0);
+      umma_commit(s_bar);
+    };
+
+    int n_kvb = 0, n_kvh = 0, n_b = 0;
+    if (tid == 0) {
+      mbar_wait(kv_bar, kv_phase);
+      issue_scores(0);
+      if (next_item < n_items) {  // look ahead: the next item's tile range (global loads, off the critical path)
+        decode(next_item, n_kvb, n_kvh, n_b);
+        s_qhi[slot ^ 1] = last_q_tile(n_kvb, n_b);
+      }
     }
-    const int i = q0 + row;
-    const bool row_ok = i < T;
-    const size_t stat = ((size_t)b * H + hq) * T + (row_ok ? i : 0);
-    const float lse2 = row_ok ? lse[stat] * kLog2e : 0.f;
-    const float dl = row_ok ? delta[stat] : 0.f;
-    const int jlo = row_jlo(ssb, i, T, window);
-    mbar_wait(mma_bar, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
+    kv_phase ^= 1;
+
+    // per-row statistics of the first tile (later tiles are fetched one tile ahead)
+    float nx_lse = 0.f, nx_dl = 0.f;
+    int nx_jlo = 0x3fffffff;
+    {
+      const int i0 = qb_lo * BQ + row;
+      const size_t st0 = ((size_t)b * H + kvh * rep) * T + (i0 < T ? i0 : 0);
+      nx_lse = i0 < T ? lse[st0] : 0.f;
+      nx_dl = i0 < T ? delta[st0] : 0.f;
+      nx_jlo = row_jlo(ssb, i0, T, window);
+    }
+
+    for (int it = 0; it < niter; ++it) {
+      const int buf = (gq0 + it) % NQB;
+      const int hq = kvh * rep + it / nq;     // query head
+      const int qb = qb_lo + it % nq;
+      const int q0 = qb * BQ;
+      uint8_t* sQ = smem + S::kQ + buf * C::TILE_BYTES;
+      uint8_t* sdO = smem + S::kdO + buf * C::TILE_BYTES;
+      // with two (Q, dO) buffers the other one was released when the previous tile's gradient MMAs retired
+      if (tid == 0 && NQB == 2 && it + 1 < niter) load_q(it + 1);
+      const int i = q0 + row;
+      const bool row_ok = i < T;
+      const float lse2 = nx_lse * kLog2e, dl = nx_dl;
+      const int jlo = nx_jlo;
+      if (it + 1 < niter) {  // next tile's statistics: the loads complete while this tile is processed
+        const int nh = kvh * rep + (it + 1) / nq, ni = (qb_lo + (it + 1) % nq) * BQ + row;
+        const size_t st2 = ((size_t)b * H + nh) * T + (ni < T ? ni : 0);
+        nx_lse = ni < T ? lse[st2] : 0.f;
+        nx_dl = ni < T ? delta[st2] : 0.f;
+        nx_jlo = row_jlo(ssb, ni, T, window);
+      }
+      // only tiles that touch the diagonal, a segment start / window edge or the ragged end need per-score tests
+      const bool need_mask = (kv0 + BKV - 1 > q0) || (q0 + BQ > T) ||
+                             (kv0 < row_jlo(ssb, min(q0 + BQ - 1, T - 1), T, window));
+      mbar_wait(s_bar, s_phase);
+      s_phase ^= 1;
+      tc_fence_after();
 
 #pragma unroll 1
-    for (int cc = 0; cc < 2; ++cc) {
-      const int c4 = half * 2 + cc;
-      uint32_t rs[32], rp[32];
-      tmem_ld32(tS + lane_base + c4 * 32, rs);
-      tmem_ld32(tdP + lane_base + c4 * 32, rp);
-      tmem_ld_wait();
-      float p[32], ds[32];
-#pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int jj = kv0 + c4 * 32 + j;
-        const bool ok = (jj >= jlo) && (jj <= i);
-        const float pv = ok ? exp2f(__uint_as_float(rs[j]) * scale_log2 - lse2) : 0.f;
-        p[j] = pv;
-        ds[j] = pv * (__uint_as_float(rp[j]) - dl);
-      }
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        uint4 v, w;
-        v.x = pack_bf16(p[q * 8 + 0], p[q * 8 + 1]);
-        v.y = pack_bf16(p[q * 8 + 2], p[q * 8 + 3]);
-        v.z = pack_bf16(p[q * 8 + 4], p[q * 8 + 5]);
-        v.w = pack_bf16(p[q * 8 + 6], p[q * 8 + 7]);
-        w.x = pack_bf16(ds[q * 8 + 0], ds[q * 8 + 1]);
-        w.y = pack_bf16(ds[q * 8 + 2], ds[q * 8 + 3]);
-        w.z = pack_bf16(ds[q * 8 + 4], ds[q * 8 + 5]);
-        w.w = pack_bf16(ds[q * 8 + 6], ds[q * 8 + 7]);
-        ptile_store(sP, row, c4 * 4 + q, v);
-        ptile_store(sdS, row, c4 * 4 + q, w);
-      }
-    }
-    fence_proxy_async_smem();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) {
-      tc_fence_after();
-#pragma unroll
-      for (int ks = 0; ks < BQ / 16; ++ks)  // dV[kv,hd] += Pᵀ[kv,q] dO[q,hd]
-        umma_bf16(tdV, ptile_mnmajor(smem_u32(sP), ks), C::mnmajor(smem_u32(sdO), ks), idesc_kv, (it > 0) || (ks > 0));
-#pragma unroll
-      for (int ks = 0; ks < BQ / 16; ++ks)  // dK[kv,hd] += dSᵀ[kv,q] Q[q,hd]
-        umma_bf16(tdK, ptile_mnmajor(smem_u32(sdS), ks), C::mnmajor(smem_u32(sQ), ks), idesc_kv, (it > 0) || (ks > 0));
-#pragma unroll
-      for (int ks = 0; ks < BKV / 16; ++ks)  // dQ[q,hd] = dS[q,kv] K[kv,hd]
-        umma_bf16(tdQ, ptile_kmajor(smem_u32(sdS), ks), C::mnmajor(smem_u32(sK), ks), idesc_q, ks > 0);
-      umma_commit(mma_bar);
-    }
-    mbar_wait(mma_bar, mma_phase);
-    mma_phase ^= 1;
-    tc_fence_after();
-    if (NQB == 1 && tid == 0 && it + 1 < niter) load_q(it + 1);  // single buffer: free only now
-    // dQ tile -> smem row (aliases the consumed P/dS tiles) -> bulk reduce-add into the fp32 workspace
-    {
-      uint8_t* myrow = sP + row * S::kdQRow + half * (HH * 4);
-#pragma unroll
-      for (int c0 = 0; c0 < HH; c0 += 8) {
-        uint32_t r[8];
-        tmem_ld8(tdQ + lane_base + half * HH + c0, r);
+      for (int cc = 0; cc < 2; ++cc) {
+        const int c4 = half * 2 + cc;
+        uint32_t rs[32], rp[32];
+        tmem_ld32(tS + lane_base + c4 * 32, rs);
+        tmem_ld32(tdP + lane_base + c4 * 32, rp);
         tmem_ld_wait();
-        *reinterpret_cast<uint4*>(myrow + c0 * 4) = make_uint4(r[0], r[1], r[2], r[3]);
-        *reinterpret_cast<uint4*>(myrow + c0 * 4 + 16) = make_uint4(r[4], r[5], r[6], r[7]);
+        float p[32], ds[32];
+        if (need_mask) {
+          const int jb = kv0 + c4 * 32;
+          const unsigned span = static_cast<unsigned>(i - jlo);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float pv = fast_exp2(fmaf(__uint_as_float(rs[j]), scale_log2, -lse2));
+            p[j] = (row_ok && visible(jb + j, jlo, span)) ? pv : 0.f;
+            ds[j] = p[j] * (__uint_as_float(rp[j]) - dl);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            p[j] = fast_exp2(fmaf(__uint_as_float(rs[j]), scale_log2, -lse2));
+            ds[j] = p[j] * (__uint_as_float(rp[j]) - dl);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 v, w;
+          v.x = pack_bf16(p[q * 8 + 0], p[q * 8 + 1]);
+          v.y = pack_bf16(p[q * 8 + 2], p[q * 8 + 3]);
+          v.z = pack_bf16(p[q * 8 + 4], p[q * 8 + 5]);
+          v.w = pack_bf16(p[q * 8 + 6], p[q * 8 + 7]);
+          w.x = pack_bf16(ds[q * 8 + 0], ds[q * 8 + 1]);
+          w.y = pack_bf16(ds[q * 8 + 2], ds[q * 8 + 3]);
+          w.z = pack_bf16(ds[q * 8 + 4], ds[q * 8 + 5]);
+          w.w = pack_bf16(ds[q * 8 + 6], ds[q * 8 + 7]);
+          ptile_store(sP, row, c4 * 4 + q, v);
+          ptile_store(sdS, row, c4 * 4 + q, w);
+        }
       }
       fence_proxy_async_smem();
-      if (row_ok) {
-        float* g = dq_ws + (((size_t)b * H + hq) * T + i) * HD + half * HH;
-        asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
-                     "r"(smem_u32(myrow)), "r"(HH * 4)
-                     : "memory");
-      }
-      asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-      asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-    }
-    tc_fence_before();
-    __syncthreads();  // P/dS region and the S/dQ TMEM columns are free again
-  }
-
-  // dK (scaled) and dV -> bf16 into the k / v column blocks of dqkv (TMEM lane = kv row)
-  {
-    const int j = kv0 + row;
-    __nv_bfloat16* gk = dqkv + ((size_t)b * T + min(j, T - 1)) * W + kcol + half * HH;
-    __nv_bfloat16* gv = dqkv + ((size_t)b * T + min(j, T - 1)) * W + vcol + half * HH;
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
 #pragma unroll
-    for (int c0 = 0; c0 < HH; c0 += 8) {
-      uint32_t rk[8], rv[8];
-      if (niter > 0) {  // CTA-uniform
+        for (int ks = 0; ks < BQ / 16; ++ks)  // dV[kv,hd] += Pᵀ[kv,q] dO[q,hd]
+          umma_bf16(tdV, ptile_mnmajor(smem_u32(sP), ks), C::mnmajor(smem_u32(sdO), ks), idesc_kv, (it > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < BQ / 16; ++ks)  // dK[kv,hd] += dSᵀ[kv,q] Q[q,hd]
+          umma_bf16(tdK, ptile_mnmajor(smem_u32(sdS), ks), C::mnmajor(smem_u32(sQ), ks), idesc_kv, (it > 0) || (ks > 0));
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks)  // dQ[q,hd] = dS[q,kv] K[kv,hd]
+          umma_bf16(tdQ, ptile_kmajor(smem_u32(sdS), ks), C::mnmajor(smem_u32(sK), ks), idesc_q, ks > 0);
+        umma_commit(g_bar);
+        // pipelined: the next tile's scores queue up right behind (their TMEM columns and operands are free)
+        if (kPipe && it + 1 < niter) issue_scores(it + 1);
+      }
+      mbar_wait(g_bar, g_phase);
+      g_phase ^= 1;
+      tc_fence_after();
+      if (tid == 0) {
+        if (NQB == 1 && it + 1 < niter) load_q(it + 1);  // single buffer: free only now
+        // last tile of the item: K, V, Q, dO buffers are all free -> request the next item's tiles now
+        if (it + 1 == niter && next_item < n_items) request_item(n_kvb, n_kvh, n_b, gq0 + niter);
+      }
+      // dQ tile -> smem -> reduce-add into the fp32 workspace [B*H, T, hd].  The read-completion of the previous
+      // tile's bulk operations is only awaited right before the staging is rewritten.
+      if constexpr (S::kTmaDq) {
+        // per warp: rows 32*(warp&3).., this thread's half; swizzled {kdQBoxCols, 32} boxes, 1-2 TMA tensor
+        // reduce-adds per warp (rows beyond T are clipped by the 3-D map)
+        constexpr int BC = S::kdQBoxCols, NB = S::kdQBoxes, BOX_BYTES = 32 * BC * 4, ROWB = BC * 4;
+        uint8_t* wbase = sdQ + (warp * NB) * BOX_BYTES;  // warp w owns boxes [w*NB, w*NB+NB)
+        const int lr = tid & 31;
+        if (lr == 0) bulk_wait_read0();
+        __syncwarp();
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) {
+          uint32_t r[8];
+          tmem_ld8(tdQ + lane_base + half * HH + c0, r);
+          tmem_ld_wait();
+          const int bx = c0 / BC, cc = (c0 % BC) * 4;  // box, byte column inside the box row
+          uint8_t* rowp = wbase + bx * BOX_BYTES + lr * ROWB;
+          const int sw = (ROWB == 128) ? (lr & 7) : ((lr >> 1) & 3);
+          *reinterpret_cast<uint4*>(rowp + (((cc >> 4) ^ sw) << 4)) = make_uint4(r[0], r[1], r[2], r[3]);
+          *reinterpret_cast<uint4*>(rowp + ((((cc >> 4) + 1) ^ sw) << 4)) = make_uint4(r[4], r[5], r[6], r[7]);
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lr == 0) {
+#pragma unroll
+          for (int bx = 0; bx < NB; ++bx) {
+            asm volatile(
+                "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(&tm_dq)),
+                "r"(smem_u32(wbase + bx * BOX_BYTES)), "r"(half * HH + bx * BC), "r"(q0 + (warp & 3) * 32), "r"(b * H + hq)
+                : "memory");
+          }
+          bulk_commit();
+          if (!kPipe) bulk_wait_read0();  // staging aliases the P/dS tiles
+        }
+        if (!kPipe) __syncwarp();
+      } else {
+        uint8_t* myrow = sdQ + row * S::kdQRow + half * (HH * 4);
+        bulk_wait_read0();
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) {
+          uint32_t r[8];
+          tmem_ld8(tdQ + lane_base + half * HH + c0, r);
+          tmem_ld_wait();
+          *reinterpret_cast<uint4*>(myrow + c0 * 4) = make_uint4(r[0], r[1], r[2], r[3]);
+          *reinterpret_cast<uint4*>(myrow + c0 * 4 + 16) = make_uint4(r[4], r[5], r[6], r[7]);
+        }
+        fence_proxy_async_smem();
+        if (row_ok) {
+          float* g = dq_ws + (((size_t)b * H + hq) * T + i) * HD + half * HH;
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(g),
+                       "r"(smem_u32(myrow)), "r"(HH * 4)
+                       : "memory");
+        }
+        bulk_commit();
+        if (!kPipe) bulk_wait_read0();  // staging aliases the P/dS tiles
+      }
+      if (!kPipe) {
+        tc_fence_before();
+        __syncthreads();  // P/dS region and the S/dQ TMEM columns are free again
+        if (tid == 0 && it + 1 < niter) {
+          tc_fence_after();
+          issue_scores(it + 1);
+        }
+      }
+    }
+    gq0 += niter;
+
+    // dK (scaled) and dV -> bf16 into the k / v column blocks of dqkv (TMEM lane = kv row).  The next item's
+    // tiles are already in flight; its first gradient MMA (which overwrites these columns) is only issued
+    // after the next block-wide barrier.
+    {
+      const int j = kv0 + row;
+      __nv_bfloat16* gk = dqkv + ((size_t)b * T + min(j, T - 1)) * W + kcol + half * HH;
+      __nv_bfloat16* gv = dqkv + ((size_t)b * T + min(j, T - 1)) * W + vcol + half * HH;
+#pragma unroll
+      for (int c0 = 0; c0 < HH; c0 += 8) {
+        uint32_t rk[8], rv[8];
         tmem_ld8(tdK + lane_base + half * HH + c0, rk);
         tmem_ld8(tdV + lane_base + half * HH + c0, rv);
         tmem_ld_wait();
-      } else {
-#pragma unroll
-        for (int q = 0; q < 8; ++q) rk[q] = rv[q] = 0u;
-      }
-      if (j < T) {
-        uint4 a, c;
-        a.x = pack_bf16(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale);
-        a.y = pack_bf16(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale);
-        a.z = pack_bf16(__uint_as_float(rk[4]) * scale, __uint_as_float(rk[5]) * scale);
-        a.w = pack_bf16(__uint_as_float(rk[6]) * scale, __uint_as_float(rk[7]) * scale);
-        c.x = pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]));
-        c.y = pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
-        c.z = pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]));
-        c.w = pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
-        *reinterpret_cast<uint4*>(gk + c0) = a;
-        *reinterpret_cast<uint4*>(gv + c0) = c;
+        if (j < T) {
+          uint4 a, c;
+          a.x = pack_bf16(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale);
+          a.y = pack_bf16(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale);
+          a.z = pack_bf16(__uint_as_float(rk[4]) * scale, __uint_as_float(rk[5]) * scale);
+          a.w = pack_bf16(__uint_as_float(rk[6]) * scale, __uint_as_float(rk[7]) * scale);
+          c.x = pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]));
+          c.y = pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
+          c.z = pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]));
+          c.w = pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
+          *reinterpret_cast<uint4*>(gk + c0) = a;
+          *reinterpret_cast<uint4*>(gv + c0) = c;
+        }
       }
     }
+    tc_fence_before();
+    __syncthreads();  // s_qhi[slot^1] visible; dK/dV columns drained before the next item's MMAs
+    tc_fence_after();
   }
+  bulk_wait_read0();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -697,6 +856,15 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   if (rc) return rc;
   float* delta = reinterpret_cast<float*>(ws);
   float* dq_ws = delta + delta_floats(B, T, H);  // 256-byte aligned: bulk reduce-adds and float4 reads need 16
+  CUtensorMap tdq;
+  memset(&tdq, 0, sizeof(tdq));
+  if (S::kTmaDq) {
+    const uint64_t dims[3] = {(uint64_t)HD, (uint64_t)T, (uint64_t)B * H};
+    const uint64_t str[2] = {(uint64_t)HD * 4, (uint64_t)T * HD * 4};
+    const uint32_t box[3] = {(uint32_t)S::kdQBoxCols, 32u, 1u};
+    rc = make_tmap_f32(&tdq, dq_ws, 3, dims, str, box, S::kdQBoxCols * 4);
+    if (rc) return rc;
+  }
   CGPT_CHECK(cudaMemsetAsync(dq_ws, 0, (size_t)B * H * T * HD * sizeof(float), st));
   {
     const long long warps = (long long)B * T * H;
@@ -712,9 +880,10 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
     configured = true;
   }
-  dim3 grid((T + BKV - 1) / BKV, Hk, B);
-  kern<<<grid, 256, S::kDynamic, st>>>(tq, td, seg, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, T, H, Hk,
-                                       window, scale);
+  const int n_items = ((T + BKV - 1) / BKV) * Hk * B;
+  const int grid = n_items < num_sms() ? n_items : num_sms();
+  kern<<<grid, 256, S::kDynamic, st>>>(tq, td, tdq, seg, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, B, T,
+                                       H, Hk, window, scale);
   count_launch();
   CGPT_LAUNCH_CHECK();
   {
