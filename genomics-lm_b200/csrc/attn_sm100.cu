@@ -59,7 +59,10 @@ __device__ __forceinline__ uint64_t ptile_mnmajor(uint32_t base, int ks) {  // r
 // thread `row` stores 8 consecutive bf16 (one 16-byte chunk `chunk` in 0..15) of its row
 __device__ __forceinline__ void ptile_store(uint8_t* base, int row, int chunk, uint4 v) {
   const int atom = chunk >> 3, c = chunk & 7;
-  *reinterpret_cast<uint4*>(base + atom * 16384 + row * 128 + ((c ^ (row & 7)) << 4)) = v;
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(smem_u32(base) + atom * 16384 + row * 128 +
+                                                                  ((c ^ (row & 7)) << 4)),
+               "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w)
+               : "memory");
 }
 
 template <int HD>
@@ -214,8 +217,8 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
     mma_phase ^= 1;
     tc_fence_after();
 
-    // a tile strictly below the diagonal and at/after every row's jlo needs no per-score test
-    const bool need_mask = (kv0 + BKV - 1 > q0) || (kv0 < row_jlo(ssb, min(q0 + BQ - 1, T - 1), T, window));
+    // per-score tests only for rows that do not see the whole kv tile (diagonal, segment start, window, ragged end)
+    const bool need_mask = (i >= T) || (kv0 + BKV - 1 > i) || (kv0 < jlo);
     // pass 1: row maximum over my 64 columns (raw scores: the scale is positive).  Rows past the end
     // (jlo > i) have span = 0xffffffff... guarded by row_valid below.
     const unsigned span = static_cast<unsigned>(i - jlo);
@@ -538,14 +541,15 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
     kv_phase ^= 1;
 
     // per-row statistics of the first tile (later tiles are fetched one tile ahead)
+    // (raw loads only: the first dependent use is one tile later, so no warp stalls on them)
     float nx_lse = 0.f, nx_dl = 0.f;
-    int nx_jlo = 0x3fffffff;
+    int nx_ss = 0;
     {
       const int i0 = qb_lo * BQ + row;
       const size_t st0 = ((size_t)b * H + kvh * rep) * T + (i0 < T ? i0 : 0);
       nx_lse = i0 < T ? lse[st0] : 0.f;
       nx_dl = i0 < T ? delta[st0] : 0.f;
-      nx_jlo = row_jlo(ssb, i0, T, window);
+      nx_ss = (ssb && i0 < T) ? ssb[i0] : 0;
     }
 
     for (int it = 0; it < niter; ++it) {
@@ -560,17 +564,17 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const int i = q0 + row;
       const bool row_ok = i < T;
       const float lse2 = nx_lse * kLog2e, dl = nx_dl;
-      const int jlo = nx_jlo;
+      int jlo = row_ok ? nx_ss : 0x3fffffff;
+      if (window > 0) jlo = max(jlo, i - window + 1);
       if (it + 1 < niter) {  // next tile's statistics: the loads complete while this tile is processed
         const int nh = kvh * rep + (it + 1) / nq, ni = (qb_lo + (it + 1) % nq) * BQ + row;
         const size_t st2 = ((size_t)b * H + nh) * T + (ni < T ? ni : 0);
         nx_lse = ni < T ? lse[st2] : 0.f;
         nx_dl = ni < T ? delta[st2] : 0.f;
-        nx_jlo = row_jlo(ssb, ni, T, window);
+        nx_ss = (ssb && ni < T) ? ssb[ni] : 0;
       }
-      // only tiles that touch the diagonal, a segment start / window edge or the ragged end need per-score tests
-      const bool need_mask = (kv0 + BKV - 1 > q0) || (q0 + BQ > T) ||
-                             (kv0 < row_jlo(ssb, min(q0 + BQ - 1, T - 1), T, window));
+      // per-score tests only for rows that do not see the whole kv tile (diagonal, segment start, window, ragged end)
+      const bool need_mask = !row_ok || (kv0 + BKV - 1 > i) || (kv0 < jlo);
       mbar_wait(s_bar, s_phase);
       s_phase ^= 1;
       tc_fence_after();
@@ -650,16 +654,24 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
         const int lr = tid & 31;
         if (lr == 0) bulk_wait_read0();
         __syncwarp();
+        uint32_t rq[HH];
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) {  // issue all loads, wait once
+          uint32_t (&r8)[8] = *reinterpret_cast<uint32_t(*)[8]>(&rq[c0]);
+          tmem_ld8(tdQ + lane_base + half * HH + c0, r8);
+        }
+        tmem_ld_wait();
 #pragma unroll
         for (int c0 = 0; c0 < HH; c0 += 8) {
-          uint32_t r[8];
-          tmem_ld8(tdQ + lane_base + half * HH + c0, r);
-          tmem_ld_wait();
           const int bx = c0 / BC, cc = (c0 % BC) * 4;  // box, byte column inside the box row
-          uint8_t* rowp = wbase + bx * BOX_BYTES + lr * ROWB;
+          const uint32_t rowp = smem_u32(wbase + bx * BOX_BYTES + lr * ROWB);
           const int sw = (ROWB == 128) ? (lr & 7) : ((lr >> 1) & 3);
-          *reinterpret_cast<uint4*>(rowp + (((cc >> 4) ^ sw) << 4)) = make_uint4(r[0], r[1], r[2], r[3]);
-          *reinterpret_cast<uint4*>(rowp + ((((cc >> 4) + 1) ^ sw) << 4)) = make_uint4(r[4], r[5], r[6], r[7]);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + (((cc >> 4) ^ sw) << 4)), "r"(rq[c0]),
+                       "r"(rq[c0 + 1]), "r"(rq[c0 + 2]), "r"(rq[c0 + 3])
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + ((((cc >> 4) + 1) ^ sw) << 4)),
+                       "r"(rq[c0 + 4]), "r"(rq[c0 + 5]), "r"(rq[c0 + 6]), "r"(rq[c0 + 7])
+                       : "memory");
         }
         fence_proxy_async_smem();
         __syncwarp();
@@ -715,13 +727,18 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
       const int j = kv0 + row;
       __nv_bfloat16* gk = dqkv + ((size_t)b * T + min(j, T - 1)) * W + kcol + half * HH;
       __nv_bfloat16* gv = dqkv + ((size_t)b * T + min(j, T - 1)) * W + vcol + half * HH;
+      uint32_t rka[HH], rva[HH];
 #pragma unroll
-      for (int c0 = 0; c0 < HH; c0 += 8) {
-        uint32_t rk[8], rv[8];
-        tmem_ld8(tdK + lane_base + half * HH + c0, rk);
-        tmem_ld8(tdV + lane_base + half * HH + c0, rv);
-        tmem_ld_wait();
-        if (j < T) {
+      for (int c0 = 0; c0 < HH; c0 += 8) {  // all TMEM loads in flight, one wait
+        tmem_ld8(tdK + lane_base + half * HH + c0, *reinterpret_cast<uint32_t(*)[8]>(&rka[c0]));
+        tmem_ld8(tdV + lane_base + half * HH + c0, *reinterpret_cast<uint32_t(*)[8]>(&rva[c0]));
+      }
+      tmem_ld_wait();
+      if (j < T) {
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) {
+          const uint32_t* rk = &rka[c0];
+          const uint32_t* rv = &rva[c0];
           uint4 a, c;
           a.x = pack_bf16(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale);
           a.y = pack_bf16(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale);
