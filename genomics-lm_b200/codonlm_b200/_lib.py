@@ -46,10 +46,12 @@ SIGNATURES = {
     "cgpt_rope_qk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cgpt_swiglu_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp]),
     "cgpt_swiglu_bwd": (_i, [_vp, _i64, _vp, _i64, _vp, _i, _i, _vp]),
-    "cgpt_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "cgpt_attn_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, C.c_uint64, C.c_uint64, _vp]),
     "cgpt_attn_bwd_workspace": (_i64, [_i, _i, _i, _i, _i]),
-    "cgpt_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
-    "cgpt_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "cgpt_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, C.c_uint64, C.c_uint64,
+                           _vp]),
+    "cgpt_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, C.c_uint64, C.c_uint64, _vp]),
+    "cgpt_dropout": (_i, [_vp, _vp, _vp, _i, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
     "cgpt_skinny_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "cgpt_skinny_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
     "cgpt_ce_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i64, _vp]),

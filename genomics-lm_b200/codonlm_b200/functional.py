@@ -290,26 +290,51 @@ class OffsetHeadFn(Function):
         return dx, None, db1, None, db2, dw1, dw2
 
 
-class AttentionFn(Function):
-    """softmax(QKᵀ/sqrt(hd) + mask)V on packed qkv with optional RoPE — model_tiny_gpt.py:94-131."""
+class DropoutFn(Function):
+    """y = (residual) + dropout(x): nn.Dropout on the embedding (model_tiny_gpt.py:312) and on the MLP branch
+    (:57,147) with the residual add fused.  The Philox mask is a function of (seed, offset) drawn from torch's
+    CUDA generator; backward re-applies it to the gradient, nothing is stored."""
 
     @staticmethod
-    def forward(ctx, qkv, seg_start, rope, B, T, H, Hk, hd, window):
+    def forward(ctx, x, residual, p):
+        seed, off = ops.philox_state(x.device, x.numel())
+        ctx.rng = (seed, off, p)
+        ctx.has_res = residual is not None
+        return ops.dropout(x.contiguous(), None if residual is None else residual.contiguous(), p, seed, off)
+
+    @staticmethod
+    def backward(ctx, g):
+        seed, off, p = ctx.rng
+        g = g.contiguous()
+        return ops.dropout(g, None, p, seed, off), (g if ctx.has_res else None), None
+
+
+class AttentionFn(Function):
+    """softmax(QKᵀ/sqrt(hd) + mask)V on packed qkv with optional RoPE and attention-probability dropout —
+    model_tiny_gpt.py:94-131."""
+
+    @staticmethod
+    def forward(ctx, qkv, seg_start, rope, B, T, H, Hk, hd, window, dropout_p=0.0):
         if rope is not None:
             ops.rope_qk(qkv, rope[0], rope[1], B, T, H, Hk, hd)  # in place: the QKV GEMM output has no other reader
-        out, lse = ops.attn_fwd(qkv, seg_start, B, T, H, Hk, hd, window=window)
+        seed = off = 0
+        if dropout_p > 0.0:
+            seed, off = ops.philox_state(qkv.device, 4)  # the mask is indexed by (b,h,i,j); one offset tick per call
+        out, lse = ops.attn_fwd(qkv, seg_start, B, T, H, Hk, hd, window=window, dropout_p=dropout_p, seed=seed,
+                                offset=off)
         ctx.save_for_backward(qkv, out, lse)
-        ctx.aux = (seg_start, rope, B, T, H, Hk, hd, window)
+        ctx.aux = (seg_start, rope, B, T, H, Hk, hd, window, dropout_p, seed, off)
         return out
 
     @staticmethod
     def backward(ctx, g):
         qkv, out, lse = ctx.saved_tensors
-        seg_start, rope, B, T, H, Hk, hd, window = ctx.aux
-        dqkv = ops.attn_bwd(qkv, seg_start, out, g.contiguous(), lse, B, T, H, Hk, hd, window=window)
+        seg_start, rope, B, T, H, Hk, hd, window, dropout_p, seed, off = ctx.aux
+        dqkv = ops.attn_bwd(qkv, seg_start, out, g.contiguous(), lse, B, T, H, Hk, hd, window=window,
+                            dropout_p=dropout_p, seed=seed, offset=off)
         if rope is not None:
             ops.rope_qk(dqkv, rope[0], rope[1], B, T, H, Hk, hd, inverse=True)
-        return dqkv, None, None, None, None, None, None, None, None
+        return dqkv, None, None, None, None, None, None, None, None, None
 
 
 TC_HEAD_MIN_ROWS = 4096  # below this the fp32 FMA head kernels are used (launch-bound sizes, tests)

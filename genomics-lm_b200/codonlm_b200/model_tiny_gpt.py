@@ -212,14 +212,16 @@ class SwiGLU(nn.Module, _ShadowMixin):
 
     def forward(self, x, residual=None):
         _require_cuda(self.w_gate.weight, "SwiGLU weights")
-        _check_dropout(self, self.dropout.p)
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
         wgu, wd = self._shadows()
         r2 = None if residual is None else residual.reshape(-1, shp[-1])
-        out = Fn.MlpSwiGLUFn.apply(xb.contiguous(), r2, wgu, wd, self.w_gate.weight, self.w_up.weight,
+        drop = self.training and self.dropout.p > 0.0
+        out = Fn.MlpSwiGLUFn.apply(xb.contiguous(), None if drop else r2, wgu, wd, self.w_gate.weight, self.w_up.weight,
                                    self.w_down.weight)
+        if drop:  # dropout sits between the MLP and the residual add (:57,152)
+            out = Fn.DropoutFn.apply(out, r2, float(self.dropout.p))
         return out.view(shp[:-1] + (out.shape[-1],))
 
 
@@ -233,22 +235,18 @@ class GeluMLP(nn.Sequential, _ShadowMixin):
     def forward(self, x, residual=None):
         fc1, fc2 = self[0], self[2]
         _require_cuda(fc1.weight, "MLP weights")
-        _check_dropout(self, self[3].p)
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
         w1, w2 = self._get_shadow("mlp", (fc1.weight, fc2.weight),
                                   lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
         r2 = None if residual is None else residual.reshape(-1, shp[-1])
-        out = Fn.MlpGeluFn.apply(xb.contiguous(), r2, w1, fc1.bias, w2, fc2.bias, fc1.weight, fc2.weight)
+        drop = self.training and self[3].p > 0.0
+        out = Fn.MlpGeluFn.apply(xb.contiguous(), None if drop else r2, w1, fc1.bias, w2, fc2.bias, fc1.weight,
+                                 fc2.weight)
+        if drop:  # nn.Dropout is the last child of the Sequential (:147); the residual add follows it (:152)
+            out = Fn.DropoutFn.apply(out, r2, float(self[3].p))
         return out.view(shp[:-1] + (out.shape[-1],))
-
-
-def _check_dropout(module: nn.Module, p: float):
-    if module.training and p > 0.0:
-        raise NotImplementedError(
-            "codonlm_b200: dropout > 0 in training mode is not implemented yet; build the model with dropout=0.0 "
-            "(eval mode ignores dropout exactly like the reference)")
 
 
 class CausalSelfAttention(nn.Module, _ShadowMixin):
@@ -286,7 +284,6 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
 
     def forward(self, x, attn_mask=None, residual=None):
         _require_cuda(self.query.weight, "attention weights")
-        _check_dropout(self, self.dropout.p)
         B, T, Cdim = x.size()
         H = self.n_head
         hd = Cdim // H
@@ -306,9 +303,10 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
                                       self.query.weight, self.key.weight, self.value.weight,
                                       self.query.bias, self.key.bias, self.value.bias)
         rope = self.rotary_emb.half_tables(T, x.device) if self.rotary_emb is not None else None
-        y = Fn.AttentionFn.apply(qkv, spec.seg_start, rope, B, T, H, Hk, hd, int(spec.window or 0))
+        attn_p = float(self.dropout.p) if self.training else 0.0  # dropout on the probabilities (:104,129)
+        y = Fn.AttentionFn.apply(qkv, spec.seg_start, rope, B, T, H, Hk, hd, int(spec.window or 0), attn_p)
         if not self.use_sdpa:
-            # the reference's manual branch keeps the probabilities for introspection (:128)
+            # the reference's manual branch keeps the (pre-dropout) probabilities for introspection (:128)
             with torch.no_grad():
                 self.last_attn = ops.attn_probs(qkv.detach(), spec.seg_start, B, T, H, Hk, hd, int(spec.window or 0))
         r2 = None if residual is None else residual.reshape(B * T, Cdim)
@@ -518,7 +516,8 @@ class TinyGPT(nn.Module):
                 x = x + self.pos_emb(torch.arange(0, T, device=idx.device).unsqueeze(0))
         else:
             x = Fn.EmbedFn.apply(idx, self.tok_emb.weight, None if self.pos_emb is None else self.pos_emb.weight)
-        _check_dropout(self, self.drop.p)
+        if self.training and self.drop.p > 0.0:  # self.drop(x) (:312)
+            x = Fn.DropoutFn.apply(x, None, float(self.drop.p))
         return x
 
     def class_weights(self):

@@ -202,31 +202,50 @@ def swiglu_bwd(gu, dact, hp):
 
 
 # ------------------------------------------------------------------ attention
-def attn_fwd(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None):
+def philox_state(device: torch.device, n_random: int):
+    """(seed, offset) from torch's CUDA generator, advanced by n_random: torch.manual_seed governs dropout
+    (reference tests/test_attention_dropout.py:62-78) without any kernel launch or host sync."""
+    gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+    seed, off = gen.initial_seed(), gen.get_offset()
+    gen.set_offset(off + (int(n_random) + 3) // 4 * 4)
+    return seed & 0xFFFFFFFFFFFFFFFF, off
+
+
+def dropout(x: torch.Tensor, residual: Optional[torch.Tensor], p: float, seed: int, offset: int, out_bf16=False):
+    """out = (residual) + x * mask / (1-p); x fp32, numel % 4 == 0."""
+    _dev(x)
+    out = torch.empty(x.shape, dtype=bf16 if out_bf16 else f32, device=x.device)
+    check(_L().cgpt_dropout(x.data_ptr(), _p(residual), out.data_ptr(), int(out_bf16), x.numel(), float(p), seed, offset,
+                            _stream()))
+    return out
+
+
+def attn_fwd(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None, dropout_p=0.0, seed=0, offset=0):
     _dev(qkv)
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
     out = torch.empty((B * T, H * hd), dtype=bf16, device=qkv.device)
     lse = torch.empty((B, H, T), dtype=f32, device=qkv.device)
     check(_L().cgpt_attn_fwd(qkv.data_ptr(), _p(seg_start), out.data_ptr(), lse.data_ptr(), B, T, H, Hk, hd,
-                             int(window or 0), float(scale), _stream()))
+                             int(window or 0), float(scale), float(dropout_p), seed, offset, _stream()))
     return out, lse
 
 
-def attn_bwd(qkv, seg_start, out, dout, lse, B, T, H, Hk, hd, window=0, scale=None):
+def attn_bwd(qkv, seg_start, out, dout, lse, B, T, H, Hk, hd, window=0, scale=None, dropout_p=0.0, seed=0, offset=0):
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
     dqkv = torch.empty_like(qkv)
     nbytes = _L().cgpt_attn_bwd_workspace(B, T, H, Hk, hd)
     ws = torch.empty((nbytes // 4,), dtype=f32, device=qkv.device)
     check(_L().cgpt_attn_bwd(qkv.data_ptr(), _p(seg_start), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-                             dqkv.data_ptr(), ws.data_ptr(), B, T, H, Hk, hd, int(window or 0), float(scale), _stream()))
+                             dqkv.data_ptr(), ws.data_ptr(), B, T, H, Hk, hd, int(window or 0), float(scale),
+                             float(dropout_p), seed, offset, _stream()))
     return dqkv
 
 
-def attn_probs(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None):
+def attn_probs(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None, dropout_p=0.0, seed=0, offset=0):
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
     att = torch.empty((B, H, T, T), dtype=f32, device=qkv.device)
     check(_L().cgpt_attn_probs(qkv.data_ptr(), _p(seg_start), att.data_ptr(), B, T, H, Hk, hd, int(window or 0),
-                               float(scale), _stream()))
+                               float(scale), float(dropout_p), seed, offset, _stream()))
     return att
 
 

@@ -122,7 +122,7 @@ template <int HD>
 __global__ void __launch_bounds__(256, FwdSmem<HD>::kTwoCtas ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restrict__ seg_start,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int Hk, int window,
-                float scale_log2, int smem_bytes) {
+                float scale_log2, int smem_bytes, const DropoutCfg drop) {
   using C = HeadCfg<HD>;
   using S = FwdSmem<HD>;
   constexpr int TMEM_COLS = 256;
@@ -271,6 +271,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
           lsum += p[j];
         }
       }
+      if (drop.thresh) {  // dropout on the (still unnormalised) probabilities; the row sum stays undropped (:104,129)
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const uint4 rb = attn_dropout_bits(drop, b * H + h, i, (kv0 + c4 * 32) / 4 + j4);
+          p[4 * j4 + 0] = rb.x >= drop.thresh ? p[4 * j4 + 0] * drop.inv_keep : 0.f;
+          p[4 * j4 + 1] = rb.y >= drop.thresh ? p[4 * j4 + 1] * drop.inv_keep : 0.f;
+          p[4 * j4 + 2] = rb.z >= drop.thresh ? p[4 * j4 + 2] * drop.inv_keep : 0.f;
+          p[4 * j4 + 3] = rb.w >= drop.thresh ? p[4 * j4 + 3] * drop.inv_keep : 0.f;
+        }
+      }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         uint4 v;
@@ -397,7 +407,8 @@ __global__ void __launch_bounds__(256, 1)
 attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                 const __grid_constant__ CUtensorMap tm_dq, const int32_t* __restrict__ seg_start,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                float* __restrict__ dq_ws, int Bsz, int T, int H, int Hk, int window, float scale) {
+                float* __restrict__ dq_ws, int Bsz, int T, int H, int Hk, int window, float scale,
+                const DropoutCfg drop) {
   using C = HeadCfg<HD>;
   using S = BwdSmem<HD>;
   constexpr int TMEM_COLS = 512;
@@ -603,6 +614,21 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
             ds[j] = p[j] * (__uint_as_float(rp[j]) - dl);
           }
         }
+        if (drop.thresh) {  // P feeds dV as dropout(P); dS = P * (dP * mask/(1-p) - delta)
+#pragma unroll
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const uint4 rb = attn_dropout_bits(drop, b * H + hq, i, (kv0 + c4 * 32) / 4 + j4);
+            const uint32_t bits[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int j = 4 * j4 + e;
+              const float mk = bits[e] >= drop.thresh ? drop.inv_keep : 0.f;
+              const float pj = p[j];
+              ds[j] = pj * (__uint_as_float(rp[j]) * mk - dl);
+              p[j] = pj * mk;
+            }
+          }
+        }
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 v, w;
@@ -790,7 +816,7 @@ __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfl
 // (b, h, i) row, SIMT dot products.  O(T^2 hd) and not tuned: never on the training path.
 __global__ void attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ seg,
                                   float* __restrict__ att, int B, int T, int H, int Hk, int hd, int window,
-                                  float scale) {
+                                  float scale, const DropoutCfg drop) {
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (long long)B * H * T) return;
@@ -828,7 +854,15 @@ __global__ void attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const i
   }
   se = warp_sum(se);
   const float inv = 1.f / se;
-  for (int j = lane; j < T; j += 32) row[j] *= inv;
+  for (int j = lane; j < T; j += 32) {
+    float v = row[j] * inv;
+    if (drop.thresh) {
+      const uint4 rb = attn_dropout_bits(drop, b * H + h, i, j >> 2);
+      const uint32_t bit = (j & 3) == 0 ? rb.x : ((j & 3) == 1 ? rb.y : ((j & 3) == 2 ? rb.z : rb.w));
+      v = bit >= drop.thresh ? v * drop.inv_keep : 0.f;
+    }
+    row[j] = v;
+  }
 }
 
 inline size_t delta_floats(int B, int T, int H) { return ((size_t)B * H * T + 63) / 64 * 64; }
@@ -842,7 +876,7 @@ int make_qkv_tmap(CUtensorMap* tm, const void* base, int B, int T, int W, int aw
 
 template <int HD>
 int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B, int T, int H, int Hk, int window,
-               float scale, cudaStream_t st) {
+               float scale, const DropoutCfg& drop, cudaStream_t st) {
   using S = FwdSmem<HD>;
   CUtensorMap tm;
   int rc = make_qkv_tmap(&tm, qkv, B, T, (H + 2 * Hk) * HD, HeadCfg<HD>::AW);
@@ -855,7 +889,7 @@ int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B
   }
   dim3 grid((T + BQ - 1) / BQ, H, B);
   kern<<<grid, 256, S::kDynamic, st>>>(tm, seg, reinterpret_cast<__nv_bfloat16*>(out), lse, T, H, Hk, window,
-                                       scale * kLog2e, S::kDynamic);
+                                       scale * kLog2e, S::kDynamic, drop);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;
@@ -863,7 +897,7 @@ int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B
 
 template <int HD>
 int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse, void* dqkv,
-               void* ws, int B, int T, int H, int Hk, int window, float scale, cudaStream_t st) {
+               void* ws, int B, int T, int H, int Hk, int window, float scale, const DropoutCfg& drop, cudaStream_t st) {
   using S = BwdSmem<HD>;
   const int W = (H + 2 * Hk) * HD;
   CUtensorMap tq, td;
@@ -900,7 +934,7 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   const int n_items = ((T + BKV - 1) / BKV) * Hk * B;
   const int grid = n_items < num_sms() ? n_items : num_sms();
   kern<<<grid, 256, S::kDynamic, st>>>(tq, td, tdq, seg, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, B, T,
-                                       H, Hk, window, scale);
+                                       H, Hk, window, scale, drop);
   count_launch();
   CGPT_LAUNCH_CHECK();
   {
@@ -941,12 +975,14 @@ using namespace cgpt;
 extern "C" {
 
 int cgpt_attn_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B, int T, int H, int Hk, int hd,
-                  int window, float scale, cgpt_stream_t stream) {
+                  int window, float scale, float dropout_p, uint64_t seed, uint64_t offset, cgpt_stream_t stream) {
+  CGPT_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_fwd: dropout_p=%f must be in [0,1)", dropout_p);
+  const DropoutCfg drop = make_dropout(dropout_p, seed, offset);
   CGPT_REQUIRE(qkv && out && lse, "attn_fwd: null pointer");
   int rc = check_attn_args("attn_fwd", B, T, H, Hk, hd);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CALL(HD) launch_fwd<HD>(qkv, seg, out, lse, B, T, H, Hk, window, scale, st)
+#define CALL(HD) launch_fwd<HD>(qkv, seg, out, lse, B, T, H, Hk, window, scale, drop, st)
   DISPATCH_HD(hd, CALL)
 #undef CALL
 }
@@ -957,24 +993,28 @@ int64_t cgpt_attn_bwd_workspace(int B, int T, int H, int Hk, int hd) {
 }
 
 int cgpt_attn_bwd(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse, void* dqkv,
-                  void* ws, int B, int T, int H, int Hk, int hd, int window, float scale, cgpt_stream_t stream) {
+                  void* ws, int B, int T, int H, int Hk, int hd, int window, float scale, float dropout_p, uint64_t seed,
+                  uint64_t offset, cgpt_stream_t stream) {
+  CGPT_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_bwd: dropout_p=%f must be in [0,1)", dropout_p);
+  const DropoutCfg drop = make_dropout(dropout_p, seed, offset);
   CGPT_REQUIRE(qkv && out && dout && lse && dqkv && ws, "attn_bwd: null pointer");
   CGPT_REQUIRE((reinterpret_cast<uintptr_t>(ws) & 255) == 0, "attn_bwd: workspace must be 256-byte aligned");
   int rc = check_attn_args("attn_bwd", B, T, H, Hk, hd);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CALL(HD) launch_bwd<HD>(qkv, seg, out, dout, lse, dqkv, ws, B, T, H, Hk, window, scale, st)
+#define CALL(HD) launch_bwd<HD>(qkv, seg, out, dout, lse, dqkv, ws, B, T, H, Hk, window, scale, drop, st)
   DISPATCH_HD(hd, CALL)
 #undef CALL
 }
 
 int cgpt_attn_probs(const void* qkv, const int32_t* seg, float* att, int B, int T, int H, int Hk, int hd, int window,
-                    float scale, cgpt_stream_t stream) {
+                    float scale, float dropout_p, uint64_t seed, uint64_t offset, cgpt_stream_t stream) {
+  const DropoutCfg drop = make_dropout(dropout_p, seed, offset);
   CGPT_REQUIRE(qkv && att, "attn_probs: null pointer");
   CGPT_REQUIRE(B > 0 && T > 0 && H > 0 && Hk > 0 && H % Hk == 0 && hd % 2 == 0, "attn_probs: bad sizes");
   const long long warps = (long long)B * H * T;
   attn_probs_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), seg, att, B, T, H, Hk, hd, window, scale);
+      reinterpret_cast<const __nv_bfloat16*>(qkv), seg, att, B, T, H, Hk, hd, window, scale, drop);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

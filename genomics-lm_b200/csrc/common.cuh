@@ -222,6 +222,39 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- Philox4x32-10 (counter-based RNG for dropout: the mask is recomputed in backward, never stored)
+__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += 0x9E3779B9u;
+    key.y += 0xBB67AE85u;
+  }
+  return ctr;
+}
+struct DropoutCfg {
+  uint32_t thresh;  // keep iff random u32 >= thresh  (thresh = p * 2^32); 0 = dropout off
+  float inv_keep;   // 1 / (1 - p)
+  uint2 key;        // seed
+  uint32_t off_lo, off_hi;  // generator offset: separates successive calls under the same seed
+};
+__host__ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset) {
+  DropoutCfg d;
+  const double t = (double)p * 4294967296.0;
+  d.thresh = p <= 0.f ? 0u : (t >= 4294967295.0 ? 4294967295u : (uint32_t)t);
+  d.inv_keep = p < 1.f ? 1.f / (1.f - p) : 0.f;
+  d.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+  d.off_lo = (uint32_t)offset;
+  d.off_hi = (uint32_t)(offset >> 32);
+  return d;
+}
+// attention-probability mask for 4 consecutive key positions j4*4..j4*4+3 of query row i, head bh
+__device__ __forceinline__ uint4 attn_dropout_bits(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t j4) {
+  return philox4x32_10(make_uint2(d.key.x ^ d.off_lo, d.key.y ^ d.off_hi), make_uint4(j4, i, bh, 0x61747400u));
+}
+
 // ---- small math
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 __device__ __forceinline__ float gelu_erf_grad(float x) {

@@ -456,6 +456,32 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, long lon
   }
 }
 
+// ============================================================ dropout (Philox mask recomputed from seed/offset)
+// out = (residual) + x * mask / (1-p); x fp32; out fp32 or bf16.  4 elements per Philox call.
+template <bool OUT_BF16>
+__global__ void dropout_kernel(const float4* __restrict__ x, const float4* __restrict__ residual, void* __restrict__ out,
+                               long long n4, DropoutCfg d) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const uint4 r = philox4x32_10(d.key, make_uint4((uint32_t)i + d.off_lo, (uint32_t)(i >> 32) + d.off_hi, 0u, 0x656c7700u));
+    float4 v = x[i];
+    v.x = r.x >= d.thresh ? v.x * d.inv_keep : 0.f;
+    v.y = r.y >= d.thresh ? v.y * d.inv_keep : 0.f;
+    v.z = r.z >= d.thresh ? v.z * d.inv_keep : 0.f;
+    v.w = r.w >= d.thresh ? v.w * d.inv_keep : 0.f;
+    if (residual) {
+      const float4 q = residual[i];
+      v.x += q.x;
+      v.y += q.y;
+      v.z += q.z;
+      v.w += q.w;
+    }
+    if constexpr (OUT_BF16)
+      reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16(v.x, v.y), pack_bf16(v.z, v.w));
+    else
+      reinterpret_cast<float4*>(out)[i] = v;
+  }
+}
+
 // ============================================================ AdamW (torch.optim.AdamW semantics)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float lr,
@@ -690,6 +716,23 @@ int cgpt_swiglu_bwd(const void* gu, int64_t ldgu, const void* dact, int64_t ldac
   swiglu_bwd_kernel<<<grid_for((long long)M * h / 2, 256), 256, 0, ST(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(gu), ldgu, reinterpret_cast<const __nv_bfloat16*>(dact), ldact,
       reinterpret_cast<__nv_bfloat16*>(dgu), M, h);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_dropout(const float* x, const float* residual, void* out, int out_bf16, int64_t n, float p, uint64_t seed,
+                 uint64_t offset, cgpt_stream_t stream) {
+  CGPT_REQUIRE(x && out && n > 0 && n % 4 == 0, "dropout: n=%lld must be a positive multiple of 4", (long long)n);
+  CGPT_REQUIRE(p >= 0.f && p < 1.f, "dropout: p=%f must be in [0,1)", p);
+  const DropoutCfg d = make_dropout(p, seed, offset);
+  const long long n4 = n / 4;
+  if (out_bf16)
+    dropout_kernel<true><<<grid_for(n4, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(x),
+                                                                     reinterpret_cast<const float4*>(residual), out, n4, d);
+  else
+    dropout_kernel<false><<<grid_for(n4, 256), 256, 0, ST(stream)>>>(reinterpret_cast<const float4*>(x),
+                                                                      reinterpret_cast<const float4*>(residual), out, n4, d);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

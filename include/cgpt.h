@@ -139,16 +139,19 @@ int cgpt_swiglu_bwd(const void* gu, int64_t ldgu, const void* dact, int64_t ldac
  * seg_start int32 [B,T] from cgpt_segment_starts();
  * GQA: query head h reads kv head h / (H/Hk)       (:94-96, without the repeat_interleave copy).
  * out bf16 [B*T, H*hd]; lse fp32 [B,H,T] (natural-log logsumexp of the scaled scores). */
+/* dropout_p > 0 (training, :104,129): probabilities are dropped (scaled by 1/(1-p)) before P·V with a
+ * Philox4x32-10 mask keyed by (seed, offset, b, h, i, j); backward regenerates the same mask. */
 int cgpt_attn_fwd(const void* qkv, const int32_t* seg_start /*nullable*/, void* out, float* lse, int B, int T, int H,
-                  int Hk, int hd, int window, float scale, cgpt_stream_t stream);
+                  int Hk, int hd, int window, float scale, float dropout_p, uint64_t seed, uint64_t offset,
+                  cgpt_stream_t stream);
 /* dqkv bf16 [B*T,(H+2Hk)*hd]; `ws` fp32 workspace of cgpt_attn_bwd_workspace() bytes. */
 int64_t cgpt_attn_bwd_workspace(int B, int T, int H, int Hk, int hd);
 int cgpt_attn_bwd(const void* qkv, const int32_t* seg_start, const void* out, const void* dout, const float* lse,
                   void* dqkv, void* ws, int B, int T, int H, int Hk, int hd, int window, float scale,
-                  cgpt_stream_t stream);
+                  float dropout_p, uint64_t seed, uint64_t offset, cgpt_stream_t stream);
 /* Introspection path (use_sdpa=False, :116-131): dense probabilities att fp32 [B,H,T,T]. */
 int cgpt_attn_probs(const void* qkv, const int32_t* seg_start, float* att, int B, int T, int H, int Hk, int hd,
-                    int window, float scale, cgpt_stream_t stream);
+                    int window, float scale, float dropout_p, uint64_t seed, uint64_t offset, cgpt_stream_t stream);
 
 /* ---------------------------------------------------------------- LM / aux heads --------- */
 /* out[M,N] = x[M,d]·w[N,d]ᵀ (+bias), fp32 FMA, N <= 128
@@ -171,6 +174,13 @@ int cgpt_ce_bwd(const float* logits, const float* row_lse, const int64_t* target
                 const int32_t* next_boundary, const float* class_w, const float* sums,
                 const float* gscale /*device scalar, nullable = 1*/, float coef, float* dlogits, int B, int T,
                 int V, int shift, float smoothing, int64_t ignore_index, cgpt_stream_t stream);
+
+/* ---------------------------------------------------------------- dropout ---------------- */
+/* out = (residual) + x * mask / (1-p)   nn.Dropout on the embedding (:312) and the MLP output (:57,147).
+ * x, residual fp32; out fp32 or bf16; n % 4 == 0.  The mask is a pure function of (seed, offset, index):
+ * backward calls this again on the gradient with the same (seed, offset). */
+int cgpt_dropout(const float* x, const float* residual /*nullable*/, void* out, int out_bf16, int64_t n, float p,
+                 uint64_t seed, uint64_t offset, cgpt_stream_t stream);
 
 /* ---------------------------------------------------------------- optimiser -------------- */
 /* torch.optim.AdamW step on a flat fp32 buffer (loop.py:681-731 param groups are separate calls);

@@ -400,3 +400,60 @@ def test_split_head_on_tensor_cores_is_fp32_accurate(ops):
         assert (w.grad.double() - rdw).abs().max().item() <= 3e-5 * rdw.abs().max().item()
         if has_b:
             assert (b.grad.double() - go.double().sum(0)).abs().max().item() <= 3e-5 * go.double().sum(0).abs().max().item()
+
+
+# ------------------------------------------------------------------------------------------ dropout
+def test_elementwise_dropout_mask_statistics_and_backward(ops):
+    n = 1 << 20
+    x = torch.ones(n, device=DEV)
+    res = torch.full((n,), 2.0, device=DEV)
+    for p in (0.1, 0.5):
+        y = ops.dropout(x, None, p, seed=1234, offset=8)
+        keep = (y != 0).float().mean().item()
+        assert abs(keep - (1 - p)) < 4e-3
+        assert torch.allclose(y[y != 0], torch.full_like(y[y != 0], 1 / (1 - p)))
+        assert torch.equal(y, ops.dropout(x, None, p, seed=1234, offset=8))          # pure function of (seed, offset)
+        assert not torch.equal(y, ops.dropout(x, None, p, seed=1234, offset=12))
+        assert not torch.equal(y, ops.dropout(x, None, p, seed=1235, offset=8))
+        yr = ops.dropout(x, res, p, seed=1234, offset=8)
+        assert torch.equal(yr, y + 2.0)
+        g = torch.randn(n, device=DEV)
+        gb = ops.dropout(g, None, p, seed=1234, offset=8, out_bf16=True)             # backward: same mask on the grad
+        assert torch.equal(gb, (g * y).to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("case", [(2, 256, 2, 2, 64, None, 3), (1, 200, 4, 2, 32, None, 3), (2, 130, 2, 1, 48, 40, 3)])
+def test_attention_dropout_matches_masked_reference(ops, case):
+    """Dropout on the attention probabilities: extract the kernel's own Philox mask through the dense
+    probability kernel, then compare fwd and bwd with an fp32 reference that uses that mask."""
+    B, T, H, Hk, hd, window, sep = case
+    p, seed, off = 0.2, 77, 16
+    g = torch.Generator().manual_seed(21)
+    idx, _ = O.synthetic_batch(B, T, seed=6, realistic=True)
+    idx = idx.to(DEV)
+    qkv = torch.randn(B * T, (H + 2 * Hk) * hd, generator=g).to(torch.bfloat16).to(DEV)
+    ss = ops.segment_starts(idx, sep)
+    kw = dict(window=window or 0)
+    pr0 = ops.attn_probs(qkv, ss, B, T, H, Hk, hd, **kw)
+    pr1 = ops.attn_probs(qkv, ss, B, T, H, Hk, hd, dropout_p=p, seed=seed, offset=off, **kw)
+    vis = pr0 > 0
+    mask = torch.where(vis, pr1 / pr0.clamp_min(1e-30), torch.zeros_like(pr0))       # 0 or 1/(1-p)
+    kept = (mask[vis] > 0).float().mean().item()
+    assert abs(kept - (1 - p)) < 2e-2
+    assert torch.allclose(mask[vis & (mask > 0)], torch.tensor(1 / (1 - p), device=DEV), rtol=1e-5)
+    out, lse = ops.attn_fwd(qkv, ss, B, T, H, Hk, hd, dropout_p=p, seed=seed, offset=off, **kw)
+    out2, _ = ops.attn_fwd(qkv, ss, B, T, H, Hk, hd, dropout_p=p, seed=seed, offset=off, **kw)
+    assert torch.equal(out, out2)
+    q32 = qkv.float().requires_grad_(True)
+    _, _, probs = _attn_ref(q32, idx, B, T, H, Hk, hd, window, sep)
+    W = (H + 2 * Hk) * hd
+    v = q32.view(B, T, W)[..., (H + Hk) * hd:].view(B, T, Hk, hd).transpose(1, 2).repeat_interleave(H // Hk, dim=1)
+    ry = ((probs * mask) @ v).transpose(1, 2).reshape(B * T, H * hd)
+    assert (out.float() - ry).abs().max().item() <= 3e-2
+    dout = (torch.randn(B * T, H * hd, generator=g) * 0.5).to(torch.bfloat16).to(DEV)
+    ry.backward(dout.float())
+    dqkv = ops.attn_bwd(qkv, ss, out, dout, lse, B, T, H, Hk, hd, dropout_p=p, seed=seed, offset=off, **kw)
+    for name, sl in (("dq", slice(0, H * hd)), ("dk", slice(H * hd, (H + Hk) * hd)), ("dv", slice((H + Hk) * hd, W))):
+        a, r = dqkv.float()[:, sl], q32.grad[:, sl]
+        rel = ((a - r).norm() / r.norm()).item()
+        assert rel <= 3e-2, f"{name} rel-norm err {rel}"

@@ -281,3 +281,47 @@ def test_trainstep_flat_buffers_match_plain_autograd_and_torch_adamw():
     for _ in range(5):
         l1 = ts.step(idx, tgt).item()
     assert l1 < l0
+
+
+def test_training_mode_dropout_is_seeded_and_off_in_eval():  # reference tests/test_attention_dropout.py:19-85
+    from codonlm_b200 import TinyGPT
+    for kw in (dict(), dict(use_swiglu=True, use_rope=True)):
+        torch.manual_seed(0)
+        m = TinyGPT(vocab_size=68, block_size=64, n_layer=2, n_head=2, n_embd=64, dropout=0.1, use_sdpa=True, **kw).to(DEV)
+        assert not any("dropout" in k for k in m.state_dict())          # dropout adds no state
+        x = torch.randint(4, 68, (4, 64), device=DEV)
+        m.train()
+        torch.manual_seed(123)
+        l1, loss1 = m(x, x)
+        loss1.backward()
+        g1 = m.blocks[0].attn.query.weight.grad.clone()
+        torch.manual_seed(123)
+        m.zero_grad()
+        l2, loss2 = m(x, x)
+        loss2.backward()
+        assert torch.equal(l1, l2) and torch.equal(g1, m.blocks[0].attn.query.weight.grad)  # torch.manual_seed governs it
+        l3, _ = m(x, x)
+        assert not torch.equal(l1, l3)                                   # the generator offset advanced
+        m.eval()
+        with torch.no_grad():
+            e1, _ = m(x)
+            e2, _ = m(x)
+        assert torch.equal(e1, e2)
+        # eval output == the same weights in a dropout=0 model
+        m0 = TinyGPT(vocab_size=68, block_size=64, n_layer=2, n_head=2, n_embd=64, dropout=0.0, use_sdpa=True, **kw).to(DEV)
+        m0.load_state_dict(m.state_dict(), strict=True)
+        m0.eval()
+        with torch.no_grad():
+            e0, _ = m0(x)
+        assert torch.equal(e0, e1)
+        # training still reduces the loss with dropout on
+        m.train()
+        opt = torch.optim.AdamW(m.parameters(), lr=3e-3)
+        first = None
+        for _ in range(8):
+            _, loss = m(x, x)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            opt.step()
+            first = first if first is not None else loss.item()
+        assert loss.item() < first
