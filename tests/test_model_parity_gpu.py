@@ -299,7 +299,10 @@ def test_training_mode_dropout_is_seeded_and_off_in_eval():  # reference tests/t
         m.zero_grad()
         l2, loss2 = m(x, x)
         loss2.backward()
-        assert torch.equal(l1, l2) and torch.equal(g1, m.blocks[0].attn.query.weight.grad)  # torch.manual_seed governs it
+        g2 = m.blocks[0].attn.query.weight.grad
+        assert torch.equal(l1, l2)                                       # torch.manual_seed governs the masks
+        # same masks => same gradient up to the summation order of the fp32 atomics (split-K wgrad, dQ reduce-add)
+        assert (g1 - g2).abs().max().item() <= 1e-3 * g1.abs().max().item()
         l3, _ = m(x, x)
         assert not torch.equal(l1, l3)                                   # the generator offset advanced
         m.eval()
