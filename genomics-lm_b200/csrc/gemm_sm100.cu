@@ -34,7 +34,8 @@ struct GemmParams {
   int out_f32;
   int accumulate;
   long long ldc;
-  int tma_out;  // 1: out (and aux_out) are written through the TMA maps tmC / tmX
+  int tma_out;  // bit0: out leaves through tmC (store / reduce-add); bit1: tmX is valid (aux_out store, aux load
+                // or residual load)
   int debug;  // bit0: skip global stores, bit1: skip TMEM loads, bit2: skip the whole epilogue body (probe only)
 };
 
@@ -129,14 +130,14 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const CUtens
     __nv_bfloat16* dst = (GELU && pass == 1) ? p.aux_out : reinterpret_cast<__nv_bfloat16*>(p.out);
     const long long ld = (GELU && pass == 1) ? p.ldaux : p.ldc;
     if (dst == nullptr) break;
-    if (p.tma_out) {  // the staging buffer may still be feeding the previous bulk store
+    if (p.tma_out & 1) {  // the staging buffer may still be feeding the previous bulk store
       if (lane == 0) bulk_wait_read0();
       __syncwarp();
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       sts128(stg_cell(stg, lane, j), make_uint4(src[4 * j], src[4 * j + 1], src[4 * j + 2], src[4 * j + 3]));
-    if (p.tma_out) {
+    if (p.tma_out & 1) {
       // staging layout == CU_TENSOR_MAP_SWIZZLE_64B of a {32 col, 32 row} bf16 box: one asynchronous bulk store,
       // clipped by the hardware at the M / N edges; the warp moves on immediately
       fence_proxy_async_smem();
@@ -275,6 +276,93 @@ __device__ __forceinline__ void epi_chunk_f32(const GemmParams& p, uint32_t tadd
   __syncwarp();
 }
 
+// ---- fully TMA-fed epilogues: the per-element operand (aux / residual) arrives in the staging buffer through a
+// bulk tensor load, is combined with the accumulator in the row layout (thread = row), written back to the same
+// swizzled cells and leaves through a bulk tensor store (or reduce-add for split-K).  No per-thread global access.
+__device__ __forceinline__ void epi_chunk_mulaux_tma(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
+                                                     uint32_t taddr, uint32_t stg, int lane, int row0, int n0,
+                                                     uint32_t bias_s, uint64_t* bar, uint32_t& phase) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  if (lane == 0) {
+    bulk_wait_read0();  // the previous store has finished reading the staging buffer
+    mbar_expect_tx(bar, 32 * 64);
+    tma_load_2d_s(stg, tmX, bar, n0, row0);
+  }
+  tmem_ld_wait();
+  mbar_wait(bar, phase);
+  phase ^= 1;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t cell = stg_cell(stg, lane, j);
+    const uint4 a = lds128(cell);
+    const uint4 b0 = lds128(bias_s + j * 32), b1 = lds128(bias_s + j * 32 + 16);
+    const float2 a0 = unpack_bf16(a.x), a1 = unpack_bf16(a.y), a2 = unpack_bf16(a.z), a3 = unpack_bf16(a.w);
+    uint4 o;
+    o.x = pack_bf16((__uint_as_float(r[8 * j + 0]) + __uint_as_float(b0.x)) * a0.x,
+                    (__uint_as_float(r[8 * j + 1]) + __uint_as_float(b0.y)) * a0.y);
+    o.y = pack_bf16((__uint_as_float(r[8 * j + 2]) + __uint_as_float(b0.z)) * a1.x,
+                    (__uint_as_float(r[8 * j + 3]) + __uint_as_float(b0.w)) * a1.y);
+    o.z = pack_bf16((__uint_as_float(r[8 * j + 4]) + __uint_as_float(b1.x)) * a2.x,
+                    (__uint_as_float(r[8 * j + 5]) + __uint_as_float(b1.y)) * a2.y);
+    o.w = pack_bf16((__uint_as_float(r[8 * j + 6]) + __uint_as_float(b1.z)) * a3.x,
+                    (__uint_as_float(r[8 * j + 7]) + __uint_as_float(b1.w)) * a3.y);
+    sts128(cell, o);
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, stg, n0, row0);
+    bulk_commit();
+  }
+}
+
+__device__ __forceinline__ void epi_chunk_f32_tma(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
+                                                  uint32_t taddr, uint32_t stg, int lane, int row0, int n0,
+                                                  uint32_t bias_s, uint64_t* bar, uint32_t& phase) {
+  uint32_t r[16];
+  tmem_ld16(taddr, r);
+  const bool has_res = p.residual != nullptr;
+  if (lane == 0) {
+    bulk_wait_read0();
+    if (has_res) {
+      mbar_expect_tx(bar, 32 * 64);
+      tma_load_2d_s(stg, tmX, bar, n0, row0);
+    }
+  }
+  tmem_ld_wait();
+  if (has_res) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+  } else {
+    __syncwarp();
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t cell = stg_cell(stg, lane, j);
+    const uint4 b = lds128(bias_s + j * 16);
+    float4 v = make_float4(__uint_as_float(r[4 * j]) + __uint_as_float(b.x), __uint_as_float(r[4 * j + 1]) + __uint_as_float(b.y),
+                           __uint_as_float(r[4 * j + 2]) + __uint_as_float(b.z), __uint_as_float(r[4 * j + 3]) + __uint_as_float(b.w));
+    if (has_res) {
+      const uint4 q = lds128(cell);
+      v.x += __uint_as_float(q.x);
+      v.y += __uint_as_float(q.y);
+      v.z += __uint_as_float(q.z);
+      v.w += __uint_as_float(q.w);
+    }
+    sts128(cell, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    if (p.accumulate)
+      tma_reduce_add_2d(tmC, stg, n0, row0);
+    else
+      tma_store_2d(tmC, stg, n0, row0);
+    bulk_commit();
+  }
+}
+
 template <int BN, int STAGES>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
@@ -283,7 +371,7 @@ struct SmemLayout {
   static constexpr int kStgOff = STAGES * kStageBytes;
   static constexpr int kBiasOff = kStgOff + kEpiWarps * kStgBytesPerWarp;  // 2 x BN floats (per accumulator buffer)
   static constexpr int kBarOff = kBiasOff + 2 * BN * 4;
-  static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16;
+  static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16 + kEpiWarps * 8;  // + one mbarrier per epilogue warp
   // slack for aligning the base up to 1024 B (the kernel traps if it does not fit; in practice the dynamic
   // window starts 1 KB into the CTA's shared memory and is already aligned)
   static constexpr int kDynamic = (kTotal + 1024 <= 232448) ? kTotal + 1024 : 232448;
@@ -303,6 +391,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + STAGES;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint64_t* epi_bar = tempty_bar + 4;  // [kEpiWarps]: completion of the epilogue's own TMA loads
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -324,6 +413,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(&tfull_bar[1], 1);
     mbar_init(&tempty_bar[0], kEpiWarps);
     mbar_init(&tempty_bar[1], kEpiWarps);
+#pragma unroll
+    for (int e = 0; e < kEpiWarps; ++e) mbar_init(&epi_bar[e], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -418,6 +509,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int grp = ew >> 2;  // 0..3: which quarter of the column chunks
     const uint32_t stg = smem_u32(smem + L::kStgOff + ew * kStgBytesPerWarp);
     const bool bf16_rowmath = !p.out_f32 && p.epilogue != CGPT_EPI_MUL_AUX;
+    const bool tma_io = (p.tma_out & 1) && (p.out_f32 || p.epilogue == CGPT_EPI_MUL_AUX);
+    uint32_t epi_phase = 0;
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const int n_blk = w % p.tiles_n;
@@ -439,6 +532,22 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int row0 = m_blk * BM + q * 32;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (p.debug & 4) {
+      } else if (tma_io && !p.out_f32) {
+#pragma unroll 1
+        for (int c = grp; c < BN / 32; c += 4) {
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 >= p.N) break;  // warp-uniform
+          epi_chunk_mulaux_tma(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128, &epi_bar[ew],
+                               epi_phase);
+        }
+      } else if (tma_io) {
+#pragma unroll 1
+        for (int c = grp; c < BN / 16; c += 4) {
+          const int n0 = n_blk * BN + c * 16;
+          if (n0 >= p.N) break;  // warp-uniform
+          epi_chunk_f32_tma(p, &tmC, &tmX, tbase + c * 16, stg, lane, row0, n0, bias_tile + c * 64, &epi_bar[ew],
+                            epi_phase);
+        }
       } else if (bf16_rowmath) {
 #pragma unroll 1
         for (int c = grp; c < BN / 32; c += 4) {
@@ -461,7 +570,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
     }
-    if (p.tma_out && lane == 0) bulk_wait0();  // smem must outlive the bulk stores that read it
+    if ((p.tma_out & 1) && lane == 0) bulk_wait0();  // smem must outlive the bulk stores that read it
   }
 
   tc_fence_before();
@@ -564,27 +673,39 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
     }
     p.debug = dbg;
   }
-  // bf16 outputs that satisfy the TMA alignment rules leave through asynchronous bulk tensor stores
+  // Outputs (and the per-element epilogue operands) that satisfy the TMA alignment rules move through
+  // asynchronous bulk tensor copies: {32 bf16 | 16 fp32} x 32-row boxes in the 64-byte-swizzled staging layout.
   CUtensorMap tc, tx;
   memset(&tc, 0, sizeof(tc));
   memset(&tx, 0, sizeof(tx));
   p.tma_out = 0;
-  const bool bf16_rowmath = !a->out_f32 && a->epilogue != CGPT_EPI_MUL_AUX;
-  const bool c_ok = ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0) && ((a->ldc * 2) % 16 == 0);
-  const bool x_ok = a->aux_out == nullptr ||
-                    (((reinterpret_cast<uintptr_t>(a->aux_out) & 15) == 0) && ((a->ldaux * 2) % 16 == 0));
-  if (bf16_rowmath && c_ok && x_ok) {
-    const uint64_t dimsC[2] = {(uint64_t)a->N, (uint64_t)a->M};
-    const uint32_t boxC[2] = {32, 32};
-    const uint64_t strC[1] = {(uint64_t)a->ldc * 2};
-    rc = make_tmap_bf16(&tc, a->out, 2, dimsC, strC, boxC, 64);
-    if (rc) return rc;
-    if (a->aux_out) {
-      const uint64_t strX[1] = {(uint64_t)a->ldaux * 2};
-      rc = make_tmap_bf16(&tx, a->aux_out, 2, dimsC, strX, boxC, 64);
+  {
+    const int esz = a->out_f32 ? 4 : 2;
+    const bool c_ok = ((reinterpret_cast<uintptr_t>(a->out) & 15) == 0) && ((a->ldc * esz) % 16 == 0);
+    const void* xptr = a->epilogue == CGPT_EPI_MUL_AUX ? a->aux : (a->aux_out ? a->aux_out : (const void*)a->residual);
+    const int xsz = (a->residual && a->epilogue != CGPT_EPI_MUL_AUX && !a->aux_out) ? 4 : 2;
+    const long long xld = xsz == 4 ? a->ldc : a->ldaux;
+    const bool x_ok = xptr == nullptr || (((reinterpret_cast<uintptr_t>(xptr) & 15) == 0) && ((xld * xsz) % 16 == 0));
+    // combinations the TMA epilogues do not cover fall back to the per-thread path
+    const bool combo_ok = !(a->epilogue == CGPT_EPI_MUL_AUX && (a->out_f32 || a->residual)) &&
+                          !(a->out_f32 && a->epilogue != CGPT_EPI_NONE) && !(a->residual && a->accumulate);
+    if (c_ok && x_ok && combo_ok) {
+      const uint64_t dimsC[2] = {(uint64_t)a->N, (uint64_t)a->M};
+      const uint32_t boxC[2] = {a->out_f32 ? 16u : 32u, 32u};
+      const uint64_t strC[1] = {(uint64_t)a->ldc * esz};
+      rc = a->out_f32 ? make_tmap_f32(&tc, a->out, 2, dimsC, strC, boxC, 64)
+                      : make_tmap_bf16(&tc, a->out, 2, dimsC, strC, boxC, 64);
       if (rc) return rc;
+      p.tma_out = 1;
+      if (xptr) {
+        const uint32_t boxX[2] = {xsz == 4 ? 16u : 32u, 32u};
+        const uint64_t strX[1] = {(uint64_t)xld * xsz};
+        rc = xsz == 4 ? make_tmap_f32(&tx, xptr, 2, dimsC, strX, boxX, 64)
+                      : make_tmap_bf16(&tx, xptr, 2, dimsC, strX, boxX, 64);
+        if (rc) return rc;
+        p.tma_out |= 2;
+      }
     }
-    p.tma_out = 1;
   }
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
