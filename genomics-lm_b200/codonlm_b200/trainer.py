@@ -173,6 +173,11 @@ class TrainStep:
         dev = self.groups[0].flat.device
         self._xb = self._yb = None
         self._dev = dev
+        # step-dependent AdamW scalars on the device, one row per group: [lr, 1-b1^t, sqrt(1-b2^t)] (graph replay)
+        self._hyper = torch.zeros((len(self.groups), 3), dtype=torch.float32, device=dev)
+        self._hyper_host = torch.zeros((len(self.groups), 3), dtype=torch.float32).pin_memory() if dev.type == "cuda" \
+            else torch.zeros((len(self.groups), 3))
+        self._graph = None
 
     # ------------------------------------------------------------------ pieces
     def zero_grad(self):
@@ -190,19 +195,80 @@ class TrainStep:
         gscale = 1.0 / (micro_batches * self.world)  # mean over micro-batches and ranks (loop.py:145-150)
         for bk in self.buckets:
             bk.finish()
-        for g in self.groups:
+        self._push_hyper(lr_scale)
+        for gi, g in enumerate(self.groups):
             ops.adamw(g.flat, g.grad, g.m, g.v, None, g.lr * lr_scale, self.betas[0], self.betas[1], self.eps,
-                      g.weight_decay, self.step_count, gscale)
+                      g.weight_decay, self.step_count, gscale, dev_hyper=self._hyper[gi])
         # the kernel wrote the masters behind autograd's back: invalidate the bf16 shadow caches
         bump_shadow_generation()
 
+    def _push_hyper(self, lr_scale: float):
+        t = self.step_count
+        for gi, g in enumerate(self.groups):
+            self._hyper_host[gi, 0] = g.lr * lr_scale
+            self._hyper_host[gi, 1] = 1.0 - self.betas[0] ** t
+            self._hyper_host[gi, 2] = math.sqrt(1.0 - self.betas[1] ** t)
+        self._hyper.copy_(self._hyper_host, non_blocking=True)
+
     # ------------------------------------------------------------------ the step
-    def step(self, xb, yb, lr_scale: float = 1.0):
-        """Device-resident inputs; returns the total loss as a 0-dim device tensor (no host sync)."""
+    def _eager_step(self, xb, yb, lr_scale: float = 1.0):
         self.zero_grad()
         loss, _ = self.forward_backward(xb, yb)
         self.optimizer_step(lr_scale)
         return loss
+
+    def capture(self, B: int, T: int, warmup: int = 3):
+        """Capture forward + backward + AdamW for a fixed (B, T) into one CUDA graph (single-GPU, dropout off):
+        removes every launch gap and all Python work from the step.  step() then replays it."""
+        if self.world > 1:
+            raise RuntimeError("capture(): the data-parallel all-reduce is not captured; run eagerly")
+        if self.model.training and getattr(self.model, "dropout_p", 0.0) > 0.0:
+            raise RuntimeError("capture(): dropout draws its Philox offset on the host; run eagerly")
+        self._gx = torch.zeros((B, T), dtype=torch.int64, device=self._dev)
+        self._gy = torch.zeros((B, T), dtype=torch.int64, device=self._dev)
+        self._gx[:, :] = 4
+        self._gy[:, :-1] = 4
+        snap = [(g.flat.clone(), g.m.clone(), g.v.clone()) for g in self.groups]
+        count = self.step_count
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                self._eager_step(self._gx, self._gy)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        self.step_count += 1
+        self._push_hyper(1.0)
+        self.step_count -= 1
+        with torch.cuda.graph(graph):
+            self.zero_grad()
+            loss, _ = self.forward_backward(self._gx, self._gy)
+            gscale = 1.0 / self.world
+            for gi, g in enumerate(self.groups):
+                ops.adamw(g.flat, g.grad, g.m, g.v, None, g.lr, self.betas[0], self.betas[1], self.eps,
+                          g.weight_decay, 1, gscale, dev_hyper=self._hyper[gi])
+            self._gloss = loss
+        # undo the warm-up / capture-time updates: capture must not change the training state
+        for g, (f, m, v) in zip(self.groups, snap):
+            g.flat.copy_(f)
+            g.m.copy_(m)
+            g.v.copy_(v)
+        self.step_count = count
+        bump_shadow_generation()
+        self._graph = graph
+        self._graph_shape = (B, T)
+
+    def step(self, xb, yb, lr_scale: float = 1.0):
+        """Device-resident inputs; returns the total loss as a 0-dim device tensor (no host sync)."""
+        if self._graph is not None and tuple(xb.shape) == self._graph_shape:
+            self._gx.copy_(xb, non_blocking=True)
+            self._gy.copy_(yb, non_blocking=True)
+            self.step_count += 1
+            self._push_hyper(lr_scale)
+            self._graph.replay()
+            bump_shadow_generation()
+            return self._gloss
+        return self._eager_step(xb, yb, lr_scale)
 
     def step_host(self, xb_pinned, yb_pinned, lr_scale: float = 1.0) -> float:
         """Host buffers in, host scalar out: H2D of the batch and D2H of the loss are part of the call."""

@@ -485,7 +485,13 @@ __global__ void dropout_kernel(const float4* __restrict__ x, const float4* __res
 // ============================================================ AdamW (torch.optim.AdamW semantics)
 __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float lr,
-                             float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale) {
+                             float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
+                             const float* __restrict__ hyper) {
+  if (hyper) {  // step-dependent scalars live on the device so that a captured CUDA graph can be replayed
+    lr = hyper[0];
+    bc1 = hyper[1];
+    bc2_sqrt = hyper[2];
+  }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gr = g[i] * gscale;
     float pv = p[i] * (1.f - lr * wd);
@@ -739,12 +745,13 @@ int cgpt_dropout(const float* x, const float* residual, void* out, int out_bf16,
 }
 
 int cgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, int64_t n, float lr, float beta1,
-               float beta2, float eps, float weight_decay, int step, float grad_scale, cgpt_stream_t stream) {
+               float beta2, float eps, float weight_decay, int step, float grad_scale, const float* dev_hyper,
+               cgpt_stream_t stream) {
   CGPT_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
   adamw_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n,
-                                                         lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale);
+                                                         lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale, dev_hyper);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

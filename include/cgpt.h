@@ -185,9 +185,11 @@ int cgpt_dropout(const float* x, const float* residual /*nullable*/, void* out, 
 /* ---------------------------------------------------------------- optimiser -------------- */
 /* torch.optim.AdamW step on a flat fp32 buffer (loop.py:681-731 param groups are separate calls);
  * g is multiplied by grad_scale first (grad-accum / DDP mean, loop.py:145-150); optional bf16 shadow. */
+/* dev_hyper (nullable): device array [lr, 1-beta1^step, sqrt(1-beta2^step)] that overrides lr/step, so a
+ * captured CUDA graph of the whole step can be replayed while the host advances the schedule. */
 int cgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16 /*nullable*/, int64_t n,
                float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
-               cgpt_stream_t stream);
+               const float* dev_hyper, cgpt_stream_t stream);
 
 #ifdef __cplusplus
 }
