@@ -21,7 +21,7 @@ class GemmArgs(C.Structure):
     _fields_ = [("a", _vp), ("b", _vp), ("a_mn_major", _i), ("b_mn_major", _i), ("lda", _i64), ("ldb", _i64),
                 ("M", _i), ("N", _i), ("K", _i), ("split_k", _i), ("bias", _vp), ("epilogue", _i), ("aux", _vp),
                 ("aux_out", _vp), ("ldaux", _i64), ("residual", _vp), ("out", _vp), ("out_f32", _i),
-                ("accumulate", _i), ("ldc", _i64)]
+                ("accumulate", _i), ("ldc", _i64), ("colsum", _vp)]
 
 
 # name -> (restype, argtypes); must list every symbol include/cgpt.h declares (tests check this)
@@ -38,7 +38,7 @@ SIGNATURES = {
     "cgpt_embed_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cgpt_embed_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "cgpt_layernorm_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _f, _vp]),
-    "cgpt_layernorm_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
+    "cgpt_layernorm_bwd": (_i, [_vp, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _vp]),
     "cgpt_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
     "cgpt_cast_f32_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "cgpt_split3_f32_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _vp]),

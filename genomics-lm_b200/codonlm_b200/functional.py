@@ -16,16 +16,31 @@ from .ops import EPI_GELU, EPI_MUL_AUX, EPI_NONE, bf16, f32
 
 _SMS = 148
 
-# bf16 copies of fp32 gradient tensors, produced by the kernel that wrote the fp32 one (LayerNorm backward)
-# and consumed by the next Function's backward instead of a separate cast pass.  Keyed by data_ptr.
+# Side channel from LayerNorm backward to the backward of the residual linear right before it: the bf16 copy
+# and the column sums of the fp32 gradient tensor dx, produced by the same kernel that wrote dx.  It holds at
+# most ONE entry (the consumer runs before the next LayerNorm backward) and the entry is dropped when it is
+# used or replaced, so a recycled device address can never be matched against a stale entry.
 _BF16_SIDE = {}
 
 
-def _bf16_of(g: torch.Tensor) -> torch.Tensor:
+def _bf16_of(g: torch.Tensor):
+    """(bf16 copy of g, column sums of g or None)."""
     hit = _BF16_SIDE.pop(g.data_ptr(), None)
-    if hit is not None and hit.shape == g.shape:
+    if hit is not None and hit[0].shape == g.shape:
         return hit
-    return ops.cast_bf16(g)
+    return ops.cast_bf16(g), None
+
+
+def _bias_grad(gb: torch.Tensor, n: int, master, colsum):
+    """Bias gradient = column sums of the output gradient: taken from the producer when it already has them."""
+    if colsum is None:
+        return _colsum(gb, n, master=master)
+    mg = _main_grad(master)
+    if mg is not None:
+        mg.add_(colsum)
+        _done(master)
+        return None
+    return colsum
 
 
 def _main_grad(p):
@@ -124,9 +139,12 @@ class ResidualLayerNormFn(Function):
             dy = gyb
         else:
             return gx, None, None, None
+        dxsum = torch.zeros_like(gamma)
         dx, dxb = ops.layernorm_bwd(dy.contiguous(), x, gamma, mean, rstd, None if gx is None else gx.contiguous(),
-                                    dgamma, dbeta, want_bf16=True)
-        _BF16_SIDE[dx.data_ptr()] = dxb  # the upstream residual GEMM's backward wants dx as a bf16 operand
+                                    dgamma, dbeta, want_bf16=True, dx_colsum=dxsum)
+        # the upstream residual GEMM's backward wants dx as a bf16 operand and its column sums as the bias gradient
+        _BF16_SIDE.clear()
+        _BF16_SIDE[dx.data_ptr()] = (dxb, dxsum)
         if mg is not None:
             _done(gam_p)
             _done(bet_p)
@@ -162,7 +180,7 @@ class PackedLinearFn(Function):
         M, K = x.shape
         N = w_sh.shape[0]
         g = g.contiguous()
-        gb = _bf16_of(g) if g.dtype == f32 else g
+        gb, gsum = _bf16_of(g) if g.dtype == f32 else (g, None)
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=bf16, device=x.device)
@@ -173,7 +191,10 @@ class PackedLinearFn(Function):
             grads.append(_wgrad(gb, x, n, k_in, dy_off=r0, master=ctx.masters[i]))
         if ctx.has_bias:
             for i, (r0, n) in enumerate(ctx.rows):
-                grads.append(_colsum(gb, n, master=ctx.masters[nw + i], off=r0))
+                if gsum is not None and nw == 1:
+                    grads.append(_bias_grad(gb, n, ctx.masters[nw + i], gsum))
+                else:
+                    grads.append(_colsum(gb, n, master=ctx.masters[nw + i], off=r0))
         return (dx, None, None, g if ctx.has_res else None, None, None, *grads)
 
 
@@ -204,13 +225,20 @@ class MlpGeluFn(Function):
         n_out = w2_sh.shape[0]
         g = g.contiguous()
         b1, b2, w1, w2 = ctx.masters
-        gb = _bf16_of(g)
+        gb, gsum = _bf16_of(g)
         dw2 = _wgrad(gb, act, n_out, F, master=w2)
-        db2 = _colsum(gb, n_out, master=b2)
+        db2 = _bias_grad(gb, n_out, b2, gsum)
         dpre = torch.empty((M, F), dtype=bf16, device=h.device)
-        ops.gemm(gb, w2_sh, dpre, M=M, N=F, K=n_out, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=F)
+        fuse = (F % 8 == 0)  # TMA-aligned: the GEMM epilogue also produces the fc1 bias gradient
+        mb1 = _main_grad(b1)
+        db1 = (mb1 if mb1 is not None else torch.zeros((F,), dtype=f32, device=h.device)) if fuse else None
+        ops.gemm(gb, w2_sh, dpre, M=M, N=F, K=n_out, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=F, colsum=db1)
         dw1 = _wgrad(dpre, h, F, d, master=w1)
-        db1 = _colsum(dpre, F, master=b1)
+        if not fuse:
+            db1 = _colsum(dpre, F, master=b1)
+        elif mb1 is not None:
+            _done(b1)
+            db1 = None
         dh = torch.empty((M, d), dtype=bf16, device=h.device)
         ops.gemm(dpre, w1_sh, dh, M=M, N=d, K=F, b_mn=True)
         return dh, (g if ctx.has_res else None), None, db1, None, db2, dw1, dw2
@@ -245,7 +273,7 @@ class MlpSwiGLUFn(Function):
         n_out = wd_sh.shape[0]
         g = g.contiguous()
         w_gate, w_up, w_down = ctx.masters
-        gb = _bf16_of(g)
+        gb, _ = _bf16_of(g)
         dwd = _wgrad(gb, act, n_out, hid, master=w_down)        # [d, hid] (unpadded, odd pitch allowed)
         dact = torch.empty((M, hp), dtype=bf16, device=hin.device)
         ops.gemm(gb, wd_sh, dact, M=M, N=hp, K=n_out, b_mn=True)
@@ -282,12 +310,23 @@ class OffsetHeadFn(Function):
         dw2 = _wgrad(gb, act, d, d, master=w2)
         db2 = _colsum(gb, d, master=b2)
         dpre = torch.empty((M, d), dtype=bf16, device=xb.device)
-        ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=d)
+        fuse = (d % 8 == 0)
+        mb1 = _main_grad(b1)
+        db1 = (mb1 if mb1 is not None else torch.zeros((d,), dtype=f32, device=xb.device)) if fuse else None
+        ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=d, colsum=db1)
         dw1 = _wgrad(dpre, xb, d, d, master=w1)
-        db1 = _colsum(dpre, d, master=b1)
+        if not fuse:
+            db1 = _colsum(dpre, d, master=b1)
+        elif mb1 is not None:
+            _done(b1)
+            db1 = None
         dx = torch.empty((M, d), dtype=bf16, device=xb.device)
         ops.gemm(dpre, w1_sh, dx, M=M, N=d, K=d, b_mn=True)
         return dx, None, db1, None, db2, dw1, dw2
+
+
+def reset_side_channel():
+    _BF16_SIDE.clear()
 
 
 class DropoutFn(Function):
@@ -306,6 +345,7 @@ class DropoutFn(Function):
     def backward(ctx, g):
         seed, off, p = ctx.rng
         g = g.contiguous()
+        _BF16_SIDE.clear()  # g's side data describes g, not dropout(g)
         return ops.dropout(g, None, p, seed, off), (g if ctx.has_res else None), None
 
 

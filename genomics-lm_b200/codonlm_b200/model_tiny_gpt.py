@@ -549,6 +549,7 @@ class TinyGPT(nn.Module):
         in_dev = idx.device
         idx = self._prep_idx(idx)
         B, T = idx.shape
+        Fn.reset_side_channel()
         x = self._embed(idx, shape_embeddings)
         spec = self.mask_spec(idx, attention_window)
         for blk in self.blocks:

@@ -105,19 +105,19 @@ def layernorm_fwd(x2d, gamma, beta, want_bf16=True, want_f32=False, eps=1e-5):
     return yb, yf, mean, rstd
 
 
-def layernorm_bwd(dy, x2d, gamma, mean, rstd, dres, dgamma, dbeta, want_bf16=False):
+def layernorm_bwd(dy, x2d, gamma, mean, rstd, dres, dgamma, dbeta, want_bf16=False, dx_colsum=None):
     M, d = x2d.shape
     dx = torch.empty((M, d), dtype=f32, device=x2d.device)
     dxb = torch.empty((M, d), dtype=bf16, device=x2d.device) if want_bf16 else None
     check(_L().cgpt_layernorm_bwd(dy.data_ptr(), 1 if dy.dtype == f32 else 0, x2d.data_ptr(), gamma.data_ptr(),
                                   mean.data_ptr(), rstd.data_ptr(), _p(dres), dx.data_ptr(), _p(dxb),
-                                  dgamma.data_ptr(), dbeta.data_ptr(), M, d, _stream()))
+                                  dgamma.data_ptr(), dbeta.data_ptr(), _p(dx_colsum), M, d, _stream()))
     return dx, dxb
 
 
 # ------------------------------------------------------------------ GEMM
 def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=None, bias=None, epilogue=EPI_NONE,
-         aux=None, aux_out=None, ldaux=0, residual=None, accumulate=False, split_k=1):
+         aux=None, aux_out=None, ldaux=0, residual=None, accumulate=False, split_k=1, colsum=None):
     """out[M,N] (+)= A·Bᵀ (+bias, epilogue).  a/b bf16; out bf16 or fp32 (by dtype)."""
     g = GemmArgs()
     g.a, g.b = a.data_ptr(), b.data_ptr()
@@ -134,6 +134,7 @@ def gemm(a, b, out, *, M, N, K, a_mn=False, b_mn=False, lda=None, ldb=None, ldc=
     g.out_f32 = 1 if out.dtype == f32 else 0
     g.accumulate = int(accumulate)
     g.ldc = int(ldc if ldc is not None else out.stride(0))
+    g.colsum = _p(colsum)
     check(_L().cgpt_gemm_bf16(C.byref(g), _stream()))
     return out
 

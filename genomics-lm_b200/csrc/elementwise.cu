@@ -227,19 +227,19 @@ __global__ void __launch_bounds__(256, (VPT <= 4) ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, int M, int d) {
+                     float* __restrict__ dbeta, float* __restrict__ dxsum, int M, int d) {
   __shared__ float red[8][VPT * 128];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
   const int nvec = d >> 2;
   const float inv_d = 1.f / d;
-  float4 gm[VPT], ag[VPT], ab[VPT];
+  float4 gm[VPT], ag[VPT], ab[VPT], ax[VPT];  // ax: column sums of dx (bias gradient of the upstream linear)
 #pragma unroll
   for (int k = 0; k < VPT; ++k) {
     const int c = lane + 32 * k;
     gm[k] = c < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-    ag[k] = ab[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ag[k] = ab[k] = ax[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
@@ -297,20 +297,27 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
         reinterpret_cast<float4*>(dx + (size_t)row * d)[c] = o;
         if (dxb)
           reinterpret_cast<uint2*>(dxb + (size_t)row * d)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+        if (dxsum) {
+          ax[k].x += o.x;
+          ax[k].y += o.y;
+          ax[k].z += o.z;
+          ax[k].w += o.w;
+        }
       }
     }
   }
   // per-CTA reduction of the column partials over its 8 warps, then one atomic per column
 #pragma unroll
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < 3; ++pass) {
+    if (pass == 2 && dxsum == nullptr) break;
     __syncthreads();
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
-      const float4 val = pass == 0 ? ag[k] : ab[k];
+      const float4 val = pass == 0 ? ag[k] : (pass == 1 ? ab[k] : ax[k]);
       *reinterpret_cast<float4*>(&red[warp][(lane + 32 * k) * 4]) = val;
     }
     __syncthreads();
-    float* dst = pass == 0 ? dgamma : dbeta;
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
     for (int c = threadIdx.x; c < d; c += blockDim.x) {
       float t = 0.f;
 #pragma unroll
@@ -632,14 +639,14 @@ int cgpt_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
 
 int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float* gamma, const float* mean,
                        const float* rstd, const float* dres, float* dx, void* dx_bf16, float* dgamma, float* dbeta,
-                       int M, int d, cgpt_stream_t stream) {
+                       float* dx_colsum, int M, int d, cgpt_stream_t stream) {
   CGPT_REQUIRE(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && M > 0, "layernorm_bwd: bad arguments");
   CGPT_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
                128 * kLnMaxVec);
   const int vpt = (d / 4 + 31) / 32;
   const int grid = grid_for((long long)M * 32, 256, vpt <= 4 ? 2 : 1);
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-#define LN_BWD(V, F) layernorm_bwd_kernel<V, F><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, M, d)
+#define LN_BWD(V, F) layernorm_bwd_kernel<V, F><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, d)
   if (dy_is_f32) {
     if (vpt <= 1) LN_BWD(1, true); else if (vpt <= 2) LN_BWD(2, true); else if (vpt <= 4) LN_BWD(4, true); else LN_BWD(8, true);
   } else {

@@ -34,6 +34,7 @@ struct GemmParams {
   int out_f32;
   int accumulate;
   long long ldc;
+  float* colsum;
   int tma_out;  // bit0: out leaves through tmC (store / reduce-add); bit1: tmX is valid (aux_out store, aux load
                 // or residual load)
   int debug;  // bit0: skip global stores, bit1: skip TMEM loads, bit2: skip the whole epilogue body (probe only)
@@ -314,6 +315,20 @@ __device__ __forceinline__ void epi_chunk_mulaux_tma(const GemmParams& p, const 
   if (lane == 0) {
     tma_store_2d(tmC, stg, n0, row0);
     bulk_commit();
+  }
+  if (p.colsum) {
+    // column sums of this 32 x 32 piece straight from the staged bf16 values (lane = column), one atomic per
+    // column: the bias gradient of the layer in front of the GELU, without re-reading the output from HBM.
+    // Rows past M were zero-filled by the aux load, so they add nothing.
+    float acc = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      uint16_t h;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(stg_cell(stg, rr, lane >> 3) + (lane & 7) * 2));
+      acc += __uint_as_float(static_cast<uint32_t>(h) << 16);
+    }
+    if (n0 + lane < p.N) atomicAdd(p.colsum + n0 + lane, acc);
+    __syncwarp();  // everyone is done with the staging buffer before the next chunk reloads it
   }
 }
 
@@ -665,6 +680,7 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
   p.out_f32 = a->out_f32;
   p.accumulate = a->accumulate;
   p.ldc = a->ldc;
+  p.colsum = a->colsum;
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -707,6 +723,8 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
       }
     }
   }
+  CGPT_REQUIRE(a->colsum == nullptr || (a->epilogue == CGPT_EPI_MUL_AUX && (p.tma_out & 1)),
+               "gemm: colsum needs the MUL_AUX epilogue on 16-byte aligned bf16 operands");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
   if (BN == 256) return dispatch_major<256, 4>(amn, bmn, ta, tb, tc, tx, p, st);

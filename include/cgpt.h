@@ -73,10 +73,11 @@ int cgpt_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
                        float* y_f32 /*nullable*/, float* mean, float* rstd, int M, int d, float eps,
                        cgpt_stream_t stream);
 /* dx = (dres) + LN'(dy); dgamma,dbeta accumulate.  dy is bf16 (dy_is_f32=0) or fp32.
- * `dx_bf16` (nullable) receives a bf16 copy of dx for the GEMMs upstream. */
+ * `dx_bf16` (nullable) receives a bf16 copy of dx for the GEMMs upstream; `dx_colsum` (nullable, [d], accumulate)
+ * receives sum_rows dx = the bias gradient of the residual linear that produced x. */
 int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const float* gamma, const float* mean,
                        const float* rstd, const float* dres /*nullable*/, float* dx, void* dx_bf16 /*nullable*/,
-                       float* dgamma, float* dbeta, int M, int d, cgpt_stream_t stream);
+                       float* dgamma, float* dbeta, float* dx_colsum /*nullable*/, int M, int d, cgpt_stream_t stream);
 
 /* ---------------------------------------------------------------- dense GEMM (tcgen05) --- */
 /* D[M,N] = A·Bᵀ with bf16 operands, fp32 accumulation in TMEM, fused epilogue.
@@ -108,6 +109,8 @@ typedef struct {
   int out_f32;
   int accumulate;        /* out_f32 only: atomically out += v */
   int64_t ldc;
+  float* colsum;         /* nullable, fp32 [N], accumulate: column sums of the (bf16-rounded) output; only with the
+                            MUL_AUX epilogue on TMA-aligned operands (bias gradient of the layer in front of a GELU) */
 } cgpt_gemm_args;
 int cgpt_gemm_bf16(const cgpt_gemm_args* args_host, cgpt_stream_t stream);
 

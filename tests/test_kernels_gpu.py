@@ -106,7 +106,9 @@ def test_layernorm_fwd_bwd(ops):
         torch.nn.functional.layer_norm(xr, (d,), gr, br, 1e-5).backward(dy)
         for dyt in (dy, dy.to(torch.bfloat16)):
             dgam, dbet = torch.zeros_like(gam), torch.zeros_like(bet)
-            dx, dxb = ops.layernorm_bwd(dyt, x, gam, mean, rstd, dres, dgam, dbet, want_bf16=True)
+            dxs = torch.ones_like(gam)
+            dx, dxb = ops.layernorm_bwd(dyt, x, gam, mean, rstd, dres, dgam, dbet, want_bf16=True, dx_colsum=dxs)
+            assert torch.allclose(dxs, 1 + dx.sum(0), rtol=1e-4, atol=1e-3 * math.sqrt(M))
             tol = 1e-4 if dyt.dtype == torch.float32 else 2e-2
             assert torch.allclose(dx, xr.grad + dres, rtol=tol, atol=tol)
             assert torch.allclose(dgam, gr.grad, rtol=tol, atol=tol * math.sqrt(M))
@@ -192,8 +194,10 @@ def test_gemm_epilogues(ops):
     assert torch.allclose(dr.float(), p32.grad[:, :Nr], rtol=1e-2, atol=1e-2)
     # multiply-by-aux epilogue (backward through GELU)
     dz = torch.empty((M, N), dtype=torch.bfloat16, device=DEV)
-    ops.gemm(A, W, dz, M=M, N=N, K=K, epilogue=ops.EPI_MUL_AUX, aux=dact, ldaux=N)
+    cs = torch.ones(N, device=DEV)
+    ops.gemm(A, W, dz, M=M, N=N, K=K, epilogue=ops.EPI_MUL_AUX, aux=dact, ldaux=N, colsum=cs)
     assert torch.allclose(dz.float(), (A.float() @ W.float().t()) * dact.float(), rtol=2e-2, atol=2e-2)
+    assert torch.allclose(cs, 1 + dz.float().sum(0), rtol=1e-4, atol=1e-3)  # fused column sums of the bf16 output
     # bias + residual -> fp32
     res = torch.randn(M, N, generator=g).to(DEV)
     o32 = torch.empty((M, N), dtype=torch.float32, device=DEV)

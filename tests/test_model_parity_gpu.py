@@ -317,12 +317,14 @@ def test_training_mode_dropout_is_seeded_and_off_in_eval():  # reference tests/t
         with torch.no_grad():
             e0, _ = m0(x)
         assert torch.equal(e0, e1)
-        # training still reduces the loss with dropout on
+        # training still reduces the loss with dropout on (next-token targets: predicting the input itself is
+        # trivial for a tied N(0,1) embedding and the loss underflows to 0)
         m.train()
+        y = torch.roll(x, -1, dims=1)
         opt = torch.optim.AdamW(m.parameters(), lr=3e-3)
         first = None
         for _ in range(8):
-            _, loss = m(x, x)
+            _, loss = m(x, y)
             opt.zero_grad(set_to_none=True)
             loss.backward()
             opt.step()
