@@ -189,6 +189,8 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        if "CGPT_KEEP_NCCL_DEBUG" not in os.environ:
+            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     from codonlm_b200 import TinyGPT, ops
     from codonlm_b200.trainer import TrainStep
