@@ -792,6 +792,405 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
   }
 }
 
+// ===================================================================================== backward, warp-specialised
+// hd <= 64.  Same work decomposition as attn_bwd_kernel (persistent CTA, items = (kv tile, kv head, batch)), but
+// the tensor-core work is driven by a dedicated warp so that it overlaps the CUDA-core math of the next tile:
+//
+//   warp 8 (one lane): TMA requests, S/dP MMAs of tile i+1 issued right behind "P/dS of tile i are in smem",
+//                      then the gradient MMAs (dV, dK, dQ) of tile i — which therefore run while the 8 math warps
+//                      already work on tile i+1.
+//   warps 0..7       : S,dP (TMEM) -> P, dS (bf16, swizzled smem, double-buffered) ; then the dQ write-out of the
+//                      PREVIOUS tile (TMEM dQ is double-buffered too) through per-warp TMA reduce-adds whose
+//                      staging aliases the P buffer that tile has just released.
+//
+// TMEM (512 cols): S 128 | dP 128 | dV hd | dK hd | dQ 2*hd.   smem: K, V, 2x(Q, dO), 2x(P, dS).
+template <int HD>
+struct BwdWsSmem {
+  using C = HeadCfg<HD>;
+  static constexpr int kK = 0;
+  static constexpr int kV = kK + C::TILE_BYTES;
+  static constexpr int kQ = kV + C::TILE_BYTES;          // 2 buffers
+  static constexpr int kdO = kQ + 2 * C::TILE_BYTES;     // 2 buffers
+  static constexpr int kP = kdO + 2 * C::TILE_BYTES;     // 2 buffers
+  static constexpr int kdS = kP + 2 * kPTileBytes;       // 2 buffers
+  static constexpr int kBar = kdS + 2 * kPTileBytes;
+  static constexpr int kTotal = kBar + 128;
+  static constexpr int kDynamic = (kTotal + 1024 <= 232448) ? kTotal + 1024 : 232448;
+  static constexpr bool kTmaDq = (HD == 32 || HD == 64);
+  static constexpr int kdQBoxCols = HD == 32 ? 16 : 32;
+  static constexpr int kdQRow = kTmaDq ? HD * 4 : HD * 4 + 16;
+  static_assert(HD <= 64, "warp-specialised backward needs 256 + 4*hd TMEM columns");
+  static_assert(128 * kdQRow <= kPTileBytes, "dQ staging must fit in one P buffer");
+  static_assert(kTotal <= 232448, "exceeds the shared memory of one CTA");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(288, 1)
+attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
+                   const __grid_constant__ CUtensorMap tm_dq, const int32_t* __restrict__ seg_start,
+                   const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
+                   float* __restrict__ dq_ws, int Bsz, int T, int H, int Hk, int window, float scale,
+                   const DropoutCfg drop, int smem_bytes) {
+  using C = HeadCfg<HD>;
+  using S = BwdWsSmem<HD>;
+  constexpr int TMEM_COLS = 512;
+  constexpr int HH = HD / 2;
+  constexpr int kMathThreads = 256;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(smem - smem_raw) + S::kTotal > smem_bytes) __trap();
+  uint8_t* sK = smem + S::kK;
+  uint8_t* sV = smem + S::kV;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
+  uint64_t* kv_bar = bars;          // K, V of an item have landed
+  uint64_t* q_bar = bars + 1;       // [2] Q, dO of a tile have landed
+  uint64_t* s_bar = bars + 3;       // S, dP of a tile are in TMEM
+  uint64_t* p_bar = bars + 4;       // [2] P, dS of a tile are in smem (and S/dP TMEM has been consumed)
+  uint64_t* g_bar = bars + 6;       // [2] dV, dK, dQ MMAs of a tile have retired
+  uint64_t* dkv_bar = bars + 8;     // the math warps have drained dK/dV of an item from TMEM
+  uint64_t* item_bar = bars + 9;    // the query-tile range of an item has been published
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  int* s_qhi = reinterpret_cast<int*>(bars + 11);  // [2]
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rep = H / Hk;
+  const int W = (H + 2 * Hk) * HD;
+  const int nqb_total = (T + BQ - 1) / BQ;
+  const int per_kvb = Hk * Bsz;
+  const int n_items = nqb_total * per_kvb;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm_qkv);
+    tma_prefetch_desc(&tm_do);
+    tma_prefetch_desc(&tm_dq);
+    mbar_init(kv_bar, 1);
+    mbar_init(&q_bar[0], 1);
+    mbar_init(&q_bar[1], 1);
+    mbar_init(s_bar, 1);
+    mbar_init(&p_bar[0], 8);
+    mbar_init(&p_bar[1], 8);
+    mbar_init(&g_bar[0], 1);
+    mbar_init(&g_bar[1], 1);
+    mbar_init(dkv_bar, 8);
+    mbar_init(item_bar, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + HD;
+  const uint32_t tdQ0 = tmem_base + 256 + 2 * HD;  // + buf * HD
+
+  auto decode = [&](int item, int& kvb, int& kvh, int& b) {
+    kvb = item / per_kvb;
+    const int r = item - kvb * per_kvb;
+    kvh = r % Hk;
+    b = r / Hk;
+  };
+
+  if (warp == 8) {
+    // ================================================================= TMA + MMA warp (one lane)
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD, true, true);
+      constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, false, true);
+      int g = 0;  // global tile counter: buffer = g & 1, barrier phase = (g >> 1) & 1
+      int n_it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
+        int kvb, kvh, b;
+        decode(item, kvb, kvh, b);
+        // query-tile range of this item
+        int hi_pos = T - 1;
+        const int kv_last = min(T - 1, kvb * BKV + BKV - 1);
+        if (window > 0) hi_pos = min(hi_pos, kv_last + window - 1);
+        if (seg_start) hi_pos = min(hi_pos, upper_bound_i32(seg_start + (size_t)b * T, T, kv_last) - 1);
+        const int qb_lo = kvb, qb_hi = min(hi_pos / BQ, nqb_total - 1);
+        const int nq = qb_hi - qb_lo + 1, niter = nq * rep;
+        s_qhi[n_it & 1] = qb_hi;
+        mbar_arrive(item_bar);
+        auto load_q = [&](int it2, int gg) {
+          const int nb = gg & 1;
+          const int nh = kvh * rep + it2 / nq, nq0 = (qb_lo + it2 % nq) * BQ;
+          mbar_expect_tx(&q_bar[nb], 2 * C::TILE_BYTES);
+          tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], nh * HD, nq0, b);
+          tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], nh * HD, nq0, b);
+        };
+        auto issue_scores = [&](int gg) {
+          const int nb = gg & 1;
+          const uint32_t q_s = smem_u32(smem + S::kQ + nb * C::TILE_BYTES), do_s = smem_u32(smem + S::kdO + nb * C::TILE_BYTES);
+          mbar_wait(&q_bar[nb], (gg >> 1) & 1);
+          tc_fence_after();
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks)
+            umma_bf16(tS, C::kmajor(q_s, ks), C::kmajor(smem_u32(sK), ks), idesc_s, ks > 0);
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks)
+            umma_bf16(tdP, C::kmajor(do_s, ks), C::kmajor(smem_u32(sV), ks), idesc_s, ks > 0);
+          umma_commit(s_bar);
+        };
+        // K, V (their smem was released when the previous item's last gradient MMAs retired, see below)
+        mbar_expect_tx(kv_bar, 2 * C::TILE_BYTES);
+        tma_tile<HD>(sK, &tm_qkv, kv_bar, (H + kvh) * HD, kvb * BKV, b);
+        tma_tile<HD>(sV, &tm_qkv, kv_bar, (H + Hk + kvh) * HD, kvb * BKV, b);
+        load_q(0, g);
+        mbar_wait(kv_bar, n_it & 1);
+        issue_scores(g);
+        for (int it = 0; it < niter; ++it, ++g) {
+          const int buf = g & 1;
+          if (it + 1 < niter) {
+            // (Q, dO) buffer of tile it+1 was last read by the gradient MMAs of tile it-1
+            if (it >= 1) mbar_wait(&g_bar[buf ^ 1], ((g - 1) >> 1) & 1);
+            load_q(it + 1, g + 1);
+          }
+          mbar_wait(&p_bar[buf], (g >> 1) & 1);  // P, dS of tile `it` are in smem; S/dP TMEM is free
+          tc_fence_after();
+          if (it + 1 < niter) issue_scores(g + 1);  // scores first: the math warps can start on tile it+1
+          if (it == 0 && n_it > 0) {  // dK/dV accumulators still hold the previous item until the math warps drain them
+            mbar_wait(dkv_bar, (n_it - 1) & 1);
+            tc_fence_after();
+          }
+          const uint32_t sP = smem_u32(smem + S::kP + buf * kPTileBytes), sdS = smem_u32(smem + S::kdS + buf * kPTileBytes);
+          const uint32_t sQ = smem_u32(smem + S::kQ + buf * C::TILE_BYTES), sdO = smem_u32(smem + S::kdO + buf * C::TILE_BYTES);
+#pragma unroll
+          for (int ks = 0; ks < BQ / 16; ++ks)  // dV[kv,hd] += Pᵀ[kv,q] dO[q,hd]
+            umma_bf16(tdV, ptile_mnmajor(sP, ks), C::mnmajor(sdO, ks), idesc_kv, (it > 0) || (ks > 0));
+#pragma unroll
+          for (int ks = 0; ks < BQ / 16; ++ks)  // dK[kv,hd] += dSᵀ[kv,q] Q[q,hd]
+            umma_bf16(tdK, ptile_mnmajor(sdS, ks), C::mnmajor(sQ, ks), idesc_kv, (it > 0) || (ks > 0));
+#pragma unroll
+          for (int ks = 0; ks < BKV / 16; ++ks)  // dQ[q,hd] = dS[q,kv] K[kv,hd]
+            umma_bf16(tdQ0 + buf * HD, ptile_kmajor(sdS, ks), C::mnmajor(smem_u32(sK), ks), idesc_q, ks > 0);
+          umma_commit(&g_bar[buf]);
+        }
+        // K/V smem (and both Q/dO buffers) are free once the last gradient MMAs have retired
+        mbar_wait(&g_bar[(g - 1) & 1], ((g - 1) >> 1) & 1);
+      }
+    }
+  } else {
+    // ================================================================= math warps
+    const int row = tid & 127, half = tid >> 7;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    const float scale_log2 = scale * kLog2e;
+    int g = 0, n_it = 0;
+    uint32_t s_phase = 0;
+
+    // dQ of tile (gg) of head hq / query tile q0 -> reduce-add into the workspace; staging = P buffer (gg & 1)
+    auto dq_phase = [&](int gg, int hq, int q0, int b) {
+      const int buf = gg & 1;
+      mbar_wait(&g_bar[buf], (gg >> 1) & 1);
+      tc_fence_after();
+      uint8_t* stage = smem + S::kP + buf * kPTileBytes;
+      const uint32_t tq = tdQ0 + buf * HD + lane_base + half * HH;
+      if constexpr (S::kTmaDq) {
+        constexpr int BC = S::kdQBoxCols, BOX_BYTES = 32 * BC * 4, ROWB = BC * 4;
+        uint8_t* wbase = stage + warp * BOX_BYTES;
+        uint32_t rq[HH];
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) tmem_ld8(tq + c0, *reinterpret_cast<uint32_t(*)[8]>(&rq[c0]));
+        tmem_ld_wait();
+        const int sw = (ROWB == 128) ? (lane & 7) : ((lane >> 1) & 3);
+        const uint32_t rowp = smem_u32(wbase + lane * ROWB);
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 4)
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + (((c0 >> 2) ^ sw) << 4)), "r"(rq[c0]),
+                       "r"(rq[c0 + 1]), "r"(rq[c0 + 2]), "r"(rq[c0 + 3])
+                       : "memory");
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          asm volatile(
+              "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                  reinterpret_cast<uint64_t>(&tm_dq)),
+              "r"(smem_u32(wbase)), "r"(half * HH), "r"(q0 + (warp & 3) * 32), "r"(b * H + hq)
+              : "memory");
+          bulk_commit();
+          bulk_wait_read0();  // the staging aliases a P buffer that the next-but-one tile rewrites
+        }
+        __syncwarp();
+      } else {
+        uint8_t* myrow = stage + row * S::kdQRow + half * (HH * 4);
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) {
+          uint32_t r[8];
+          tmem_ld8(tq + c0, r);
+          tmem_ld_wait();
+          *reinterpret_cast<uint4*>(myrow + c0 * 4) = make_uint4(r[0], r[1], r[2], r[3]);
+          *reinterpret_cast<uint4*>(myrow + c0 * 4 + 16) = make_uint4(r[4], r[5], r[6], r[7]);
+        }
+        fence_proxy_async_smem();
+        const int i = q0 + row;
+        if (i < T) {
+          float* gp = dq_ws + (((size_t)b * H + hq) * T + i) * HD + half * HH;
+          asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;" ::"l"(gp),
+                       "r"(smem_u32(myrow)), "r"(HH * 4)
+                       : "memory");
+        }
+        bulk_commit();
+        bulk_wait_read0();
+      }
+      tc_fence_before();
+    };
+
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
+      int kvb, kvh, b;
+      decode(item, kvb, kvh, b);
+      const int kv0 = kvb * BKV;
+      const int kcol = (H + kvh) * HD, vcol = (H + Hk + kvh) * HD;
+      const int32_t* ssb = seg_start ? seg_start + (size_t)b * T : nullptr;
+      mbar_wait(item_bar, n_it & 1);
+      const int qb_lo = kvb, qb_hi = s_qhi[n_it & 1];
+      const int nq = qb_hi - qb_lo + 1, niter = nq * rep;
+
+      float nx_lse = 0.f, nx_dl = 0.f;
+      int nx_ss = 0;
+      {
+        const int i0 = qb_lo * BQ + row;
+        const size_t st0 = ((size_t)b * H + kvh * rep) * T + (i0 < T ? i0 : 0);
+        nx_lse = i0 < T ? lse[st0] : 0.f;
+        nx_dl = i0 < T ? delta[st0] : 0.f;
+        nx_ss = (ssb && i0 < T) ? ssb[i0] : 0;
+      }
+      int prev_hq = 0, prev_q0 = 0;
+      for (int it = 0; it < niter; ++it, ++g) {
+        const int buf = g & 1;
+        const int hq = kvh * rep + it / nq;
+        const int q0 = (qb_lo + it % nq) * BQ;
+        const int i = q0 + row;
+        const bool row_ok = i < T;
+        const float lse2 = nx_lse * kLog2e, dl = nx_dl;
+        int jlo = row_ok ? nx_ss : 0x3fffffff;
+        if (window > 0) jlo = max(jlo, i - window + 1);
+        if (it + 1 < niter) {
+          const int nh = kvh * rep + (it + 1) / nq, ni = (qb_lo + (it + 1) % nq) * BQ + row;
+          const size_t st2 = ((size_t)b * H + nh) * T + (ni < T ? ni : 0);
+          nx_lse = ni < T ? lse[st2] : 0.f;
+          nx_dl = ni < T ? delta[st2] : 0.f;
+          nx_ss = (ssb && ni < T) ? ssb[ni] : 0;
+        }
+        const bool need_mask = !row_ok || (kv0 + BKV - 1 > i) || (kv0 < jlo);
+        // every warp has finished the dQ write-out that used this P buffer as staging (two tiles ago)
+        named_bar_sync(1, kMathThreads);
+        mbar_wait(s_bar, s_phase);
+        s_phase ^= 1;
+        tc_fence_after();
+        uint8_t* sP = smem + S::kP + buf * kPTileBytes;
+        uint8_t* sdS = smem + S::kdS + buf * kPTileBytes;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c4 = half * 2 + cc;
+          uint32_t rs[32], rp[32];
+          tmem_ld32(tS + lane_base + c4 * 32, rs);
+          tmem_ld32(tdP + lane_base + c4 * 32, rp);
+          tmem_ld_wait();
+          float p[32], ds[32];
+          if (need_mask) {
+            const int jb = kv0 + c4 * 32;
+            const unsigned span = static_cast<unsigned>(i - jlo);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float pv = fast_exp2(fmaf(__uint_as_float(rs[j]), scale_log2, -lse2));
+              p[j] = (row_ok && visible(jb + j, jlo, span)) ? pv : 0.f;
+              ds[j] = p[j] * (__uint_as_float(rp[j]) - dl);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              p[j] = fast_exp2(fmaf(__uint_as_float(rs[j]), scale_log2, -lse2));
+              ds[j] = p[j] * (__uint_as_float(rp[j]) - dl);
+            }
+          }
+          if (drop.thresh) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const uint4 rb = attn_dropout_bits(drop, b * H + hq, i, (kv0 + c4 * 32) / 4 + j4);
+              const uint32_t bits[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int j = 4 * j4 + e;
+                const float mk = bits[e] >= drop.thresh ? drop.inv_keep : 0.f;
+                const float pj = p[j];
+                ds[j] = pj * (__uint_as_float(rp[j]) * mk - dl);
+                p[j] = pj * mk;
+              }
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 v, w;
+            v.x = pack_bf16(p[q * 8 + 0], p[q * 8 + 1]);
+            v.y = pack_bf16(p[q * 8 + 2], p[q * 8 + 3]);
+            v.z = pack_bf16(p[q * 8 + 4], p[q * 8 + 5]);
+            v.w = pack_bf16(p[q * 8 + 6], p[q * 8 + 7]);
+            w.x = pack_bf16(ds[q * 8 + 0], ds[q * 8 + 1]);
+            w.y = pack_bf16(ds[q * 8 + 2], ds[q * 8 + 3]);
+            w.z = pack_bf16(ds[q * 8 + 4], ds[q * 8 + 5]);
+            w.w = pack_bf16(ds[q * 8 + 6], ds[q * 8 + 7]);
+            ptile_store(sP, row, c4 * 4 + q, v);
+            ptile_store(sdS, row, c4 * 4 + q, w);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_bar[buf]);
+        // while the tensor cores chew on this tile's gradients: write out dQ of the previous tile
+        if (it >= 1) dq_phase(g - 1, prev_hq, prev_q0, b);
+        prev_hq = hq;
+        prev_q0 = q0;
+      }
+      dq_phase(g - 1, prev_hq, prev_q0, b);  // also waits for the last gradient MMAs of the item
+
+      // dK (scaled) and dV -> bf16 into the k / v column blocks of dqkv (TMEM lane = kv row)
+      {
+        const int j = kv0 + row;
+        __nv_bfloat16* gk = dqkv + ((size_t)b * T + min(j, T - 1)) * W + kcol + half * HH;
+        __nv_bfloat16* gv = dqkv + ((size_t)b * T + min(j, T - 1)) * W + vcol + half * HH;
+        uint32_t rka[HH], rva[HH];
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) {
+          tmem_ld8(tdK + lane_base + half * HH + c0, *reinterpret_cast<uint32_t(*)[8]>(&rka[c0]));
+          tmem_ld8(tdV + lane_base + half * HH + c0, *reinterpret_cast<uint32_t(*)[8]>(&rva[c0]));
+        }
+        tmem_ld_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(dkv_bar);  // the accumulators may be overwritten by the next item
+        if (j < T) {
+#pragma unroll
+          for (int c0 = 0; c0 < HH; c0 += 8) {
+            const uint32_t* rk = &rka[c0];
+            const uint32_t* rv = &rva[c0];
+            uint4 a, c;
+            a.x = pack_bf16(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale);
+            a.y = pack_bf16(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale);
+            a.z = pack_bf16(__uint_as_float(rk[4]) * scale, __uint_as_float(rk[5]) * scale);
+            a.w = pack_bf16(__uint_as_float(rk[6]) * scale, __uint_as_float(rk[7]) * scale);
+            c.x = pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]));
+            c.y = pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
+            c.z = pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]));
+            c.w = pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
+            *reinterpret_cast<uint4*>(gk + c0) = a;
+            *reinterpret_cast<uint4*>(gv + c0) = c;
+          }
+        }
+      }
+    }
+    bulk_wait_read0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
 // dq (fp32 [B,H,T,hd]) * scale -> bf16 into the q column block of dqkv
 __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfloat16* __restrict__ dqkv, int B, int T,
                                        int H, int hd, int W, float scale) {
@@ -925,16 +1324,28 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     count_launch();
     CGPT_LAUNCH_CHECK();
   }
-  auto kern = attn_bwd_kernel<HD>;
-  static bool configured = false;
-  if (!configured) {
-    CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
-    configured = true;
-  }
   const int n_items = ((T + BKV - 1) / BKV) * Hk * B;
   const int grid = n_items < num_sms() ? n_items : num_sms();
-  kern<<<grid, 256, S::kDynamic, st>>>(tq, td, tdq, seg, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, B, T,
-                                       H, Hk, window, scale, drop);
+  if constexpr (HD <= 64) {
+    using SW = BwdWsSmem<HD>;
+    auto kern = attn_bwd_ws_kernel<HD>;
+    static bool configured = false;
+    if (!configured) {
+      CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SW::kDynamic));
+      configured = true;
+    }
+    kern<<<grid, 288, SW::kDynamic, st>>>(tq, td, tdq, seg, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, B,
+                                          T, H, Hk, window, scale, drop, SW::kDynamic);
+  } else {
+    auto kern = attn_bwd_kernel<HD>;
+    static bool configured = false;
+    if (!configured) {
+      CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
+      configured = true;
+    }
+    kern<<<grid, 256, S::kDynamic, st>>>(tq, td, tdq, seg, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, B, T,
+                                         H, Hk, window, scale, drop);
+  }
   count_launch();
   CGPT_LAUNCH_CHECK();
   {
