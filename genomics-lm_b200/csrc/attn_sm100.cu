@@ -193,13 +193,16 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
   constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
   constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
 
+  const bool leader = (warp == 0) && elect_one();
+  const uint32_t sQ_u = smem_u32(sQ), sP_u = smem_u32(sP), sKV_u = smem_u32(smem + S::kK);
+
   for (int it = 0; it < nblk; ++it) {
     const int buf = it & 1;
     const int kv0 = (kv_lo + it) * BKV;
     uint8_t* sK = smem + S::kK + buf * C::TILE_BYTES;
     uint8_t* sV = smem + S::kV + buf * C::TILE_BYTES;
-    if (tid == 0) {
-      if (it + 1 < nblk) {  // prefetch next KV tile (its buffer was released by the last PV wait)
+    if (warp == 0) {  // warp-uniform control flow (descriptors stay in uniform registers); one lane issues
+      if (it + 1 < nblk && leader) {  // prefetch next KV tile (its buffer was released by the last PV wait)
         const int nb = buf ^ 1;
         mbar_expect_tx(&kv_bar[nb], 2 * C::TILE_BYTES);
         tma_tile<HD>(smem + S::kK + nb * C::TILE_BYTES, &tm, &kv_bar[nb], kcol, kv0 + BKV, b);
@@ -208,10 +211,13 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
       if (it == 0) mbar_wait(q_bar, 0);
       mbar_wait(&kv_bar[buf], (it >> 1) & 1);
       tc_fence_after();
+      if (leader) {
 #pragma unroll
-      for (int ks = 0; ks < HD / 16; ++ks)
-        umma_bf16(tS, C::kmajor(smem_u32(sQ), ks), C::kmajor(smem_u32(sK), ks), idesc_s, ks > 0);
-      umma_commit(mma_bar);
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16(tS, C::kmajor(sQ_u, ks), C::kmajor(sKV_u + buf * C::TILE_BYTES, ks), idesc_s, ks > 0);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
@@ -296,12 +302,15 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
+      if (leader) {
 #pragma unroll
-      for (int ks = 0; ks < BKV / 16; ++ks)
-        umma_bf16(tO, ptile_kmajor(smem_u32(sP), ks), C::mnmajor(smem_u32(sV), ks), idesc_o, ks > 0);
-      umma_commit(mma_bar);
+        for (int ks = 0; ks < BKV / 16; ++ks)
+          umma_bf16(tO, ptile_kmajor(sP_u, ks), C::mnmajor(sKV_u + (S::kV - S::kK) + buf * C::TILE_BYTES, ks), idesc_o, ks > 0);
+        umma_commit(mma_bar);
+      }
+      __syncwarp();
     }
     mbar_wait(mma_bar, mma_phase);
     mma_phase ^= 1;
@@ -346,8 +355,56 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
 
 // ===================================================================================== backward
 // delta[b,h,i] = sum_c dO[i,c] * O[i,c]   (one warp per (token, head))
+// last query tile that can see each (batch, kv tile): the warp-specialised backward reads this table instead of
+// searching seg_start itself.  Side job of the first threads of the delta kernels.
+__device__ __forceinline__ void fill_qhi_tab(int e, int B, int T, const int32_t* __restrict__ seg_start, int window,
+                                             int* __restrict__ qhi_tab) {
+  const int nkb = (T + BKV - 1) / BKV;
+  if (e >= B * nkb) return;
+  const int b = e / nkb, kvb = e - b * nkb;
+  int hi_pos = T - 1;
+  const int kv_last = min(T - 1, kvb * BKV + BKV - 1);
+  if (window > 0) hi_pos = min(hi_pos, kv_last + window - 1);
+  if (seg_start) hi_pos = min(hi_pos, upper_bound_i32(seg_start + (size_t)b * T, T, kv_last) - 1);
+  qhi_tab[e] = min(hi_pos / BQ, (T + BQ - 1) / BQ - 1);
+}
+
+// delta[b,h,t] = sum_c out[b,t,h,c] * dout[b,t,h,c].  G = hd/8 threads per (token, head), 16-byte loads: the
+// whole warp reads 512 contiguous bytes of each tensor.
+template <int G>
+__global__ void attn_delta_vec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
+                                      float* __restrict__ delta, int B, int T, int H,
+                                      const int32_t* __restrict__ seg_start, int window, int* __restrict__ qhi_tab) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index
+  if (qhi_tab && e < (long long)B * ((T + BKV - 1) / BKV)) fill_qhi_tab((int)e, B, T, seg_start, window, qhi_tab);
+  const long long total = (long long)B * T * H * G;
+  float s = 0.f;
+  if (e < total) {
+    const uint4 a = reinterpret_cast<const uint4*>(o)[e];
+    const uint4 g = reinterpret_cast<const uint4*>(dout)[e];
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g.x, g.y, g.z, g.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float2 x = unpack_bf16(av[q]), y = unpack_bf16(gv[q]);
+      s = fmaf(x.x, y.x, fmaf(x.y, y.y, s));
+    }
+  }
+#pragma unroll
+  for (int off = G / 2; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (e < total && (threadIdx.x & (G - 1)) == 0) {
+    const long long w = e / G;  // (token, head)
+    const long long tok = w / H;
+    const int h = (int)(w - tok * H);
+    const long long bb = tok / T, t = tok - bb * T;
+    delta[(bb * H + h) * T + t] = s;
+  }
+}
+
+// generic head sizes (48, 96): one warp per (token, head)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
-                                  float* __restrict__ delta, int B, int T, int H, int hd) {
+                                  float* __restrict__ delta, int B, int T, int H, int hd,
+                                  const int32_t* __restrict__ seg_start, int window, int* __restrict__ qhi_tab) {
+  if (qhi_tab) fill_qhi_tab(blockIdx.x * blockDim.x + threadIdx.x, B, T, seg_start, window, qhi_tab);
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (long long)B * T * H) return;
@@ -818,24 +875,22 @@ struct BwdWsSmem {
   static constexpr int kDynamic = (kTotal + 1024 <= 232448) ? kTotal + 1024 : 232448;
   static constexpr bool kTmaDq = (HD == 32 || HD == 64);
   static constexpr int kdQBoxCols = HD == 32 ? 16 : 32;
-  static constexpr int kdQRow = kTmaDq ? HD * 4 : HD * 4 + 16;
   static_assert(HD <= 64, "warp-specialised backward needs 256 + 4*hd TMEM columns");
-  static_assert(128 * kdQRow <= kPTileBytes, "dQ staging must fit in one P buffer");
   static_assert(kTotal <= 232448, "exceeds the shared memory of one CTA");
 };
 
 template <int HD>
 __global__ void __launch_bounds__(288, 1)
 attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
-                   const __grid_constant__ CUtensorMap tm_dq, const int32_t* __restrict__ seg_start,
-                   const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
-                   float* __restrict__ dq_ws, int Bsz, int T, int H, int Hk, int window, float scale,
-                   const DropoutCfg drop, int smem_bytes) {
+                   const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dkv,
+                   const int32_t* __restrict__ seg_start,
+                   const int* __restrict__ qhi_tab, const float* __restrict__ lse, const float* __restrict__ delta,
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_ws, int Bsz, int T, int H, int Hk,
+                   int window, float scale, const DropoutCfg drop, int smem_bytes) {
   using C = HeadCfg<HD>;
   using S = BwdWsSmem<HD>;
   constexpr int TMEM_COLS = 512;
   constexpr int HH = HD / 2;
-  constexpr int kMathThreads = 256;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   if (static_cast<int>(smem - smem_raw) + S::kTotal > smem_bytes) __trap();
@@ -848,9 +903,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint64_t* p_bar = bars + 4;       // [2] P, dS of a tile are in smem (and S/dP TMEM has been consumed)
   uint64_t* g_bar = bars + 6;       // [2] dV, dK, dQ MMAs of a tile have retired
   uint64_t* dkv_bar = bars + 8;     // the math warps have drained dK/dV of an item from TMEM
-  uint64_t* item_bar = bars + 9;    // the query-tile range of an item has been published
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
-  int* s_qhi = reinterpret_cast<int*>(bars + 11);  // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rep = H / Hk;
@@ -863,6 +916,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dq);
+    tma_prefetch_desc(&tm_dkv);
     mbar_init(kv_bar, 1);
     mbar_init(&q_bar[0], 1);
     mbar_init(&q_bar[1], 1);
@@ -872,7 +926,6 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(&g_bar[0], 1);
     mbar_init(&g_bar[1], 1);
     mbar_init(dkv_bar, 8);
-    mbar_init(item_bar, 1);
     fence_mbar_init();
   }
   if (warp == 0) {
@@ -895,82 +948,101 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   };
 
   if (warp == 8) {
-    // ================================================================= TMA + MMA warp (one lane)
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
-      constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD, true, true);
-      constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, false, true);
-      int g = 0;  // global tile counter: buffer = g & 1, barrier phase = (g >> 1) & 1
-      int n_it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
-        int kvb, kvh, b;
-        decode(item, kvb, kvh, b);
-        // query-tile range of this item
-        int hi_pos = T - 1;
-        const int kv_last = min(T - 1, kvb * BKV + BKV - 1);
-        if (window > 0) hi_pos = min(hi_pos, kv_last + window - 1);
-        if (seg_start) hi_pos = min(hi_pos, upper_bound_i32(seg_start + (size_t)b * T, T, kv_last) - 1);
-        const int qb_lo = kvb, qb_hi = min(hi_pos / BQ, nqb_total - 1);
-        const int nq = qb_hi - qb_lo + 1, niter = nq * rep;
-        s_qhi[n_it & 1] = qb_hi;
-        mbar_arrive(item_bar);
-        auto load_q = [&](int it2, int gg) {
-          const int nb = gg & 1;
-          const int nh = kvh * rep + it2 / nq, nq0 = (qb_lo + it2 % nq) * BQ;
+    // ================================================================= TMA + MMA warp
+    // All 32 lanes run the control flow (so addresses and descriptors stay warp-uniform, i.e. in uniform registers);
+    // only the elected lane issues TMA / tcgen05 instructions and barrier transactions.
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD, true, true);
+    constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, false, true);
+    const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+    int g = 0;  // global tile counter: buffer = g & 1, barrier phase = (g >> 1) & 1
+    int n_it = 0;
+    // last query tile of an item (table written by attn_delta_kernel); fetched one item ahead
+    auto item_qhi = [&](int item) {
+      int kvb, kvh, b;
+      decode(item, kvb, kvh, b);
+      return qhi_tab[b * nqb_total + kvb];
+    };
+    int nx_qhi = blockIdx.x < n_items ? item_qhi(blockIdx.x) : 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
+      int kvb, kvh, b;
+      decode(item, kvb, kvh, b);
+      const int qb_lo = kvb, qb_hi = nx_qhi;
+      const int nq = qb_hi - qb_lo + 1, niter = nq * rep;
+      if (item + gridDim.x < n_items) nx_qhi = item_qhi(item + gridDim.x);
+      // (head, query tile) of the tile to load next, advanced incrementally
+      int ld_h = kvh * rep, ld_q = qb_lo;
+      auto load_q = [&](int gg) {
+        const int nb = gg & 1;
+        if (leader) {
           mbar_expect_tx(&q_bar[nb], 2 * C::TILE_BYTES);
-          tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], nh * HD, nq0, b);
-          tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], nh * HD, nq0, b);
-        };
-        auto issue_scores = [&](int gg) {
-          const int nb = gg & 1;
-          const uint32_t q_s = smem_u32(smem + S::kQ + nb * C::TILE_BYTES), do_s = smem_u32(smem + S::kdO + nb * C::TILE_BYTES);
-          mbar_wait(&q_bar[nb], (gg >> 1) & 1);
-          tc_fence_after();
+          tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], ld_h * HD, ld_q * BQ, b);
+          tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], ld_h * HD, ld_q * BQ, b);
+        }
+        if (++ld_q > qb_hi) {
+          ld_q = qb_lo;
+          ++ld_h;
+        }
+      };
+      auto issue_scores = [&](int gg) {
+        const int nb = gg & 1;
+        const uint32_t q_s = smem_u32(smem + S::kQ + nb * C::TILE_BYTES), do_s = smem_u32(smem + S::kdO + nb * C::TILE_BYTES);
+        mbar_wait(&q_bar[nb], (gg >> 1) & 1);
+        tc_fence_after();
+        if (leader) {
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks)
-            umma_bf16(tS, C::kmajor(q_s, ks), C::kmajor(smem_u32(sK), ks), idesc_s, ks > 0);
+            umma_bf16(tS, C::kmajor(q_s, ks), C::kmajor(sK_u, ks), idesc_s, ks > 0);
 #pragma unroll
           for (int ks = 0; ks < HD / 16; ++ks)
-            umma_bf16(tdP, C::kmajor(do_s, ks), C::kmajor(smem_u32(sV), ks), idesc_s, ks > 0);
+            umma_bf16(tdP, C::kmajor(do_s, ks), C::kmajor(sV_u, ks), idesc_s, ks > 0);
           umma_commit(s_bar);
-        };
-        // K, V (their smem was released when the previous item's last gradient MMAs retired, see below)
+        }
+        __syncwarp();
+      };
+      // K, V (their smem was released when the previous item's last gradient MMAs retired, see below)
+      if (leader) {
         mbar_expect_tx(kv_bar, 2 * C::TILE_BYTES);
         tma_tile<HD>(sK, &tm_qkv, kv_bar, (H + kvh) * HD, kvb * BKV, b);
         tma_tile<HD>(sV, &tm_qkv, kv_bar, (H + Hk + kvh) * HD, kvb * BKV, b);
-        load_q(0, g);
-        mbar_wait(kv_bar, n_it & 1);
-        issue_scores(g);
-        for (int it = 0; it < niter; ++it, ++g) {
-          const int buf = g & 1;
-          if (it + 1 < niter) {
-            // (Q, dO) buffer of tile it+1 was last read by the gradient MMAs of tile it-1
-            if (it >= 1) mbar_wait(&g_bar[buf ^ 1], ((g - 1) >> 1) & 1);
-            load_q(it + 1, g + 1);
-          }
-          mbar_wait(&p_bar[buf], (g >> 1) & 1);  // P, dS of tile `it` are in smem; S/dP TMEM is free
+      }
+      load_q(g);
+      mbar_wait(kv_bar, n_it & 1);
+      issue_scores(g);
+      for (int it = 0; it < niter; ++it, ++g) {
+        const int buf = g & 1;
+        if (it + 1 < niter) {
+          // (Q, dO) buffer of tile it+1 was last read by the gradient MMAs of tile it-1
+          if (it >= 1) mbar_wait(&g_bar[buf ^ 1], ((g - 1) >> 1) & 1);
+          load_q(g + 1);
+        }
+        mbar_wait(&p_bar[buf], (g >> 1) & 1);  // P, dS of tile `it` are in smem; S/dP TMEM is free
+        tc_fence_after();
+        if (it + 1 < niter) issue_scores(g + 1);  // scores first: the math warps can start on tile it+1
+        if (it == 0 && n_it > 0) {  // dK/dV accumulators still hold the previous item until the math warps drain them
+          mbar_wait(dkv_bar, (n_it - 1) & 1);
           tc_fence_after();
-          if (it + 1 < niter) issue_scores(g + 1);  // scores first: the math warps can start on tile it+1
-          if (it == 0 && n_it > 0) {  // dK/dV accumulators still hold the previous item until the math warps drain them
-            mbar_wait(dkv_bar, (n_it - 1) & 1);
-            tc_fence_after();
-          }
-          const uint32_t sP = smem_u32(smem + S::kP + buf * kPTileBytes), sdS = smem_u32(smem + S::kdS + buf * kPTileBytes);
-          const uint32_t sQ = smem_u32(smem + S::kQ + buf * C::TILE_BYTES), sdO = smem_u32(smem + S::kdO + buf * C::TILE_BYTES);
+        }
+        const uint32_t sP = smem_u32(smem + S::kP + buf * kPTileBytes), sdS = smem_u32(smem + S::kdS + buf * kPTileBytes);
+        const uint32_t sQ = smem_u32(smem + S::kQ + buf * C::TILE_BYTES), sdO = smem_u32(smem + S::kdO + buf * C::TILE_BYTES);
+        const uint32_t acc = it > 0;
+        if (leader) {
 #pragma unroll
           for (int ks = 0; ks < BQ / 16; ++ks)  // dV[kv,hd] += Pᵀ[kv,q] dO[q,hd]
-            umma_bf16(tdV, ptile_mnmajor(sP, ks), C::mnmajor(sdO, ks), idesc_kv, (it > 0) || (ks > 0));
+            umma_bf16(tdV, ptile_mnmajor(sP, ks), C::mnmajor(sdO, ks), idesc_kv, acc || (ks > 0));
 #pragma unroll
           for (int ks = 0; ks < BQ / 16; ++ks)  // dK[kv,hd] += dSᵀ[kv,q] Q[q,hd]
-            umma_bf16(tdK, ptile_mnmajor(sdS, ks), C::mnmajor(sQ, ks), idesc_kv, (it > 0) || (ks > 0));
+            umma_bf16(tdK, ptile_mnmajor(sdS, ks), C::mnmajor(sQ, ks), idesc_kv, acc || (ks > 0));
 #pragma unroll
           for (int ks = 0; ks < BKV / 16; ++ks)  // dQ[q,hd] = dS[q,kv] K[kv,hd]
-            umma_bf16(tdQ0 + buf * HD, ptile_kmajor(sdS, ks), C::mnmajor(smem_u32(sK), ks), idesc_q, ks > 0);
+            umma_bf16(tdQ0 + buf * HD, ptile_kmajor(sdS, ks), C::mnmajor(sK_u, ks), idesc_q, ks > 0);
           umma_commit(&g_bar[buf]);
         }
-        // K/V smem (and both Q/dO buffers) are free once the last gradient MMAs have retired
-        mbar_wait(&g_bar[(g - 1) & 1], ((g - 1) >> 1) & 1);
+        __syncwarp();
       }
+      // K/V smem (and both Q/dO buffers) are free once the last gradient MMAs have retired
+      mbar_wait(&g_bar[(g - 1) & 1], ((g - 1) >> 1) & 1);
     }
   } else {
     // ================================================================= math warps
@@ -985,11 +1057,14 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int buf = gg & 1;
       mbar_wait(&g_bar[buf], (gg >> 1) & 1);
       tc_fence_after();
-      uint8_t* stage = smem + S::kP + buf * kPTileBytes;
+      // staging = the 4 KB of the P tile that THIS warp writes (atom `half`, rows 32*(warp&3)..): no other warp's
+      // P stores can touch it, so only the issuing thread's own read-completion wait orders its reuse
+      uint8_t* stage = smem + S::kP + buf * kPTileBytes + half * 16384 + (warp & 3) * 4096;
       const uint32_t tq = tdQ0 + buf * HD + lane_base + half * HH;
       if constexpr (S::kTmaDq) {
         constexpr int BC = S::kdQBoxCols, BOX_BYTES = 32 * BC * 4, ROWB = BC * 4;
-        uint8_t* wbase = stage + warp * BOX_BYTES;
+        static_assert(BOX_BYTES <= 4096, "per-warp dQ staging");
+        uint8_t* wbase = stage;
         uint32_t rq[HH];
 #pragma unroll
         for (int c0 = 0; c0 < HH; c0 += 8) tmem_ld8(tq + c0, *reinterpret_cast<uint32_t(*)[8]>(&rq[c0]));
@@ -1009,12 +1084,11 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                   reinterpret_cast<uint64_t>(&tm_dq)),
               "r"(smem_u32(wbase)), "r"(half * HH), "r"(q0 + (warp & 3) * 32), "r"(b * H + hq)
               : "memory");
-          bulk_commit();
-          bulk_wait_read0();  // the staging aliases a P buffer that the next-but-one tile rewrites
+          bulk_commit();  // read completion is awaited at the top of the next tile (the staging aliases a P buffer)
         }
-        __syncwarp();
       } else {
-        uint8_t* myrow = stage + row * S::kdQRow + half * (HH * 4);
+        static_assert(32 * HH * 4 <= 4096 && (HH * 4) % 16 == 0, "per-warp dQ staging");
+        uint8_t* myrow = stage + lane * (HH * 4);
 #pragma unroll
         for (int c0 = 0; c0 < HH; c0 += 8) {
           uint32_t r[8];
@@ -1032,10 +1106,24 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                        : "memory");
         }
         bulk_commit();
-        bulk_wait_read0();
       }
       tc_fence_before();
     };
+
+    // row statistics of the first tile of an item and its query-tile range, fetched one item ahead
+    float nx_lse = 0.f, nx_dl = 0.f;
+    int nx_ss = 0, nx_qhi = 0;
+    auto prefetch_item = [&](int item) {
+      int kvb, kvh, b;
+      decode(item, kvb, kvh, b);
+      const int i0 = kvb * BQ + row;
+      const size_t st0 = ((size_t)b * H + kvh * rep) * T + (i0 < T ? i0 : 0);
+      nx_qhi = qhi_tab[b * nqb_total + kvb];
+      nx_lse = i0 < T ? lse[st0] : 0.f;
+      nx_dl = i0 < T ? delta[st0] : 0.f;
+      nx_ss = (seg_start && i0 < T) ? seg_start[(size_t)b * T + i0] : 0;
+    };
+    if (blockIdx.x < n_items) prefetch_item(blockIdx.x);
 
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
       int kvb, kvh, b;
@@ -1043,39 +1131,32 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int kv0 = kvb * BKV;
       const int kcol = (H + kvh) * HD, vcol = (H + Hk + kvh) * HD;
       const int32_t* ssb = seg_start ? seg_start + (size_t)b * T : nullptr;
-      mbar_wait(item_bar, n_it & 1);
-      const int qb_lo = kvb, qb_hi = s_qhi[n_it & 1];
+      const int qb_lo = kvb, qb_hi = nx_qhi;
       const int nq = qb_hi - qb_lo + 1, niter = nq * rep;
-
-      float nx_lse = 0.f, nx_dl = 0.f;
-      int nx_ss = 0;
-      {
-        const int i0 = qb_lo * BQ + row;
-        const size_t st0 = ((size_t)b * H + kvh * rep) * T + (i0 < T ? i0 : 0);
-        nx_lse = i0 < T ? lse[st0] : 0.f;
-        nx_dl = i0 < T ? delta[st0] : 0.f;
-        nx_ss = (ssb && i0 < T) ? ssb[i0] : 0;
-      }
       int prev_hq = 0, prev_q0 = 0;
+      int hq = kvh * rep, qb = qb_lo;  // (head, query tile) of tile `it`, advanced incrementally
       for (int it = 0; it < niter; ++it, ++g) {
         const int buf = g & 1;
-        const int hq = kvh * rep + it / nq;
-        const int q0 = (qb_lo + it % nq) * BQ;
+        const int q0 = qb * BQ;
         const int i = q0 + row;
         const bool row_ok = i < T;
         const float lse2 = nx_lse * kLog2e, dl = nx_dl;
         int jlo = row_ok ? nx_ss : 0x3fffffff;
         if (window > 0) jlo = max(jlo, i - window + 1);
         if (it + 1 < niter) {
-          const int nh = kvh * rep + (it + 1) / nq, ni = (qb_lo + (it + 1) % nq) * BQ + row;
+          const int nh = qb < qb_hi ? hq : hq + 1, ni = (qb < qb_hi ? qb + 1 : qb_lo) * BQ + row;
           const size_t st2 = ((size_t)b * H + nh) * T + (ni < T ? ni : 0);
           nx_lse = ni < T ? lse[st2] : 0.f;
           nx_dl = ni < T ? delta[st2] : 0.f;
           nx_ss = (ssb && ni < T) ? ssb[ni] : 0;
+        } else if (item + gridDim.x < n_items) {
+          prefetch_item(item + gridDim.x);
         }
         const bool need_mask = !row_ok || (kv0 + BKV - 1 > i) || (kv0 < jlo);
-        // every warp has finished the dQ write-out that used this P buffer as staging (two tiles ago)
-        named_bar_sync(1, kMathThreads);
+        // the dQ write-out issued during the previous tile staged in the part of the P buffer this warp is about to
+        // rewrite: the issuing threads wait until their reduce-adds have read the smem
+        bulk_wait_read0();
+        __syncwarp();
         mbar_wait(s_bar, s_phase);
         s_phase ^= 1;
         tc_fence_after();
@@ -1143,14 +1224,19 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         if (it >= 1) dq_phase(g - 1, prev_hq, prev_q0, b);
         prev_hq = hq;
         prev_q0 = q0;
+        if (++qb > qb_hi) {
+          qb = qb_lo;
+          ++hq;
+        }
       }
       dq_phase(g - 1, prev_hq, prev_q0, b);  // also waits for the last gradient MMAs of the item
 
-      // dK (scaled) and dV -> bf16 into the k / v column blocks of dqkv (TMEM lane = kv row)
+      // dK (scaled) and dV -> bf16 into the k / v column blocks of dqkv (TMEM lane = kv row).  Staged in this warp's
+      // own 4 KB of dS buffer 0 (free: every gradient MMA of the item has retired) and written by two TMA stores,
+      // which clip the rows past T.
       {
-        const int j = kv0 + row;
-        __nv_bfloat16* gk = dqkv + ((size_t)b * T + min(j, T - 1)) * W + kcol + half * HH;
-        __nv_bfloat16* gv = dqkv + ((size_t)b * T + min(j, T - 1)) * W + vcol + half * HH;
+        constexpr int ROWB = HH * 2;  // bytes per staged row: 64 / 32 -> TMA swizzle of that span, else none
+        uint8_t* stg = smem + S::kdS + half * 16384 + (warp & 3) * 4096;
         uint32_t rka[HH], rva[HH];
 #pragma unroll
         for (int c0 = 0; c0 < HH; c0 += 8) {
@@ -1161,27 +1247,36 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(dkv_bar);  // the accumulators may be overwritten by the next item
-        if (j < T) {
+        const int sw = ROWB == 64 ? ((lane >> 1) & 3) : (ROWB == 32 ? ((lane >> 2) & 1) : 0);
+        const uint32_t rowk = smem_u32(stg + lane * ROWB), rowv = rowk + 32 * ROWB;
 #pragma unroll
-          for (int c0 = 0; c0 < HH; c0 += 8) {
-            const uint32_t* rk = &rka[c0];
-            const uint32_t* rv = &rva[c0];
-            uint4 a, c;
-            a.x = pack_bf16(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale);
-            a.y = pack_bf16(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale);
-            a.z = pack_bf16(__uint_as_float(rk[4]) * scale, __uint_as_float(rk[5]) * scale);
-            a.w = pack_bf16(__uint_as_float(rk[6]) * scale, __uint_as_float(rk[7]) * scale);
-            c.x = pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]));
-            c.y = pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]));
-            c.z = pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]));
-            c.w = pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7]));
-            *reinterpret_cast<uint4*>(gk + c0) = a;
-            *reinterpret_cast<uint4*>(gv + c0) = c;
-          }
+        for (int c0 = 0; c0 < HH; c0 += 8) {
+          const uint32_t* rk = &rka[c0];
+          const uint32_t* rv = &rva[c0];
+          const uint32_t off = static_cast<uint32_t>(((c0 >> 3) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowk + off),
+                       "r"(pack_bf16(__uint_as_float(rk[0]) * scale, __uint_as_float(rk[1]) * scale)),
+                       "r"(pack_bf16(__uint_as_float(rk[2]) * scale, __uint_as_float(rk[3]) * scale)),
+                       "r"(pack_bf16(__uint_as_float(rk[4]) * scale, __uint_as_float(rk[5]) * scale)),
+                       "r"(pack_bf16(__uint_as_float(rk[6]) * scale, __uint_as_float(rk[7]) * scale))
+                       : "memory");
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowv + off),
+                       "r"(pack_bf16(__uint_as_float(rv[0]), __uint_as_float(rv[1]))),
+                       "r"(pack_bf16(__uint_as_float(rv[2]), __uint_as_float(rv[3]))),
+                       "r"(pack_bf16(__uint_as_float(rv[4]), __uint_as_float(rv[5]))),
+                       "r"(pack_bf16(__uint_as_float(rv[6]), __uint_as_float(rv[7])))
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {  // read completion is awaited (by this lane) before the warp next writes its dS rows
+          tma_store_3d(&tm_dkv, smem_u32(stg), kcol + half * HH, kv0 + (warp & 3) * 32, b);
+          tma_store_3d(&tm_dkv, smem_u32(stg) + 32 * ROWB, vcol + half * HH, kv0 + (warp & 3) * 32, b);
+          bulk_commit();
         }
       }
     }
-    bulk_wait_read0();
+    bulk_wait_read0();  // every thread that issued reduce-adds drains its own groups before the smem goes away
   }
   tc_fence_before();
   __syncthreads();
@@ -1194,19 +1289,21 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 // dq (fp32 [B,H,T,hd]) * scale -> bf16 into the q column block of dqkv
 __global__ void attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfloat16* __restrict__ dqkv, int B, int T,
                                        int H, int hd, int W, float scale) {
-  const int hd4 = hd >> 2;
-  const long long total = (long long)B * H * T * hd4;
+  const int hd8 = hd >> 3;
+  const long long total = (long long)B * H * T * hd8;
   for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
        e += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(e % hd4);
-    long long r = e / hd4;
+    const int c8 = (int)(e % hd8);
+    long long r = e / hd8;
     const int t = (int)(r % T);
     r /= T;
     const int h = (int)(r % H);
     const int b = (int)(r / H);
-    const float4 v = reinterpret_cast<const float4*>(dq_ws)[e];
-    uint2 o = make_uint2(pack_bf16(v.x * scale, v.y * scale), pack_bf16(v.z * scale, v.w * scale));
-    *reinterpret_cast<uint2*>(dqkv + ((size_t)b * T + t) * W + h * hd + c4 * 4) = o;
+    const float4 v = reinterpret_cast<const float4*>(dq_ws)[2 * e];
+    const float4 w = reinterpret_cast<const float4*>(dq_ws)[2 * e + 1];
+    const uint4 o = make_uint4(pack_bf16(v.x * scale, v.y * scale), pack_bf16(v.z * scale, v.w * scale),
+                               pack_bf16(w.x * scale, w.y * scale), pack_bf16(w.z * scale, w.w * scale));
+    *reinterpret_cast<uint4*>(dqkv + ((size_t)b * T + t) * W + h * hd + c8 * 8) = o;
   }
 }
 
@@ -1265,6 +1362,7 @@ __global__ void attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const i
 }
 
 inline size_t delta_floats(int B, int T, int H) { return ((size_t)B * H * T + 63) / 64 * 64; }
+inline size_t qhi_floats(int B, int T) { return ((size_t)B * ((T + BKV - 1) / BKV) + 63) / 64 * 64; }
 
 int make_qkv_tmap(CUtensorMap* tm, const void* base, int B, int T, int W, int aw) {
   const uint64_t dims[3] = {(uint64_t)W, (uint64_t)T, (uint64_t)B};
@@ -1305,7 +1403,8 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   rc = make_qkv_tmap(&td, dout, B, T, H * HD, HeadCfg<HD>::AW);
   if (rc) return rc;
   float* delta = reinterpret_cast<float*>(ws);
-  float* dq_ws = delta + delta_floats(B, T, H);  // 256-byte aligned: bulk reduce-adds and float4 reads need 16
+  int* qhi_tab = reinterpret_cast<int*>(delta + delta_floats(B, T, H));
+  float* dq_ws = delta + delta_floats(B, T, H) + qhi_floats(B, T);  // 256-byte aligned: bulk reduce-adds need 16
   CUtensorMap tdq;
   memset(&tdq, 0, sizeof(tdq));
   if (S::kTmaDq) {
@@ -1315,12 +1414,28 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     rc = make_tmap_f32(&tdq, dq_ws, 3, dims, str, box, S::kdQBoxCols * 4);
     if (rc) return rc;
   }
+  CUtensorMap tdkv;  // dK / dV stores of the warp-specialised kernel: [hd/2 columns x 32 rows] boxes of dqkv
+  memset(&tdkv, 0, sizeof(tdkv));
+  if constexpr (HD <= 64) {
+    const uint64_t dims[3] = {(uint64_t)W, (uint64_t)T, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)W * 2, (uint64_t)T * W * 2};
+    const uint32_t box[3] = {(uint32_t)(HD / 2), 32u, 1u};
+    rc = make_tmap_bf16(&tdkv, dqkv, 3, dims, str, box, HD);  // swizzle span = row bytes (64 / 32) or none
+    if (rc) return rc;
+  }
   CGPT_CHECK(cudaMemsetAsync(dq_ws, 0, (size_t)B * H * T * HD * sizeof(float), st));
   {
-    const long long warps = (long long)B * T * H;
-    attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(out),
-                                                                   reinterpret_cast<const __nv_bfloat16*>(dout), delta, B,
-                                                                   T, H, HD);
+    const __nv_bfloat16* po = reinterpret_cast<const __nv_bfloat16*>(out);
+    const __nv_bfloat16* pd = reinterpret_cast<const __nv_bfloat16*>(dout);
+    constexpr int G = HD / 8;
+    if constexpr (G == 2 || G == 4 || G == 8 || G == 16) {
+      const long long chunks = (long long)B * T * H * G;  // >= B * kv tiles, so the table job fits too
+      attn_delta_vec_kernel<G><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(po, pd, delta, B, T, H, seg, window,
+                                                                               qhi_tab);
+    } else {
+      const long long warps = (long long)B * T * H;
+      attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(po, pd, delta, B, T, H, HD, seg, window, qhi_tab);
+    }
     count_launch();
     CGPT_LAUNCH_CHECK();
   }
@@ -1334,7 +1449,7 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
       CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SW::kDynamic));
       configured = true;
     }
-    kern<<<grid, 288, SW::kDynamic, st>>>(tq, td, tdq, seg, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, B,
+    kern<<<grid, 288, SW::kDynamic, st>>>(tq, td, tdq, tdkv, seg, qhi_tab, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, B,
                                           T, H, Hk, window, scale, drop, SW::kDynamic);
   } else {
     auto kern = attn_bwd_kernel<HD>;
@@ -1349,7 +1464,7 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   count_launch();
   CGPT_LAUNCH_CHECK();
   {
-    const long long n = (long long)B * H * T * (HD / 4);
+    const long long n = (long long)B * H * T * (HD / 8);
     long long g = (n + 255) / 256;
     if (g > (long long)num_sms() * 8) g = (long long)num_sms() * 8;
     attn_dq_convert_kernel<<<(unsigned)g, 256, 0, st>>>(dq_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), B, T, H, HD, W,
@@ -1400,7 +1515,8 @@ int cgpt_attn_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, in
 
 int64_t cgpt_attn_bwd_workspace(int B, int T, int H, int Hk, int hd) {
   (void)Hk;
-  return (int64_t)sizeof(float) * ((int64_t)cgpt::delta_floats(B, T, H) + (int64_t)B * H * T * hd);
+  return (int64_t)sizeof(float) *
+         ((int64_t)cgpt::delta_floats(B, T, H) + (int64_t)cgpt::qhi_floats(B, T) + (int64_t)B * H * T * hd);
 }
 
 int cgpt_attn_bwd(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse, void* dqkv,
