@@ -72,6 +72,31 @@ def _wgrad(dy: torch.Tensor, x: torch.Tensor, n_out: int, k_in: int, dy_ld=None,
     return dw
 
 
+def _wgrad_into(dy: torch.Tensor, x: torch.Tensor, n_out: int, k_in: int, dw: torch.Tensor):
+    """dw[n_out, k_in] += dyᵀ · x into an existing fp32 matrix (split-K over the tokens)."""
+    Mtok = x.shape[0]
+    tiles = ((n_out + 127) // 128) * ((k_in + 255) // 256)
+    split = ops.pick_split_k(tiles, (Mtok + 63) // 64, _SMS)
+    ops.gemm(dy, x, dw, M=n_out, N=k_in, K=Mtok, a_mn=True, b_mn=True, lda=dy.stride(0), ldb=x.stride(0), ldc=k_in,
+             accumulate=True, split_k=split)
+
+
+def _packed_slots(masters, rows):
+    """main_grad slots of `masters` when all exist, lie back to back in memory and cover `rows` without gaps."""
+    slots = [_main_grad(m) for m in masters]
+    if not slots or any(s is None for s in slots):
+        return None
+    r = 0
+    for s, (r0, n) in zip(slots, rows):
+        if r0 != r or s.shape[0] != n:
+            return None
+        r += n
+    for a, b in zip(slots[:-1], slots[1:]):
+        if a.data_ptr() + a.numel() * a.element_size() != b.data_ptr():
+            return None
+    return slots
+
+
 def _colsum(dy: torch.Tensor, n: int, master=None, off: int = 0):
     mg = _main_grad(master)
     out = mg if mg is not None else torch.zeros((n,), dtype=f32, device=dy.device)
@@ -187,14 +212,31 @@ class PackedLinearFn(Function):
             ops.gemm(gb, w_sh, dx, M=M, N=K, K=N, b_mn=True)
         nw = len(ctx.rows)
         grads: List[Optional[torch.Tensor]] = []
-        for i, ((r0, n), k_in) in enumerate(zip(ctx.rows, ctx.k_in)):
-            grads.append(_wgrad(gb, x, n, k_in, dy_off=r0, master=ctx.masters[i]))
+        # gradient slots that sit back to back in the flat buffer (trainer._packed_order) form one [N, K] matrix:
+        # one wgrad GEMM / one column sum instead of one per nn.Linear
+        w_slots = _packed_slots(ctx.masters[:nw], ctx.rows)
+        if nw > 1 and w_slots is not None and len(set(ctx.k_in)) == 1:
+            packed = torch.as_strided(w_slots[0], (N, K), (K, 1))
+            _wgrad_into(gb, x, N, K, packed)
+            for m in ctx.masters[:nw]:
+                _done(m)
+            grads.extend([None] * nw)
+        else:
+            for i, ((r0, n), k_in) in enumerate(zip(ctx.rows, ctx.k_in)):
+                grads.append(_wgrad(gb, x, n, k_in, dy_off=r0, master=ctx.masters[i]))
         if ctx.has_bias:
-            for i, (r0, n) in enumerate(ctx.rows):
-                if gsum is not None and nw == 1:
-                    grads.append(_bias_grad(gb, n, ctx.masters[nw + i], gsum))
-                else:
-                    grads.append(_colsum(gb, n, master=ctx.masters[nw + i], off=r0))
+            b_slots = _packed_slots(ctx.masters[nw:], ctx.rows)
+            if nw > 1 and b_slots is not None:
+                ops.colsum_bf16(gb, torch.as_strided(b_slots[0], (N,), (1,)), N=N, ld=gb.stride(0))
+                for m in ctx.masters[nw:]:
+                    _done(m)
+                grads.extend([None] * nw)
+            else:
+                for i, (r0, n) in enumerate(ctx.rows):
+                    if gsum is not None and nw == 1:
+                        grads.append(_bias_grad(gb, n, ctx.masters[nw + i], gsum))
+                    else:
+                        grads.append(_colsum(gb, n, master=ctx.masters[nw + i], off=r0))
         return (dx, None, None, g if ctx.has_res else None, None, None, *grads)
 
 

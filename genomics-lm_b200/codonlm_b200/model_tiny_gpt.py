@@ -172,6 +172,28 @@ def bump_shadow_generation():
     _SHADOW_GEN[0] += 1
 
 
+def flat_shadow(p):
+    """bf16 view of parameter `p` inside the trainer's flat shadow buffer (trainer.FlatGroup), or None when the
+    model is not driven by TrainStep.  The fused AdamW kernel keeps it current; a master that was written through
+    autograd-visible ops since (load_state_dict, manual edits: its _version moved) is re-cast here."""
+    sh = getattr(p, "_cgpt_shadow", None)
+    if sh is None or not p.is_cuda:
+        return None
+    if p._version != p._cgpt_shadow_version:
+        with torch.no_grad():
+            ops.cast_bf16(p.detach().reshape(1, -1), out=sh.view(1, -1))
+        p._cgpt_shadow_version = p._version
+    return sh
+
+
+def _adjacent(tensors):
+    """True when the tensors sit back to back in memory (same dtype), i.e. form one packed row-major matrix."""
+    for a, b in zip(tensors[:-1], tensors[1:]):
+        if a.dtype != b.dtype or a.data_ptr() + a.numel() * a.element_size() != b.data_ptr():
+            return False
+    return True
+
+
 class _ShadowMixin:
     """bf16 (and packed) copies of the fp32 master parameters, rebuilt when a master changes."""
 
@@ -238,8 +260,10 @@ class GeluMLP(nn.Sequential, _ShadowMixin):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
-        w1, w2 = self._get_shadow("mlp", (fc1.weight, fc2.weight),
-                                  lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
+        w1, w2 = flat_shadow(fc1.weight), flat_shadow(fc2.weight)
+        if w1 is None or w2 is None:
+            w1, w2 = self._get_shadow("mlp", (fc1.weight, fc2.weight),
+                                      lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
         r2 = None if residual is None else residual.reshape(-1, shp[-1])
         drop = self.training and self[3].p > 0.0
         out = Fn.MlpGeluFn.apply(xb.contiguous(), None if drop else r2, w1, fc1.bias, w2, fc2.bias, fc1.weight,
@@ -268,8 +292,20 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
         self.rotary_emb = RotaryEmbedding(dim=head_dim, max_position_embeddings=block_size) if use_rope else None
         self.last_attn = None
 
+    def packed_param_groups(self):
+        """Parameters evaluated as one packed operand, in packed row order (trainer._packed_order)."""
+        return [(self.query.weight, self.key.weight, self.value.weight),
+                (self.query.bias, self.key.bias, self.value.bias)]
+
     def _shadows(self):
         q, k, v = self.query, self.key, self.value
+        ws = [flat_shadow(m.weight) for m in (q, k, v)]
+        wp = flat_shadow(self.proj.weight)
+        bs = [q.bias.data, k.bias.data, v.bias.data]
+        if wp is not None and all(w is not None for w in ws) and _adjacent(ws) and _adjacent(bs):
+            # the three slices of the flat buffers already ARE the packed operands
+            n, d = sum(w.shape[0] for w in ws), ws[0].shape[1]
+            return torch.as_strided(ws[0], (n, d), (d, 1)), torch.as_strided(bs[0], (n,), (1,)), wp
 
         def build():
             d = q.weight.shape[1]
@@ -360,8 +396,10 @@ class _OffsetMLP(nn.Sequential, _ShadowMixin):
         shp = x.shape
         x2 = x.reshape(-1, shp[-1])
         xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
-        w1, w2 = self._get_shadow("off", (fc1.weight, fc2.weight),
-                                  lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
+        w1, w2 = flat_shadow(fc1.weight), flat_shadow(fc2.weight)
+        if w1 is None or w2 is None:
+            w1, w2 = self._get_shadow("off", (fc1.weight, fc2.weight),
+                                      lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
         out = Fn.OffsetHeadFn.apply(xb.contiguous(), w1, fc1.bias, w2, fc2.bias, fc1.weight, fc2.weight)
         return out.view(shp)
 

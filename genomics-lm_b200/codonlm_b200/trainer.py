@@ -34,10 +34,37 @@ def split_param_groups(model) -> Dict[str, List[tuple]]:
         seen.add(id(p))
         named.append((name, p))
     named.reverse()
+    named = _packed_order(model, named)
     groups = {"head": [], "backbone": []}
     for name, p in named:
         groups["head" if any(m in name for m in HEAD_GROUP_MARKERS) else "backbone"].append((name, p))
     return groups
+
+
+def _packed_order(model, named):
+    """Parameters that a module evaluates as ONE packed operand (query|key|value weights and biases,
+    CausalSelfAttention.packed_param_groups) are made neighbours, in packed order, so that their slices of the
+    flat master / shadow / gradient buffers form one contiguous matrix: no per-step packing copies, one wgrad."""
+    packs = []
+    for m in model.modules():
+        f = getattr(m, "packed_param_groups", None)
+        if f is not None:
+            packs.extend(tuple(g) for g in f())
+    name_of = {id(p): n for n, p in named}
+    member = {}
+    for gi, g in enumerate(packs):
+        if all(id(p) in name_of for p in g):
+            for p in g:
+                member[id(p)] = gi
+    out, emitted = [], set()
+    for n, p in named:
+        gi = member.get(id(p))
+        if gi is None:
+            out.append((n, p))
+        elif gi not in emitted:
+            emitted.add(gi)
+            out.extend((name_of[id(q)], q) for q in packs[gi])
+    return out
 
 
 class FlatGroup:
@@ -58,6 +85,9 @@ class FlatGroup:
         self.grad = torch.zeros(off, dtype=torch.float32, device=dev)
         self.m = torch.zeros(off, dtype=torch.float32, device=dev)
         self.v = torch.zeros(off, dtype=torch.float32, device=dev)
+        # bf16 copy of the masters, the tensor-core operand: written by the AdamW kernel together with the master,
+        # so a training step contains no cast kernels at all (model_tiny_gpt.flat_shadow hands out views of it)
+        self.shadow = torch.zeros(off, dtype=torch.bfloat16, device=dev)
         with torch.no_grad():
             for p, o in zip(self.params, self.offsets):
                 view = self.flat[o:o + p.numel()].view_as(p)
@@ -66,6 +96,9 @@ class FlatGroup:
                 p.grad = None
                 # kernels accumulate straight into this slot (functional._main_grad); autograd never sees a grad
                 p.main_grad = self.grad[o:o + p.numel()].view_as(p)
+                p._cgpt_shadow = self.shadow[o:o + p.numel()].view_as(p)
+                p._cgpt_shadow_version = p._version
+            self.shadow.copy_(self.flat)
 
 
 class GradBuckets:
@@ -197,8 +230,8 @@ class TrainStep:
             bk.finish()
         self._push_hyper(lr_scale)
         for gi, g in enumerate(self.groups):
-            ops.adamw(g.flat, g.grad, g.m, g.v, None, g.lr * lr_scale, self.betas[0], self.betas[1], self.eps,
-                      g.weight_decay, self.step_count, gscale, dev_hyper=self._hyper[gi])
+            ops.adamw(g.flat, g.grad, g.m, g.v, g.shadow if g.shadow.is_cuda else None, g.lr * lr_scale, self.betas[0],
+                      self.betas[1], self.eps, g.weight_decay, self.step_count, gscale, dev_hyper=self._hyper[gi])
         # the kernel wrote the masters behind autograd's back: invalidate the bf16 shadow caches
         bump_shadow_generation()
 
@@ -245,7 +278,7 @@ class TrainStep:
             loss, _ = self.forward_backward(self._gx, self._gy)
             gscale = 1.0 / self.world
             for gi, g in enumerate(self.groups):
-                ops.adamw(g.flat, g.grad, g.m, g.v, None, g.lr, self.betas[0], self.betas[1], self.eps,
+                ops.adamw(g.flat, g.grad, g.m, g.v, g.shadow, g.lr, self.betas[0], self.betas[1], self.eps,
                           g.weight_decay, 1, gscale, dev_hyper=self._hyper[gi])
             self._gloss = loss
         # undo the warm-up / capture-time updates: capture must not change the training state
@@ -253,6 +286,7 @@ class TrainStep:
             g.flat.copy_(f)
             g.m.copy_(m)
             g.v.copy_(v)
+            g.shadow.copy_(f)
         self.step_count = count
         bump_shadow_generation()
         self._graph = graph

@@ -146,6 +146,46 @@ __global__ void embed_bwd_tok_kernel(const int64_t* __restrict__ idx, const floa
   }
 }
 
+// Small vocabularies (the codon table: ~68 rows): a CTA owns 32 columns and a token range; each of its 8 warps
+// keeps a PRIVATE [vocab, 32] table in shared memory (plain read-modify-write: a lane only ever touches its own
+// column, so no atomics and no contention however skewed the token histogram is) and walks every 8th token with
+// kUnroll tokens in flight, so the loop is bound by HBM rather than by one dependent load chain per token.
+constexpr int kEmbTokWarps = 8, kEmbTokUnroll = 8;
+__global__ void __launch_bounds__(kEmbTokWarps * 32)
+embed_bwd_tok_small_kernel(const int64_t* __restrict__ idx, const float* __restrict__ dx, float* __restrict__ dtok,
+                           int M, int d, int vocab, int toks_per_cta) {
+  extern __shared__ float table[];  // [warps][vocab][32]
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + lane;
+  const bool col_ok = c < d;
+  const int m0 = blockIdx.x * toks_per_cta;
+  const int m1 = min(M, m0 + toks_per_cta);
+  for (int i = threadIdx.x; i < kEmbTokWarps * vocab * 32; i += blockDim.x) table[i] = 0.f;
+  __syncthreads();
+  float* mine = table + (size_t)warp * vocab * 32 + lane;
+  for (int m = m0 + warp; m < m1; m += kEmbTokWarps * kEmbTokUnroll) {
+    int v[kEmbTokUnroll];
+    float x[kEmbTokUnroll];
+#pragma unroll
+    for (int u = 0; u < kEmbTokUnroll; ++u) {
+      const int mm = m + u * kEmbTokWarps;
+      int64_t t = mm < m1 ? idx[mm] : 0;
+      v[u] = static_cast<int>(t < 0 ? 0 : (t >= vocab ? vocab - 1 : t));
+      x[u] = (mm < m1 && col_ok) ? __ldg(dx + (size_t)mm * d + c) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < kEmbTokUnroll; ++u) mine[v[u] * 32] += x[u];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < vocab * 32; i += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < kEmbTokWarps; ++w) acc += table[(size_t)w * vocab * 32 + i];
+    const int row = i >> 5, cc = blockIdx.y * 32 + (i & 31);
+    if (cc < d && acc != 0.f) atomicAdd(dtok + (size_t)row * d + cc, acc);
+  }
+}
+
 __global__ void embed_bwd_pos_kernel(const float4* __restrict__ dx, float4* __restrict__ dpos, int B, int T,
                                      int d4) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -592,6 +632,34 @@ int cgpt_embed_bwd(const int64_t* idx, const float* dx, float* dtok_w, float* dp
   CGPT_REQUIRE(d % 4 == 0, "embed_bwd: d=%d must be a multiple of 4", d);
   const int M = B * T;
   const int max_smem = 200 * 1024;
+  if ((size_t)kEmbTokWarps * vocab * 32 * 4 <= 96 * 1024) {
+    const size_t smem = (size_t)kEmbTokWarps * vocab * 32 * 4;
+    const int col_tiles = (d + 31) / 32;
+    int per_sm = (int)((200 * 1024) / (smem + 1024));
+    if (per_sm > 4) per_sm = 4;
+    int tok_ctas = (per_sm * num_sms() + col_tiles - 1) / col_tiles;
+    if (tok_ctas > (M + 63) / 64) tok_ctas = (M + 63) / 64;
+    if (tok_ctas < 1) tok_ctas = 1;
+    const int toks = (M + tok_ctas - 1) / tok_ctas;
+    tok_ctas = (M + toks - 1) / toks;
+    static size_t configured_small = 0;
+    if (smem > 48 * 1024 && smem > configured_small) {
+      CGPT_CHECK(cudaFuncSetAttribute(embed_bwd_tok_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured_small = smem;
+    }
+    embed_bwd_tok_small_kernel<<<dim3(tok_ctas, col_tiles), kEmbTokWarps * 32, smem, ST(stream)>>>(idx, dx, dtok_w, M, d,
+                                                                                                vocab, toks);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+    if (dpos_w) {
+      const size_t n = (size_t)T * (d / 4);
+      embed_bwd_pos_kernel<<<(unsigned)((n + 127) / 128), 128, 0, ST(stream)>>>(
+          reinterpret_cast<const float4*>(dx), reinterpret_cast<float4*>(dpos_w), B, T, d / 4);
+      count_launch();
+      CGPT_LAUNCH_CHECK();
+    }
+    return 0;
+  }
   int cols = d;
   while ((size_t)vocab * cols * 4 > (size_t)max_smem) cols = (cols + 1) / 2;
   cols = (cols + 3) / 4 * 4;

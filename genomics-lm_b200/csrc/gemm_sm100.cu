@@ -41,28 +41,70 @@ struct GemmParams {
 };
 
 // gelu(x) = x*Phi(x) and gelu'(x) = Phi(x) + x*phi(x) with ONE special-function op (the exp of phi):
-// Phi(-|x|) = mills(|x|) * phi(x), mills(t) = (1-Phi(t))/phi(t) as a degree-9 polynomial on [0, 5.5]
-// fitted for relative error (1.5e-4 in fp32 Horner form, i.e. 30x below the bf16 rounding of the outputs and
-// uniform in the tails); beyond 5.5 phi underflows the result anyway.  The reciprocal of the classic
-// Abramowitz-Stegun form would double the load on the 16-lane XU pipe, which bounds this epilogue.
-__device__ __forceinline__ void gelu_and_grad(float x, float& y, float& dy) {
-  const float t = fminf(fabsf(x), 5.5f);
-  float m = fmaf(t, -1.94302522e-06f, 5.95369164e-05f);
-  m = fmaf(m, t, -0.000801238087f);
-  m = fmaf(m, t, 0.0062706394f);
-  m = fmaf(m, t, -0.0319994484f);
-  m = fmaf(m, t, 0.114027142f);
-  m = fmaf(m, t, -0.299928687f);
-  m = fmaf(m, t, 0.612206331f);
-  m = fmaf(m, t, -0.997367484f);
-  m = fmaf(m, t, 1.25322612f);
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-0.72134752f * x * x));  // exp(-x^2/2)
-  const float phi = 0.3989422804f * e;
-  const float h = m * phi;  // Phi(-|x|)
-  const float cdf = x >= 0.f ? 1.f - h : h;
-  y = x * cdf;
-  dy = fmaf(x, phi, cdf);
+// Phi(-|x|) = mills(|x|) * phi(x), mills(t) = (1-Phi(t))/phi(t) as a degree-7 polynomial on [0, 5.5] fitted for
+// relative error (6.9e-4 in fp32 Horner form: |dPhi| <= 3.3e-4, |dgelu| <= 1.1e-4, an order of magnitude below the
+// bf16 rounding of the two outputs, and uniform in the tails); beyond 5.5 phi underflows the result anyway.
+// The epilogue of the K=512 GEMMs is the long pole of those kernels (4 epilogue warps per scheduler, stalled on
+// fixed-latency dependencies), so two columns are evaluated per instruction with packed fp32
+// (FFMA2/FMUL2/FADD2), 1/sqrt(2 pi) rides in the exponent, and NP pairs advance in lock step.
+// Returns the results packed to bf16x2 (low half = first column of the pair).
+template <int NP>
+__device__ __forceinline__ void gelu_and_grad2(const uint64_t (&x)[NP], uint32_t (&y_bf)[NP], uint32_t (&dy_bf)[NP]) {
+  uint64_t t[NP], m[NP], phi[NP], cdf[NP];
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    float x0, x1;
+    f2_unpack(x[k], x0, x1);
+    t[k] = f2_pack(fminf(fabsf(x0), 5.5f), fminf(fabsf(x1), 5.5f));
+  }
+  // log2 of phi(x) = -x^2/2 * log2(e) + log2(1/sqrt(2 pi))
+#pragma unroll
+  for (int k = 0; k < NP; ++k) phi[k] = f2_mul(x[k], x[k]);
+#pragma unroll
+  for (int k = 0; k < NP; ++k) phi[k] = f2_fma(phi[k], f2_splat(-0.72134752f), f2_splat(-1.32574806f));
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    float a0, a1, e0, e1;
+    f2_unpack(phi[k], a0, a1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
+    phi[k] = f2_pack(e0, e1);
+  }
+  // m = -mills(t): the sign is folded into the coefficients so that 1/2 - Phi(-|x|) is one FMA below
+#pragma unroll
+  for (int k = 0; k < NP; ++k) m[k] = f2_fma(t[k], f2_splat(4.36487171e-05f), f2_splat(-0.00106563710f));
+#pragma unroll
+  for (int k = 0; k < NP; ++k) m[k] = f2_fma(m[k], t[k], f2_splat(0.0110329464f));
+#pragma unroll
+  for (int k = 0; k < NP; ++k) m[k] = f2_fma(m[k], t[k], f2_splat(-0.0638432875f));
+#pragma unroll
+  for (int k = 0; k < NP; ++k) m[k] = f2_fma(m[k], t[k], f2_splat(0.231174618f));
+#pragma unroll
+  for (int k = 0; k < NP; ++k) m[k] = f2_fma(m[k], t[k], f2_splat(-0.563592315f));
+#pragma unroll
+  for (int k = 0; k < NP; ++k) m[k] = f2_fma(m[k], t[k], f2_splat(0.983467042f));
+#pragma unroll
+  for (int k = 0; k < NP; ++k) m[k] = f2_fma(m[k], t[k], f2_splat(-1.25250721f));
+  // Phi(x) = 1/2 + copysign(1/2 - Phi(-|x|), x); 1/2 - h >= 0, so the sign is a plain OR
+#pragma unroll
+  for (int k = 0; k < NP; ++k) m[k] = f2_fma(m[k], phi[k], f2_splat(0.5f));
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    float q0, q1, x0, x1;
+    f2_unpack(m[k], q0, q1);
+    f2_unpack(x[k], x0, x1);
+    q0 = __uint_as_float(__float_as_uint(q0) | (__float_as_uint(x0) & 0x80000000u));
+    q1 = __uint_as_float(__float_as_uint(q1) | (__float_as_uint(x1) & 0x80000000u));
+    cdf[k] = f2_add(f2_pack(q0, q1), f2_splat(0.5f));
+  }
+#pragma unroll
+  for (int k = 0; k < NP; ++k) {
+    float y0, y1, d0, d1;
+    f2_unpack(f2_mul(x[k], cdf[k]), y0, y1);
+    f2_unpack(f2_fma(x[k], phi[k], cdf[k]), d0, d1);
+    y_bf[k] = pack_bf16(y0, y1);
+    dy_bf[k] = pack_bf16(d0, d1);
+  }
 }
 
 __device__ __forceinline__ void red_add_v4(float* p, float4 v) {
@@ -108,21 +150,30 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const CUtens
   tmem_ld_wait();
   uint32_t act[16], dact[GELU ? 16 : 1];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const uint4 bu = lds128(bias_s + j * 16);  // broadcast read
-    float v0 = __uint_as_float(r[4 * j]) + __uint_as_float(bu.x), v1 = __uint_as_float(r[4 * j + 1]) + __uint_as_float(bu.y);
-    float v2 = __uint_as_float(r[4 * j + 2]) + __uint_as_float(bu.z), v3 = __uint_as_float(r[4 * j + 3]) + __uint_as_float(bu.w);
+  for (int j = 0; j < 4; ++j) {  // 8 columns = 4 packed pairs per step
+    const uint4 b0 = lds128(bias_s + j * 32), b1 = lds128(bias_s + j * 32 + 16);  // broadcast reads
+    const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint64_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      v[e] = f2_add(f2_pack(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1])),
+                    f2_pack(__uint_as_float(bv[2 * e]), __uint_as_float(bv[2 * e + 1])));
     if constexpr (GELU) {
-      float d0, d1, d2, d3;
-      gelu_and_grad(v0, v0, d0);
-      gelu_and_grad(v1, v1, d1);
-      gelu_and_grad(v2, v2, d2);
-      gelu_and_grad(v3, v3, d3);
-      dact[2 * j] = pack_bf16(d0, d1);
-      dact[2 * j + 1] = pack_bf16(d2, d3);
+      uint32_t y4[4], d4[4];
+      gelu_and_grad2<4>(v, y4, d4);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        act[4 * j + e] = y4[e];
+        dact[4 * j + e] = d4[e];
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        float o0, o1;
+        f2_unpack(v[e], o0, o1);
+        act[4 * j + e] = pack_bf16(o0, o1);
+      }
     }
-    act[2 * j] = pack_bf16(v0, v1);
-    act[2 * j + 1] = pack_bf16(v2, v3);
   }
   const int rl_in = lane >> 2, cell = lane & 3;
 #pragma unroll
