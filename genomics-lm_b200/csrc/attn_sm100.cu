@@ -851,25 +851,28 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
 
 // ===================================================================================== backward, warp-specialised
 // hd <= 64.  Same work decomposition as attn_bwd_kernel (persistent CTA, items = (kv tile, kv head, batch)), but
-// the tensor-core work is driven by a dedicated warp so that it overlaps the CUDA-core math of the next tile:
+// the tensor-core work is driven by a dedicated warp and the (item, query tile) sequence is ONE continuous tile
+// stream: with segment masks most items see only 1-3 query tiles, so nothing may drain at an item boundary.
 //
-//   warp 8 (one lane): TMA requests, S/dP MMAs of tile i+1 issued right behind "P/dS of tile i are in smem",
-//                      then the gradient MMAs (dV, dK, dQ) of tile i — which therefore run while the 8 math warps
-//                      already work on tile i+1.
-//   warps 0..7       : S,dP (TMEM) -> P, dS (bf16, swizzled smem, double-buffered) ; then the dQ write-out of the
-//                      PREVIOUS tile (TMEM dQ is double-buffered too) through per-warp TMA reduce-adds whose
-//                      staging aliases the P buffer that tile has just released.
+//   warp 8 : warp-uniform control flow, one elected lane issues.  Runs one tile ahead with the loads and the S/dP
+//            MMAs — across item boundaries too (K/V are double-buffered, the next item's K/V are requested as soon
+//            as the previous item's last gradient MMAs have retired) — then issues the gradient MMAs (dV, dK, dQ)
+//            of the current tile, which therefore run while the math warps already work on the next one.
+//   warps 0..7 : S,dP (TMEM) -> P (single buffer, released by a commit right behind the dV MMAs), dS (double-
+//            buffered) as bf16 in swizzled smem; then the dQ write-out of the PREVIOUS tile (TMEM dQ is
+//            double-buffered) through per-warp TMA reduce-adds staged in the warp's own rows of the dS buffer that
+//            tile has released; at the end of an item dK/dV leave through TMA stores staged in the P buffer.
 //
-// TMEM (512 cols): S 128 | dP 128 | dV hd | dK hd | dQ 2*hd.   smem: K, V, 2x(Q, dO), 2x(P, dS).
+// TMEM (512 cols): S 128 | dP 128 | dV hd | dK hd | dQ 2*hd.   smem: 2x(K, V), 2x(Q, dO), P, 2x dS.
 template <int HD>
 struct BwdWsSmem {
   using C = HeadCfg<HD>;
-  static constexpr int kK = 0;
-  static constexpr int kV = kK + C::TILE_BYTES;
-  static constexpr int kQ = kV + C::TILE_BYTES;          // 2 buffers
-  static constexpr int kdO = kQ + 2 * C::TILE_BYTES;     // 2 buffers
-  static constexpr int kP = kdO + 2 * C::TILE_BYTES;     // 2 buffers
-  static constexpr int kdS = kP + 2 * kPTileBytes;       // 2 buffers
+  static constexpr int kK = 0;                            // 2 buffers
+  static constexpr int kV = kK + 2 * C::TILE_BYTES;       // 2 buffers
+  static constexpr int kQ = kV + 2 * C::TILE_BYTES;       // 2 buffers
+  static constexpr int kdO = kQ + 2 * C::TILE_BYTES;      // 2 buffers
+  static constexpr int kP = kdO + 2 * C::TILE_BYTES;      // 1 buffer
+  static constexpr int kdS = kP + kPTileBytes;            // 2 buffers
   static constexpr int kBar = kdS + 2 * kPTileBytes;
   static constexpr int kTotal = kBar + 128;
   static constexpr int kDynamic = (kTotal + 1024 <= 232448) ? kTotal + 1024 : 232448;
@@ -894,30 +897,38 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   if (static_cast<int>(smem - smem_raw) + S::kTotal > smem_bytes) __trap();
-  uint8_t* sK = smem + S::kK;
-  uint8_t* sV = smem + S::kV;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
-  uint64_t* kv_bar = bars;          // K, V of an item have landed
-  uint64_t* q_bar = bars + 1;       // [2] Q, dO of a tile have landed
-  uint64_t* s_bar = bars + 3;       // S, dP of a tile are in TMEM
-  uint64_t* p_bar = bars + 4;       // [2] P, dS of a tile are in smem (and S/dP TMEM has been consumed)
-  uint64_t* g_bar = bars + 6;       // [2] dV, dK, dQ MMAs of a tile have retired
-  uint64_t* dkv_bar = bars + 8;     // the math warps have drained dK/dV of an item from TMEM
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_bar = bars;          // [2] K, V of an item have landed (buffer = item ordinal & 1)
+  uint64_t* q_bar = bars + 2;       // [2] Q, dO of a tile have landed
+  uint64_t* s_bar = bars + 4;       // S, dP of a tile are in TMEM
+  uint64_t* p_bar = bars + 5;       // [2] P, dS of a tile are in smem (and S/dP TMEM has been consumed)
+  uint64_t* g_bar = bars + 7;       // [2] dV, dK, dQ MMAs of a tile have retired
+  uint64_t* dkv_bar = bars + 9;     // the math warps have drained dK/dV of an item from TMEM
+  uint64_t* pfree_bar = bars + 10;  // the dV MMAs of a tile have retired: the P buffer may be rewritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rep = H / Hk;
   const int W = (H + 2 * Hk) * HD;
   const int nqb_total = (T + BQ - 1) / BQ;
-  const int per_kvb = Hk * Bsz;
-  const int n_items = nqb_total * per_kvb;
+  // Work order.  An item is one kv tile of one (batch, kv head).  Items are paired (kv tile k with kv tile
+  // nkb-1-k of the same head: k+1 plus nkb-k query tiles, i.e. equal work under a causal mask) and the pairs are
+  // dealt round-robin, head-major: a CTA runs the two halves of its pair back to back, and the ~148 pairs in
+  // flight belong to a few dozen heads, so their dQ rows (fp32 reduce-add targets) and Q/dO tiles stay in L2
+  // instead of being fetched from HBM once per kv tile.
+  const int nkb = nqb_total, npk = (nkb + 1) / 2;
+  const int n_pairs = npk * Hk * Bsz;
+  const int G = gridDim.x;
+  const int n_virtual = 2 * ((n_pairs + G - 1) / G) * G;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
     tma_prefetch_desc(&tm_do);
     tma_prefetch_desc(&tm_dq);
     tma_prefetch_desc(&tm_dkv);
-    mbar_init(kv_bar, 1);
+    mbar_init(&kv_bar[0], 1);
+    mbar_init(&kv_bar[1], 1);
+    mbar_init(pfree_bar, 1);
     mbar_init(&q_bar[0], 1);
     mbar_init(&q_bar[1], 1);
     mbar_init(s_bar, 1);
@@ -940,12 +951,26 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + HD;
   const uint32_t tdQ0 = tmem_base + 256 + 2 * HD;  // + buf * HD
 
-  auto decode = [&](int item, int& kvb, int& kvh, int& b) {
-    kvb = item / per_kvb;
-    const int r = item - kvb * per_kvb;
-    kvh = r % Hk;
-    b = r / Hk;
+  // virtual item v = round * G + cta; rounds 2r and 2r+1 are the two halves of pair (cta + r * G)
+  auto decode = [&](int v, int& kvb, int& kvh, int& b) -> bool {
+    const int rnd = v / G, c = v - rnd * G;
+    const int pi = c + (rnd >> 1) * G;
+    if (pi >= n_pairs) return false;
+    const int bh = pi / npk;
+    const int kk = (pi - bh * npk + bh) % npk;  // rotated by the head index: a CTA's pairs cycle through all k
+    kvb = (rnd & 1) ? nkb - 1 - kk : kk;
+    if ((rnd & 1) && kvb == kk) return false;  // middle tile of an odd count: no partner
+    kvh = bh % Hk;
+    b = bh / Hk;
+    return true;
   };
+  auto next_item = [&](int v) {
+    int kvb, kvh, b;
+    for (v += G; v < n_virtual; v += G)
+      if (decode(v, kvb, kvh, b)) return v;
+    return -1;
+  };
+  const int first_item = blockIdx.x < n_pairs ? static_cast<int>(blockIdx.x) : -1;
 
   if (warp == 8) {
     // ================================================================= TMA + MMA warp
@@ -955,95 +980,120 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
     constexpr uint32_t idesc_kv = umma_idesc_bf16(128, HD, true, true);
     constexpr uint32_t idesc_q = umma_idesc_bf16(128, HD, false, true);
-    const uint32_t sK_u = smem_u32(sK), sV_u = smem_u32(sV);
+    const uint32_t sK_u = smem_u32(smem + S::kK), sV_u = smem_u32(smem + S::kV);  // + kvbuf * TILE_BYTES
     int g = 0;  // global tile counter: buffer = g & 1, barrier phase = (g >> 1) & 1
     int n_it = 0;
-    // last query tile of an item (table written by attn_delta_kernel); fetched one item ahead
+    // last query tile of an item (table written by the delta kernel); fetched one item ahead
     auto item_qhi = [&](int item) {
       int kvb, kvh, b;
       decode(item, kvb, kvh, b);
       return qhi_tab[b * nqb_total + kvb];
     };
-    int nx_qhi = blockIdx.x < n_items ? item_qhi(blockIdx.x) : 0;
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
+    auto load_kv = [&](int kvb, int kvh, int b, int ordinal) {
+      const int kb = ordinal & 1;
+      if (leader) {
+        mbar_expect_tx(&kv_bar[kb], 2 * C::TILE_BYTES);
+        tma_tile<HD>(smem + S::kK + kb * C::TILE_BYTES, &tm_qkv, &kv_bar[kb], (H + kvh) * HD, kvb * BKV, b);
+        tma_tile<HD>(smem + S::kV + kb * C::TILE_BYTES, &tm_qkv, &kv_bar[kb], (H + Hk + kvh) * HD, kvb * BKV, b);
+      }
+    };
+    auto load_q = [&](int gg, int head, int qb, int b) {
+      const int nb = gg & 1;
+      if (leader) {
+        mbar_expect_tx(&q_bar[nb], 2 * C::TILE_BYTES);
+        tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], head * HD, qb * BQ, b);
+        tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], head * HD, qb * BQ, b);
+      }
+    };
+    auto issue_scores = [&](int gg, int ordinal) {  // S = Q K^T, dP = dO V^T of tile gg with the K/V of item `ordinal`
+      const int nb = gg & 1, kb = ordinal & 1;
+      const uint32_t q_s = smem_u32(smem + S::kQ + nb * C::TILE_BYTES), do_s = smem_u32(smem + S::kdO + nb * C::TILE_BYTES);
+      const uint32_t k_s = sK_u + kb * C::TILE_BYTES, v_s = sV_u + kb * C::TILE_BYTES;
+      mbar_wait(&q_bar[nb], (gg >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16(tS, C::kmajor(q_s, ks), C::kmajor(k_s, ks), idesc_s, ks > 0);
+#pragma unroll
+        for (int ks = 0; ks < HD / 16; ++ks)
+          umma_bf16(tdP, C::kmajor(do_s, ks), C::kmajor(v_s, ks), idesc_s, ks > 0);
+        umma_commit(s_bar);
+      }
+      __syncwarp();
+    };
+    int nx_qhi = first_item >= 0 ? item_qhi(first_item) : 0;
+    if (first_item >= 0) {  // prologue of the stream: the first item's K/V and its first tile
+      int kvb, kvh, b;
+      decode(first_item, kvb, kvh, b);
+      load_kv(kvb, kvh, b, 0);
+      load_q(0, kvh * rep, kvb, b);
+      mbar_wait(&kv_bar[0], 0);
+      issue_scores(0, 0);
+    }
+    for (int item = first_item, nxt; item >= 0; item = nxt, ++n_it) {
       int kvb, kvh, b;
       decode(item, kvb, kvh, b);
+      nxt = next_item(item);
       const int qb_lo = kvb, qb_hi = nx_qhi;
       const int nq = qb_hi - qb_lo + 1, niter = nq * rep;
-      if (item + gridDim.x < n_items) nx_qhi = item_qhi(item + gridDim.x);
-      // (head, query tile) of the tile to load next, advanced incrementally
-      int ld_h = kvh * rep, ld_q = qb_lo;
-      auto load_q = [&](int gg) {
-        const int nb = gg & 1;
-        if (leader) {
-          mbar_expect_tx(&q_bar[nb], 2 * C::TILE_BYTES);
-          tma_tile<HD>(smem + S::kQ + nb * C::TILE_BYTES, &tm_qkv, &q_bar[nb], ld_h * HD, ld_q * BQ, b);
-          tma_tile<HD>(smem + S::kdO + nb * C::TILE_BYTES, &tm_do, &q_bar[nb], ld_h * HD, ld_q * BQ, b);
-        }
+      int nkvb = 0, nkvh = 0, nb_ = 0;
+      if (nxt >= 0) {
+        decode(nxt, nkvb, nkvh, nb_);
+        nx_qhi = item_qhi(nxt);
+      }
+      const int kb = n_it & 1;
+      int ld_h = kvh * rep, ld_q = qb_lo;  // (head, query tile) of tile `it`, advanced incrementally
+      for (int it = 0; it < niter; ++it, ++g) {
+        const int buf = g & 1;
+        const bool last = it + 1 == niter;
+        const bool has_next = !last || nxt >= 0;
         if (++ld_q > qb_hi) {
           ld_q = qb_lo;
           ++ld_h;
         }
-      };
-      auto issue_scores = [&](int gg) {
-        const int nb = gg & 1;
-        const uint32_t q_s = smem_u32(smem + S::kQ + nb * C::TILE_BYTES), do_s = smem_u32(smem + S::kdO + nb * C::TILE_BYTES);
-        mbar_wait(&q_bar[nb], (gg >> 1) & 1);
-        tc_fence_after();
-        if (leader) {
-#pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks)
-            umma_bf16(tS, C::kmajor(q_s, ks), C::kmajor(sK_u, ks), idesc_s, ks > 0);
-#pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks)
-            umma_bf16(tdP, C::kmajor(do_s, ks), C::kmajor(sV_u, ks), idesc_s, ks > 0);
-          umma_commit(s_bar);
+        if (has_next) {
+          // tile g-1 has retired: the (Q, dO) buffer of tile g+1 is free, and at the first tile of an item so are
+          // the K/V of the previous item, whose buffer the NEXT item's K/V go into
+          if (g >= 1) mbar_wait(&g_bar[buf ^ 1], ((g - 1) >> 1) & 1);
+          if (it == 0 && nxt >= 0) load_kv(nkvb, nkvh, nb_, n_it + 1);
+          if (!last)
+            load_q(g + 1, ld_h, ld_q, b);
+          else
+            load_q(g + 1, nkvh * rep, nkvb, nb_);
         }
-        __syncwarp();
-      };
-      // K, V (their smem was released when the previous item's last gradient MMAs retired, see below)
-      if (leader) {
-        mbar_expect_tx(kv_bar, 2 * C::TILE_BYTES);
-        tma_tile<HD>(sK, &tm_qkv, kv_bar, (H + kvh) * HD, kvb * BKV, b);
-        tma_tile<HD>(sV, &tm_qkv, kv_bar, (H + Hk + kvh) * HD, kvb * BKV, b);
-      }
-      load_q(g);
-      mbar_wait(kv_bar, n_it & 1);
-      issue_scores(g);
-      for (int it = 0; it < niter; ++it, ++g) {
-        const int buf = g & 1;
-        if (it + 1 < niter) {
-          // (Q, dO) buffer of tile it+1 was last read by the gradient MMAs of tile it-1
-          if (it >= 1) mbar_wait(&g_bar[buf ^ 1], ((g - 1) >> 1) & 1);
-          load_q(g + 1);
-        }
-        mbar_wait(&p_bar[buf], (g >> 1) & 1);  // P, dS of tile `it` are in smem; S/dP TMEM is free
+        mbar_wait(&p_bar[buf], (g >> 1) & 1);  // P, dS of tile g are in smem; S/dP TMEM is free
         tc_fence_after();
-        if (it + 1 < niter) issue_scores(g + 1);  // scores first: the math warps can start on tile it+1
+        if (has_next) {  // scores first: the math warps can start on the next tile
+          if (last) mbar_wait(&kv_bar[kb ^ 1], ((n_it + 1) >> 1) & 1);
+          issue_scores(g + 1, last ? n_it + 1 : n_it);
+        }
         if (it == 0 && n_it > 0) {  // dK/dV accumulators still hold the previous item until the math warps drain them
           mbar_wait(dkv_bar, (n_it - 1) & 1);
           tc_fence_after();
         }
-        const uint32_t sP = smem_u32(smem + S::kP + buf * kPTileBytes), sdS = smem_u32(smem + S::kdS + buf * kPTileBytes);
+        const uint32_t sP = smem_u32(smem + S::kP), sdS = smem_u32(smem + S::kdS + buf * kPTileBytes);
         const uint32_t sQ = smem_u32(smem + S::kQ + buf * C::TILE_BYTES), sdO = smem_u32(smem + S::kdO + buf * C::TILE_BYTES);
+        const uint32_t k_s = sK_u + kb * C::TILE_BYTES;
         const uint32_t acc = it > 0;
         if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < BQ / 16; ++ks)  // dV[kv,hd] += Pᵀ[kv,q] dO[q,hd]
+          for (int ks = 0; ks < BQ / 16; ++ks)  // dV[kv,hd] += P^T[kv,q] dO[q,hd]
             umma_bf16(tdV, ptile_mnmajor(sP, ks), C::mnmajor(sdO, ks), idesc_kv, acc || (ks > 0));
+          umma_commit(pfree_bar);  // the single P buffer is free as soon as these have retired
 #pragma unroll
-          for (int ks = 0; ks < BQ / 16; ++ks)  // dK[kv,hd] += dSᵀ[kv,q] Q[q,hd]
+          for (int ks = 0; ks < BQ / 16; ++ks)  // dK[kv,hd] += dS^T[kv,q] Q[q,hd]
             umma_bf16(tdK, ptile_mnmajor(sdS, ks), C::mnmajor(sQ, ks), idesc_kv, acc || (ks > 0));
 #pragma unroll
           for (int ks = 0; ks < BKV / 16; ++ks)  // dQ[q,hd] = dS[q,kv] K[kv,hd]
-            umma_bf16(tdQ0 + buf * HD, ptile_kmajor(sdS, ks), C::mnmajor(sK_u, ks), idesc_q, ks > 0);
+            umma_bf16(tdQ0 + buf * HD, ptile_kmajor(sdS, ks), C::mnmajor(k_s, ks), idesc_q, ks > 0);
           umma_commit(&g_bar[buf]);
         }
         __syncwarp();
       }
-      // K/V smem (and both Q/dO buffers) are free once the last gradient MMAs have retired
-      mbar_wait(&g_bar[(g - 1) & 1], ((g - 1) >> 1) & 1);
     }
+    // every MMA has retired before the CTA tears down its TMEM / smem
+    if (g >= 1) mbar_wait(&g_bar[(g - 1) & 1], ((g - 1) >> 1) & 1);
   } else {
     // ================================================================= math warps
     const int row = tid & 127, half = tid >> 7;
@@ -1057,9 +1107,9 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       const int buf = gg & 1;
       mbar_wait(&g_bar[buf], (gg >> 1) & 1);
       tc_fence_after();
-      // staging = the 4 KB of the P tile that THIS warp writes (atom `half`, rows 32*(warp&3)..): no other warp's
-      // P stores can touch it, so only the issuing thread's own read-completion wait orders its reuse
-      uint8_t* stage = smem + S::kP + buf * kPTileBytes + half * 16384 + (warp & 3) * 4096;
+      // staging = the 4 KB of the dS tile that THIS warp writes (atom `half`, rows 32*(warp&3)..): no other warp's
+      // dS stores can touch it, so only the issuing thread's own read-completion wait orders its reuse
+      uint8_t* stage = smem + S::kdS + buf * kPTileBytes + half * 16384 + (warp & 3) * 4096;
       const uint32_t tq = tdQ0 + buf * HD + lane_base + half * HH;
       if constexpr (S::kTmaDq) {
         constexpr int BC = S::kdQBoxCols, BOX_BYTES = 32 * BC * 4, ROWB = BC * 4;
@@ -1123,11 +1173,12 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       nx_dl = i0 < T ? delta[st0] : 0.f;
       nx_ss = (seg_start && i0 < T) ? seg_start[(size_t)b * T + i0] : 0;
     };
-    if (blockIdx.x < n_items) prefetch_item(blockIdx.x);
+    if (first_item >= 0) prefetch_item(first_item);
 
-    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++n_it) {
+    for (int item = first_item, nxt; item >= 0; item = nxt, ++n_it) {
       int kvb, kvh, b;
       decode(item, kvb, kvh, b);
+      nxt = next_item(item);
       const int kv0 = kvb * BKV;
       const int kcol = (H + kvh) * HD, vcol = (H + Hk + kvh) * HD;
       const int32_t* ssb = seg_start ? seg_start + (size_t)b * T : nullptr;
@@ -1149,18 +1200,19 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           nx_lse = ni < T ? lse[st2] : 0.f;
           nx_dl = ni < T ? delta[st2] : 0.f;
           nx_ss = (ssb && ni < T) ? ssb[ni] : 0;
-        } else if (item + gridDim.x < n_items) {
-          prefetch_item(item + gridDim.x);
+        } else if (nxt >= 0) {
+          prefetch_item(nxt);
         }
         const bool need_mask = !row_ok || (kv0 + BKV - 1 > i) || (kv0 < jlo);
-        // the dQ write-out issued during the previous tile staged in the part of the P buffer this warp is about to
-        // rewrite: the issuing threads wait until their reduce-adds have read the smem
+        // the dQ write-out issued during the previous tile was staged in the part of the dS buffer this warp is
+        // about to rewrite (and dK/dV of the previous item in its part of P): the issuing threads wait until their
+        // bulk copies have read the smem
         bulk_wait_read0();
         __syncwarp();
         mbar_wait(s_bar, s_phase);
         s_phase ^= 1;
         tc_fence_after();
-        uint8_t* sP = smem + S::kP + buf * kPTileBytes;
+        uint8_t* sP = smem + S::kP;
         uint8_t* sdS = smem + S::kdS + buf * kPTileBytes;
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
@@ -1201,6 +1253,9 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
               }
             }
           }
+          // the single P buffer: the dV MMAs of the previous tile must have retired (they were issued right behind
+          // this tile's S/dP MMAs, so this rarely waits)
+          if (cc == 0 && g >= 1) mbar_wait(pfree_bar, (g - 1) & 1);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             uint4 v, w;
@@ -1232,11 +1287,11 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       dq_phase(g - 1, prev_hq, prev_q0, b);  // also waits for the last gradient MMAs of the item
 
       // dK (scaled) and dV -> bf16 into the k / v column blocks of dqkv (TMEM lane = kv row).  Staged in this warp's
-      // own 4 KB of dS buffer 0 (free: every gradient MMA of the item has retired) and written by two TMA stores,
-      // which clip the rows past T.
+      // own 4 KB of the P buffer (free: every gradient MMA of the item has retired, and the dQ reduce-adds in flight
+      // were staged in dS) and written by two TMA stores, which clip the rows past T.
       {
         constexpr int ROWB = HH * 2;  // bytes per staged row: 64 / 32 -> TMA swizzle of that span, else none
-        uint8_t* stg = smem + S::kdS + half * 16384 + (warp & 3) * 4096;
+        uint8_t* stg = smem + S::kP + half * 16384 + (warp & 3) * 4096;
         uint32_t rka[HH], rva[HH];
 #pragma unroll
         for (int c0 = 0; c0 < HH; c0 += 8) {
@@ -1440,9 +1495,11 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     CGPT_LAUNCH_CHECK();
   }
   const int n_items = ((T + BKV - 1) / BKV) * Hk * B;
-  const int grid = n_items < num_sms() ? n_items : num_sms();
+  int grid = n_items < num_sms() ? n_items : num_sms();
   if constexpr (HD <= 64) {
     using SW = BwdWsSmem<HD>;
+    const int n_pairs = (((T + BKV - 1) / BKV + 1) / 2) * Hk * B;  // the kernel deals kv tiles in balanced pairs
+    grid = n_pairs < num_sms() ? n_pairs : num_sms();
     auto kern = attn_bwd_ws_kernel<HD>;
     static bool configured = false;
     if (!configured) {
