@@ -919,7 +919,6 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const int nkb = nqb_total, npk = (nkb + 1) / 2;
   const int n_pairs = npk * Hk * Bsz;
   const int G = gridDim.x;
-  const int n_virtual = 2 * ((n_pairs + G - 1) / G) * G;
 
   if (tid == 0) {
     tma_prefetch_desc(&tm_qkv);
@@ -951,26 +950,60 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + HD;
   const uint32_t tdQ0 = tmem_base + 256 + 2 * HD;  // + buf * HD
 
-  // virtual item v = round * G + cta; rounds 2r and 2r+1 are the two halves of pair (cta + r * G)
-  auto decode = [&](int v, int& kvb, int& kvh, int& b) -> bool {
-    const int rnd = v / G, c = v - rnd * G;
-    const int pi = c + (rnd >> 1) * G;
-    if (pi >= n_pairs) return false;
-    const int bh = pi / npk;
-    const int kk = (pi - bh * npk + bh) % npk;  // rotated by the head index: a CTA's pairs cycle through all k
-    kvb = (rnd & 1) ? nkb - 1 - kk : kk;
-    if ((rnd & 1) && kvb == kk) return false;  // middle tile of an odd count: no partner
-    kvh = bh % Hk;
-    b = bh / Hk;
-    return true;
+  // Item cursor: walks this CTA's pairs (cta, cta + G, ...) and the two halves of each pair without any division
+  // in the loop (runtime divisors cost ~100 instructions each, and every warp role walks the same sequence).
+  struct Cursor {
+    int pi, bh, kk0, bhm, kvh, b, sub, kvb;
+    bool valid;
   };
-  auto next_item = [&](int v) {
-    int kvb, kvh, b;
-    for (v += G; v < n_virtual; v += G)
-      if (decode(v, kvb, kvh, b)) return v;
-    return -1;
+  const int qG = G / npk, rG = G - qG * npk, qGm = qG % npk, qH = qG / Hk, rH = qG - qH * Hk;
+  auto rot = [&](const Cursor& c) {  // pair slot rotated by the head index: a CTA's pairs cycle through all k
+    const int kk = c.kk0 + c.bhm;
+    return kk >= npk ? kk - npk : kk;
   };
-  const int first_item = blockIdx.x < n_pairs ? static_cast<int>(blockIdx.x) : -1;
+  auto cursor_begin = [&]() {
+    Cursor c;
+    c.pi = blockIdx.x;
+    c.valid = c.pi < n_pairs;
+    c.bh = c.pi / npk;
+    c.kk0 = c.pi - c.bh * npk;
+    c.bhm = c.bh % npk;
+    c.b = c.bh / Hk;
+    c.kvh = c.bh - c.b * Hk;
+    c.sub = 0;
+    c.kvb = rot(c);
+    return c;
+  };
+  auto cursor_next = [&](Cursor c) {
+    if (c.sub == 0) {  // second half of the pair: the mirrored kv tile (absent for the middle tile of an odd count)
+      c.sub = 1;
+      const int kk = rot(c);
+      if (nkb - 1 - kk != kk) {
+        c.kvb = nkb - 1 - kk;
+        return c;
+      }
+    }
+    c.sub = 0;
+    c.pi += G;
+    if (c.pi >= n_pairs) {
+      c.valid = false;
+      return c;
+    }
+    c.kk0 += rG;
+    const int carry = c.kk0 >= npk;
+    if (carry) c.kk0 -= npk;
+    c.bh += qG + carry;
+    c.bhm += qGm + carry;
+    while (c.bhm >= npk) c.bhm -= npk;
+    c.kvh += rH + carry;
+    c.b += qH;
+    while (c.kvh >= Hk) {
+      c.kvh -= Hk;
+      ++c.b;
+    }
+    c.kvb = rot(c);
+    return c;
+  };
 
   if (warp == 8) {
     // ================================================================= TMA + MMA warp
@@ -984,11 +1017,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     int g = 0;  // global tile counter: buffer = g & 1, barrier phase = (g >> 1) & 1
     int n_it = 0;
     // last query tile of an item (table written by the delta kernel); fetched one item ahead
-    auto item_qhi = [&](int item) {
-      int kvb, kvh, b;
-      decode(item, kvb, kvh, b);
-      return qhi_tab[b * nqb_total + kvb];
-    };
+    auto item_qhi = [&](const Cursor& c) { return qhi_tab[c.b * nqb_total + c.kvb]; };
     auto load_kv = [&](int kvb, int kvh, int b, int ordinal) {
       const int kb = ordinal & 1;
       if (leader) {
@@ -1022,26 +1051,22 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       __syncwarp();
     };
-    int nx_qhi = first_item >= 0 ? item_qhi(first_item) : 0;
-    if (first_item >= 0) {  // prologue of the stream: the first item's K/V and its first tile
-      int kvb, kvh, b;
-      decode(first_item, kvb, kvh, b);
-      load_kv(kvb, kvh, b, 0);
-      load_q(0, kvh * rep, kvb, b);
+    Cursor cur = cursor_begin();
+    int nx_qhi = cur.valid ? item_qhi(cur) : 0;
+    if (cur.valid) {  // prologue of the stream: the first item's K/V and its first tile
+      load_kv(cur.kvb, cur.kvh, cur.b, 0);
+      load_q(0, cur.kvh * rep, cur.kvb, cur.b);
       mbar_wait(&kv_bar[0], 0);
       issue_scores(0, 0);
     }
-    for (int item = first_item, nxt; item >= 0; item = nxt, ++n_it) {
-      int kvb, kvh, b;
-      decode(item, kvb, kvh, b);
-      nxt = next_item(item);
+    for (; cur.valid; ++n_it) {
+      const int kvb = cur.kvb, kvh = cur.kvh, b = cur.b;
+      const Cursor nx = cursor_next(cur);
+      const int nxt = nx.valid ? 0 : -1;
       const int qb_lo = kvb, qb_hi = nx_qhi;
       const int nq = qb_hi - qb_lo + 1, niter = nq * rep;
-      int nkvb = 0, nkvh = 0, nb_ = 0;
-      if (nxt >= 0) {
-        decode(nxt, nkvb, nkvh, nb_);
-        nx_qhi = item_qhi(nxt);
-      }
+      const int nkvb = nx.kvb, nkvh = nx.kvh, nb_ = nx.b;
+      if (nx.valid) nx_qhi = item_qhi(nx);
       const int kb = n_it & 1;
       int ld_h = kvh * rep, ld_q = qb_lo;  // (head, query tile) of tile `it`, advanced incrementally
       for (int it = 0; it < niter; ++it, ++g) {
@@ -1064,10 +1089,10 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
         mbar_wait(&p_bar[buf], (g >> 1) & 1);  // P, dS of tile g are in smem; S/dP TMEM is free
         tc_fence_after();
-        if (has_next) {  // scores first: the math warps can start on the next tile
-          if (last) mbar_wait(&kv_bar[kb ^ 1], ((n_it + 1) >> 1) & 1);
-          issue_scores(g + 1, last ? n_it + 1 : n_it);
-        }
+        // Within an item the next tile's scores go first, so that the math warps can start on it while the
+        // gradient MMAs run.  After an item's LAST tile the math warps first need those gradients (dQ write-out,
+        // dK/dV epilogue), so there the order is reversed.
+        if (has_next && !last) issue_scores(g + 1, n_it);
         if (it == 0 && n_it > 0) {  // dK/dV accumulators still hold the previous item until the math warps drain them
           mbar_wait(dkv_bar, (n_it - 1) & 1);
           tc_fence_after();
@@ -1090,7 +1115,12 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           umma_commit(&g_bar[buf]);
         }
         __syncwarp();
+        if (has_next && last) {
+          mbar_wait(&kv_bar[kb ^ 1], ((n_it + 1) >> 1) & 1);
+          issue_scores(g + 1, n_it + 1);
+        }
       }
+      cur = nx;
     }
     // every MMA has retired before the CTA tears down its TMEM / smem
     if (g >= 1) mbar_wait(&g_bar[(g - 1) & 1], ((g - 1) >> 1) & 1);
@@ -1163,9 +1193,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     // row statistics of the first tile of an item and its query-tile range, fetched one item ahead
     float nx_lse = 0.f, nx_dl = 0.f;
     int nx_ss = 0, nx_qhi = 0;
-    auto prefetch_item = [&](int item) {
-      int kvb, kvh, b;
-      decode(item, kvb, kvh, b);
+    auto prefetch_item = [&](const Cursor& c) {
+      const int kvb = c.kvb, kvh = c.kvh, b = c.b;
       const int i0 = kvb * BQ + row;
       const size_t st0 = ((size_t)b * H + kvh * rep) * T + (i0 < T ? i0 : 0);
       nx_qhi = qhi_tab[b * nqb_total + kvb];
@@ -1173,12 +1202,12 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       nx_dl = i0 < T ? delta[st0] : 0.f;
       nx_ss = (seg_start && i0 < T) ? seg_start[(size_t)b * T + i0] : 0;
     };
-    if (first_item >= 0) prefetch_item(first_item);
+    Cursor cur = cursor_begin();
+    if (cur.valid) prefetch_item(cur);
 
-    for (int item = first_item, nxt; item >= 0; item = nxt, ++n_it) {
-      int kvb, kvh, b;
-      decode(item, kvb, kvh, b);
-      nxt = next_item(item);
+    for (; cur.valid; ++n_it) {
+      const int kvb = cur.kvb, kvh = cur.kvh, b = cur.b;
+      const Cursor nx = cursor_next(cur);
       const int kv0 = kvb * BKV;
       const int kcol = (H + kvh) * HD, vcol = (H + Hk + kvh) * HD;
       const int32_t* ssb = seg_start ? seg_start + (size_t)b * T : nullptr;
@@ -1200,8 +1229,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           nx_lse = ni < T ? lse[st2] : 0.f;
           nx_dl = ni < T ? delta[st2] : 0.f;
           nx_ss = (ssb && ni < T) ? ssb[ni] : 0;
-        } else if (nxt >= 0) {
-          prefetch_item(nxt);
+        } else if (nx.valid) {
+          prefetch_item(nx);
         }
         const bool need_mask = !row_ok || (kv0 + BKV - 1 > i) || (kv0 < jlo);
         // the dQ write-out issued during the previous tile was staged in the part of the dS buffer this warp is
@@ -1330,6 +1359,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           bulk_commit();
         }
       }
+      cur = nx;
     }
     bulk_wait_read0();  // every thread that issued reduce-adds drains its own groups before the smem goes away
   }
