@@ -355,6 +355,417 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
 
 // ===================================================================================== backward
 // delta[b,h,i] = sum_c dO[i,c] * O[i,c]   (one warp per (token, head))
+// ---------------------------------------------------------------- work order shared by the persistent kernels
+// Items are (tile index k of nt, head, batch).  Under a causal mask tile k costs k+1 (forward: kv tiles per query
+// tile) or nt-k (backward: query tiles per kv tile) units, so items are dealt in PAIRS (k, nt-1-k) of one head —
+// equal work — round-robin and head-major: the ~148 pairs in flight belong to a few dozen heads, whose K/V, Q/dO and
+// dQ rows therefore stay in L2.  The cursor walks one CTA's pairs without divisions in the loop.
+struct PairCursor {
+  int pi, bh, kk0, bhm, head, b, sub, k;  // k = tile index of the current item
+  bool valid;
+  int G, nt, npk, nheads, n_pairs, qG, rG, qGm, qH, rH;
+  __device__ __forceinline__ int rot() const {  // pair slot rotated by the head index: a CTA's pairs cycle through all k
+    const int kk = kk0 + bhm;
+    return kk >= npk ? kk - npk : kk;
+  }
+  __device__ __forceinline__ void begin(int cta, int grid, int n_tiles, int heads, int batch, bool high_first) {
+    G = grid; nt = n_tiles; npk = (n_tiles + 1) / 2; nheads = heads; n_pairs = npk * heads * batch;
+    qG = G / npk; rG = G - qG * npk; qGm = qG % npk; qH = qG / heads; rH = qG - qH * heads;
+    pi = cta;
+    valid = pi < n_pairs;
+    bh = pi / npk;
+    kk0 = pi - bh * npk;
+    bhm = bh % npk;
+    b = bh / heads;
+    head = bh - b * heads;
+    sub = 0;
+    flip = high_first;
+    k = flip ? nt - 1 - rot() : rot();
+  }
+  bool flip;  // false: the low index of a pair first; true: the high index first
+  __device__ __forceinline__ void next() {
+    if (sub == 0) {  // second half of the pair: the mirrored tile (absent for the middle tile of an odd count)
+      sub = 1;
+      const int kk = rot();
+      if (nt - 1 - kk != kk) {
+        k = flip ? kk : nt - 1 - kk;
+        return;
+      }
+    }
+    sub = 0;
+    pi += G;
+    if (pi >= n_pairs) {
+      valid = false;
+      return;
+    }
+    kk0 += rG;
+    const int carry = kk0 >= npk;
+    if (carry) kk0 -= npk;
+    bh += qG + carry;
+    bhm += qGm + carry;
+    while (bhm >= npk) bhm -= npk;
+    head += rH + carry;
+    b += qH;
+    while (head >= nheads) {
+      head -= nheads;
+      ++b;
+    }
+    k = flip ? nt - 1 - rot() : rot();
+  }
+};
+
+// ===================================================================================== forward, hd <= 64
+// Persistent, warp-specialised, one continuous (query tile, kv tile) stream:
+//   warp 9 : TMA producer — Q per item (double-buffered), (K, V) tiles through a kStages ring.
+//   warp 8 : MMA issuer (warp-uniform control flow, elected lane) — S(t) = Q K^T into the S buffer t&1, then
+//            O_t = P(t-1) V into the O buffer (t-1)&1: the scores of the next tile are computed while the softmax
+//            warps still work on the current one.
+//   warps 0..7 : softmax (thread = query row x column half): two passes over S in TMEM, P (bf16) into the P buffer
+//            t&1, then fold O_{t-1} (TMEM) into the register accumulator with the rescale factor of that tile.
+//            The output leaves through TMA stores staged in the warp's own rows of the P buffer.
+// TMEM (512 cols): S0 128 | S1 128 | O0 hd | O1 hd.
+template <int HD>
+struct FwdWsSmem {
+  using C = HeadCfg<HD>;
+  static constexpr int kStages = 3;
+  static constexpr int kQ = 0;                                   // 2 buffers
+  static constexpr int kK = kQ + 2 * C::TILE_BYTES;              // kStages
+  static constexpr int kV = kK + kStages * C::TILE_BYTES;        // kStages
+  static constexpr int kP = kV + kStages * C::TILE_BYTES;        // 2 buffers
+  static constexpr int kXchg = kP + 2 * kPTileBytes;             // 3 x 256 floats: row max (2 buffers) / row sum exchange
+  static constexpr int kBar = kXchg + 3 * 256 * 4;
+  static constexpr int kTotal = kBar + 256;
+  static constexpr int kDynamic = kTotal + 1024;
+  static_assert(HD <= 64 && kDynamic <= 232448, "warp-specialised forward: shared memory");
+};
+
+template <int HD>
+__global__ void __launch_bounds__(320, 1)
+attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out,
+                   const int32_t* __restrict__ seg_start, float* __restrict__ lse, int Bsz, int T, int H, int Hk,
+                   int window, float scale_log2, const DropoutCfg drop, int smem_bytes) {
+  using C = HeadCfg<HD>;
+  using S = FwdWsSmem<HD>;
+  constexpr int NS = S::kStages;
+  constexpr int HH = HD / 2;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  if (static_cast<int>(smem - smem_raw) + S::kTotal > smem_bytes) __trap();
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
+  uint64_t* q_full = bars;            // [2]
+  uint64_t* q_empty = bars + 2;       // [2] every S MMA of the item has retired
+  uint64_t* kv_full = bars + 4;       // [NS]
+  uint64_t* kv_empty = bars + 4 + NS; // [NS] the P·V MMAs that read the stage have retired
+  uint64_t* s_bar = bars + 4 + 2 * NS;   // [2]
+  uint64_t* p_bar = s_bar + 2;           // [2] P of a tile is in smem (and its S buffer has been consumed)
+  uint64_t* o_bar = p_bar + 2;           // [2] P·V of a tile has retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_bar + 2);
+  float* xchg = reinterpret_cast<float*>(smem + S::kXchg);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rep = H / Hk;
+  const int nqb = (T + BQ - 1) / BQ;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tm);
+    tma_prefetch_desc(&tm_out);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&q_full[i], 1);
+      mbar_init(&q_empty[i], 1);
+      mbar_init(&s_bar[i], 1);
+      mbar_init(&p_bar[i], 8);
+      mbar_init(&o_bar[i], 1);
+    }
+    for (int i = 0; i < NS; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 0) {
+    __syncwarp();
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS0 = tmem_base, tO0 = tmem_base + 256;  // S buffer b at tS0 + 128 b, O buffer b at tO0 + HD b
+
+  // kv-tile range of an item: [row_jlo(first row) / BKV, qb]
+  auto kv_lo_of = [&](int qb, int b) { return row_jlo(seg_start ? seg_start + (size_t)b * T : nullptr, qb * BQ, T, window) / BKV; };
+
+  if (warp == 9) {
+    // ================================================================= TMA producer
+    const bool leader = elect_one();
+    PairCursor cur;
+    cur.begin(blockIdx.x, gridDim.x, nqb, H, Bsz, true);
+    int nx_lo = cur.valid ? kv_lo_of(cur.k, cur.b) : 0;
+    uint32_t t = 0;
+    for (int n_it = 0; cur.valid; ++n_it) {
+      const int qb = cur.k, h = cur.head, b = cur.b, kv_lo = nx_lo;
+      const int kvh = h / rep;
+      cur.next();
+      if (cur.valid) nx_lo = kv_lo_of(cur.k, cur.b);  // fetched one item ahead
+      const int qbuf = n_it & 1;
+      mbar_wait(&q_empty[qbuf], ((n_it >> 1) & 1) ^ 1);
+      if (leader) {
+        mbar_expect_tx(&q_full[qbuf], C::TILE_BYTES);
+        tma_tile<HD>(smem + S::kQ + qbuf * C::TILE_BYTES, &tm, &q_full[qbuf], h * HD, qb * BQ, b);
+      }
+      for (int kvb = kv_lo; kvb <= qb; ++kvb, ++t) {
+        const int st = t % NS;
+        mbar_wait(&kv_empty[st], ((t / NS) & 1) ^ 1);
+        if (leader) {
+          mbar_expect_tx(&kv_full[st], 2 * C::TILE_BYTES);
+          tma_tile<HD>(smem + S::kK + st * C::TILE_BYTES, &tm, &kv_full[st], (H + kvh) * HD, kvb * BKV, b);
+          tma_tile<HD>(smem + S::kV + st * C::TILE_BYTES, &tm, &kv_full[st], (H + Hk + kvh) * HD, kvb * BKV, b);
+        }
+      }
+    }
+  } else if (warp == 8) {
+    // ================================================================= MMA issuer
+    const bool leader = elect_one();
+    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
+    constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
+    const uint32_t sQ_u = smem_u32(smem + S::kQ), sK_u = smem_u32(smem + S::kK), sV_u = smem_u32(smem + S::kV);
+    const uint32_t sP_u = smem_u32(smem + S::kP);
+    auto issue_pv = [&](uint32_t tt) {  // O buffer tt&1 = P(tt) V(tt); releases the (K, V) stage of the tile
+      const uint32_t pb = tt & 1, st = tt % NS;
+      mbar_wait(&p_bar[pb], (tt >> 1) & 1);
+      tc_fence_after();
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < BKV / 16; ++ks)
+          umma_bf16(tO0 + pb * HD, ptile_kmajor(sP_u + pb * kPTileBytes, ks), C::mnmajor(sV_u + st * C::TILE_BYTES, ks),
+                    idesc_o, ks > 0);
+        umma_commit(&o_bar[pb]);
+        umma_commit(&kv_empty[st]);
+      }
+      __syncwarp();
+    };
+    PairCursor cur;
+    cur.begin(blockIdx.x, gridDim.x, nqb, H, Bsz, true);
+    int nx_lo = cur.valid ? kv_lo_of(cur.k, cur.b) : 0;
+    uint32_t t = 0;
+    for (int n_it = 0; cur.valid; ++n_it) {
+      const int qb = cur.k, kv_lo = nx_lo;
+      cur.next();
+      if (cur.valid) nx_lo = kv_lo_of(cur.k, cur.b);
+      const int qbuf = n_it & 1;
+      mbar_wait(&q_full[qbuf], (n_it >> 1) & 1);
+      for (int kvb = kv_lo; kvb <= qb; ++kvb, ++t) {
+        const uint32_t st = t % NS, sb = t & 1;
+        mbar_wait(&kv_full[st], (t / NS) & 1);
+        // the S buffer t&1 was consumed by the softmax of tile t-2: awaited by issue_pv(t-2) one iteration ago
+        tc_fence_after();
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < HD / 16; ++ks)
+            umma_bf16(tS0 + sb * 128, C::kmajor(sQ_u + qbuf * C::TILE_BYTES, ks), C::kmajor(sK_u + st * C::TILE_BYTES, ks),
+                      idesc_s, ks > 0);
+          umma_commit(&s_bar[sb]);
+          if (kvb == qb) umma_commit(&q_empty[qbuf]);  // last S MMA of the item: its Q buffer is free after this
+        }
+        __syncwarp();
+        if (t >= 1) issue_pv(t - 1);
+      }
+    }
+    if (t >= 1) {
+      issue_pv(t - 1);
+      mbar_wait(&o_bar[(t - 1) & 1], ((t - 1) >> 1) & 1);  // every MMA has retired before the CTA tears down
+    }
+  } else {
+    // ================================================================= softmax warps
+    const int row = tid & 127, half = tid >> 7;
+    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
+    PairCursor cur;
+    cur.begin(blockIdx.x, gridDim.x, nqb, H, Bsz, true);
+    // own row's segment start and the tile's first row's, fetched one item ahead
+    int nx_ss = 0, nx_ss0 = 0;
+    auto prefetch_item = [&](const PairCursor& c) {
+      const int i0 = c.k * BQ;
+      nx_ss0 = seg_start ? seg_start[(size_t)c.b * T + i0] : 0;
+      nx_ss = (seg_start && i0 + row < T) ? seg_start[(size_t)c.b * T + i0 + row] : 0;
+    };
+    if (cur.valid) prefetch_item(cur);
+    uint32_t t = 0;
+    while (cur.valid) {
+      const int qb = cur.k, h = cur.head, b = cur.b;
+      const int q0 = qb * BQ, i = q0 + row;
+      const bool row_valid = i < T;
+      int jlo = row_valid ? nx_ss : 0x3fffffff, jlo0 = nx_ss0;
+      if (window > 0) {
+        jlo = row_valid ? max(jlo, i - window + 1) : jlo;
+        jlo0 = max(jlo0, q0 - window + 1);
+      }
+      const int kv_lo = jlo0 / BKV;
+      cur.next();
+      if (cur.valid) prefetch_item(cur);
+      const unsigned span = static_cast<unsigned>(i - jlo);
+      float m_run = -INFINITY, l_run = 0.f, alpha_pend = 1.f;
+      float o_acc[HH];
+#pragma unroll
+      for (int c = 0; c < HH; ++c) o_acc[c] = 0.f;
+      // O_{tt} (TMEM) folded into the accumulator with the rescale factor of tile tt
+      auto fold = [&](uint32_t tt, float alpha) {
+        const uint32_t ob = tt & 1;
+        mbar_wait(&o_bar[ob], (tt >> 1) & 1);
+        tc_fence_after();
+        uint32_t r[HH];
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) tmem_ld8(tO0 + ob * HD + lane_base + half * HH + c0, *reinterpret_cast<uint32_t(*)[8]>(&r[c0]));
+        tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < HH; ++c) o_acc[c] = fmaf(o_acc[c], alpha, __uint_as_float(r[c]));
+        tc_fence_before();
+      };
+      for (int kvb = kv_lo; kvb <= qb; ++kvb, ++t) {
+        const uint32_t sb = t & 1;
+        const int kv0 = kvb * BKV;
+        uint8_t* sP = smem + S::kP + sb * kPTileBytes;
+        float* xw = xchg + sb * 256 + (1 - half) * 128 + row;
+        float* xr = xchg + sb * 256 + half * 128 + row;
+        // bulk stores staged in this warp's rows of the P buffers (the previous item's output) have read their smem
+        bulk_wait_read0();
+        __syncwarp();
+        mbar_wait(&s_bar[sb], (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tS = tS0 + sb * 128;
+        // A row sees the column interval [jlo, i].  Per 32-column chunk the whole WARP (32 consecutive rows) votes:
+        // chunk visible to every row -> no per-score tests; to no row -> skipped (no TMEM read, no exp); mixed -> tested.
+        // On a diagonal tile only the 32x32 blocks on the diagonal are mixed.
+        unsigned cls[2];  // 0 = all visible, 1 = none, 2 = mixed
+        float mraw = -INFINITY;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c4 = half * 2 + cc;
+          const int jb = kv0 + c4 * 32;
+          const bool full = row_valid && jb >= jlo && jb + 31 <= i;
+          const bool none = !row_valid || jb > i || jb + 31 < jlo;
+          cls[cc] = __all_sync(0xffffffffu, full) ? 0u : (__all_sync(0xffffffffu, none) ? 1u : 2u);
+          if (cls[cc] == 1u) continue;
+          uint32_t r[32];
+          tmem_ld32(tS + lane_base + c4 * 32, r);
+          tmem_ld_wait();
+          if (cls[cc] == 2u) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              mraw = fmaxf(mraw, (row_valid && visible(jb + j, jlo, span)) ? __uint_as_float(r[j]) : -INFINITY);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, __uint_as_float(r[j]));
+          }
+        }
+        const float mloc = mraw * scale_log2;
+        *xw = mloc;
+        named_bar_sync(1, 256);
+        const float m_new = fmaxf(m_run, fmaxf(mloc, *xr));
+        const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
+        const float alpha = fast_exp2(m_run - m_safe);
+        float lsum = 0.f;
+        const float neg_m = -m_safe;
+#pragma unroll 1
+        for (int cc = 0; cc < 2; ++cc) {
+          const int c4 = half * 2 + cc;
+          if (cls[cc] == 1u) {  // nothing visible: the P chunk is zero
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ptile_store(sP, row, c4 * 4 + q, make_uint4(0u, 0u, 0u, 0u));
+            continue;
+          }
+          uint32_t r[32];
+          tmem_ld32(tS + lane_base + c4 * 32, r);
+          tmem_ld_wait();
+          float p[32];
+          if (cls[cc] == 2u) {
+            const int jb = kv0 + c4 * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float pv = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2, neg_m));
+              p[j] = (row_valid && visible(jb + j, jlo, span)) ? pv : 0.f;
+              lsum += p[j];
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              p[j] = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2, neg_m));
+              lsum += p[j];
+            }
+          }
+          if (drop.thresh) {  // dropout on the (still unnormalised) probabilities; the row sum stays undropped (:104,129)
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const uint4 rb = attn_dropout_bits(drop, b * H + h, i, (kv0 + c4 * 32) / 4 + j4);
+              p[4 * j4 + 0] = rb.x >= drop.thresh ? p[4 * j4 + 0] * drop.inv_keep : 0.f;
+              p[4 * j4 + 1] = rb.y >= drop.thresh ? p[4 * j4 + 1] * drop.inv_keep : 0.f;
+              p[4 * j4 + 2] = rb.z >= drop.thresh ? p[4 * j4 + 2] * drop.inv_keep : 0.f;
+              p[4 * j4 + 3] = rb.w >= drop.thresh ? p[4 * j4 + 3] * drop.inv_keep : 0.f;
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint4 v;
+            v.x = pack_bf16(p[q * 8 + 0], p[q * 8 + 1]);
+            v.y = pack_bf16(p[q * 8 + 2], p[q * 8 + 3]);
+            v.z = pack_bf16(p[q * 8 + 4], p[q * 8 + 5]);
+            v.w = pack_bf16(p[q * 8 + 6], p[q * 8 + 7]);
+            ptile_store(sP, row, c4 * 4 + q, v);
+          }
+        }
+        l_run = l_run * alpha + lsum;
+        m_run = m_new;
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_bar[sb]);
+        // while the tensor cores work on this tile's P·V: fold the previous tile of the item
+        if (kvb > kv_lo) fold(t - 1, alpha_pend);
+        alpha_pend = alpha;
+      }
+      fold(t - 1, alpha_pend);  // last tile of the item (also: its P buffer is free now)
+      // combine the two halves' row sums
+      {
+        float* xw = xchg + 2 * 256 + (1 - half) * 128 + row;  // third buffer: never aliases a row-max exchange
+        float* xr = xchg + 2 * 256 + half * 128 + row;
+        *xw = l_run;
+        named_bar_sync(1, 256);
+        const float l_tot = l_run + *xr;
+        const float inv = 1.f / l_tot;
+        // output rows -> bf16, staged in this warp's rows of the last tile's P buffer, one TMA store per warp
+        constexpr int ROWB = HH * 2;
+        uint8_t* stg = smem + S::kP + ((t - 1) & 1) * kPTileBytes + half * 16384 + (warp & 3) * 4096;
+        const int sw = ROWB == 64 ? ((lane >> 1) & 3) : (ROWB == 32 ? ((lane >> 2) & 1) : 0);
+        const uint32_t rowp = smem_u32(stg + lane * ROWB);
+#pragma unroll
+        for (int c0 = 0; c0 < HH; c0 += 8) {
+          const uint32_t off = static_cast<uint32_t>(((c0 >> 3) ^ sw) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + off),
+                       "r"(pack_bf16(o_acc[c0 + 0] * inv, o_acc[c0 + 1] * inv)),
+                       "r"(pack_bf16(o_acc[c0 + 2] * inv, o_acc[c0 + 3] * inv)),
+                       "r"(pack_bf16(o_acc[c0 + 4] * inv, o_acc[c0 + 5] * inv)),
+                       "r"(pack_bf16(o_acc[c0 + 6] * inv, o_acc[c0 + 7] * inv))
+                       : "memory");
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_3d(&tm_out, smem_u32(stg), h * HD + half * HH, q0 + (warp & 3) * 32, b);
+          bulk_commit();
+        }
+        if (half == 0 && row_valid) lse[((size_t)b * H + h) * T + i] = (m_run + log2f(l_tot)) * kLn2;
+      }
+    }
+    bulk_wait_read0();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 // last query tile that can see each (batch, kv tile): the warp-specialised backward reads this table instead of
 // searching seg_start itself.  Side job of the first threads of the delta kernels.
 __device__ __forceinline__ void fill_qhi_tab(int e, int B, int T, const int32_t* __restrict__ seg_start, int window,
@@ -1232,7 +1643,6 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         } else if (nx.valid) {
           prefetch_item(nx);
         }
-        const bool need_mask = !row_ok || (kv0 + BKV - 1 > i) || (kv0 < jlo);
         // the dQ write-out issued during the previous tile was staged in the part of the dS buffer this warp is
         // about to rewrite (and dK/dV of the previous item in its part of P): the issuing threads wait until their
         // bulk copies have read the smem
@@ -1246,13 +1656,27 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
           const int c4 = half * 2 + cc;
+          // the warp (32 consecutive rows) classifies the 32-column chunk: visible to every row -> no per-score
+          // tests; to no row -> zeros, nothing read or exponentiated; mixed (the diagonal 32x32 blocks) -> tested
+          const int jb = kv0 + c4 * 32;
+          const bool full = row_ok && jb >= jlo && jb + 31 <= i;
+          const bool none = !row_ok || jb > i || jb + 31 < jlo;
+          const bool w_full = __all_sync(0xffffffffu, full), w_none = __all_sync(0xffffffffu, none);
+          if (w_none) {
+            if (cc == 0 && g >= 1) mbar_wait(pfree_bar, (g - 1) & 1);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              ptile_store(sP, row, c4 * 4 + q, make_uint4(0u, 0u, 0u, 0u));
+              ptile_store(sdS, row, c4 * 4 + q, make_uint4(0u, 0u, 0u, 0u));
+            }
+            continue;
+          }
           uint32_t rs[32], rp[32];
           tmem_ld32(tS + lane_base + c4 * 32, rs);
           tmem_ld32(tdP + lane_base + c4 * 32, rp);
           tmem_ld_wait();
           float p[32], ds[32];
-          if (need_mask) {
-            const int jb = kv0 + c4 * 32;
+          if (!w_full) {
             const unsigned span = static_cast<unsigned>(i - jlo);
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
@@ -1459,19 +1883,38 @@ int make_qkv_tmap(CUtensorMap* tm, const void* base, int B, int T, int W, int aw
 template <int HD>
 int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B, int T, int H, int Hk, int window,
                float scale, const DropoutCfg& drop, cudaStream_t st) {
-  using S = FwdSmem<HD>;
   CUtensorMap tm;
   int rc = make_qkv_tmap(&tm, qkv, B, T, (H + 2 * Hk) * HD, HeadCfg<HD>::AW);
   if (rc) return rc;
-  auto kern = attn_fwd_kernel<HD>;
-  static bool configured = false;
-  if (!configured) {
-    CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
-    configured = true;
+  if constexpr (HD <= 64) {
+    using SW = FwdWsSmem<HD>;
+    CUtensorMap to;  // output stores: [hd/2 columns x 32 rows] boxes of out [B, T, H*hd]
+    const uint64_t dims[3] = {(uint64_t)H * HD, (uint64_t)T, (uint64_t)B};
+    const uint64_t str[2] = {(uint64_t)H * HD * 2, (uint64_t)T * H * HD * 2};
+    const uint32_t box[3] = {(uint32_t)(HD / 2), 32u, 1u};
+    rc = make_tmap_bf16(&to, out, 3, dims, str, box, HD);  // swizzle span = row bytes (64 / 32) or none
+    if (rc) return rc;
+    auto kern = attn_fwd_ws_kernel<HD>;
+    static bool configured = false;
+    if (!configured) {
+      CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SW::kDynamic));
+      configured = true;
+    }
+    const int n_pairs = (((T + BQ - 1) / BQ + 1) / 2) * H * B;  // the kernel deals query tiles in balanced pairs
+    const int grid = n_pairs < num_sms() ? n_pairs : num_sms();
+    kern<<<grid, 320, SW::kDynamic, st>>>(tm, to, seg, lse, B, T, H, Hk, window, scale * kLog2e, drop, SW::kDynamic);
+  } else {
+    using S = FwdSmem<HD>;
+    auto kern = attn_fwd_kernel<HD>;
+    static bool configured = false;
+    if (!configured) {
+      CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kDynamic));
+      configured = true;
+    }
+    dim3 grid((T + BQ - 1) / BQ, H, B);
+    kern<<<grid, 256, S::kDynamic, st>>>(tm, seg, reinterpret_cast<__nv_bfloat16*>(out), lse, T, H, Hk, window,
+                                         scale * kLog2e, S::kDynamic, drop);
   }
-  dim3 grid((T + BQ - 1) / BQ, H, B);
-  kern<<<grid, 256, S::kDynamic, st>>>(tm, seg, reinterpret_cast<__nv_bfloat16*>(out), lse, T, H, Hk, window,
-                                       scale * kLog2e, S::kDynamic, drop);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;
