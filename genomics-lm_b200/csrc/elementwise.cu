@@ -284,8 +284,15 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
   for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
-    float4 xh[VPT], dyv[VPT];
+    float4 xh[VPT], dyv[VPT], rv[VPT];
     float s1 = 0.f, s2 = 0.f;
+    // every load of the row is issued before the first use: one HBM round trip per row, not two
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int c = lane + 32 * k;
+      rv[k] = (dres && c < nvec) ? __ldg(reinterpret_cast<const float4*>(dres + (size_t)row * d) + c)
+                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 #pragma unroll
     for (int k = 0; k < VPT; ++k) {
       const int c = lane + 32 * k;
@@ -327,13 +334,10 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
         o.y = rs * (dyv[k].y * gm[k].y - m1 - xh[k].y * m2);
         o.z = rs * (dyv[k].z * gm[k].z - m1 - xh[k].z * m2);
         o.w = rs * (dyv[k].w * gm[k].w - m1 - xh[k].w * m2);
-        if (dres) {
-          const float4 r = reinterpret_cast<const float4*>(dres + (size_t)row * d)[c];
-          o.x += r.x;
-          o.y += r.y;
-          o.z += r.z;
-          o.w += r.w;
-        }
+        o.x += rv[k].x;
+        o.y += rv[k].y;
+        o.z += rv[k].z;
+        o.w += rv[k].w;
         reinterpret_cast<float4*>(dx + (size_t)row * d)[c] = o;
         if (dxb)
           reinterpret_cast<uint2*>(dxb + (size_t)row * d)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
