@@ -162,7 +162,7 @@ def run_reference(args):
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def config_dict(args, world, note=None):
@@ -343,7 +343,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             base = cpu_reference_steps(args.layers, args.seq, steps=8, warmup=1, budget_s=25)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -426,5 +426,22 @@ def main():
         run_ours(args)
 
 
+def _emit(line: dict):
+    """The ONE JSON line goes to the process's real stdout; everything else any library prints while the bench
+    runs (NCCL's version banner, torchrun warnings, ...) was redirected to stderr by _guard_stdout()."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = 1
+
+
+def _guard_stdout():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)  # fd 1 -> stderr for the rest of the run (C libraries included)
+
+
 if __name__ == "__main__":
+    _guard_stdout()
     main()
