@@ -328,6 +328,59 @@ __device__ __forceinline__ void epi_chunk_f32(const GemmParams& p, uint32_t tadd
   __syncwarp();
 }
 
+// MUL_AUX with prefetched aux (BN = 256, 3-stage variant): the aux piece already sits (or is about to land) in
+// this chunk's own staging buffer; the product is written in place and leaves as one TMA bulk store.  `bar` is the
+// warp's mbarrier for the first chunk of a tile (it covers the loads of both chunks), nullptr for the second.
+__device__ __forceinline__ void epi_chunk_mulaux_pf(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr,
+                                                    uint32_t stg, int lane, int row0, int n0, uint32_t bias_s,
+                                                    uint64_t* bar, uint32_t& phase) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  if (bar != nullptr) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t cell = stg_cell(stg, lane, j);
+    const uint4 a = lds128(cell);
+    const uint4 b0 = lds128(bias_s + j * 32), b1 = lds128(bias_s + j * 32 + 16);
+    const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+    const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint32_t o[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const uint64_t acc2 = f2_add(f2_pack(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1])),
+                                   f2_pack(__uint_as_float(bv[2 * e]), __uint_as_float(bv[2 * e + 1])));
+      const uint64_t a2 = f2_pack(__uint_as_float(av[e] << 16), __uint_as_float(av[e] & 0xffff0000u));
+      float o0, o1;
+      f2_unpack(f2_mul(acc2, a2), o0, o1);
+      o[e] = pack_bf16(o0, o1);
+    }
+    sts128(cell, make_uint4(o[0], o[1], o[2], o[3]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, stg, n0, row0);
+    bulk_commit();
+  }
+  if (p.colsum) {
+    // column sums of this 32 x 32 piece straight from the staged bf16 values (lane = column), one atomic per
+    // column: the bias gradient of the layer in front of the GELU, without re-reading the output from HBM.
+    // Rows past M were zero-filled by the aux load, so they add nothing.
+    float acc = 0.f;
+#pragma unroll
+    for (int rr = 0; rr < 32; ++rr) {
+      uint16_t h;
+      asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(stg_cell(stg, rr, lane >> 3) + (lane & 7) * 2));
+      acc += __uint_as_float(static_cast<uint32_t>(h) << 16);
+    }
+    if (n0 + lane < p.N) atomicAdd(p.colsum + n0 + lane, acc);
+  }
+}
+
 // ---- fully TMA-fed epilogues: the per-element operand (aux / residual) arrives in the staging buffer through a
 // bulk tensor load, is combined with the accumulator in the row layout (thread = row), written back to the same
 // swizzled cells and leaves through a bulk tensor store (or reduce-add for split-K).  No per-thread global access.
@@ -435,7 +488,11 @@ struct SmemLayout {
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStgOff = STAGES * kStageBytes;
-  static constexpr int kBiasOff = kStgOff + kEpiWarps * kStgBytesPerWarp;  // 2 x BN floats (per accumulator buffer)
+  // BN = 256 with 3 stages is the MUL_AUX variant: the freed stage pays for a second staging buffer per warp, so
+  // that the aux pieces of BOTH column chunks of a tile can be requested before the accumulator is ready
+  static constexpr bool kAuxPrefetch = (BN == 256 && STAGES == 3);
+  static constexpr int kStgPerWarp = kAuxPrefetch ? 2 * kStgBytesPerWarp : kStgBytesPerWarp;
+  static constexpr int kBiasOff = kStgOff + kEpiWarps * kStgPerWarp;  // 2 x BN floats (per accumulator buffer)
   static constexpr int kBarOff = kBiasOff + 2 * BN * 4;
   static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16 + kEpiWarps * 8;  // + one mbarrier per epilogue warp
   // slack for aligning the base up to 1024 B (the kernel traps if it does not fit; in practice the dynamic
@@ -573,7 +630,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int ew = warp - 2;
     const int q = warp & 3;   // TMEM lane quadrant this warp may access
     const int grp = ew >> 2;  // 0..3: which quarter of the column chunks
-    const uint32_t stg = smem_u32(smem + L::kStgOff + ew * kStgBytesPerWarp);
+    const uint32_t stg = smem_u32(smem + L::kStgOff + ew * L::kStgPerWarp);
     const bool bf16_rowmath = !p.out_f32 && p.epilogue != CGPT_EPI_MUL_AUX;
     const bool tma_io = (p.tma_out & 1) && (p.out_f32 || p.epilogue == CGPT_EPI_MUL_AUX);
     uint32_t epi_phase = 0;
@@ -592,12 +649,42 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (p.bias != nullptr && ks == 0 && cb < p.N) bv = __ldg(p.bias + cb);
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_tile + (ew * 32 + lane) * 4), "f"(bv) : "memory");
       }
+      const int row0 = m_blk * BM + q * 32;
+      if constexpr (L::kAuxPrefetch) {
+        // MUL_AUX: the aux pieces of this warp's two column chunks start their trip from HBM now, while the
+        // mainloop of the tile is still running (one mbarrier, armed with the bytes of both)
+        if (tma_io && !p.out_f32) {
+          if (lane == 0) {
+            bulk_wait_read0();  // the previous tile's stores have read both staging halves
+            int nvalid = 0;
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) nvalid += (n_blk * BN + (grp + 4 * ci) * 32 < p.N) ? 1 : 0;
+            if (nvalid) {
+              mbar_expect_tx(&epi_bar[ew], nvalid * kStgBytesPerWarp);
+#pragma unroll
+              for (int ci = 0; ci < 2; ++ci) {
+                const int n0 = n_blk * BN + (grp + 4 * ci) * 32;
+                if (n0 < p.N) tma_load_2d_s(stg + ci * kStgBytesPerWarp, &tmX, &epi_bar[ew], n0, row0);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
       named_bar_sync(1, kEpiWarps * 32);
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
-      const int row0 = m_blk * BM + q * 32;
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (p.debug & 4) {
+      } else if (L::kAuxPrefetch && tma_io && !p.out_f32) {
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+          const int c = grp + 4 * ci;
+          const int n0 = n_blk * BN + c * 32;
+          if (n0 < p.N)  // warp-uniform
+            epi_chunk_mulaux_pf(p, &tmC, tbase + c * 32, stg + ci * kStgBytesPerWarp, lane, row0, n0, bias_tile + c * 128,
+                                ci == 0 ? &epi_bar[ew] : nullptr, epi_phase);
+        }
       } else if (tma_io && !p.out_f32) {
 #pragma unroll 1
         for (int c = grp; c < BN / 32; c += 4) {
@@ -778,7 +865,12 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
                "gemm: colsum needs the MUL_AUX epilogue on 16-byte aligned bf16 operands");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
-  if (BN == 256) return dispatch_major<256, 4>(amn, bmn, ta, tb, tc, tx, p, st);
+  if (BN == 256) {
+    // ×aux epilogue: 3 pipeline stages + a second staging buffer per epilogue warp (aux prefetch), see SmemLayout
+    if (a->epilogue == CGPT_EPI_MUL_AUX && (p.tma_out & 1) && !a->out_f32)
+      return dispatch_major<256, 3>(amn, bmn, ta, tb, tc, tx, p, st);
+    return dispatch_major<256, 4>(amn, bmn, ta, tb, tc, tx, p, st);
+  }
   if (BN == 128) return dispatch_major<128, 6>(amn, bmn, ta, tb, tc, tx, p, st);
   return dispatch_major<64, 8>(amn, bmn, ta, tb, tc, tx, p, st);
 }
