@@ -482,15 +482,19 @@ __device__ __forceinline__ void epi_chunk_f32_tma(const GemmParams& p, const CUt
   }
 }
 
-template <int BN, int STAGES>
+// TWO: CTA-pair mode (cta_group::2).  The pair computes a 256 x BN tile: each CTA holds its own 128 rows of A and
+// HALF of the B tile (the tensor cores of both SMs read both halves), and keeps its 128 x BN slice of the
+// accumulator in its own TMEM.  Per CTA the operand traffic through shared memory drops from 48 KB to 32 KB per
+// k-block, which is what the epilogue's staging traffic was competing with.
+template <int BN, int STAGES, bool TWO = false>
 struct SmemLayout {
   static constexpr int kABytes = BM * BK * 2;
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = (TWO ? BN / 2 : BN) * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStgOff = STAGES * kStageBytes;
   // BN = 256 with 3 stages is the MUL_AUX variant: the freed stage pays for a second staging buffer per warp, so
   // that the aux pieces of BOTH column chunks of a tile can be requested before the accumulator is ready
-  static constexpr bool kAuxPrefetch = (BN == 256 && STAGES == 3);
+  static constexpr bool kAuxPrefetch = (BN == 256 && STAGES == (TWO ? 5 : 3));
   static constexpr int kStgPerWarp = kAuxPrefetch ? 2 * kStgBytesPerWarp : kStgBytesPerWarp;
   static constexpr int kBiasOff = kStgOff + kEpiWarps * kStgPerWarp;  // 2 x BN floats (per accumulator buffer)
   static constexpr int kBarOff = kBiasOff + 2 * BN * 4;
@@ -501,11 +505,16 @@ struct SmemLayout {
   static_assert(kTotal <= 232448, "exceeds the 227 KB of shared memory per CTA");
 };
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, bool TWO>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmX, const GemmParams p) {
-  using L = SmemLayout<BN, STAGES>;
+  using L = SmemLayout<BN, STAGES, TWO>;
+  constexpr int BNL = TWO ? BN / 2 : BN;  // rows of B this CTA loads
+  // persistent worker = one CTA, or one CTA pair; p.tiles_m counts 128-row (256-row for pairs) tiles
+  const uint32_t cta_rank = TWO ? cluster_ctarank() : 0u;
+  const int unit = TWO ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_units = TWO ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   if (static_cast<int>(smem - smem_raw) + L::kTotal > L::kDynamic) __trap();
@@ -534,18 +543,24 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     mbar_init(&tfull_bar[0], 1);
     mbar_init(&tfull_bar[1], 1);
-    mbar_init(&tempty_bar[0], kEpiWarps);
-    mbar_init(&tempty_bar[1], kEpiWarps);
+    mbar_init(&tempty_bar[0], kEpiWarps * (TWO ? 2 : 1));  // pair mode: the leader's barrier hears both CTAs
+    mbar_init(&tempty_bar[1], kEpiWarps * (TWO ? 2 : 1));
 #pragma unroll
     for (int e = 0; e < kEpiWarps; ++e) mbar_init(&epi_bar[e], 1);
     fence_mbar_init();
   }
   if (warp == 1) {
-    tmem_alloc(tmem_slot, 2 * BN);
-    tmem_relinquish();
+    if constexpr (TWO) {
+      tmem_alloc_2sm(tmem_slot, 2 * BN);
+      tmem_relinquish_2sm();
+    } else {
+      tmem_alloc(tmem_slot, 2 * BN);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -554,30 +569,51 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       int s = 0;
       uint32_t ph = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      for (int w = unit; w < total_work; w += n_units) {
         const int n_blk = w % p.tiles_n;
-        const int m_blk = (w / p.tiles_n) % p.tiles_m;
+        const int m_blk = ((w / p.tiles_n) % p.tiles_m) * (TWO ? 2 : 1) + cta_rank;  // 128-row block
         const int ks = w / (p.tiles_n * p.tiles_m);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
+        const int n_off = n_blk * BN + static_cast<int>(cta_rank) * BNL;  // pair mode: this CTA's half of the B tile
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[s], ph ^ 1);
           uint8_t* sa = smem + s * L::kStageBytes;
           uint8_t* sb = sa + L::kABytes;
-          mbar_expect_tx(&full_bar[s], L::kStageBytes);
-          if constexpr (!A_MN) {
-            tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m_blk * BM);
-          } else {
+          if constexpr (TWO) {
+            // both CTAs' bytes are accounted on the LEADER's barrier, which its MMA issuer waits on
+            const uint32_t fb = mapa_u32(smem_u32(&full_bar[s]), 0);
+            if (cta_rank == 0) mbar_expect_tx(&full_bar[s], 2 * L::kStageBytes);
+            if constexpr (!A_MN) {
+              tma_load_2d_2sm(sa, &tmA, fb, kb * BK, m_blk * BM);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BM / 64; ++j)
-              tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m_blk * BM + j * 64, kb * BK);
-          }
-          if constexpr (!B_MN) {
-            tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n_blk * BN);
-          } else {
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d_2sm(sa + j * (BK * 128), &tmA, fb, m_blk * BM + j * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d_2sm(sb, &tmB, fb, kb * BK, n_off);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BN / 64; ++j)
-              tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], n_blk * BN + j * 64, kb * BK);
+              for (int j = 0; j < BNL / 64; ++j)
+                tma_load_2d_2sm(sb + j * (BK * 128), &tmB, fb, n_off + j * 64, kb * BK);
+            }
+          } else {
+            mbar_expect_tx(&full_bar[s], L::kStageBytes);
+            if constexpr (!A_MN) {
+              tma_load_2d(sa, &tmA, &full_bar[s], kb * BK, m_blk * BM);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 64; ++j)
+                tma_load_2d(sa + j * (BK * 128), &tmA, &full_bar[s], m_blk * BM + j * 64, kb * BK);
+            }
+            if constexpr (!B_MN) {
+              tma_load_2d(sb, &tmB, &full_bar[s], kb * BK, n_blk * BN);
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                tma_load_2d(sb + j * (BK * 128), &tmB, &full_bar[s], n_blk * BN + j * 64, kb * BK);
+            }
           }
           if (++s == STAGES) {
             s = 0;
@@ -587,13 +623,13 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (elect_one()) {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, A_MN, B_MN);
+    // ------------------------------------------------------------ MMA issuer (pair mode: the leader CTA only)
+    if (elect_one() && cta_rank == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(TWO ? 2 * BM : BM, BN, A_MN, B_MN);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      for (int w = unit; w < total_work; w += n_units, ++it) {
         const int ks = w / (p.tiles_n * p.tiles_m);
         const int kb0 = ks * p.kb_per_split;
         const int kb1 = min(p.kb_total, kb0 + p.kb_per_split);
@@ -612,15 +648,20 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                      : umma_smem_desc(sa + k * 32, 16, 1024, kLayoutSW128);
             const uint64_t bd = B_MN ? umma_smem_desc(sb + k * 2048, BK * 128, 1024, kLayoutSW128)
                                      : umma_smem_desc(sb + k * 32, 16, 1024, kLayoutSW128);
-            umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0) || (k > 0));
+            if constexpr (TWO)
+              umma_bf16_2sm(d_tmem, ad, bd, idesc, (kb > kb0) || (k > 0));
+            else
+              umma_bf16(d_tmem, ad, bd, idesc, (kb > kb0) || (k > 0));
           }
-          umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot (in both CTAs of a pair) when these MMAs retire
+          if constexpr (TWO) umma_commit_2sm(&empty_bar[s]); else umma_commit(&empty_bar[s]);
           if (++s == STAGES) {
             s = 0;
             ph ^= 1;
           }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs of a pair)
+        if constexpr (TWO) umma_commit_2sm(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
       }
     }
   } else {
@@ -635,9 +676,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const bool tma_io = (p.tma_out & 1) && (p.out_f32 || p.epilogue == CGPT_EPI_MUL_AUX);
     uint32_t epi_phase = 0;
     int it = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+    const uint32_t tempty_leader[2] = {TWO ? mapa_u32(smem_u32(&tempty_bar[0]), 0) : 0u,
+                                       TWO ? mapa_u32(smem_u32(&tempty_bar[1]), 0) : 0u};
+    for (int w = unit; w < total_work; w += n_units, ++it) {
       const int n_blk = w % p.tiles_n;
-      const int m_blk = (w / p.tiles_n) % p.tiles_m;
+      const int m_blk = ((w / p.tiles_n) % p.tiles_m) * (TWO ? 2 : 1) + cta_rank;  // 128-row block
       const int ks = w / (p.tiles_n * p.tiles_m);
       const int acc = it & 1;
       // this tile's bias slice -> smem (zeros when there is none), before the accumulator is even ready.
@@ -721,44 +764,65 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if constexpr (TWO) mbar_arrive_cluster(tempty_leader[acc]); else mbar_arrive(&tempty_bar[acc]);
+      }
     }
     if ((p.tma_out & 1) && lane == 0) bulk_wait0();  // smem must outlive the bulk stores that read it
   }
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (TWO) cluster_sync_all();  // neither CTA leaves (or frees TMEM) while its peer may still touch it
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 2 * BN);
+    if constexpr (TWO) tmem_dealloc_2sm(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
   }
 }
 
-template <int BN, bool A_MN, bool B_MN, int STAGES>
+template <int BN, bool A_MN, bool B_MN, int STAGES, bool TWO = false>
 int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, const CUtensorMap& tx,
            const GemmParams& p, cudaStream_t st) {
-  using L = SmemLayout<BN, STAGES>;
-  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES>;
+  using L = SmemLayout<BN, STAGES, TWO>;
+  auto kern = gemm_bf16_kernel<BN, A_MN, B_MN, STAGES, TWO>;
   static bool configured = false;
   if (!configured) {
     CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kDynamic));
     configured = true;
   }
   const int total = p.tiles_m * p.tiles_n * p.split_k;
-  const int grid = total < num_sms() ? total : num_sms();
-  kern<<<grid, kThreads, L::kDynamic, st>>>(ta, tb, tc, tx, p);
+  if constexpr (TWO) {
+    const int pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(2 * (total < pairs ? total : pairs));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L::kDynamic;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 2;
+    attr.val.clusterDim.y = 1;
+    attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    CGPT_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tx, p));
+  } else {
+    const int grid = total < num_sms() ? total : num_sms();
+    kern<<<grid, kThreads, L::kDynamic, st>>>(ta, tb, tc, tx, p);
+  }
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, bool TWO = false>
 int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc,
                    const CUtensorMap& tx, const GemmParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BN, false, false, STAGES>(ta, tb, tc, tx, p, st);
-  if (!a_mn && b_mn) return launch<BN, false, true, STAGES>(ta, tb, tc, tx, p, st);
-  if (a_mn && b_mn) return launch<BN, true, true, STAGES>(ta, tb, tc, tx, p, st);
-  return launch<BN, true, false, STAGES>(ta, tb, tc, tx, p, st);
+  if (!a_mn && !b_mn) return launch<BN, false, false, STAGES, TWO>(ta, tb, tc, tx, p, st);
+  if (!a_mn && b_mn) return launch<BN, false, true, STAGES, TWO>(ta, tb, tc, tx, p, st);
+  if (a_mn && b_mn) return launch<BN, true, true, STAGES, TWO>(ta, tb, tc, tx, p, st);
+  return launch<BN, true, false, STAGES, TWO>(ta, tb, tc, tx, p, st);
 }
 
 }  // namespace
@@ -776,6 +840,13 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
   CGPT_REQUIRE(a->epilogue != CGPT_EPI_MUL_AUX || a->aux, "gemm: MUL_AUX needs aux");
 
   const int BN = a->N > 128 ? 256 : (a->N > 64 ? 128 : 64);
+  // CTA-pair mode (cta_group::2) for the 256-wide tiles; CGPT_GEMM_2CTA=0 falls back to one CTA per tile (A/B probe)
+  static int pair_env = -1;
+  if (pair_env < 0) {
+    const char* e = getenv("CGPT_GEMM_2CTA");
+    pair_env = e ? atoi(e) : 1;
+  }
+  const bool two = pair_env != 0 && BN == 256 && a->M > cgpt::BM && (num_sms() % 2 == 0);
   CUtensorMap ta, tb;
   int rc;
   {
@@ -792,7 +863,7 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
     const uint64_t dimsK[2] = {(uint64_t)a->K, (uint64_t)a->N};
     const uint64_t dimsMN[2] = {(uint64_t)a->N, (uint64_t)a->K};
     const uint64_t str[1] = {(uint64_t)a->ldb * 2};
-    const uint32_t boxK[2] = {64, (uint32_t)BN};
+    const uint32_t boxK[2] = {64, (uint32_t)(two ? BN / 2 : BN)};  // pair mode: each CTA loads half of the B tile
     const uint32_t boxMN[2] = {64, (uint32_t)cgpt::BK};
     rc = a->b_mn_major ? make_tmap_bf16(&tb, a->b, 2, dimsMN, str, boxMN, 128)
                        : make_tmap_bf16(&tb, a->b, 2, dimsK, str, boxK, 128);
@@ -802,7 +873,7 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
   p.M = a->M;
   p.N = a->N;
   p.K = a->K;
-  p.tiles_m = (a->M + cgpt::BM - 1) / cgpt::BM;
+  p.tiles_m = two ? (a->M + 2 * cgpt::BM - 1) / (2 * cgpt::BM) : (a->M + cgpt::BM - 1) / cgpt::BM;
   p.tiles_n = (a->N + BN - 1) / BN;
   p.kb_total = (a->K + cgpt::BK - 1) / cgpt::BK;
   int split = a->split_k < p.kb_total ? a->split_k : p.kb_total;
@@ -866,9 +937,13 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   const bool amn = a->a_mn_major != 0, bmn = a->b_mn_major != 0;
   if (BN == 256) {
-    // ×aux epilogue: 3 pipeline stages + a second staging buffer per epilogue warp (aux prefetch), see SmemLayout
-    if (a->epilogue == CGPT_EPI_MUL_AUX && (p.tma_out & 1) && !a->out_f32)
-      return dispatch_major<256, 3>(amn, bmn, ta, tb, tc, tx, p, st);
+    // ×aux epilogue: one pipeline stage less + a second staging buffer per epilogue warp (aux prefetch), see SmemLayout
+    const bool auxpf = a->epilogue == CGPT_EPI_MUL_AUX && (p.tma_out & 1) && !a->out_f32;
+    if (two) {
+      if (auxpf) return dispatch_major<256, 5, true>(amn, bmn, ta, tb, tc, tx, p, st);
+      return dispatch_major<256, 6, true>(amn, bmn, ta, tb, tc, tx, p, st);
+    }
+    if (auxpf) return dispatch_major<256, 3>(amn, bmn, ta, tb, tc, tx, p, st);
     return dispatch_major<256, 4>(amn, bmn, ta, tb, tc, tx, p, st);
   }
   if (BN == 128) return dispatch_major<128, 6>(amn, bmn, ta, tb, tc, tx, p, st);
