@@ -383,7 +383,7 @@ def step_breakdown(step, batch, path, ms_step):
     torch.cuda.synchronize()
     t0.record()
     for _ in range(nsteps):
-        step.step(*batch)
+        step._eager_step(*batch)  # eager: a CUDA-graph replay would bypass the wrapped ops
     t1.record()
     torch.cuda.synchronize()
     for n in names:

@@ -438,6 +438,60 @@ colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __r
   }
 }
 
+// Wide variant (N % 8 == 0, 16-byte aligned rows): a lane owns 8 consecutive columns (one 16-byte load), a warp 256
+// columns = 512 contiguous bytes of a row, four rows in flight per warp.
+__global__ void __launch_bounds__(256)
+colsum_bf16_vec_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
+                       int rows_per_cta) {
+  __shared__ float red[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 256 + 8 * lane;
+  const int r0 = blockIdx.y * rows_per_cta;
+  const int r1 = min(M, r0 + rows_per_cta);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (col < N) {
+    const __nv_bfloat16* base = x + col;
+    int r = r0 + warp;
+    for (; r + 24 < r1; r += 32) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(base + (size_t)(r + 8 * u) * ld);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const uint32_t w4[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16(w4[q]);
+          acc[2 * q] += f.x;
+          acc[2 * q + 1] += f.y;
+        }
+      }
+    }
+    for (; r < r1; r += 8) {
+      const uint4 v = *reinterpret_cast<const uint4*>(base + (size_t)r * ld);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float2 f = unpack_bf16(w4[q]);
+        acc[2 * q] += f.x;
+        acc[2 * q + 1] += f.y;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[warp][8 * lane + j] = acc[j];
+  __syncthreads();
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  if (c < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int w2 = 0; w2 < 8; ++w2) t += red[w2][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
 // ============================================================ RoPE on the q|k blocks of packed qkv (in place)
 __global__ void rope_qk_kernel(__nv_bfloat16* __restrict__ qkv, const float* __restrict__ cos_t,
                                const float* __restrict__ sin_t, int M, int T, int nheads, int hd, long long ld,
@@ -760,6 +814,18 @@ int cgpt_split3_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t rows
 
 int cgpt_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, cgpt_stream_t stream) {
   CGPT_REQUIRE(x && out && M > 0 && N > 0 && ld >= N && ld % 2 == 0, "colsum: bad arguments");
+  if (N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    const int ct = (N + 255) / 256;
+    int rc = (4 * num_sms() + ct - 1) / ct;
+    int rows = (M + rc - 1) / rc;
+    if (rows < 64) rows = 64;
+    rc = (M + rows - 1) / rows;
+    colsum_bf16_vec_kernel<<<dim3(ct, rc), 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(x), ld, out, M, N,
+                                                                 rows);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+    return 0;
+  }
   const int col_tiles = (N + 63) / 64;
   int row_ctas = (4 * num_sms() + col_tiles - 1) / col_tiles;
   int rows = (M + row_ctas - 1) / row_ctas;
