@@ -482,6 +482,39 @@ __device__ __forceinline__ void epi_chunk_f32_tma(const GemmParams& p, const CUt
   }
 }
 
+// fp32 output + fp32 residual with prefetched residual (pair mode, 3-stage variant): the residual piece already
+// sits (or is about to land) in this chunk's own staging buffer; the sum is written in place and leaves as one TMA
+// bulk store.  `bar` is the warp's mbarrier for the first chunk of a tile (it covers all four loads), else nullptr.
+__device__ __forceinline__ void epi_chunk_f32_res_pf(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr,
+                                                     uint32_t stg, int lane, int row0, int n0, uint32_t bias_s,
+                                                     uint64_t* bar, uint32_t& phase) {
+  uint32_t r[16];
+  tmem_ld16(taddr, r);
+  if (bar != nullptr) {
+    mbar_wait(bar, phase);
+    phase ^= 1;
+  }
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t cell = stg_cell(stg, lane, j);
+    const uint4 b = lds128(bias_s + j * 16);
+    const uint4 q = lds128(cell);
+    float4 v;
+    v.x = __uint_as_float(r[4 * j]) + __uint_as_float(b.x) + __uint_as_float(q.x);
+    v.y = __uint_as_float(r[4 * j + 1]) + __uint_as_float(b.y) + __uint_as_float(q.y);
+    v.z = __uint_as_float(r[4 * j + 2]) + __uint_as_float(b.z) + __uint_as_float(q.z);
+    v.w = __uint_as_float(r[4 * j + 3]) + __uint_as_float(b.w) + __uint_as_float(q.w);
+    sts128(cell, make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w)));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, stg, n0, row0);
+    bulk_commit();
+  }
+}
+
 // TWO: CTA-pair mode (cta_group::2).  The pair computes a 256 x BN tile: each CTA holds its own 128 rows of A and
 // HALF of the B tile (the tensor cores of both SMs read both halves), and keeps its 128 x BN slice of the
 // accumulator in its own TMEM.  Per CTA the operand traffic through shared memory drops from 48 KB to 32 KB per
@@ -495,7 +528,10 @@ struct SmemLayout {
   // BN = 256 with 3 stages is the MUL_AUX variant: the freed stage pays for a second staging buffer per warp, so
   // that the aux pieces of BOTH column chunks of a tile can be requested before the accumulator is ready
   static constexpr bool kAuxPrefetch = (BN == 256 && STAGES == (TWO ? 5 : 3));
-  static constexpr int kStgPerWarp = kAuxPrefetch ? 2 * kStgBytesPerWarp : kStgBytesPerWarp;
+  // pair mode with 3 stages is the fp32 + residual variant (proj / fc2 forward): four staging buffers per warp, so
+  // that the residual pieces of ALL FOUR 16-column chunks of a tile are requested before the accumulator is ready
+  static constexpr bool kResPrefetch = (BN == 256 && TWO && STAGES == 3);
+  static constexpr int kStgPerWarp = (kResPrefetch ? 4 : (kAuxPrefetch ? 2 : 1)) * kStgBytesPerWarp;
   static constexpr int kBiasOff = kStgOff + kEpiWarps * kStgPerWarp;  // 2 x BN floats (per accumulator buffer)
   static constexpr int kBarOff = kBiasOff + 2 * BN * 4;
   static constexpr int kTotal = kBarOff + (2 * STAGES + 4) * 8 + 16 + kEpiWarps * 8;  // + one mbarrier per epilogue warp
@@ -714,11 +750,40 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
         }
       }
+      if constexpr (L::kResPrefetch) {
+        // fp32 + residual: the residual pieces of this warp's four column chunks start their trip now
+        if (tma_io && p.out_f32 && p.residual != nullptr) {
+          if (lane == 0) {
+            bulk_wait_read0();  // the previous tile's stores have read all four staging buffers
+            int nvalid = 0;
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) nvalid += (n_blk * BN + (grp + 4 * ci) * 16 < p.N) ? 1 : 0;
+            if (nvalid) {
+              mbar_expect_tx(&epi_bar[ew], nvalid * kStgBytesPerWarp);
+#pragma unroll
+              for (int ci = 0; ci < 4; ++ci) {
+                const int n0 = n_blk * BN + (grp + 4 * ci) * 16;
+                if (n0 < p.N) tma_load_2d_s(stg + ci * kStgBytesPerWarp, &tmX, &epi_bar[ew], n0, row0);
+              }
+            }
+          }
+          __syncwarp();
+        }
+      }
       named_bar_sync(1, kEpiWarps * 32);
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (p.debug & 4) {
+      } else if (L::kResPrefetch && tma_io && p.out_f32 && p.residual != nullptr) {
+#pragma unroll
+        for (int ci = 0; ci < 4; ++ci) {
+          const int c = grp + 4 * ci;
+          const int n0 = n_blk * BN + c * 16;
+          if (n0 < p.N)  // warp-uniform
+            epi_chunk_f32_res_pf(p, &tmC, tbase + c * 16, stg + ci * kStgBytesPerWarp, lane, row0, n0, bias_tile + c * 64,
+                                 ci == 0 ? &epi_bar[ew] : nullptr, epi_phase);
+        }
       } else if (L::kAuxPrefetch && tma_io && !p.out_f32) {
 #pragma unroll
         for (int ci = 0; ci < 2; ++ci) {
@@ -940,6 +1005,14 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
     // ×aux epilogue: one pipeline stage less + a second staging buffer per epilogue warp (aux prefetch), see SmemLayout
     const bool auxpf = a->epilogue == CGPT_EPI_MUL_AUX && (p.tma_out & 1) && !a->out_f32;
     if (two) {
+      // fp32 + residual at short K (proj forward): epilogue-latency-bound, see SmemLayout::kResPrefetch
+      static int respf_kmax = -1;
+      if (respf_kmax < 0) {
+        const char* e = getenv("CGPT_GEMM_RESPF_KMAX");
+        respf_kmax = e ? atoi(e) : 1024;
+      }
+      if (a->out_f32 && a->residual && (p.tma_out & 1) && (p.tma_out & 2) && !a->accumulate && a->K <= respf_kmax)
+        return dispatch_major<256, 3, true>(amn, bmn, ta, tb, tc, tx, p, st);
       if (auxpf) return dispatch_major<256, 5, true>(amn, bmn, ta, tb, tc, tx, p, st);
       return dispatch_major<256, 6, true>(amn, bmn, ta, tb, tc, tx, p, st);
     }
