@@ -482,6 +482,41 @@ __device__ __forceinline__ void epi_chunk_f32_tma(const GemmParams& p, const CUt
   }
 }
 
+// bias + GELU with the two outputs (activation, GELU') staged in SEPARATE buffers (variants with two staging
+// buffers per warp): every 8-column group is stored to smem as soon as it is computed, so only the accumulator row
+// and one group's temporaries are live — the register budget that made ptxas serialise the chains — and the two
+// bulk stores leave together without a read-completion wait between them.
+__device__ __forceinline__ void epi_chunk_gelu_2buf(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
+                                                    uint32_t taddr, uint32_t stg, int lane, int row0, int n0,
+                                                    uint32_t bias_s) {
+  uint32_t r[32];
+  tmem_ld32(taddr, r);
+  if (lane == 0) bulk_wait_read0();  // the previous chunk's stores have read both buffers
+  __syncwarp();
+  tmem_ld_wait();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {  // 8 columns = 4 packed pairs per step
+    const uint4 b0 = lds128(bias_s + j * 32), b1 = lds128(bias_s + j * 32 + 16);  // broadcast reads
+    const uint32_t bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    uint64_t v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      v[e] = f2_add(f2_pack(__uint_as_float(r[8 * j + 2 * e]), __uint_as_float(r[8 * j + 2 * e + 1])),
+                    f2_pack(__uint_as_float(bv[2 * e]), __uint_as_float(bv[2 * e + 1])));
+    uint32_t y4[4], d4[4];
+    gelu_and_grad2<4>(v, y4, d4);
+    sts128(stg_cell(stg, lane, j), make_uint4(y4[0], y4[1], y4[2], y4[3]));
+    sts128(stg_cell(stg + kStgBytesPerWarp, lane, j), make_uint4(d4[0], d4[1], d4[2], d4[3]));
+  }
+  fence_proxy_async_smem();
+  __syncwarp();
+  if (lane == 0) {
+    tma_store_2d(tmC, stg, n0, row0);
+    if (p.aux_out != nullptr) tma_store_2d(tmX, stg + kStgBytesPerWarp, n0, row0);
+    bulk_commit();
+  }
+}
+
 // fp32 output + fp32 residual with prefetched residual (pair mode, 3-stage variant): the residual piece already
 // sits (or is about to land) in this chunk's own staging buffer; the sum is written in place and leaves as one TMA
 // bulk store.  `bar` is the warp's mbarrier for the first chunk of a tile (it covers all four loads), else nullptr.
@@ -814,7 +849,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = grp; c < BN / 32; c += 4) {
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= p.N) break;  // warp-uniform
-          if (p.epilogue == CGPT_EPI_GELU)
+          if (L::kAuxPrefetch && p.epilogue == CGPT_EPI_GELU && (p.tma_out & 1) && (p.aux_out == nullptr || (p.tma_out & 2)))
+            epi_chunk_gelu_2buf(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128);
+          else if (p.epilogue == CGPT_EPI_GELU)
             epi_chunk_bf16<true>(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128);
           else
             epi_chunk_bf16<false>(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128);
@@ -1013,7 +1050,9 @@ extern "C" int cgpt_gemm_bf16(const cgpt_gemm_args* a, cgpt_stream_t stream) {
       }
       if (a->out_f32 && a->residual && (p.tma_out & 1) && (p.tma_out & 2) && !a->accumulate && a->K <= respf_kmax)
         return dispatch_major<256, 3, true>(amn, bmn, ta, tb, tc, tx, p, st);
-      if (auxpf) return dispatch_major<256, 5, true>(amn, bmn, ta, tb, tc, tx, p, st);
+      // GELU(+GELU') shares the layout with two staging buffers per warp (one per output)
+      if (auxpf || (a->epilogue == CGPT_EPI_GELU && (p.tma_out & 1) && !a->out_f32))
+        return dispatch_major<256, 5, true>(amn, bmn, ta, tb, tc, tx, p, st);
       return dispatch_major<256, 6, true>(amn, bmn, ta, tb, tc, tx, p, st);
     }
     if (auxpf) return dispatch_major<256, 3>(amn, bmn, ta, tb, tc, tx, p, st);
