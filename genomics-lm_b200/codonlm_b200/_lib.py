@@ -50,6 +50,8 @@ SIGNATURES = {
     "cgpt_attn_bwd_workspace": (_i64, [_i, _i, _i, _i, _i]),
     "cgpt_attn_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, C.c_uint64, C.c_uint64,
                            _vp]),
+    "cgpt_attn_bwd_colsum": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, C.c_uint64,
+                                  C.c_uint64, _vp]),
     "cgpt_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, C.c_uint64, C.c_uint64, _vp]),
     "cgpt_dropout": (_i, [_vp, _vp, _vp, _i, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
     "cgpt_skinny_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),

@@ -21,6 +21,7 @@ _SMS = 148
 # most ONE entry (the consumer runs before the next LayerNorm backward) and the entry is dropped when it is
 # used or replaced, so a recycled device address can never be matched against a stale entry.
 _BF16_SIDE = {}
+_QKV_SIDE = {}  # dqkv.data_ptr() -> column sums of dqkv taken inside the attention backward kernels
 
 
 def _bf16_of(g: torch.Tensor):
@@ -226,11 +227,22 @@ class PackedLinearFn(Function):
                 grads.append(_wgrad(gb, x, n, k_in, dy_off=r0, master=ctx.masters[i]))
         if ctx.has_bias:
             b_slots = _packed_slots(ctx.masters[nw:], ctx.rows)
+            qsum = _QKV_SIDE.pop(g.data_ptr(), None)
+            _QKV_SIDE.clear()
+            if qsum is not None and qsum.numel() != N:
+                qsum = None
             if nw > 1 and b_slots is not None:
-                ops.colsum_bf16(gb, torch.as_strided(b_slots[0], (N,), (1,)), N=N, ld=gb.stride(0))
+                packed_b = torch.as_strided(b_slots[0], (N,), (1,))
+                if qsum is not None:
+                    packed_b.add_(qsum)
+                else:
+                    ops.colsum_bf16(gb, packed_b, N=N, ld=gb.stride(0))
                 for m in ctx.masters[nw:]:
                     _done(m)
                 grads.extend([None] * nw)
+            elif qsum is not None:
+                for i, (r0, n) in enumerate(ctx.rows):
+                    grads.append(_bias_grad(gb, n, ctx.masters[nw + i], qsum[r0:r0 + n]))
             else:
                 for i, (r0, n) in enumerate(ctx.rows):
                     if gsum is not None and nw == 1:
@@ -369,6 +381,7 @@ class OffsetHeadFn(Function):
 
 def reset_side_channel():
     _BF16_SIDE.clear()
+    _QKV_SIDE.clear()
 
 
 class DropoutFn(Function):
@@ -412,10 +425,16 @@ class AttentionFn(Function):
     def backward(ctx, g):
         qkv, out, lse = ctx.saved_tensors
         seg_start, rope, B, T, H, Hk, hd, window, dropout_p, seed, off = ctx.aux
+        # without RoPE dqkv is final here, so the kernels also take its column sums (the q|k|v bias gradients) and
+        # hand them to the QKV linear's backward through the side channel
+        csum = torch.zeros(((H + 2 * Hk) * hd,), dtype=f32, device=qkv.device) if rope is None else None
         dqkv = ops.attn_bwd(qkv, seg_start, out, g.contiguous(), lse, B, T, H, Hk, hd, window=window,
-                            dropout_p=dropout_p, seed=seed, offset=off)
+                            dropout_p=dropout_p, seed=seed, offset=off, colsum=csum)
+        _QKV_SIDE.clear()
         if rope is not None:
             ops.rope_qk(dqkv, rope[0], rope[1], B, T, H, Hk, hd, inverse=True)
+        else:
+            _QKV_SIDE[dqkv.data_ptr()] = csum
         return dqkv, None, None, None, None, None, None, None, None, None
 
 

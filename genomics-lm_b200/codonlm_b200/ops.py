@@ -231,14 +231,16 @@ def attn_fwd(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None, dropout_p=0.
     return out, lse
 
 
-def attn_bwd(qkv, seg_start, out, dout, lse, B, T, H, Hk, hd, window=0, scale=None, dropout_p=0.0, seed=0, offset=0):
+def attn_bwd(qkv, seg_start, out, dout, lse, B, T, H, Hk, hd, window=0, scale=None, dropout_p=0.0, seed=0, offset=0,
+             colsum=None):
+    """dqkv; `colsum` (fp32 [(H+2Hk)*hd], accumulated) also receives the column sums of dqkv (q|k|v bias grads)."""
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
     dqkv = torch.empty_like(qkv)
     nbytes = _L().cgpt_attn_bwd_workspace(B, T, H, Hk, hd)
     ws = torch.empty((nbytes // 4,), dtype=f32, device=qkv.device)
-    check(_L().cgpt_attn_bwd(qkv.data_ptr(), _p(seg_start), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
-                             dqkv.data_ptr(), ws.data_ptr(), B, T, H, Hk, hd, int(window or 0), float(scale),
-                             float(dropout_p), seed, offset, _stream()))
+    check(_L().cgpt_attn_bwd_colsum(qkv.data_ptr(), _p(seg_start), out.data_ptr(), dout.data_ptr(), lse.data_ptr(),
+                                    dqkv.data_ptr(), ws.data_ptr(), _p(colsum), B, T, H, Hk, hd, int(window or 0),
+                                    float(scale), float(dropout_p), seed, offset, _stream()))
     return dqkv
 
 

@@ -1299,8 +1299,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                    const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dkv,
                    const int32_t* __restrict__ seg_start,
                    const int* __restrict__ qhi_tab, const float* __restrict__ lse, const float* __restrict__ delta,
-                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_ws, int Bsz, int T, int H, int Hk,
-                   int window, float scale, const DropoutCfg drop, int smem_bytes) {
+                   __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_ws, float* __restrict__ dqkv_colsum,
+                   int Bsz, int T, int H, int Hk, int window, float scale, const DropoutCfg drop, int smem_bytes) {
   using C = HeadCfg<HD>;
   using S = BwdWsSmem<HD>;
   constexpr int TMEM_COLS = 512;
@@ -1782,6 +1782,24 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           tma_store_3d(&tm_dkv, smem_u32(stg) + 32 * ROWB, vcol + half * HH, kv0 + (warp & 3) * 32, b);
           bulk_commit();
         }
+        if (dqkv_colsum != nullptr && lane < HH) {
+          // column sums of the staged (bf16-rounded) dK / dV piece, lane = column: the key / value bias gradients
+          // without re-reading dqkv from HBM.  kv rows past T hold exact zeros (their P and dS columns are masked).
+          float sk = 0.f, sv = 0.f;
+          const uint32_t cb = smem_u32(stg) + (lane & 7) * 2;
+#pragma unroll
+          for (int rr = 0; rr < 32; ++rr) {
+            const int swr = ROWB == 64 ? ((rr >> 1) & 3) : (ROWB == 32 ? ((rr >> 2) & 1) : 0);
+            const uint32_t a = cb + rr * ROWB + (((lane >> 3) ^ swr) << 4);
+            uint16_t hk, hv;
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hk) : "r"(a));
+            asm volatile("ld.shared.u16 %0, [%1];" : "=h"(hv) : "r"(a + 32 * ROWB));
+            sk += __uint_as_float(static_cast<uint32_t>(hk) << 16);
+            sv += __uint_as_float(static_cast<uint32_t>(hv) << 16);
+          }
+          atomicAdd(dqkv_colsum + kcol + half * HH + lane, sk);
+          atomicAdd(dqkv_colsum + vcol + half * HH + lane, sv);
+        }
       }
       cur = nx;
     }
@@ -1795,24 +1813,50 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   }
 }
 
-// dq (fp32 [B,H,T,hd]) * scale -> bf16 into the q column block of dqkv
-__global__ void attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfloat16* __restrict__ dqkv, int B, int T,
-                                       int H, int hd, int W, float scale) {
+// dq (fp32 [B,H,T,hd]) * scale -> bf16 into the q column block of dqkv; optionally also the column sums of the
+// (bf16-rounded) result = the query bias gradient.  CTA = up to 256 rows of one (batch, head); a thread owns 8
+// columns (two 16-byte loads, one 16-byte store).
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfloat16* __restrict__ dqkv, int T, int H, int hd, int W,
+                       float scale, float* __restrict__ colsum) {
+  __shared__ float red[256][8];
   const int hd8 = hd >> 3;
-  const long long total = (long long)B * H * T * hd8;
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total;
-       e += (long long)gridDim.x * blockDim.x) {
-    const int c8 = (int)(e % hd8);
-    long long r = e / hd8;
-    const int t = (int)(r % T);
-    r /= T;
-    const int h = (int)(r % H);
-    const int b = (int)(r / H);
-    const float4 v = reinterpret_cast<const float4*>(dq_ws)[2 * e];
-    const float4 w = reinterpret_cast<const float4*>(dq_ws)[2 * e + 1];
-    const uint4 o = make_uint4(pack_bf16(v.x * scale, v.y * scale), pack_bf16(v.z * scale, v.w * scale),
-                               pack_bf16(w.x * scale, w.y * scale), pack_bf16(w.z * scale, w.w * scale));
-    *reinterpret_cast<uint4*>(dqkv + ((size_t)b * T + t) * W + h * hd + c8 * 8) = o;
+  const int rpi = 256 / hd8;  // rows per iteration
+  const int tid = threadIdx.x;
+  const int r = tid / hd8, c8 = tid - r * hd8;
+  const bool active = r < rpi;
+  const int bh = blockIdx.y, b = bh / H, h = bh - b * H;
+  const int t0 = blockIdx.x * 256, t1 = min(T, t0 + 256);
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+  if (active) {
+    for (int t = t0 + r; t < t1; t += rpi) {
+      const float4* src = reinterpret_cast<const float4*>(dq_ws + ((size_t)bh * T + t) * hd + c8 * 8);
+      const float4 v = src[0], w = src[1];
+      const uint4 o = make_uint4(pack_bf16(v.x * scale, v.y * scale), pack_bf16(v.z * scale, v.w * scale),
+                                 pack_bf16(w.x * scale, w.y * scale), pack_bf16(w.z * scale, w.w * scale));
+      *reinterpret_cast<uint4*>(dqkv + ((size_t)b * T + t) * W + h * hd + c8 * 8) = o;
+      if (colsum != nullptr) {
+        const uint32_t ov[4] = {o.x, o.y, o.z, o.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16(ov[q]);
+          acc[2 * q] += f.x;
+          acc[2 * q + 1] += f.y;
+        }
+      }
+    }
+  }
+  if (colsum == nullptr) return;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) red[tid][j] = active ? acc[j] : 0.f;
+  __syncthreads();
+  if (tid < hd) {
+    const int cc8 = tid >> 3, j = tid & 7;
+    float tsum = 0.f;
+    for (int rr = 0; rr < rpi; ++rr) tsum += red[rr * hd8 + cc8][j];
+    atomicAdd(colsum + h * hd + tid, tsum);
   }
 }
 
@@ -1922,7 +1966,8 @@ int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B
 
 template <int HD>
 int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse, void* dqkv,
-               void* ws, int B, int T, int H, int Hk, int window, float scale, const DropoutCfg& drop, cudaStream_t st) {
+               void* ws, float* colsum, int B, int T, int H, int Hk, int window, float scale, const DropoutCfg& drop,
+               cudaStream_t st) {
   using S = BwdSmem<HD>;
   const int W = (H + 2 * Hk) * HD;
   CUtensorMap tq, td;
@@ -1979,8 +2024,8 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
       CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SW::kDynamic));
       configured = true;
     }
-    kern<<<grid, 288, SW::kDynamic, st>>>(tq, td, tdq, tdkv, seg, qhi_tab, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, B,
-                                          T, H, Hk, window, scale, drop, SW::kDynamic);
+    kern<<<grid, 288, SW::kDynamic, st>>>(tq, td, tdq, tdkv, seg, qhi_tab, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws,
+                                          colsum, B, T, H, Hk, window, scale, drop, SW::kDynamic);
   } else {
     auto kern = attn_bwd_kernel<HD>;
     static bool configured = false;
@@ -1994,14 +2039,14 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   count_launch();
   CGPT_LAUNCH_CHECK();
   {
-    const long long n = (long long)B * H * T * (HD / 8);
-    long long g = (n + 255) / 256;
-    if (g > (long long)num_sms() * 8) g = (long long)num_sms() * 8;
-    attn_dq_convert_kernel<<<(unsigned)g, 256, 0, st>>>(dq_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), B, T, H, HD, W,
-                                                        scale);
+    // hd <= 64: the k / v column sums came out of the main kernel's epilogue, the q part comes out of this one
+    float* qsum = (HD <= 64) ? colsum : nullptr;
+    attn_dq_convert_kernel<<<dim3((T + 255) / 256, B * H), 256, 0, st>>>(dq_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), T, H,
+                                                                        HD, W, scale, qsum);
     count_launch();
     CGPT_LAUNCH_CHECK();
   }
+  if (colsum != nullptr && HD > 64) return cgpt_colsum_bf16(dqkv, W, colsum, B * T, W, reinterpret_cast<cgpt_stream_t>(st));
   return 0;
 }
 
@@ -2052,6 +2097,13 @@ int64_t cgpt_attn_bwd_workspace(int B, int T, int H, int Hk, int hd) {
 int cgpt_attn_bwd(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse, void* dqkv,
                   void* ws, int B, int T, int H, int Hk, int hd, int window, float scale, float dropout_p, uint64_t seed,
                   uint64_t offset, cgpt_stream_t stream) {
+  return cgpt_attn_bwd_colsum(qkv, seg, out, dout, lse, dqkv, ws, nullptr, B, T, H, Hk, hd, window, scale, dropout_p, seed,
+                              offset, stream);
+}
+
+int cgpt_attn_bwd_colsum(const void* qkv, const int32_t* seg, const void* out, const void* dout, const float* lse,
+                         void* dqkv, void* ws, float* dqkv_colsum, int B, int T, int H, int Hk, int hd, int window,
+                         float scale, float dropout_p, uint64_t seed, uint64_t offset, cgpt_stream_t stream) {
   CGPT_REQUIRE(dropout_p >= 0.f && dropout_p < 1.f, "attn_bwd: dropout_p=%f must be in [0,1)", dropout_p);
   const DropoutCfg drop = make_dropout(dropout_p, seed, offset);
   CGPT_REQUIRE(qkv && out && dout && lse && dqkv && ws, "attn_bwd: null pointer");
@@ -2059,7 +2111,7 @@ int cgpt_attn_bwd(const void* qkv, const int32_t* seg, const void* out, const vo
   int rc = check_attn_args("attn_bwd", B, T, H, Hk, hd);
   if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
-#define CALL(HD) launch_bwd<HD>(qkv, seg, out, dout, lse, dqkv, ws, B, T, H, Hk, window, scale, drop, st)
+#define CALL(HD) launch_bwd<HD>(qkv, seg, out, dout, lse, dqkv, ws, dqkv_colsum, B, T, H, Hk, window, scale, drop, st)
   DISPATCH_HD(hd, CALL)
 #undef CALL
 }

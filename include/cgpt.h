@@ -152,6 +152,12 @@ int64_t cgpt_attn_bwd_workspace(int B, int T, int H, int Hk, int hd);
 int cgpt_attn_bwd(const void* qkv, const int32_t* seg_start, const void* out, const void* dout, const float* lse,
                   void* dqkv, void* ws, int B, int T, int H, int Hk, int hd, int window, float scale,
                   float dropout_p, uint64_t seed, uint64_t offset, cgpt_stream_t stream);
+/* Same, and dqkv_colsum[(H+2Hk)*hd] (fp32, nullable) += column sums of dqkv: the gradients of the query | key | value
+ * biases (nn.Linear biases at :85-93), taken inside the kernels instead of by another pass over dqkv. */
+int cgpt_attn_bwd_colsum(const void* qkv, const int32_t* seg_start, const void* out, const void* dout,
+                         const float* lse, void* dqkv, void* ws, float* dqkv_colsum, int B, int T, int H, int Hk,
+                         int hd, int window, float scale, float dropout_p, uint64_t seed, uint64_t offset,
+                         cgpt_stream_t stream);
 /* Introspection path (use_sdpa=False, :116-131): dense probabilities att fp32 [B,H,T,T]. */
 int cgpt_attn_probs(const void* qkv, const int32_t* seg_start, float* att, int B, int T, int H, int Hk, int hd,
                     int window, float scale, float dropout_p, uint64_t seed, uint64_t offset, cgpt_stream_t stream);

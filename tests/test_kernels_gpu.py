@@ -406,6 +406,28 @@ def test_split_head_on_tensor_cores_is_fp32_accurate(ops):
             assert (b.grad.double() - go.double().sum(0)).abs().max().item() <= 3e-5 * go.double().sum(0).abs().max().item()
 
 
+@pytest.mark.parametrize("case", [(2, 300, 4, 4, 64, 0), (1, 257, 4, 2, 32, 0), (2, 130, 2, 1, 48, 40), (1, 200, 2, 2, 128, 0)])
+def test_attention_backward_fused_bias_column_sums(ops, case):
+    """cgpt_attn_bwd_colsum: the q|k|v bias gradients taken inside the backward kernels equal the column sums of
+    the dqkv they wrote (same bf16-rounded values; fp32 accumulation order differs), and accumulate into the buffer."""
+    B, T, H, Hk, hd, window = case
+    g = torch.Generator().manual_seed(5)
+    W = (H + 2 * Hk) * hd
+    qkv = torch.randn(B * T, W, generator=g).to(DEV).to(torch.bfloat16)
+    idx = torch.randint(4, 68, (B, T), generator=g)
+    idx[:, T // 3] = 3
+    ss = ops.segment_starts(idx.to(DEV), 3)
+    out, lse = ops.attn_fwd(qkv, ss, B, T, H, Hk, hd, window=window)
+    dout = torch.randn(B * T, H * hd, generator=g).to(DEV).to(torch.bfloat16)
+    base = torch.full((W,), 0.5, device=DEV)
+    csum = base.clone()
+    dqkv = ops.attn_bwd(qkv, ss, out, dout, lse, B, T, H, Hk, hd, window=window, colsum=csum)
+    ref = dqkv.float().sum(0)
+    assert torch.equal(dqkv, ops.attn_bwd(qkv, ss, out, dout, lse, B, T, H, Hk, hd, window=window))
+    err = (csum - base - ref).abs().max().item()
+    assert err <= 1e-4 * max(1.0, ref.abs().max().item()), err
+
+
 # ------------------------------------------------------------------------------------------ dropout
 def test_elementwise_dropout_mask_statistics_and_backward(ops):
     n = 1 << 20
