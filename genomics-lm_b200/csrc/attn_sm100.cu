@@ -768,9 +768,11 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
 
 // last query tile that can see each (batch, kv tile): the warp-specialised backward reads this table instead of
 // searching seg_start itself.  Side job of the first threads of the delta kernels.
+__device__ __forceinline__ int qhi_ctr_index(int B, int T) { return (B * ((T + BKV - 1) / BKV) + 63) / 64 * 64; }
 __device__ __forceinline__ void fill_qhi_tab(int e, int B, int T, const int32_t* __restrict__ seg_start, int window,
-                                             int* __restrict__ qhi_tab) {
+                                             int* __restrict__ qhi_tab, int ctr_init) {
   const int nkb = (T + BKV - 1) / BKV;
+  if (e == 0) qhi_tab[qhi_ctr_index(B, T)] = ctr_init;  // work counter of the backward kernel (first unclaimed pair)
   if (e >= B * nkb) return;
   const int b = e / nkb, kvb = e - b * nkb;
   int hi_pos = T - 1;
@@ -785,9 +787,10 @@ __device__ __forceinline__ void fill_qhi_tab(int e, int B, int T, const int32_t*
 template <int G>
 __global__ void attn_delta_vec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                       float* __restrict__ delta, int B, int T, int H,
-                                      const int32_t* __restrict__ seg_start, int window, int* __restrict__ qhi_tab) {
+                                      const int32_t* __restrict__ seg_start, int window, int* __restrict__ qhi_tab,
+                                      int ctr_init) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index
-  if (qhi_tab && e < (long long)B * ((T + BKV - 1) / BKV)) fill_qhi_tab((int)e, B, T, seg_start, window, qhi_tab);
+  if (qhi_tab && e < (long long)B * ((T + BKV - 1) / BKV)) fill_qhi_tab((int)e, B, T, seg_start, window, qhi_tab, ctr_init);
   const long long total = (long long)B * T * H * G;
   float s = 0.f;
   if (e < total) {
@@ -814,8 +817,9 @@ __global__ void attn_delta_vec_kernel(const __nv_bfloat16* __restrict__ o, const
 // generic head sizes (48, 96): one warp per (token, head)
 __global__ void attn_delta_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                   float* __restrict__ delta, int B, int T, int H, int hd,
-                                  const int32_t* __restrict__ seg_start, int window, int* __restrict__ qhi_tab) {
-  if (qhi_tab) fill_qhi_tab(blockIdx.x * blockDim.x + threadIdx.x, B, T, seg_start, window, qhi_tab);
+                                  const int32_t* __restrict__ seg_start, int window, int* __restrict__ qhi_tab,
+                                  int ctr_init) {
+  if (qhi_tab) fill_qhi_tab(blockIdx.x * blockDim.x + threadIdx.x, B, T, seg_start, window, qhi_tab, ctr_init);
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (long long)B * T * H) return;
@@ -1285,7 +1289,7 @@ struct BwdWsSmem {
   static constexpr int kP = kdO + 2 * C::TILE_BYTES;      // 1 buffer
   static constexpr int kdS = kP + kPTileBytes;            // 2 buffers
   static constexpr int kBar = kdS + 2 * kPTileBytes;
-  static constexpr int kTotal = kBar + 128;
+  static constexpr int kTotal = kBar + 128 + 8 * 8 + 8 * 16;  // + work ring: 8 mbarriers, 8 pair descriptors
   static constexpr int kDynamic = (kTotal + 1024 <= 232448) ? kTotal + 1024 : 232448;
   static constexpr bool kTmaDq = (HD == 32 || HD == 64);
   static constexpr int kdQBoxCols = HD == 32 ? 16 : 32;
@@ -1298,7 +1302,7 @@ __global__ void __launch_bounds__(288, 1)
 attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constant__ CUtensorMap tm_do,
                    const __grid_constant__ CUtensorMap tm_dq, const __grid_constant__ CUtensorMap tm_dkv,
                    const int32_t* __restrict__ seg_start,
-                   const int* __restrict__ qhi_tab, const float* __restrict__ lse, const float* __restrict__ delta,
+                   int* __restrict__ qhi_tab, const float* __restrict__ lse, const float* __restrict__ delta,
                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_ws, float* __restrict__ dqkv_colsum,
                    int Bsz, int T, int H, int Hk, int window, float scale, const DropoutCfg drop, int smem_bytes) {
   using C = HeadCfg<HD>;
@@ -1317,6 +1321,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint64_t* dkv_bar = bars + 9;     // the math warps have drained dK/dV of an item from TMEM
   uint64_t* pfree_bar = bars + 10;  // the dV MMAs of a tile have retired: the P buffer may be rewritten
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* sched_bar = bars + 16;                                 // [8] a pair descriptor has been published
+  int4* sched = reinterpret_cast<int4*>(bars + 24);                // [8] {pair slot kk, kv head, batch, valid}
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int rep = H / Hk;
@@ -1339,6 +1345,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(&kv_bar[0], 1);
     mbar_init(&kv_bar[1], 1);
     mbar_init(pfree_bar, 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&sched_bar[i], 1);
     mbar_init(&q_bar[0], 1);
     mbar_init(&q_bar[1], 1);
     mbar_init(s_bar, 1);
@@ -1361,58 +1368,38 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + HD;
   const uint32_t tdQ0 = tmem_base + 256 + 2 * HD;  // + buf * HD
 
-  // Item cursor: walks this CTA's pairs (cta, cta + G, ...) and the two halves of each pair without any division
-  // in the loop (runtime divisors cost ~100 instructions each, and every warp role walks the same sequence).
+  // Work distribution.  The first pair of a CTA is its block index; every further pair is claimed from a global
+  // counter (initialised to the grid size by the delta kernel), so CTAs that drew short items (segment masks make
+  // the work per kv tile vary a lot) simply claim more.  Warp 8 claims one pair ahead, decodes it and publishes
+  // the descriptor through an 8-slot ring in shared memory; the math warps follow the same sequence from the ring.
   struct Cursor {
-    int pi, bh, kk0, bhm, kvh, b, sub, kvb;
+    int kk, kvh, b, sub, kvb;
     bool valid;
   };
-  const int qG = G / npk, rG = G - qG * npk, qGm = qG % npk, qH = qG / Hk, rH = qG - qH * Hk;
-  auto rot = [&](const Cursor& c) {  // pair slot rotated by the head index: a CTA's pairs cycle through all k
-    const int kk = c.kk0 + c.bhm;
-    return kk >= npk ? kk - npk : kk;
-  };
-  auto cursor_begin = [&]() {
-    Cursor c;
-    c.pi = blockIdx.x;
-    c.valid = c.pi < n_pairs;
-    c.bh = c.pi / npk;
-    c.kk0 = c.pi - c.bh * npk;
-    c.bhm = c.bh % npk;
-    c.b = c.bh / Hk;
-    c.kvh = c.bh - c.b * Hk;
+  int* work_ctr = qhi_tab + qhi_ctr_index(Bsz, T);
+  auto first_half = [&](Cursor& c) {
     c.sub = 0;
-    c.kvb = rot(c);
-    return c;
+    c.kvb = c.kk;
   };
-  auto cursor_next = [&](Cursor c) {
-    if (c.sub == 0) {  // second half of the pair: the mirrored kv tile (absent for the middle tile of an odd count)
+  // second half of the pair: the mirrored kv tile (absent for the middle tile of an odd count)
+  auto second_half = [&](Cursor& c) {
+    if (c.sub == 0 && nkb - 1 - c.kk != c.kk) {
       c.sub = 1;
-      const int kk = rot(c);
-      if (nkb - 1 - kk != kk) {
-        c.kvb = nkb - 1 - kk;
-        return c;
-      }
+      c.kvb = nkb - 1 - c.kk;
+      return true;
     }
-    c.sub = 0;
-    c.pi += G;
-    if (c.pi >= n_pairs) {
-      c.valid = false;
-      return c;
-    }
-    c.kk0 += rG;
-    const int carry = c.kk0 >= npk;
-    if (carry) c.kk0 -= npk;
-    c.bh += qG + carry;
-    c.bhm += qGm + carry;
-    while (c.bhm >= npk) c.bhm -= npk;
-    c.kvh += rH + carry;
-    c.b += qH;
-    while (c.kvh >= Hk) {
-      c.kvh -= Hk;
-      ++c.b;
-    }
-    c.kvb = rot(c);
+    return false;
+  };
+  auto ring_read = [&](uint32_t n) {  // pair number n of this CTA (consumers)
+    const uint32_t slot = n & 7;
+    mbar_wait(&sched_bar[slot], (n >> 3) & 1);
+    const int4 d = sched[slot];
+    Cursor c;
+    c.kk = d.x;
+    c.kvh = d.y;
+    c.b = d.z;
+    c.valid = d.w != 0;
+    first_half(c);
     return c;
   };
 
@@ -1462,7 +1449,46 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       }
       __syncwarp();
     };
-    Cursor cur = cursor_begin();
+    // publisher side of the work ring
+    uint32_t n_pub = 0;  // pairs published so far
+    auto publish = [&](int pi) {  // decode pair index pi (>= n_pairs: end of work), publish, return its first item
+      Cursor c;
+      c.valid = pi < n_pairs;
+      const int bh = c.valid ? pi / npk : 0;
+      const int kk0 = pi - bh * npk;
+      c.kk = (kk0 + bh) % npk;  // pair slot rotated by the head index (consecutive pairs of a head differ in weight)
+      c.b = bh / Hk;
+      c.kvh = bh - c.b * Hk;
+      first_half(c);
+      const uint32_t slot = n_pub & 7;
+      if (lane == 0) {
+        sched[slot] = make_int4(c.kk, c.kvh, c.b, c.valid ? 1 : 0);
+        mbar_arrive(&sched_bar[slot]);  // release: the descriptor is visible to whoever observes the phase
+      }
+      ++n_pub;
+      return c;
+    };
+    auto claim = [&]() {  // next unclaimed pair; the value is first used one pair later, so the latency is hidden
+      int v = 0;
+      if (lane == 0) v = atomicAdd(work_ctr, 1);
+      return v;
+    };
+    int claimed = 0;       // lane 0: pair index claimed for the pair after the current one
+    bool more = true;      // false once the end-of-work descriptor has been published
+    Cursor cur = publish(blockIdx.x);
+    more = cur.valid;
+    if (more) claimed = claim();
+    auto cursor_next = [&](Cursor c) {
+      if (second_half(c)) return c;
+      if (!more) {
+        c.valid = false;
+        return c;
+      }
+      c = publish(__shfl_sync(0xffffffffu, claimed, 0));
+      more = c.valid;
+      if (more) claimed = claim();
+      return c;
+    };
     int nx_qhi = cur.valid ? item_qhi(cur) : 0;
     if (cur.valid) {  // prologue of the stream: the first item's K/V and its first tile
       load_kv(cur.kvb, cur.kvh, cur.b, 0);
@@ -1613,7 +1639,12 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
       nx_dl = i0 < T ? delta[st0] : 0.f;
       nx_ss = (seg_start && i0 < T) ? seg_start[(size_t)b * T + i0] : 0;
     };
-    Cursor cur = cursor_begin();
+    uint32_t n_read = 0;  // pairs read from the ring so far
+    auto cursor_next = [&](Cursor c) {
+      if (second_half(c)) return c;
+      return ring_read(n_read++);
+    };
+    Cursor cur = ring_read(n_read++);
     if (cur.valid) prefetch_item(cur);
 
     for (; cur.valid; ++n_it) {
@@ -1915,7 +1946,8 @@ __global__ void attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const i
 }
 
 inline size_t delta_floats(int B, int T, int H) { return ((size_t)B * H * T + 63) / 64 * 64; }
-inline size_t qhi_floats(int B, int T) { return ((size_t)B * ((T + BKV - 1) / BKV) + 63) / 64 * 64; }
+// range table [B, kv tiles] rounded up to 64 entries, + 64 entries for the work counter
+inline size_t qhi_floats(int B, int T) { return ((size_t)B * ((T + BKV - 1) / BKV) + 63) / 64 * 64 + 64; }
 
 int make_qkv_tmap(CUtensorMap* tm, const void* base, int B, int T, int W, int aw) {
   const uint64_t dims[3] = {(uint64_t)W, (uint64_t)T, (uint64_t)B};
@@ -1997,6 +2029,9 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     if (rc) return rc;
   }
   CGPT_CHECK(cudaMemsetAsync(dq_ws, 0, (size_t)B * H * T * HD * sizeof(float), st));
+  // grid of the warp-specialised kernel = initial value of its work counter (pairs 0..grid-1 are implicit)
+  const int ws_pairs = (((T + BKV - 1) / BKV + 1) / 2) * Hk * B;
+  const int ws_grid = ws_pairs < num_sms() ? ws_pairs : num_sms();
   {
     const __nv_bfloat16* po = reinterpret_cast<const __nv_bfloat16*>(out);
     const __nv_bfloat16* pd = reinterpret_cast<const __nv_bfloat16*>(dout);
@@ -2004,10 +2039,11 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     if constexpr (G == 2 || G == 4 || G == 8 || G == 16) {
       const long long chunks = (long long)B * T * H * G;  // >= B * kv tiles, so the table job fits too
       attn_delta_vec_kernel<G><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(po, pd, delta, B, T, H, seg, window,
-                                                                               qhi_tab);
+                                                                               qhi_tab, ws_grid);
     } else {
       const long long warps = (long long)B * T * H;
-      attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(po, pd, delta, B, T, H, HD, seg, window, qhi_tab);
+      attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(po, pd, delta, B, T, H, HD, seg, window, qhi_tab,
+                                                                     ws_grid);
     }
     count_launch();
     CGPT_LAUNCH_CHECK();
@@ -2016,8 +2052,7 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   int grid = n_items < num_sms() ? n_items : num_sms();
   if constexpr (HD <= 64) {
     using SW = BwdWsSmem<HD>;
-    const int n_pairs = (((T + BKV - 1) / BKV + 1) / 2) * Hk * B;  // the kernel deals kv tiles in balanced pairs
-    grid = n_pairs < num_sms() ? n_pairs : num_sms();
+    grid = ws_grid;  // the kernel deals kv tiles in balanced pairs
     auto kern = attn_bwd_ws_kernel<HD>;
     static bool configured = false;
     if (!configured) {
