@@ -235,10 +235,10 @@ def run_ours(args):
     l0 = ops.launch_count()
     step.step(*resident[0])
     launches_per_step = ops.launch_count() - l0
-    use_graph = (world == 1) and not args.no_graph
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("CGPT_BENCH_GRAPH_DDP", "0") == "1")
     if use_graph:
         try:
-            step.capture(B, T)
+            step.capture(B, T, allow_collectives=world > 1)
             for i in range(2):
                 step.step(*resident[i % n_host])
         except Exception as exc:  # pragma: no cover - capture is an optimisation, never a requirement
@@ -345,7 +345,15 @@ def run_ours(args):
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         _emit(line)
     if world > 1:
+        # tear down with a watchdog: destroying the NCCL communicator while a captured graph still references its
+        # kernels has been seen to block; the JSON line is out, so a stuck teardown must not keep the job alive
+        killer = threading.Timer(20.0, os._exit, args=(0,))
+        killer.daemon = True
+        killer.start()
+        step._graph = None
+        torch.cuda.synchronize()
         dist.destroy_process_group()
+        killer.cancel()
 
 
 def step_breakdown(step, batch, path, ms_step):

@@ -250,11 +250,13 @@ class TrainStep:
         self.optimizer_step(lr_scale)
         return loss
 
-    def capture(self, B: int, T: int, warmup: int = 3):
-        """Capture forward + backward + AdamW for a fixed (B, T) into one CUDA graph (single-GPU, dropout off):
-        removes every launch gap and all Python work from the step.  step() then replays it."""
-        if self.world > 1:
-            raise RuntimeError("capture(): the data-parallel all-reduce is not captured; run eagerly")
+    def capture(self, B: int, T: int, warmup: int = 3, allow_collectives: bool = False):
+        """Capture forward + backward (+ bucketed all-reduce) + AdamW for a fixed (B, T) into one CUDA graph
+        (dropout off): removes every launch gap and all Python work from the step.  step() then replays it.
+        With more than one rank the NCCL all-reduces and the side stream they run on are part of the graph
+        (allow_collectives=True; every rank must capture, and replay, in lock step)."""
+        if self.world > 1 and not allow_collectives:
+            raise RuntimeError("capture(): pass allow_collectives=True to capture the bucketed all-reduce as well")
         if self.model.training and getattr(self.model, "dropout_p", 0.0) > 0.0:
             raise RuntimeError("capture(): dropout draws its Philox offset on the host; run eagerly")
         self._gx = torch.zeros((B, T), dtype=torch.int64, device=self._dev)
@@ -276,6 +278,8 @@ class TrainStep:
         with torch.cuda.graph(graph):
             self.zero_grad()
             loss, _ = self.forward_backward(self._gx, self._gy)
+            for bk in self.buckets:
+                bk.finish()
             gscale = 1.0 / self.world
             for gi, g in enumerate(self.groups):
                 ops.adamw(g.flat, g.grad, g.m, g.v, g.shadow, g.lr, self.betas[0], self.betas[1], self.eps,

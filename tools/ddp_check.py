@@ -22,9 +22,17 @@ B = 4
 data = [bench.synthetic_tokens(B, 256, seed=50 + r) for r in range(world)]
 # data-parallel: each rank its own micro-batch
 dp = TrainStep(build(), **kw, bucket_mb=1)
-for it in range(3):
-    x, y = data[rank]
-    dp.step(x.to(dev), y.to(dev))
+GRAPH = os.environ.get("CGPT_DDP_GRAPH", "0") == "1"  # the all-reduces captured in the CUDA graph with the step
+if GRAPH:
+    dp.step(*[t.to(dev) for t in data[rank]])           # first step eagerly: counts the gradient contributions
+    dp.capture(B, 256, allow_collectives=True)
+    for it in range(2):
+        x, y = data[rank]
+        dp.step(x.to(dev), y.to(dev))
+else:
+    for it in range(3):
+        x, y = data[rank]
+        dp.step(x.to(dev), y.to(dev))
 torch.cuda.synchronize()
 # reference: one process, gradient accumulation over the same micro-batches (mean of per-micro-batch means)
 ref = TrainStep(build(), **kw, process_group=None)
@@ -44,7 +52,12 @@ gathered = [torch.empty_like(flat) for _ in range(world)]
 dist.all_gather(gathered, flat)
 same = all(torch.equal(gathered[0], t) for t in gathered)
 if rank == 0:
-    print(f"ddp_check: world={world} max rel weight diff vs accumulation reference {worst:.3e}; replicas identical: {same}; "
+    print(f"ddp_check: graph={GRAPH} world={world} max rel weight diff vs accumulation reference {worst:.3e}; replicas identical: {same}; "
           f"buckets {[len(b.bounds) for b in dp.buckets]}")
     assert worst < 5e-3 and same
+import threading
+_k = threading.Timer(20.0, os._exit, args=(0,)); _k.daemon = True; _k.start()
+dp._graph = None
+torch.cuda.synchronize()
 dist.destroy_process_group()
+_k.cancel()
