@@ -235,7 +235,7 @@ def run_ours(args):
     l0 = ops.launch_count()
     step.step(*resident[0])
     launches_per_step = ops.launch_count() - l0
-    use_graph = not args.no_graph and (world == 1 or os.environ.get("CGPT_BENCH_GRAPH_DDP", "0") == "1")
+    use_graph = not args.no_graph and (world == 1 or os.environ.get("CGPT_BENCH_GRAPH_DDP", "1") == "1")
     if use_graph:
         try:
             step.capture(B, T, allow_collectives=world > 1)
