@@ -660,7 +660,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         }
         const float mloc = mraw * scale_log2;
         *xw = mloc;
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + (warp & 3), 64);  // only the two warps that share these 32 rows meet
         const float m_new = fmaxf(m_run, fmaxf(mloc, *xr));
         const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
         const float alpha = fast_exp2(m_run - m_safe);
@@ -729,7 +729,7 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         float* xw = xchg + 2 * 256 + (1 - half) * 128 + row;  // third buffer: never aliases a row-max exchange
         float* xr = xchg + 2 * 256 + half * 128 + row;
         *xw = l_run;
-        named_bar_sync(1, 256);
+        named_bar_sync(1 + (warp & 3), 64);
         const float l_tot = l_run + *xr;
         const float inv = 1.f / l_tot;
         // output rows -> bf16, staged in this warp's rows of the last tile's P buffer, one TMA store per warp
