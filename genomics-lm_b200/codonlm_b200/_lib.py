@@ -42,6 +42,7 @@ SIGNATURES = {
     "cgpt_gemm_bf16": (_i, [C.POINTER(GemmArgs), _vp]),
     "cgpt_cast_f32_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _vp]),
     "cgpt_split3_f32_bf16": (_i, [_vp, _i64, _vp, _i64, _i64, _i64, _i, _vp]),
+    "cgpt_fold_quadrants_add": (_i, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
     "cgpt_colsum_bf16": (_i, [_vp, _i64, _vp, _i, _i, _vp]),
     "cgpt_rope_qk": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "cgpt_swiglu_fwd": (_i, [_vp, _i64, _vp, _i64, _i, _i, _vp]),

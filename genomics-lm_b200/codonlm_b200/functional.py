@@ -339,18 +339,44 @@ class MlpSwiGLUFn(Function):
         return dh, (g if ctx.has_res else None), None, None, dwg, dwu, dwd
 
 
+def _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2):
+    M, d = xb.shape
+    dact = torch.empty((M, d), dtype=bf16, device=xb.device)
+    act = torch.empty((M, d), dtype=bf16, device=xb.device)
+    ops.gemm(xb, w1_sh, act, M=M, N=d, K=d, bias=b1, epilogue=EPI_GELU, aux_out=dact, ldaux=d)
+    out = torch.empty((M, d), dtype=f32, device=xb.device)
+    ops.gemm(act, w2_sh, out, M=M, N=d, K=d, bias=b2)
+    return out, act, dact
+
+
+def _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2):
+    """gb: bf16 gradient of the MLP output -> (dx bf16, db1, db2, dw1, dw2), None where accumulated in place."""
+    M, d = xb.shape
+    dw2 = _wgrad(gb, act, d, d, master=w2)
+    db2 = _colsum(gb, d, master=b2)
+    dpre = torch.empty((M, d), dtype=bf16, device=xb.device)
+    fuse = (d % 8 == 0)
+    mb1 = _main_grad(b1)
+    db1 = (mb1 if mb1 is not None else torch.zeros((d,), dtype=f32, device=xb.device)) if fuse else None
+    ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=d, colsum=db1)
+    dw1 = _wgrad(dpre, xb, d, d, master=w1)
+    if not fuse:
+        db1 = _colsum(dpre, d, master=b1)
+    elif mb1 is not None:
+        _done(b1)
+        db1 = None
+    dx = torch.empty((M, d), dtype=bf16, device=xb.device)
+    ops.gemm(dpre, w1_sh, dx, M=M, N=d, K=d, b_mn=True)
+    return dx, db1, db2, dw1, dw2
+
+
 class OffsetHeadFn(Function):
     """h_o = W2·gelu(W1·x + b1) + b2 on the post-ln_f hidden state — model_tiny_gpt.py:235-239,335.
     Input bf16, output fp32 (it feeds the fp32 LM head)."""
 
     @staticmethod
     def forward(ctx, xb, w1_sh, b1, w2_sh, b2, w1, w2):
-        M, d = xb.shape
-        dact = torch.empty((M, d), dtype=bf16, device=xb.device)
-        act = torch.empty((M, d), dtype=bf16, device=xb.device)
-        ops.gemm(xb, w1_sh, act, M=M, N=d, K=d, bias=b1, epilogue=EPI_GELU, aux_out=dact, ldaux=d)
-        out = torch.empty((M, d), dtype=f32, device=xb.device)
-        ops.gemm(act, w2_sh, out, M=M, N=d, K=d, bias=b2)
+        out, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2)
         ctx.save_for_backward(xb, dact, act, w1_sh, w2_sh)
         ctx.masters = (b1, b2, w1, w2)
         return out
@@ -358,30 +384,44 @@ class OffsetHeadFn(Function):
     @staticmethod
     def backward(ctx, g):
         xb, dact, act, w1_sh, w2_sh = ctx.saved_tensors
-        M, d = xb.shape
         b1, b2, w1, w2 = ctx.masters
         gb = ops.cast_bf16(g.contiguous())
-        dw2 = _wgrad(gb, act, d, d, master=w2)
-        db2 = _colsum(gb, d, master=b2)
-        dpre = torch.empty((M, d), dtype=bf16, device=xb.device)
-        fuse = (d % 8 == 0)
-        mb1 = _main_grad(b1)
-        db1 = (mb1 if mb1 is not None else torch.zeros((d,), dtype=f32, device=xb.device)) if fuse else None
-        ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=d, colsum=db1)
-        dw1 = _wgrad(dpre, xb, d, d, master=w1)
-        if not fuse:
-            db1 = _colsum(dpre, d, master=b1)
-        elif mb1 is not None:
-            _done(b1)
-            db1 = None
-        dx = torch.empty((M, d), dtype=bf16, device=xb.device)
-        ops.gemm(dpre, w1_sh, dx, M=M, N=d, K=d, b_mn=True)
+        dx, db1, db2, dw1, dw2 = _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2)
         return dx, None, db1, None, db2, dw1, dw2
+
+
+class OffsetLogitsFn(Function):
+    """logits_o = head(W2·gelu(W1·x + b1) + b2) as ONE autograd node (model_tiny_gpt.py:335-336): the fp32-accurate
+    head's input gradient is written as bf16 directly — the operand type of the MLP's backward GEMMs — instead of
+    an fp32 tensor that a cast kernel would re-read.  Same kernels and arithmetic as OffsetHeadFn + SplitHeadFn."""
+
+    @staticmethod
+    def forward(ctx, xb, w1_sh, b1, w2_sh, b2, w1, w2, head_w):
+        h, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2)
+        logits, h3, w3, wk = _split_head_fwd(h, head_w, None)
+        ctx.save_for_backward(xb, dact, act, w1_sh, w2_sh, h3, w3, wk)
+        ctx.masters = (b1, b2, w1, w2, head_w)
+        return logits
+
+    @staticmethod
+    def backward(ctx, g):
+        xb, dact, act, w1_sh, w2_sh, h3, w3, wk = ctx.saved_tensors
+        b1, b2, w1, w2, head_w = ctx.masters
+        M, d = xb.shape
+        gb, dhw, _ = _split_head_bwd(g, h3, w3, wk, head_w, None, (M, d, head_w.shape[0]), True, bf16)
+        dx, db1, db2, dw1, dw2 = _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2)
+        return dx, None, db1, None, db2, dw1, dw2, dhw
 
 
 def reset_side_channel():
     _BF16_SIDE.clear()
     _QKV_SIDE.clear()
+    _HEAD_W_CACHE.clear()
+
+
+def reset_head_cache():
+    """Drop the split copies of the head weights (call after writing a master behind autograd's back)."""
+    _HEAD_W_CACHE.clear()
 
 
 class DropoutFn(Function):
@@ -441,57 +481,86 @@ class AttentionFn(Function):
 TC_HEAD_MIN_ROWS = 4096  # below this the fp32 FMA head kernels are used (launch-bound sizes, tests)
 
 
+_HEAD_W_CACHE = {}  # id(w) -> (w, version, w3, wk): one split per weight and forward pass (6 head calls share the tied head)
+
+
+def _head_weight_split(w):
+    """(w3 [V, 3d] = hi|hi|lo, wk [3Vp, d] = hi;hi;lo stacked along the reduction of the input-gradient GEMM)."""
+    hit = _HEAD_W_CACHE.get(id(w))
+    if hit is not None and hit[0] is w and hit[1] == w._version:
+        return hit[2], hit[3]
+    V, d = w.shape
+    Vp = (V + 7) // 8 * 8
+    with torch.no_grad():
+        w3 = ops.split3(w.detach(), partner=True)
+        wk = torch.zeros((3 * Vp, d), dtype=bf16, device=w.device)
+        wk[0:V], wk[Vp:Vp + V], wk[2 * Vp:2 * Vp + V] = w3[:, 0:d], w3[:, d:2 * d], w3[:, 2 * d:3 * d]
+    _HEAD_W_CACHE[id(w)] = (w, w._version, w3, wk)
+    return w3, wk
+
+
+def _split_head_fwd(x, w, bias):
+    M, d = x.shape
+    V = w.shape[0]
+    x3 = ops.split3(x)                       # [M, 3d]  hi|lo|hi
+    w3, wk = _head_weight_split(w)           # [V, 3d]  hi|hi|lo
+    out = torch.empty((M, V), dtype=f32, device=x.device)
+    ops.gemm(x3, w3, out, M=M, N=V, K=3 * d, bias=bias)
+    return out, x3, w3, wk
+
+
+def _split_head_bwd(g, x3, w3, wk, wm, bm, dims, need_dx, dx_dtype=f32):
+    """-> (dx or None, dw or None, db or None); dw/db are None when accumulated into main_grad."""
+    M, d, V = dims
+    Vp = (V + 7) // 8 * 8
+    g3 = ops.split3(g.contiguous(), cols_pad=Vp)  # [M, 3Vp]  hi|lo|hi
+    dx = None
+    if need_dx:
+        # dx = g·w: reduction over the (tripled, padded) vocabulary; w as [hi; hi; lo] stacked along K
+        dx = torch.empty((M, d), dtype=dx_dtype, device=g.device)
+        ops.gemm(g3, wk, dx, M=M, N=d, K=3 * Vp, b_mn=True)
+    mw, mb = _main_grad(wm), _main_grad(bm)
+    dw = mw if mw is not None else torch.zeros((V, d), dtype=f32, device=g.device)
+    # dW = gᵀ·x with both operands as [hi|lo]: ONE stacked GEMM gives the four cross products as the quadrants of
+    # a [2Vp, 2d] scratch matrix (the tokens are read once, not three times), folded into dW by a small kernel
+    scratch = torch.zeros((2 * Vp, 2 * d), dtype=f32, device=g.device)
+    tiles = ((2 * Vp + 127) // 128) * ((2 * d + 255) // 256)
+    split = ops.pick_split_k(tiles, (M + 63) // 64, _SMS)
+    ops.gemm(g3, x3, scratch, M=2 * Vp, N=2 * d, K=M, a_mn=True, b_mn=True, lda=3 * Vp, ldb=3 * d, ldc=2 * d,
+             accumulate=True, split_k=split)
+    ops.fold_quadrants_add(scratch, dw, V, d, Vp, d)
+    db = None
+    if bm is not None:
+        db = mb if mb is not None else torch.zeros((V,), dtype=f32, device=g.device)
+        ops.colsum_bf16(g3, db, N=V, ld=3 * Vp)
+        ops.colsum_bf16(g3[:, Vp:], db, N=V, ld=3 * Vp)
+    if mw is not None:
+        _done(wm)
+        if bm is not None:
+            _done(bm)
+        return dx, None, None
+    return dx, dw, db
+
+
 class SplitHeadFn(Function):
     """The same fp32-accurate head, on tensor cores: x·wᵀ with both operands split into bf16 hi + lo parts and
     the reduction dimension tripled ([hi|lo|hi]·[hi|hi|lo]ᵀ = hi·hi + lo·hi + hi·lo, ~16 mantissa bits), so one
-    tcgen05 GEMM replaces the FMA kernel.  Backward uses the same trick for dx (one GEMM) and dW (three
-    split-K GEMMs accumulating in fp32).  LM head :327,336 and termination head :330."""
+    tcgen05 GEMM replaces the FMA kernel.  Backward uses the same trick for dx (one GEMM) and a stacked
+    [hi|lo]ᵀ[hi|lo] GEMM for dW.  LM head :327,336 and termination head :330."""
 
     @staticmethod
     def forward(ctx, x, w, bias):
-        M, d = x.shape
-        V = w.shape[0]
-        x3 = ops.split3(x)                       # [M, 3d]  hi|lo|hi
-        w3 = ops.split3(w.detach(), partner=True)  # [V, 3d]  hi|hi|lo
-        out = torch.empty((M, V), dtype=f32, device=x.device)
-        ops.gemm(x3, w3, out, M=M, N=V, K=3 * d, bias=bias)
-        ctx.save_for_backward(x3, w3)
+        out, x3, w3, wk = _split_head_fwd(x, w, bias)
+        ctx.save_for_backward(x3, w3, wk)
         ctx.masters = (w, bias)
-        ctx.dims = (M, d, V)
+        ctx.dims = (x.shape[0], x.shape[1], w.shape[0])
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x3, w3 = ctx.saved_tensors
+        x3, w3, wk = ctx.saved_tensors
         wm, bm = ctx.masters
-        M, d, V = ctx.dims
-        Vp = (V + 7) // 8 * 8
-        g3 = ops.split3(g.contiguous(), cols_pad=Vp)  # [M, 3Vp]  hi|lo|hi
-        dx = None
-        if ctx.needs_input_grad[0]:
-            # dx = g·w: reduction over the (tripled, padded) vocabulary; w as [hi; hi; lo] stacked along K
-            wk = torch.zeros((3 * Vp, d), dtype=bf16, device=g.device)
-            wk[0:V], wk[Vp:Vp + V], wk[2 * Vp:2 * Vp + V] = w3[:, 0:d], w3[:, d:2 * d], w3[:, 2 * d:3 * d]
-            dx = torch.empty((M, d), dtype=f32, device=g.device)
-            ops.gemm(g3, wk, dx, M=M, N=d, K=3 * Vp, b_mn=True)
-        mw, mb = _main_grad(wm), _main_grad(bm)
-        dw = mw if mw is not None else torch.zeros((V, d), dtype=f32, device=g.device)
-        tiles = ((V + 127) // 128) * ((d + 255) // 256)
-        split = ops.pick_split_k(tiles, (M + 63) // 64, _SMS)
-        for goff, xoff in ((0, 0), (Vp, 0), (0, d)):  # hi·hi + lo·hi + hi·lo
-            ops.gemm(g3[:, goff:], x3[:, xoff:], dw, M=V, N=d, K=M, a_mn=True, b_mn=True, lda=3 * Vp, ldb=3 * d,
-                     ldc=d, accumulate=True, split_k=split)
-        db = None
-        if bm is not None:
-            db = mb if mb is not None else torch.zeros((V,), dtype=f32, device=g.device)
-            ops.colsum_bf16(g3, db, N=V, ld=3 * Vp)
-            ops.colsum_bf16(g3[:, Vp:], db, N=V, ld=3 * Vp)
-        if mw is not None:
-            _done(wm)
-            if bm is not None:
-                _done(bm)
-            return dx, None, None
-        return dx, dw, db
+        return _split_head_bwd(g, x3, w3, wk, wm, bm, ctx.dims, ctx.needs_input_grad[0])
 
 
 class SkinnyLinearFn(Function):

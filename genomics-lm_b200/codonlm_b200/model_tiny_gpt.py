@@ -170,6 +170,7 @@ _SHADOW_GEN = [0]
 def bump_shadow_generation():
     """Call after writing master weights outside autograd's view (e.g. the fused AdamW kernel)."""
     _SHADOW_GEN[0] += 1
+    Fn.reset_head_cache()
 
 
 def flat_shadow(p):
@@ -403,6 +404,18 @@ class _OffsetMLP(nn.Sequential, _ShadowMixin):
         out = Fn.OffsetHeadFn.apply(xb.contiguous(), w1, fc1.bias, w2, fc2.bias, fc1.weight, fc2.weight)
         return out.view(shp)
 
+    def logits(self, x, head_weight):
+        """head(self(x)) as one autograd node (Fn.OffsetLogitsFn) -> [M, V] fp32."""
+        fc1, fc2 = self[0], self[2]
+        _require_cuda(fc1.weight, "offset head weights")
+        x2 = x.reshape(-1, x.shape[-1])
+        xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
+        w1, w2 = flat_shadow(fc1.weight), flat_shadow(fc2.weight)
+        if w1 is None or w2 is None:
+            w1, w2 = self._get_shadow("off", (fc1.weight, fc2.weight),
+                                      lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
+        return Fn.OffsetLogitsFn.apply(xb.contiguous(), w1, fc1.bias, w2, fc2.bias, fc1.weight, fc2.weight, head_weight)
+
 
 # ----------------------------------------------------------------------------------------------
 # the model
@@ -576,9 +589,15 @@ class TinyGPT(nn.Module):
         if len(self.offset_projs) > 0:
             xb = _CastBf16.apply(x)
             offset_logits = {}
+            M = B * T
+            fused = (M >= Fn.TC_HEAD_MIN_ROWS and self.n_embd % 8 == 0 and self.vocab_size % 4 == 0
+                     and self.vocab_size <= 128 and not _has_hooks(self.head))
             for offset in self.multi_offset_targets:
-                proj_x = self.offset_projs[str(offset)](xb)
-                offset_logits[offset] = self.head(proj_x)
+                mlp = self.offset_projs[str(offset)]
+                if fused and not _has_hooks(mlp) and not _has_hooks(mlp[0]) and not _has_hooks(mlp[2]):
+                    offset_logits[offset] = mlp.logits(xb, self.head.weight).view(B, T, -1)
+                else:
+                    offset_logits[offset] = self.head(mlp(xb))
             aux["offset_logits"] = offset_logits
         return logits, aux
 

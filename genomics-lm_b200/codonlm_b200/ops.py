@@ -177,6 +177,16 @@ def split3(src: torch.Tensor, partner: bool = False, cols_pad: Optional[int] = N
     return out
 
 
+def fold_quadrants_add(s: torch.Tensor, dst: torch.Tensor, rows: int, cols: int, row_off: int, col_off: int):
+    """dst[r,c] += s[r,c] + s[r,c+col_off] + s[r+row_off,c] + s[r+row_off,c+col_off]  (fp32)."""
+    _dev(s)
+    _req(s, f32, "s")
+    _req(dst, f32, "dst")
+    check(_L().cgpt_fold_quadrants_add(s.data_ptr(), s.stride(0), dst.data_ptr(), dst.stride(0), rows, cols, row_off,
+                                       col_off, _stream()))
+    return dst
+
+
 def colsum_bf16(x2d, out, N=None, ld=None):
     M = x2d.shape[0]
     check(_L().cgpt_colsum_bf16(x2d.data_ptr(), int(ld if ld is not None else x2d.stride(0)), out.data_ptr(), M,

@@ -406,6 +406,20 @@ __global__ void split3_kernel(const float* __restrict__ in, long long ld_in, __n
   }
 }
 
+// dst[r,c] += S[r,c] + S[r,c+co] + S[r+ro,c] + S[r+ro,c+co]: the four hi/lo cross products of a stacked split-head
+// weight-gradient GEMM ([g_hi|g_lo]^T [x_hi|x_lo]) folded into the fp32 gradient.
+__global__ void fold_quadrants_add_kernel(const float* __restrict__ s, long long lds, float* __restrict__ dst,
+                                          long long ldd, int rows, int cols, int ro, int co) {
+  const long long total = (long long)rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    const float* a = s + r * lds + c;
+    const float* b = s + (r + ro) * lds + c;
+    dst[r * ldd + c] += (a[0] + a[co]) + (b[0] + b[co]);
+  }
+}
+
 // out[n] += sum_m x[m,n]; CTA = 64 columns x a row range; 8 warps stride rows, lanes own column pairs.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
@@ -807,6 +821,18 @@ int cgpt_split3_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t rows
   CGPT_REQUIRE(in && out && rows > 0 && cols > 0 && cols_pad >= cols && ld_in >= cols, "split3: bad arguments");
   split3_kernel<<<grid_for(rows * cols_pad, 256), 256, 0, ST(stream)>>>(in, ld_in, reinterpret_cast<__nv_bfloat16*>(out),
                                                                         rows, cols, cols_pad, partner);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_fold_quadrants_add(const float* s, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int row_off,
+                            int col_off, cgpt_stream_t stream) {
+  CGPT_REQUIRE(s && dst && rows > 0 && cols > 0 && row_off >= rows && col_off >= cols && lds >= col_off + cols &&
+                   ldd >= cols,
+               "fold_quadrants_add: bad arguments");
+  fold_quadrants_add_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, ST(stream)>>>(s, lds, dst, ldd, rows, cols,
+                                                                                           row_off, col_off);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

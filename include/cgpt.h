@@ -123,6 +123,11 @@ int cgpt_cast_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t ld_out
  * tensor cores (model_tiny_gpt.py:327,336).  partner=1 writes the [hi | hi | lo] form. */
 int cgpt_split3_f32_bf16(const float* in, int64_t ld_in, void* out, int64_t rows, int64_t cols, int64_t cols_pad,
                          int partner, cgpt_stream_t stream);
+/* dst[r,c] += S[r,c] + S[r,c+col_off] + S[r+row_off,c] + S[r+row_off,c+col_off]  (r < rows, c < cols).
+ * Folds the four hi/lo cross products of the stacked split-head weight-gradient GEMM
+ * S = [g_hi | g_lo]^T [x_hi | x_lo] into the fp32 gradient of the LM head (backward of model_tiny_gpt.py:327,336). */
+int cgpt_fold_quadrants_add(const float* s, int64_t lds, float* dst, int64_t ldd, int rows, int cols, int row_off,
+                            int col_off, cgpt_stream_t stream);
 /* out[n] += sum_m x[m,n]   (bias gradients) */
 int cgpt_colsum_bf16(const void* x, int64_t ld, float* out, int M, int N, cgpt_stream_t stream);
 /* RoPE, half-split pairing i <-> i+hd/2            model_tiny_gpt.py:35-45, applied in place to the

@@ -351,6 +351,10 @@ ATTN_CASES = [
     (3, 333, 2, 2, 64, None, 3),   # B*H*T not a multiple of 4: workspace alignment
     (1, 1, 1, 1, 32, None, 3),
     (2, 129, 2, 1, 64, 1, None),   # window 1 = identity attention
+    # C5 (BASELINE configs[4]): long-context causal attention, seq 4096, 8 heads, hd 48 and 64, segment-causal / causal
+    (1, 4096, 8, 8, 48, None, 3),
+    (1, 4096, 8, 8, 64, None, None),
+    (1, 4096, 8, 4, 64, 1000, 3),
 ]
 
 

@@ -103,6 +103,11 @@ ORACLE_CASES = {
                               label_smoothing=0.05, use_sdpa=True, termination_aux=True,
                               multi_offset_targets=[2, 4, 8, 16, 32]), 2, 1024,
                          {2: 0.2, 4: 0.2, 8: 0.2, 16: 0.2, 32: 0.2}, 0.1),
+    # M = B*T = 4096 rows: the tensor-core LM head and the fused offset-logits node (Fn.OffsetLogitsFn) are active
+    "C3_d512_heads_1L_tc_head": (dict(vocab_size=68, block_size=1024, n_layer=1, n_head=8, n_embd=512, dropout=0.0,
+                                      label_smoothing=0.05, use_sdpa=True, termination_aux=True,
+                                      multi_offset_targets=[2, 4, 8, 16, 32]), 4, 1024,
+                                 {2: 0.2, 4: 0.2, 8: 0.2, 16: 0.2, 32: 0.2}, 0.1),
     "C4_gqa4_d384_hd48_2L": (dict(vocab_size=68, block_size=512, n_layer=2, n_head=8, n_kv_head=4, n_embd=384,
                                   dropout=0.0, label_smoothing=0.05, use_sdpa=True), 2, 512, None, 0.0),
     "ragged_T_333": (dict(vocab_size=69, block_size=512, n_layer=1, n_head=2, n_embd=128, dropout=0.0,
@@ -240,7 +245,8 @@ def test_weight_update_refreshes_bf16_shadows():
     assert losses[-1] < losses[0]
 
 
-def test_trainstep_flat_buffers_match_plain_autograd_and_torch_adamw():
+@pytest.mark.parametrize("batch", [4, 64])  # 64 x 64 = 4096 rows: tensor-core head + fused offset-logits nodes
+def test_trainstep_flat_buffers_match_plain_autograd_and_torch_adamw(batch):
     """TrainStep (kernels accumulate straight into the flat gradient buffer, fused AdamW) must give the same
     gradients and the same updated weights as the module under plain autograd + torch.optim.AdamW with the
     reference's two parameter groups (loop.py:681-731)."""
@@ -252,7 +258,7 @@ def test_trainstep_flat_buffers_match_plain_autograd_and_torch_adamw():
               termination_aux=True, multi_offset_targets=[2, 4], use_sdpa=True)
     m1 = TinyGPT(**kw).to(DEV).train()
     m2 = copy.deepcopy(m1)
-    idx, tgt = O.synthetic_batch(4, 64, seed=9, realistic=True)
+    idx, tgt = O.synthetic_batch(batch, 64, seed=9, realistic=True)
     idx, tgt = idx.to(DEV), tgt.to(DEV)
     ow = {2: 0.5, 4: 0.25}
     # plain path
