@@ -260,7 +260,8 @@ class MlpGeluFn(Function):
     def forward(ctx, h, x_res, w1_sh, b1, w2_sh, b2, w1, w2):
         M, d = h.shape
         F = w1_sh.shape[0]
-        dact = torch.empty((M, F), dtype=bf16, device=h.device)  # gelu'(pre), written by the same epilogue
+        # gelu'(pre), written by the same epilogue — only when a backward pass can follow (not under no_grad)
+        dact = torch.empty((M, F), dtype=bf16, device=h.device) if any(ctx.needs_input_grad) else None
         act = torch.empty((M, F), dtype=bf16, device=h.device)
         ops.gemm(h, w1_sh, act, M=M, N=F, K=d, bias=b1, epilogue=EPI_GELU, aux_out=dact, ldaux=F)
         n_out = w2_sh.shape[0]
@@ -339,9 +340,9 @@ class MlpSwiGLUFn(Function):
         return dh, (g if ctx.has_res else None), None, None, dwg, dwu, dwd
 
 
-def _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2):
+def _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd=True):
     M, d = xb.shape
-    dact = torch.empty((M, d), dtype=bf16, device=xb.device)
+    dact = torch.empty((M, d), dtype=bf16, device=xb.device) if need_bwd else None
     act = torch.empty((M, d), dtype=bf16, device=xb.device)
     ops.gemm(xb, w1_sh, act, M=M, N=d, K=d, bias=b1, epilogue=EPI_GELU, aux_out=dact, ldaux=d)
     out = torch.empty((M, d), dtype=f32, device=xb.device)
@@ -376,7 +377,7 @@ class OffsetHeadFn(Function):
 
     @staticmethod
     def forward(ctx, xb, w1_sh, b1, w2_sh, b2, w1, w2):
-        out, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2)
+        out, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, any(ctx.needs_input_grad))
         ctx.save_for_backward(xb, dact, act, w1_sh, w2_sh)
         ctx.masters = (b1, b2, w1, w2)
         return out
@@ -397,7 +398,7 @@ class OffsetLogitsFn(Function):
 
     @staticmethod
     def forward(ctx, xb, w1_sh, b1, w2_sh, b2, w1, w2, head_w):
-        h, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2)
+        h, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, any(ctx.needs_input_grad))
         logits, h3, w3, wk = _split_head_fwd(h, head_w, None)
         ctx.save_for_backward(xb, dact, act, w1_sh, w2_sh, h3, w3, wk)
         ctx.masters = (b1, b2, w1, w2, head_w)

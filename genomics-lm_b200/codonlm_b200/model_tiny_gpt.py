@@ -624,6 +624,21 @@ class TinyGPT(nn.Module):
             return logits, loss, aux
         return logits, loss
 
+    @torch.no_grad()
+    def next_token_logits(self, idx, attention_window: int | None = None):
+        """Last-position logits (B, V) = forward(idx)[0][:, -1] — what the reference's sampling loops read after a
+        full forward (src/codonlm/generate.py:14-27 `_next_token_logits`, scripts/query_model.py `next_token`),
+        for a whole batch of contexts: the final LayerNorm and the fp32 head run on B rows instead of B·T."""
+        in_dev = idx.device
+        idx = self._prep_idx(idx)
+        Fn.reset_side_channel()
+        x = self._embed(idx, None)
+        spec = self.mask_spec(idx, attention_window)
+        for blk in self.blocks:
+            x = blk(x, attn_mask=spec)
+        logits = self.head(self.ln_f(x[:, -1, :].contiguous()))
+        return logits if in_dev == idx.device else logits.to(in_dev)
+
     def forward_hidden(self, idx, shape_embeddings=None, attention_window: int | None = None):
         final = None
         for _, hidden in self.iter_hidden_states(idx, shape_embeddings=shape_embeddings,

@@ -132,12 +132,15 @@ class GradBuckets:
         # launch a bucket as soon as all contributions of all its parameters have arrived.
         self.contrib_seen = [0] * len(group.params)
         self.contrib_need = None
+        self.armed = True  # False while accumulating the non-final micro-batches of a group: nothing is launched
         for i, p in enumerate(group.params):
             p._cgpt_grad_ready = self._make_hook(i)
             p.register_post_accumulate_grad_hook(lambda _p, i=i: self._make_hook(i)())  # plain-autograd path
 
     def _make_hook(self, i):
         def hook():
+            if not self.armed:
+                return
             self.contrib_seen[i] += 1
             if self.contrib_need is None:
                 return
@@ -222,6 +225,17 @@ class TrainStep:
                                         termination_loss_weight=self.termination_loss_weight)
         total.backward()
         return total.detach(), parts
+
+    def arm_collectives(self, armed: bool):
+        """Gradient buckets are all-reduced only from the backward of a group's LAST micro-batch."""
+        for bk in self.buckets:
+            bk.armed = bool(armed)
+
+    def discard_gradients(self):
+        """Drop an aborted accumulation group: pending bucket reductions are drained, gradients zeroed."""
+        for bk in self.buckets:
+            bk.finish()
+        self.zero_grad()
 
     def optimizer_step(self, lr_scale: float = 1.0, micro_batches: int = 1):
         self.step_count += 1
@@ -316,3 +330,150 @@ class TrainStep:
         self._xb.copy_(xb_pinned, non_blocking=True)
         self._yb.copy_(yb_pinned, non_blocking=True)
         return float(self.step(self._xb, self._yb, lr_scale).item())
+
+
+# ----------------------------------------------------------------------------------------------------------
+# The caller's loop around the step: learning-rate schedule, accumulation groups, non-finite policy
+# ----------------------------------------------------------------------------------------------------------
+class NonfiniteGroupLimitError(RuntimeError):
+    """More accumulation groups were aborted than `max_nonfinite_accumulation_groups` allows (loop.py:66-67)."""
+
+
+def resolve_warmup_steps(cfg: dict, total_steps: int) -> int:
+    """`warmup_steps` (default 200) or `warmup_fraction` of the schedule, never both (loop.py:70-87)."""
+    if total_steps <= 0:
+        raise ValueError("scheduler_total_steps must be positive")
+    frac = cfg.get("warmup_fraction")
+    if frac is not None:
+        if "warmup_steps" in cfg:
+            raise ValueError("configure only one of warmup_steps or warmup_fraction")
+        frac = float(frac)
+        if not 0.0 <= frac < 1.0:
+            raise ValueError("warmup_fraction must be in [0, 1)")
+        return 0 if frac == 0.0 else max(1, int(round(total_steps * frac)))
+    steps = int(cfg.get("warmup_steps", 200))
+    if steps < 0:
+        raise ValueError("warmup_steps must be non-negative")
+    return steps
+
+
+def cosine_lr_scale(step_idx: int, warmup_steps: int, total_steps: int, min_lr_ratio: float) -> float:
+    """Multiplier of the base learning rates at optimiser step `step_idx` (0-based): linear warm-up then cosine
+    decay to min_lr/base_lr — the reference's LambdaLR lambda (loop.py:772-778)."""
+    w = max(1, int(warmup_steps))
+    if step_idx < w:
+        return float(step_idx + 1) / w
+    progress = (step_idx - w) / max(1, total_steps - w)
+    return min_lr_ratio + (1.0 - min_lr_ratio) * 0.5 * (1.0 + math.cos(math.pi * progress))
+
+
+class AccumulationHealth:
+    """Checkpointable counters of gradient-accumulation group integrity (loop.py:90-141): same fields, same
+    state_dict, so a resumed run continues the reference's bookkeeping."""
+
+    FIELDS = ("active_microbatches", "nonfinite_microbatches", "aborted_groups", "discarded_finite_microbatches")
+
+    def __init__(self):
+        self.active_microbatches = 0
+        self.nonfinite_microbatches = 0
+        self.aborted_groups = 0
+        self.discarded_finite_microbatches = 0
+
+    def record_finite_microbatch(self):
+        self.active_microbatches += 1
+
+    def complete_group(self):
+        if self.active_microbatches <= 0:
+            raise ValueError("cannot complete an empty accumulation group")
+        self.active_microbatches = 0
+
+    def abort_group(self) -> int:
+        discarded = self.active_microbatches
+        self.nonfinite_microbatches += 1
+        self.aborted_groups += 1
+        self.discarded_finite_microbatches += discarded
+        self.active_microbatches = 0
+        return discarded
+
+    def exceeds_limit(self, max_aborted_groups: int) -> bool:
+        return max_aborted_groups >= 0 and self.aborted_groups > max_aborted_groups
+
+    def metrics_dict(self) -> Dict[str, int]:
+        return {k: int(getattr(self, k)) for k in self.FIELDS}
+
+    def state_dict(self) -> Dict[str, int]:
+        state = self.metrics_dict()
+        state["active_microbatches"] = 0  # gradients are not checkpointed: resume replays from the last resolved group
+        return state
+
+    def load_state_dict(self, state: Optional[dict]):
+        state = state or {}
+        self.active_microbatches = 0
+        for k in self.FIELDS[1:]:
+            setattr(self, k, int(state.get(k, 0)))
+
+
+def run_accumulation_groups(step, microbatches: Iterable, grad_accum_steps: int, health: AccumulationHealth,
+                            max_nonfinite_groups: int = 3, lr_scale_fn=None, first_step_idx: int = 0,
+                            process_group=None):
+    """Drive `step` (a TrainStep) over an iterable of (xb, yb) micro-batches with the reference's accumulation-group
+    semantics (loop.py:1195-1262): gradients of `grad_accum_steps` finite micro-batches are summed and averaged
+    into ONE optimiser step; a micro-batch whose loss is not finite aborts the group — its gradients and those of
+    the finite micro-batches before it are discarded, the next micro-batch opens a new group — and more than
+    `max_nonfinite_groups` aborts raise NonfiniteGroupLimitError; a trailing partial group still steps.
+
+    The reference decides this with a host sync per micro-batch.  Here a group is launched back to back and
+    its per-micro-batch finite flags are read ONCE (one D2H of `grad_accum_steps` floats, max-reduced over the
+    data-parallel ranks so that every rank takes the same decision); only a group that did contain a non-finite
+    loss is replayed from the micro-batch after it, which reproduces the reference's group boundaries exactly.
+
+    Yields one dict per optimiser step: {"step", "group_size", "total_loss_sum", "next_loss_sum", "lr_scale"}."""
+    gacc = max(1, int(grad_accum_steps))
+    step_idx = int(first_step_idx)
+    queue: List[tuple] = []
+    it = iter(microbatches)
+    exhausted = False
+    while True:
+        while len(queue) < gacc and not exhausted:
+            try:
+                queue.append(next(it))
+            except StopIteration:
+                exhausted = True
+        if not queue:
+            return
+        group = queue[:gacc]
+        step.zero_grad()
+        losses, nexts = [], []
+        for k, (xb, yb) in enumerate(group):
+            step.arm_collectives(k == len(group) - 1)
+            loss, parts = step.forward_backward(xb, yb)
+            losses.append(loss.detach().reshape(1).float())
+            nexts.append(parts["next"].detach().reshape(1).float())
+        stacked = torch.cat(losses + nexts)
+        bad = (~torch.isfinite(stacked[: len(group)])).float()
+        if process_group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=process_group)
+        host = torch.cat([bad, stacked]).cpu()  # the group's only host sync
+        bad_h = host[: len(group)].tolist()
+        first_bad = next((k for k, b in enumerate(bad_h) if b > 0), None)
+        if first_bad is None:
+            for _ in group:
+                health.record_finite_microbatch()
+            scale = 1.0 if lr_scale_fn is None else float(lr_scale_fn(step_idx))
+            step.optimizer_step(lr_scale=scale, micro_batches=len(group))
+            health.complete_group()
+            vals = host[len(group):].tolist()
+            yield {"step": step_idx, "group_size": len(group), "total_loss_sum": sum(vals[: len(group)]),
+                   "next_loss_sum": sum(vals[len(group):]), "lr_scale": scale}
+            step_idx += 1
+            queue = queue[len(group):]
+        else:
+            for _ in range(first_bad):
+                health.record_finite_microbatch()
+            health.abort_group()
+            step.discard_gradients()
+            queue = queue[first_bad + 1:]
+            if health.exceeds_limit(max_nonfinite_groups):
+                raise NonfiniteGroupLimitError(
+                    f"nonfinite accumulation groups exceeded configured maximum {max_nonfinite_groups}: "
+                    f"{health.aborted_groups}")

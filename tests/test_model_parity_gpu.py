@@ -150,6 +150,34 @@ def _tiny(**kw):
     return TinyGPT(**base).to(DEV).eval()
 
 
+def test_batched_next_codon_inference_c4():
+    """BASELINE configs[3] 'batched next-codon inference': last-position logits + argmax for a batch of contexts
+    (the reference reads logits[:, -1] after a full forward: generate.py:14-27).  next_token_logits() must equal
+    the full forward's last row, match the oracle within the logit gate, and give the oracle's argmax bit-exactly
+    wherever the oracle's own top-2 margin is resolvable; eval-mode forward must not depend on grad mode."""
+    ctor = dict(vocab_size=68, block_size=512, n_layer=2, n_head=8, n_kv_head=4, n_embd=384, dropout=0.0,
+                label_smoothing=0.05, use_sdpa=True)
+    cfg = O.make_cfg(**ctor)
+    sd = O.init_state_dict(cfg, seed=1337, emb_scale=0.02)
+    model = _build(ctor, sd).eval()
+    for B in (1, 8, 16):  # 16 x 512 = 8192 rows: the tensor-core head serves the full forward
+        idx, _ = O.synthetic_batch(B, 512, seed=21 + B, realistic=True)
+        idx = idx.to(DEV)
+        with torch.no_grad():
+            full, loss = model(idx)
+            last = model.next_token_logits(idx)
+        assert loss is None and last.shape == (B, 68)
+        assert (last - full[:, -1]).abs().max().item() <= 2e-4
+        full_grad_mode, _ = model(idx)
+        assert torch.allclose(full_grad_mode, full, rtol=0, atol=1e-6)
+        ref = O.forward({k: v.to(DEV) for k, v in sd.items()}, cfg, idx)["logits"][:, -1]
+        err = (last - ref).abs().max().item()
+        assert err <= LOGIT_TOL, f"last-position logits err {err}"
+        srt = ref.sort(-1, descending=True).values
+        safe = (srt[:, 0] - srt[:, 1]) > 2 * err
+        assert torch.equal(last.argmax(-1)[safe], ref.argmax(-1)[safe])
+
+
 def test_forward_shapes_and_pad_loss():  # tests/test_models.py:7-27, test_toggles_smoke.py
     for kw in (dict(), dict(use_sdpa=True), dict(use_swiglu=True), dict(use_rope=True),
                dict(n_head=4, n_kv_head=2, n_embd=64), dict(tie_embeddings=False)):
@@ -287,6 +315,41 @@ def test_trainstep_flat_buffers_match_plain_autograd_and_torch_adamw(batch):
     for _ in range(5):
         l1 = ts.step(idx, tgt).item()
     assert l1 < l0
+
+
+def test_accumulation_groups_equal_mean_of_microbatch_gradients():
+    """run_accumulation_groups on the real TrainStep: two micro-batches per optimiser step must equal plain autograd on
+    the mean of the two micro-batch losses + torch AdamW (loop.py:145-150 'mean of per-micro-batch means'), follow
+    the cosine schedule, and discard a group whose loss is not finite (all-PAD targets -> NaN)."""
+    import copy
+    from codonlm_b200 import TinyGPT, training_loss
+    from codonlm_b200.trainer import (AccumulationHealth, TrainStep, cosine_lr_scale, run_accumulation_groups,
+                                      split_param_groups)
+    torch.manual_seed(5)
+    kw = dict(vocab_size=68, block_size=64, n_layer=2, n_head=2, n_embd=64, dropout=0.0, label_smoothing=0.05,
+              use_sdpa=True)
+    m1 = TinyGPT(**kw).to(DEV).train()
+    m2 = copy.deepcopy(m1)
+    mbs = [tuple(t.to(DEV) for t in O.synthetic_batch(4, 64, seed=30 + i, realistic=True)) for i in range(4)]
+    bad = (mbs[0][0], torch.zeros_like(mbs[0][1]))  # every target PAD -> NaN loss, aborts its group
+    g = split_param_groups(m1)
+    opt = torch.optim.AdamW([p for _, p in g["backbone"]], lr=3e-3, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8)
+    sched = lambda i: cosine_lr_scale(i, 1, 4, 0.1)  # noqa: E731
+    for i, pair in enumerate((mbs[0:2], mbs[2:4])):
+        for pg in opt.param_groups:
+            pg["lr"] = 3e-3 * sched(i)
+        opt.zero_grad()
+        sum(training_loss(m1, x, y)[0] for x, y in pair).div(2).backward()
+        opt.step()
+    ts = TrainStep(m2, lr=3e-3, weight_decay=0.05)
+    health = AccumulationHealth()
+    stream = [mbs[0], mbs[1], mbs[2], bad, mbs[2], mbs[3]]  # third group: [mbs2, bad] aborted, then [mbs2, mbs3]
+    out = list(run_accumulation_groups(ts, stream, 2, health, max_nonfinite_groups=3, lr_scale_fn=sched))
+    assert [o["group_size"] for o in out] == [2, 2] and ts.step_count == 2
+    assert health.metrics_dict() == {"active_microbatches": 0, "nonfinite_microbatches": 1, "aborted_groups": 1,
+                                     "discarded_finite_microbatches": 1}
+    for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.allclose(p1, p2, rtol=1e-3, atol=5e-5), n
 
 
 def test_training_mode_dropout_is_seeded_and_off_in_eval():  # reference tests/test_attention_dropout.py:19-85
