@@ -350,8 +350,9 @@ def _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd=True):
     return out, act, dact
 
 
-def _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2):
-    """gb: bf16 gradient of the MLP output -> (dx bf16, db1, db2, dw1, dw2), None where accumulated in place."""
+def _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2, dx_into=None):
+    """gb: bf16 gradient of the MLP output -> (dx bf16, db1, db2, dw1, dw2), None where accumulated in place.
+    With `dx_into` (fp32 [M, d]) the input gradient is ADDED to it by the GEMM instead (returns dx None)."""
     M, d = xb.shape
     dw2 = _wgrad(gb, act, d, d, master=w2)
     db2 = _colsum(gb, d, master=b2)
@@ -366,6 +367,9 @@ def _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2):
     elif mb1 is not None:
         _done(b1)
         db1 = None
+    if dx_into is not None:
+        ops.gemm(dpre, w1_sh, dx_into, M=M, N=d, K=d, b_mn=True, accumulate=True)
+        return None, db1, db2, dw1, dw2
     dx = torch.empty((M, d), dtype=bf16, device=xb.device)
     ops.gemm(dpre, w1_sh, dx, M=M, N=d, K=d, b_mn=True)
     return dx, db1, db2, dw1, dw2
@@ -389,29 +393,6 @@ class OffsetHeadFn(Function):
         gb = ops.cast_bf16(g.contiguous())
         dx, db1, db2, dw1, dw2 = _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2)
         return dx, None, db1, None, db2, dw1, dw2
-
-
-class OffsetLogitsFn(Function):
-    """logits_o = head(W2·gelu(W1·x + b1) + b2) as ONE autograd node (model_tiny_gpt.py:335-336): the fp32-accurate
-    head's input gradient is written as bf16 directly — the operand type of the MLP's backward GEMMs — instead of
-    an fp32 tensor that a cast kernel would re-read.  Same kernels and arithmetic as OffsetHeadFn + SplitHeadFn."""
-
-    @staticmethod
-    def forward(ctx, xb, w1_sh, b1, w2_sh, b2, w1, w2, head_w):
-        h, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, any(ctx.needs_input_grad))
-        logits, h3, w3, wk = _split_head_fwd(h, head_w, None)
-        ctx.save_for_backward(xb, dact, act, w1_sh, w2_sh, h3, w3, wk)
-        ctx.masters = (b1, b2, w1, w2, head_w)
-        return logits
-
-    @staticmethod
-    def backward(ctx, g):
-        xb, dact, act, w1_sh, w2_sh, h3, w3, wk = ctx.saved_tensors
-        b1, b2, w1, w2, head_w = ctx.masters
-        M, d = xb.shape
-        gb, dhw, _ = _split_head_bwd(g, h3, w3, wk, head_w, None, (M, d, head_w.shape[0]), True, bf16)
-        dx, db1, db2, dw1, dw2 = _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2)
-        return dx, None, db1, None, db2, dw1, dw2, dhw
 
 
 def reset_side_channel():
@@ -500,18 +481,19 @@ def _head_weight_split(w):
     return w3, wk
 
 
-def _split_head_fwd(x, w, bias):
+def _split_head_fwd(x, w, bias, x3=None):
     M, d = x.shape
     V = w.shape[0]
-    x3 = ops.split3(x)                       # [M, 3d]  hi|lo|hi
+    if x3 is None:
+        x3 = ops.split3(x)                   # [M, 3d]  hi|lo|hi
     w3, wk = _head_weight_split(w)           # [V, 3d]  hi|hi|lo
     out = torch.empty((M, V), dtype=f32, device=x.device)
     ops.gemm(x3, w3, out, M=M, N=V, K=3 * d, bias=bias)
     return out, x3, w3, wk
 
 
-def _split_head_bwd(g, x3, w3, wk, wm, bm, dims, need_dx, dx_dtype=f32):
-    """-> (dx or None, dw or None, db or None); dw/db are None when accumulated into main_grad."""
+def _split_head_bwd(g, x3, w3, wk, wm, bm, dims, need_dx, dx_dtype=f32, dw_into=None):
+    """-> (dx or None, dw or None, db or None); dw/db are None when accumulated into main_grad (or `dw_into`)."""
     M, d, V = dims
     Vp = (V + 7) // 8 * 8
     g3 = ops.split3(g.contiguous(), cols_pad=Vp)  # [M, 3Vp]  hi|lo|hi
@@ -521,7 +503,7 @@ def _split_head_bwd(g, x3, w3, wk, wm, bm, dims, need_dx, dx_dtype=f32):
         dx = torch.empty((M, d), dtype=dx_dtype, device=g.device)
         ops.gemm(g3, wk, dx, M=M, N=d, K=3 * Vp, b_mn=True)
     mw, mb = _main_grad(wm), _main_grad(bm)
-    dw = mw if mw is not None else torch.zeros((V, d), dtype=f32, device=g.device)
+    dw = mw if mw is not None else (dw_into if dw_into is not None else torch.zeros((V, d), dtype=f32, device=g.device))
     # dW = gᵀ·x with both operands as [hi|lo]: ONE stacked GEMM gives the four cross products as the quadrants of
     # a [2Vp, 2d] scratch matrix (the tokens are read once, not three times), folded into dW by a small kernel
     scratch = torch.zeros((2 * Vp, 2 * d), dtype=f32, device=g.device)
@@ -540,7 +522,83 @@ def _split_head_bwd(g, x3, w3, wk, wm, bm, dims, need_dx, dx_dtype=f32):
         if bm is not None:
             _done(bm)
         return dx, None, None
-    return dx, dw, db
+    return dx, (None if dw_into is not None else dw), db
+
+
+class HeadsFn(Function):
+    """Everything that reads the final hidden state, as ONE autograd node (model_tiny_gpt.py:326-337): LM head,
+    termination head and the offset heads (MLP + shared LM head).  The hidden state is split into bf16 hi|lo|hi
+    once (its hi part is the offset MLPs' bf16 operand), and in backward every branch ADDS its input gradient to one
+    fp32 buffer from inside its own kernel — no cast of the hidden state and no elementwise gradient sums.
+
+    Inputs: x fp32 [M, d], head weight, termination weight/bias (or None), then per offset
+    (w1_sh, b1, w2_sh, b2, w1, w2).  Outputs: logits, termination logits (if any), one logits tensor per offset."""
+
+    @staticmethod
+    def forward(ctx, x, head_w, term_w, term_b, *off):
+        M, d = x.shape
+        n_off = len(off) // 6
+        need_bwd = any(ctx.needs_input_grad)
+        x3 = ops.split3(x)
+        logits, _, w3, wk = _split_head_fwd(x, head_w, None, x3=x3)
+        outs = [logits]
+        if term_w is not None:
+            outs.append(ops.skinny_linear_fwd(x, term_w, term_b))
+        xb = x3[:, :d]  # bf16(x): row pitch 3d
+        saved = [x, x3, w3, wk]
+        for o in range(n_off):
+            w1_sh, b1, w2_sh, b2, w1, w2 = off[6 * o:6 * o + 6]
+            h, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd)
+            lo, h3, _, _ = _split_head_fwd(h, head_w, None)
+            outs.append(lo)
+            saved += [dact, act, w1_sh, w2_sh, h3]
+        if need_bwd:
+            ctx.save_for_backward(*saved)
+        ctx.masters = (head_w, term_w, term_b) + tuple(off)
+        ctx.n_off = n_off
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *gs):
+        saved = ctx.saved_tensors
+        x, x3, w3, wk = saved[:4]
+        head_w, term_w, term_b = ctx.masters[:3]
+        off = ctx.masters[3:]
+        M, d = x.shape
+        V = head_w.shape[0]
+        xb = x3[:, :d]
+        g_logits = gs[0]
+        g_term = gs[1] if term_w is not None else None
+        g_off = gs[(2 if term_w is not None else 1):]
+        dhw = None if _main_grad(head_w) is not None else torch.zeros((V, d), dtype=f32, device=x.device)
+        if g_logits is not None:
+            dx, _, _ = _split_head_bwd(g_logits, x3, w3, wk, head_w, None, (M, d, V), True, f32, dw_into=dhw)
+        else:
+            dx = torch.zeros((M, d), dtype=f32, device=x.device)
+        dtw = dtb = None
+        if g_term is not None:
+            mw, mb = _main_grad(term_w), _main_grad(term_b)
+            dtw = mw if mw is not None else torch.zeros_like(term_w)
+            dtb = None
+            if term_b is not None:
+                dtb = mb if mb is not None else torch.zeros((term_w.shape[0],), dtype=f32, device=x.device)
+            ops.skinny_linear_bwd(g_term.contiguous(), x, term_w, dx, True, dtw, dtb)
+            if mw is not None:
+                _done(term_w)
+                if term_b is not None:
+                    _done(term_b)
+                dtw = dtb = None
+        grads = []
+        for o in range(ctx.n_off):
+            dact, act, w1_sh, w2_sh, h3 = saved[4 + 5 * o:9 + 5 * o]
+            _, b1, _, b2, w1, w2 = off[6 * o:6 * o + 6]
+            if g_off[o] is None:
+                grads += [None] * 6
+                continue
+            gb, _, _ = _split_head_bwd(g_off[o], h3, w3, wk, head_w, None, (M, d, V), True, bf16, dw_into=dhw)
+            _, db1, db2, dw1, dw2 = _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2, dx_into=dx)
+            grads += [None, db1, None, db2, dw1, dw2]
+        return (dx, dhw, dtw, dtb, *grads)
 
 
 class SplitHeadFn(Function):

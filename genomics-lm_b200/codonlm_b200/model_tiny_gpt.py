@@ -404,17 +404,15 @@ class _OffsetMLP(nn.Sequential, _ShadowMixin):
         out = Fn.OffsetHeadFn.apply(xb.contiguous(), w1, fc1.bias, w2, fc2.bias, fc1.weight, fc2.weight)
         return out.view(shp)
 
-    def logits(self, x, head_weight):
-        """head(self(x)) as one autograd node (Fn.OffsetLogitsFn) -> [M, V] fp32."""
+    def shadows(self):
+        """bf16 operands (w1, w2): views of the trainer's flat shadow buffer, else cached casts of the masters."""
         fc1, fc2 = self[0], self[2]
         _require_cuda(fc1.weight, "offset head weights")
-        x2 = x.reshape(-1, x.shape[-1])
-        xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())
         w1, w2 = flat_shadow(fc1.weight), flat_shadow(fc2.weight)
         if w1 is None or w2 is None:
             w1, w2 = self._get_shadow("off", (fc1.weight, fc2.weight),
                                       lambda: (ops.cast_bf16(fc1.weight), ops.cast_bf16(fc2.weight)))
-        return Fn.OffsetLogitsFn.apply(xb.contiguous(), w1, fc1.bias, w2, fc2.bias, fc1.weight, fc2.weight, head_weight)
+        return w1, w2
 
 
 # ----------------------------------------------------------------------------------------------
@@ -580,24 +578,45 @@ class TinyGPT(nn.Module):
             self._lw_cache = (key, bool(torch.all(lw == 1.0).item()))
         return None if self._lw_cache[1] else lw
 
+    def _heads_fused_ok(self, M):
+        mods = [self.head] + ([self.termination_head] if self.termination_head is not None else [])
+        for mlp in self.offset_projs.values():
+            mods += [mlp, mlp[0], mlp[2]]
+        return (M >= Fn.TC_HEAD_MIN_ROWS and self.n_embd % 8 == 0 and self.vocab_size % 4 == 0
+                and self.vocab_size <= 128 and self.head.bias is None
+                and (self.termination_head is None or self.termination_n_classes <= 128)
+                and not any(_has_hooks(m) for m in mods))
+
     def _heads(self, x, B, T):
         """x: (B,T,d) fp32 after ln_f -> logits, aux dict."""
-        logits = self.head(x)
         aux = {}
+        if self._heads_fused_ok(B * T):
+            # one autograd node for everything that reads the final hidden state (Fn.HeadsFn)
+            x2 = x.reshape(B * T, -1).float().contiguous()
+            th = self.termination_head
+            args = []
+            for offset in self.multi_offset_targets:
+                mlp = self.offset_projs[str(offset)]
+                w1, w2 = mlp.shadows()
+                args += [w1, mlp[0].bias, w2, mlp[2].bias, mlp[0].weight, mlp[2].weight]
+            outs = Fn.HeadsFn.apply(x2, self.head.weight, None if th is None else th.weight,
+                                    None if th is None else th.bias, *args)
+            logits = outs[0].view(B, T, -1)
+            k = 1
+            if th is not None:
+                aux["termination_logits"] = outs[1].view(B, T, -1)
+                k = 2
+            if len(self.offset_projs) > 0:
+                aux["offset_logits"] = {o: outs[k + i].view(B, T, -1) for i, o in enumerate(self.multi_offset_targets)}
+            return logits, aux
+        logits = self.head(x)
         if self.termination_head is not None:
             aux["termination_logits"] = self.termination_head(x)
         if len(self.offset_projs) > 0:
             xb = _CastBf16.apply(x)
             offset_logits = {}
-            M = B * T
-            fused = (M >= Fn.TC_HEAD_MIN_ROWS and self.n_embd % 8 == 0 and self.vocab_size % 4 == 0
-                     and self.vocab_size <= 128 and not _has_hooks(self.head))
             for offset in self.multi_offset_targets:
-                mlp = self.offset_projs[str(offset)]
-                if fused and not _has_hooks(mlp) and not _has_hooks(mlp[0]) and not _has_hooks(mlp[2]):
-                    offset_logits[offset] = mlp.logits(xb, self.head.weight).view(B, T, -1)
-                else:
-                    offset_logits[offset] = self.head(mlp(xb))
+                offset_logits[offset] = self.head(self.offset_projs[str(offset)](xb))
             aux["offset_logits"] = offset_logits
         return logits, aux
 
