@@ -218,7 +218,13 @@ def run_ours(args):
         s.record()
         r = orig_gemm(a, b, out, M=M, N=N, K=K, **kw)
         e.record()
-        gemm_events.append((s, e, 2.0 * M * N * K))
+        nbytes = 2.0 * (M * K + N * K) + M * N * out.element_size()
+        for extra in ("aux", "aux_out"):
+            if kw.get(extra) is not None:
+                nbytes += 2.0 * M * N
+        if kw.get("residual") is not None or kw.get("accumulate"):
+            nbytes += 4.0 * M * N
+        gemm_events.append((s, e, 2.0 * M * N * K, nbytes))
         return r
 
     def sync_all():
@@ -312,10 +318,17 @@ def run_ours(args):
         toks_step = B * T * world
         value = toks_step * args.steps / (ms_total / 1e3)
         fpt = train_flops_per_token(args.layers, 512, T)
-        gemm_ms = sum(s.elapsed_time(e) for s, e, _ in gemm_events)
-        gemm_flops = sum(f for _, _, f in gemm_events)
+        gemm_ms = sum(ev[0].elapsed_time(ev[1]) for ev in gemm_events)
+        gemm_flops = sum(ev[2] for ev in gemm_events)
+        gemm_bytes = sum(ev[3] for ev in gemm_events)
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
+        traffic = traffic_src = None
+        tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")  # from the committed ncu launch list
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                tj = json.load(f)
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -330,7 +343,10 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "roofline": {"kernel": "gemm_bf16_kernel (tcgen05, all instances in the step)", "bound": "tensor",
                          "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                         "traffic": None, "peak_source": f"bf16_tflops_sustained, {peak_src}",
+                         "traffic": traffic, "traffic_unit": "bytes of DRAM read+write per launch (ncu, family average)",
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_launch": gemm_bytes / max(1, len(gemm_events)),
+                         "peak_source": f"bf16_tflops_sustained, {peak_src}",
                          "launches_per_step": len(gemm_events) // max(1, args.steps),
                          "share_of_step": gemm_ms / roof_ms_total,
                          "timed_in": ("eager instrumented repeat of the K steps right after the timed region "
