@@ -342,6 +342,11 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
         rope = self.rotary_emb.half_tables(T, x.device) if self.rotary_emb is not None else None
         attn_p = float(self.dropout.p) if self.training else 0.0  # dropout on the probabilities (:104,129)
         y = Fn.AttentionFn.apply(qkv, spec.seg_start, rope, B, T, H, Hk, hd, int(spec.window or 0), attn_p)
+        sink = self.__dict__.get("_kv_sink")
+        if sink is not None:  # prefill of the incremental-decode cache: the (rotated) key / value column blocks
+            q3 = qkv.view(B, T, -1)
+            sink[0][:, :T].copy_(q3[:, :, nq:nq + nk])
+            sink[1][:, :T].copy_(q3[:, :, nq + nk:])
         if not self.use_sdpa:
             # the reference's manual branch keeps the (pre-dropout) probabilities for introspection (:128)
             with torch.no_grad():
@@ -350,6 +355,30 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
         out = Fn.PackedLinearFn.apply(y, w_proj, self.proj.bias.detach(), r2, ((0, Cdim),), True, self.proj.weight,
                                       self.proj.bias)
         return out.view(B, T, Cdim)
+
+
+    def decode(self, x, k_cache, v_cache, lo, t, window=0, residual=None):
+        """One new position per sequence (x: (B, 1, d) bf16) against the K/V cache; appends position t."""
+        B, _, Cdim = x.size()
+        H = self.n_head
+        hd = Cdim // H
+        Hk = self.n_kv_head if self.n_kv_head is not None else H
+        if H % Hk != 0:
+            raise ValueError("n_head must be divisible by n_kv_head for GQA")
+        xb = x.reshape(B, Cdim)
+        w_qkv, b_qkv, w_proj = self._shadows()
+        nq, nk = self.query.weight.shape[0], self.key.weight.shape[0]
+        qkv = Fn.PackedLinearFn.apply(xb.contiguous(), w_qkv, b_qkv, None, ((0, nq), (nq, nk), (nq + nk, nk)), False,
+                                      self.query.weight, self.key.weight, self.value.weight,
+                                      self.query.bias, self.key.bias, self.value.bias)
+        if self.rotary_emb is not None:
+            cos, sin = self.rotary_emb.half_tables(t + 1, x.device)
+            ops.rope_qk(qkv, cos[t:t + 1], sin[t:t + 1], B, 1, H, Hk, hd)
+        y = ops.attn_decode(qkv, k_cache, v_cache, lo, t, H, Hk, hd, window=window)
+        r2 = None if residual is None else residual.reshape(B, Cdim)
+        out = Fn.PackedLinearFn.apply(y, w_proj, self.proj.bias.detach(), r2, ((0, Cdim),), True, self.proj.weight,
+                                      self.proj.bias)
+        return out.view(B, 1, Cdim)
 
 
 class Block(nn.Module):
@@ -386,6 +415,34 @@ class Block(nn.Module):
         else:
             x2 = self.mlp(h.view(B, T, d), residual=x2).reshape(B * T, d)
         return x2.view(B, T, d)
+
+
+def _block_decode(blk, x, k_cache, v_cache, lo, t, window):
+    """Block.forward for one new position per sequence, attention against the K/V cache (eval mode, no hooks)."""
+    B, _, d = x.shape
+    x2 = x.reshape(B, d)
+    x2, h = blk.ln1.fused(x2.contiguous())
+    x2 = blk.attn.decode(h.view(B, 1, d), k_cache, v_cache, lo, t, window, residual=x2).reshape(B, d)
+    x2, h = blk.ln2.fused(x2.contiguous())
+    x2 = blk.mlp(h.view(B, 1, d), residual=x2).reshape(B, d)
+    return x2.view(B, 1, d)
+
+
+class DecodeState:
+    """K/V caches of an incremental decode: per layer bf16 [B, max_len, Hk*hd], the number of cached positions and
+    the first visible position of every sequence (start of its current <SEP> segment)."""
+
+    def __init__(self, model, batch: int, max_len: int):
+        dev = model.tok_emb.weight.device
+        hd = model.n_embd // model.n_head
+        hk = model.n_kv_head if model.n_kv_head is not None else model.n_head
+        self.max_len = int(max_len)
+        self.batch = int(batch)
+        self.k = [torch.empty((batch, self.max_len, hk * hd), dtype=bf16, device=dev) for _ in range(model.n_layer)]
+        self.v = [torch.empty((batch, self.max_len, hk * hd), dtype=bf16, device=dev) for _ in range(model.n_layer)]
+        self.length = 0
+        self.seg_lo = torch.zeros((batch,), dtype=torch.int32, device=dev)
+        self.window = 0
 
 
 class _OffsetMLP(nn.Sequential, _ShadowMixin):
@@ -658,6 +715,56 @@ class TinyGPT(nn.Module):
         logits = self.head(self.ln_f(x[:, -1, :].contiguous()))
         return logits if in_dev == idx.device else logits.to(in_dev)
 
+    @torch.no_grad()
+    def prefill(self, idx, state: "DecodeState | None" = None, max_len: int | None = None,
+                attention_window: int | None = None):
+        """Full forward over the prompts idx (B, T) that also fills the K/V caches -> (last-position logits (B, V),
+        state).  With decode_step() this is the cached form of the reference's sampling loops, which re-run the whole
+        context for every generated token (generate.py:14-27, query_model.py:186-213): same logits, O(T) per token."""
+        idx = self._prep_idx(idx)
+        B, T = idx.shape
+        if state is None:
+            state = DecodeState(self, B, max_len or self.block_size)
+        if T > state.max_len or B != state.batch:
+            raise ValueError(f"prompt of {B}x{T} tokens does not fit a decode state of {state.batch}x{state.max_len}")
+        Fn.reset_side_channel()
+        x = self._embed(idx, None)
+        spec = self.mask_spec(idx, attention_window)
+        for layer, blk in enumerate(self.blocks):
+            blk.attn.__dict__["_kv_sink"] = (state.k[layer], state.v[layer])
+            try:
+                x = blk(x, attn_mask=spec)
+            finally:
+                blk.attn.__dict__["_kv_sink"] = None
+        state.length = T
+        state.window = int(spec.window or 0)
+        if spec.seg_start is not None:
+            state.seg_lo = spec.seg_start[:, -1].to(torch.int32).contiguous()
+        else:
+            state.seg_lo.zero_()
+        return self.head(self.ln_f(x[:, -1, :].contiguous())), state
+
+    @torch.no_grad()
+    def decode_step(self, tokens, state: "DecodeState"):
+        """Append one token per sequence (tokens (B,), the token AT position state.length) and return the logits
+        (B, V) for the following position — equal to forward(context + token)[0][:, -1]."""
+        t = state.length
+        if t >= state.max_len or (self.pos_emb is not None and t >= self.block_size):
+            raise IndexError(f"decode position {t} exceeds the cache / block size; re-prefill a cropped context "
+                             "(the reference crops to the last block_size tokens, generate.py:20-21)")
+        dev = self.tok_emb.weight.device
+        tok = tokens.to(dev).long().reshape(state.batch, 1).contiguous()
+        if self.sep_id is not None:  # a <SEP> opens a new segment at its own position (cumsum(idx == sep), :290)
+            state.seg_lo = torch.where(tok.view(-1) == int(self.sep_id), torch.full_like(state.seg_lo, t), state.seg_lo)
+        Fn.reset_side_channel()
+        pos_w = None if self.pos_emb is None else self.pos_emb.weight[t:t + 1]
+        x = Fn.EmbedFn.apply(tok, self.tok_emb.weight, pos_w)
+        lo = state.seg_lo if self.sep_id is not None else None
+        for layer, blk in enumerate(self.blocks):
+            x = _block_decode(blk, x, state.k[layer], state.v[layer], lo, t, state.window)
+        state.length = t + 1
+        return self.head(self.ln_f(x[:, -1, :].contiguous()))
+
     def forward_hidden(self, idx, shape_embeddings=None, attention_window: int | None = None):
         final = None
         for _, hidden in self.iter_hidden_states(idx, shape_embeddings=shape_embeddings,
@@ -695,4 +802,4 @@ class NoPropTinyGPT(_OutOfScope):
     pass
 
 
-__all__ = ["TinyGPT", "NoPropBlock", "NoPropTinyGPT"]
+__all__ = ["TinyGPT", "NoPropBlock", "NoPropTinyGPT", "DecodeState"]

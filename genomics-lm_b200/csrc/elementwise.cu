@@ -420,6 +420,98 @@ __global__ void fold_quadrants_add_kernel(const float* __restrict__ s, long long
   }
 }
 
+// ---------------------------------------------------------------------------------------- incremental decode
+// One new token per sequence against a (K, V) cache: out[b,h,:] = softmax(q·K[lo..t]ᵀ·scale)·V[lo..t], where the
+// row at position t is the new token's own (k, v) (taken from qkv_new and appended to the cache by the first head of
+// each kv group).  Memory-bound: every cached K and V row is read once per query head.  CTA = one (b, h), 128 threads.
+__global__ void __launch_bounds__(128)
+attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv_new, __nv_bfloat16* __restrict__ k_cache,
+                   __nv_bfloat16* __restrict__ v_cache, const int32_t* __restrict__ lo, __nv_bfloat16* __restrict__ out,
+                   int t, int Tmax, int H, int Hk, int hd, int window, float scale_log2) {
+  extern __shared__ float dsm[];
+  float* q_s = dsm;                  // [hd]
+  float* red = dsm + hd;             // [128 / (hd/8)] x hd partial outputs, also the block reductions
+  float* sc = red + 128 * 8;         // [t + 1 - jlo] scores / probabilities
+  const int b = blockIdx.x / H, h = blockIdx.x - b * H;
+  const int rep = H / Hk, kvh = h / rep;
+  const int W = (H + 2 * Hk) * hd, KW = Hk * hd;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const __nv_bfloat16* qrow = qkv_new + (size_t)b * W + h * hd;
+  const __nv_bfloat16* knew = qkv_new + (size_t)b * W + (H + kvh) * hd;
+  const __nv_bfloat16* vnew = qkv_new + (size_t)b * W + (H + Hk + kvh) * hd;
+  const __nv_bfloat16* kc = k_cache + (size_t)b * Tmax * KW + kvh * hd;
+  const __nv_bfloat16* vc = v_cache + (size_t)b * Tmax * KW + kvh * hd;
+  int jlo = lo ? lo[b] : 0;
+  if (window > 0) jlo = max(jlo, t - window + 1);
+  for (int c = tid; c < hd; c += 128) q_s[c] = __bfloat162float(qrow[c]) * scale_log2;
+  __syncthreads();
+  const int n = t + 1 - jlo, nv = hd / 8;
+  float mx = -INFINITY;
+  for (int r = tid; r < n; r += 128) {
+    const int j = jlo + r;
+    const uint4* kr = reinterpret_cast<const uint4*>(j == t ? knew : kc + (size_t)j * KW);
+    float s = 0.f;
+    for (int v8 = 0; v8 < nv; ++v8) {
+      const uint4 u = kr[v8];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        s = fmaf(q_s[8 * v8 + 2 * e], __uint_as_float(w[e] << 16), s);
+        s = fmaf(q_s[8 * v8 + 2 * e + 1], __uint_as_float(w[e] & 0xffff0000u), s);
+      }
+    }
+    sc[r] = s;
+    mx = fmaxf(mx, s);
+  }
+  mx = warp_max(mx);
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float sum = 0.f;
+  for (int r = tid; r < n; r += 128) {
+    const float p = exp2f(sc[r] - mx);
+    sc[r] = p;
+    sum += p;
+  }
+  sum = warp_sum(sum);
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  const float inv = 1.f / (red[0] + red[1] + red[2] + red[3]);
+  __syncthreads();
+  // P·V: a thread owns 8 output columns (one 16-byte piece of a V row) of every `rows`-th cached position
+  const int rows = 128 / nv, rg = tid / nv, dl = tid - rg * nv;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (rg < rows) {
+    for (int r = rg; r < n; r += rows) {
+      const int j = jlo + r;
+      const uint4 u = reinterpret_cast<const uint4*>(j == t ? vnew : vc + (size_t)j * KW)[dl];
+      const float p = sc[r];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        acc[2 * e] = fmaf(p, __uint_as_float(w[e] << 16), acc[2 * e]);
+        acc[2 * e + 1] = fmaf(p, __uint_as_float(w[e] & 0xffff0000u), acc[2 * e + 1]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) red[rg * hd + dl * 8 + e] = acc[e];
+  }
+  __syncthreads();
+  for (int c = tid; c < hd; c += 128) {
+    float o = 0.f;
+    for (int g = 0; g < rows; ++g) o += red[g * hd + c];
+    out[(size_t)b * H * hd + h * hd + c] = __float2bfloat16_rn(o * inv);
+  }
+  // append the new (k, v) to the cache (once per kv group; no CTA reads position t from the cache)
+  if (h == kvh * rep && tid < 2 * nv) {
+    const bool is_v = tid >= nv;
+    const int piece = is_v ? tid - nv : tid;
+    uint4* dst = reinterpret_cast<uint4*>((is_v ? v_cache : k_cache) + ((size_t)b * Tmax + t) * KW + kvh * hd);
+    dst[piece] = reinterpret_cast<const uint4*>(is_v ? vnew : knew)[piece];
+  }
+}
+
 // out[n] += sum_m x[m,n]; CTA = 64 columns x a row range; 8 warps stride rows, lanes own column pairs.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
@@ -833,6 +925,27 @@ int cgpt_fold_quadrants_add(const float* s, int64_t lds, float* dst, int64_t ldd
                "fold_quadrants_add: bad arguments");
   fold_quadrants_add_kernel<<<grid_for((long long)rows * cols, 256), 256, 0, ST(stream)>>>(s, lds, dst, ldd, rows, cols,
                                                                                            row_off, col_off);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_attn_decode(const void* qkv_new, void* k_cache, void* v_cache, const int32_t* lo, void* out, int B, int t,
+                     int Tmax, int H, int Hk, int hd, int window, float scale, cgpt_stream_t stream) {
+  CGPT_REQUIRE(qkv_new && k_cache && v_cache && out && B > 0 && t >= 0 && t < Tmax && H > 0 && Hk > 0 && H % Hk == 0 &&
+                   hd % 16 == 0 && hd <= 128 && window >= 0,
+               "attn_decode: bad arguments");
+  const size_t smem = (size_t)(hd + 128 * 8 + t + 1) * sizeof(float);
+  CGPT_REQUIRE(smem <= 200 * 1024, "attn_decode: context too long for the score buffer");
+  static size_t configured = 48 * 1024;
+  if (smem > configured) {
+    CGPT_CHECK(cudaFuncSetAttribute(attn_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = 200 * 1024;
+  }
+  attn_decode_kernel<<<B * H, 128, smem, ST(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(qkv_new), reinterpret_cast<__nv_bfloat16*>(k_cache),
+      reinterpret_cast<__nv_bfloat16*>(v_cache), lo, reinterpret_cast<__nv_bfloat16*>(out), t, Tmax, H, Hk, hd, window,
+      scale * 1.4426950408889634f);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

@@ -117,7 +117,8 @@ def test_layernorm_fwd_bwd(ops):
 
 
 # ------------------------------------------------------------------------------------------ GEMM
-GEMM_SHAPES = [(128, 256, 64), (128, 64, 64), (256, 512, 512), (300, 200, 136), (1000, 1536, 512), (64, 72, 1368)]
+GEMM_SHAPES = [(128, 256, 64), (128, 64, 64), (256, 512, 512), (300, 200, 136), (1000, 1536, 512), (64, 72, 1368),
+               (1, 256, 64), (8, 1152, 384)]  # decode-sized M
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, True), (True, False)])

@@ -183,6 +183,81 @@ def test_batched_next_codon_inference_c4():
         assert torch.equal(last.argmax(-1)[safe], ref.argmax(-1)[safe])
 
 
+DECODE_CASES = {
+    "abs_gelu_mha": dict(vocab_size=68, block_size=128, n_layer=2, n_head=4, n_embd=128, dropout=0.0, use_sdpa=True),
+    "rope_swiglu": dict(vocab_size=68, block_size=128, n_layer=2, n_head=4, n_embd=256, dropout=0.0, use_sdpa=True,
+                        use_rope=True, use_swiglu=True),
+    "gqa_hd48": dict(vocab_size=68, block_size=128, n_layer=2, n_head=8, n_kv_head=4, n_embd=384, dropout=0.0,
+                     use_sdpa=True),
+}
+
+
+@pytest.mark.parametrize("name", list(DECODE_CASES))
+@pytest.mark.parametrize("window", [None, 9])
+def test_kv_cache_decode_equals_full_forward(name, window):
+    """prefill() + decode_step() (K/V cache, cgpt_attn_decode) must give, at every generated position, the logits of
+    a full forward over the whole context — what the reference's sampling loops compute (generate.py:14-27) — and the
+    oracle's argmax wherever its top-2 margin is resolvable.  The token stream contains <EOS><SEP> boundaries, so the
+    segment rule (a <SEP> opens a new segment at its own position) is exercised inside the decoded part."""
+    ctor = DECODE_CASES[name]
+    cfg = O.make_cfg(**ctor)
+    sd = O.init_state_dict(cfg, seed=1337, emb_scale=0.02)
+    model = _build(ctor, sd).eval()
+    B, T0, n_new = 3, 37, 40
+    seq, _ = O.synthetic_batch(B, T0 + n_new, seed=4, realistic=True)
+    seq[:, T0 + 5], seq[:, T0 + 6] = 2, 3     # a segment boundary inside the decoded part
+    seq[1, T0 + 20] = 3
+    seq = seq.to(DEV)
+    logits, state = model.prefill(seq[:, :T0], attention_window=window)
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    worst = 0.0
+    for s in range(n_new):
+        ctx = seq[:, :T0 + s]
+        with torch.no_grad():
+            full = model(ctx, attention_window=window)[0][:, -1]
+        err = (logits - full).abs().max().item()
+        worst = max(worst, err)
+        assert err <= 1e-2, f"step {s}: cached logits differ from the full forward by {err}"
+        if s % 13 == 0:
+            ref = O.forward(sd_dev, cfg, ctx, attention_window=window)["logits"][:, -1]
+            e2 = (logits - ref).abs().max().item()
+            assert e2 <= LOGIT_TOL
+            srt = ref.sort(-1, descending=True).values
+            safe = (srt[:, 0] - srt[:, 1]) > 2 * e2
+            assert torch.equal(logits.argmax(-1)[safe], ref.argmax(-1)[safe])
+        logits = model.decode_step(seq[:, T0 + s], state)
+    assert state.length == T0 + n_new
+    print(f"{name} window={window}: worst cached-vs-full logit difference {worst:.2e}")
+
+
+def test_cached_generate_follows_reference_loop_rules():
+    """codonlm_b200.generate.generate: length, eos stop, cropping past block_size, and top-1 sampling equal to a loop of
+    full forwards (the reference's own procedure) while the model's top-2 margin is resolvable."""
+    from codonlm_b200.generate import generate, generate_batch
+    ctor = dict(vocab_size=68, block_size=48, n_layer=2, n_head=4, n_embd=128, dropout=0.0, use_sdpa=True)
+    torch.manual_seed(7)
+    from codonlm_b200 import TinyGPT
+    model = TinyGPT(**ctor).to(DEV).eval()
+    ctx = [1] + list(range(4, 24))
+    out = generate(model, DEV, ctx, max_new=12, topk=1)
+    assert out[: len(ctx)] == ctx and len(out) == len(ctx) + 12
+    ids = list(ctx)
+    for k in range(12):  # the reference loop: full forward per token, top-1
+        with torch.no_grad():
+            row = model(torch.tensor(ids, device=DEV).unsqueeze(0))[0][0, -1]
+        top2 = row.topk(2).values
+        if (top2[0] - top2[1]).item() < 1e-2:
+            break  # near-tie: not resolvable in bf16, stop comparing
+        assert out[len(ids)] == int(row.argmax().item()), k
+        ids.append(out[len(ids)])
+    long = generate(model, DEV, ctx, max_new=40, topk=3)  # runs past block_size: cropped like the reference
+    assert len(long) == 48
+    stop = generate(model, DEV, ctx, max_new=30, topk=1, eos_idx=out[len(ctx)])
+    assert len(stop) == len(ctx) + 1
+    batch = generate_batch(model, torch.tensor([ctx, ctx[::-1]]), max_new=100, topk=2)
+    assert batch.shape == (2, 48) and torch.equal(batch[0, : len(ctx)].cpu(), torch.tensor(ctx))
+
+
 def test_forward_shapes_and_pad_loss():  # tests/test_models.py:7-27, test_toggles_smoke.py
     for kw in (dict(), dict(use_sdpa=True), dict(use_swiglu=True), dict(use_rope=True),
                dict(n_head=4, n_kv_head=2, n_embd=64), dict(tie_embeddings=False)):
