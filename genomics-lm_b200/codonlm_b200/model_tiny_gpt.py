@@ -357,8 +357,9 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
         return out.view(B, T, Cdim)
 
 
-    def decode(self, x, k_cache, v_cache, lo, t, window=0, residual=None):
-        """One new position per sequence (x: (B, 1, d) bf16) against the K/V cache; appends position t."""
+    def decode(self, x, k_cache, v_cache, lo, t_dev, rope_row=None, window=0, residual=None):
+        """One new position per sequence (x: (B, 1, d) bf16) against the K/V cache; appends the position held in the
+        device scalar t_dev.  rope_row = (cos, sin) rows [1, hd/2] of that position."""
         B, _, Cdim = x.size()
         H = self.n_head
         hd = Cdim // H
@@ -372,9 +373,8 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
                                       self.query.weight, self.key.weight, self.value.weight,
                                       self.query.bias, self.key.bias, self.value.bias)
         if self.rotary_emb is not None:
-            cos, sin = self.rotary_emb.half_tables(t + 1, x.device)
-            ops.rope_qk(qkv, cos[t:t + 1], sin[t:t + 1], B, 1, H, Hk, hd)
-        y = ops.attn_decode(qkv, k_cache, v_cache, lo, t, H, Hk, hd, window=window)
+            ops.rope_qk(qkv, rope_row[0], rope_row[1], B, 1, H, Hk, hd)
+        y = ops.attn_decode(qkv, k_cache, v_cache, lo, 0, H, Hk, hd, window=window, t_dev=t_dev)
         r2 = None if residual is None else residual.reshape(B, Cdim)
         out = Fn.PackedLinearFn.apply(y, w_proj, self.proj.bias.detach(), r2, ((0, Cdim),), True, self.proj.weight,
                                       self.proj.bias)
@@ -417,12 +417,12 @@ class Block(nn.Module):
         return x2.view(B, T, d)
 
 
-def _block_decode(blk, x, k_cache, v_cache, lo, t, window):
+def _block_decode(blk, x, k_cache, v_cache, lo, t_dev, rope_row, window):
     """Block.forward for one new position per sequence, attention against the K/V cache (eval mode, no hooks)."""
     B, _, d = x.shape
     x2 = x.reshape(B, d)
     x2, h = blk.ln1.fused(x2.contiguous())
-    x2 = blk.attn.decode(h.view(B, 1, d), k_cache, v_cache, lo, t, window, residual=x2).reshape(B, d)
+    x2 = blk.attn.decode(h.view(B, 1, d), k_cache, v_cache, lo, t_dev, rope_row, window, residual=x2).reshape(B, d)
     x2, h = blk.ln2.fused(x2.contiguous())
     x2 = blk.mlp(h.view(B, 1, d), residual=x2).reshape(B, d)
     return x2.view(B, 1, d)
@@ -443,6 +443,14 @@ class DecodeState:
         self.length = 0
         self.seg_lo = torch.zeros((batch,), dtype=torch.int32, device=dev)
         self.window = 0
+        # device-resident step state: every kernel of a decode step reads the position from t_dev, so the step can be
+        # captured ONCE into a CUDA graph and replayed for every position (a step is ~13 launches per layer and
+        # entirely launch-bound when issued from Python)
+        self.t_dev = torch.zeros((1,), dtype=torch.int32, device=dev)
+        self.tok = torch.zeros((batch, 1), dtype=torch.int64, device=dev)
+        self.logits = None
+        self.graph = None
+        self.use_graph = True
 
 
 class _OffsetMLP(nn.Sequential, _ShadowMixin):
@@ -737,33 +745,63 @@ class TinyGPT(nn.Module):
             finally:
                 blk.attn.__dict__["_kv_sink"] = None
         state.length = T
-        state.window = int(spec.window or 0)
+        state.t_dev.fill_(T)
+        if int(spec.window or 0) != state.window:
+            state.window, state.graph = int(spec.window or 0), None
         if spec.seg_start is not None:
-            state.seg_lo = spec.seg_start[:, -1].to(torch.int32).contiguous()
+            state.seg_lo.copy_(spec.seg_start[:, -1])
         else:
             state.seg_lo.zero_()
         return self.head(self.ln_f(x[:, -1, :].contiguous())), state
 
+    def _decode_launch(self, state: "DecodeState"):
+        """The kernels of one decode step; reads state.tok / state.t_dev, advances t_dev, returns the logits."""
+        dev = self.tok_emb.weight.device
+        tok, t_dev = state.tok, state.t_dev
+        if self.sep_id is not None:  # a <SEP> opens a new segment at its own position (cumsum(idx == sep), :290)
+            state.seg_lo.copy_(torch.where(tok.view(-1) == int(self.sep_id), t_dev.expand(state.batch), state.seg_lo))
+        t_idx = t_dev.long()
+        pos_row = None if self.pos_emb is None else self.pos_emb.weight.index_select(0, t_idx)
+        rope_row = None
+        if self.use_rope:
+            cos, sin = self.blocks[0].attn.rotary_emb.half_tables(state.max_len, dev)
+            rope_row = (cos.index_select(0, t_idx), sin.index_select(0, t_idx))
+        x = Fn.EmbedFn.apply(tok, self.tok_emb.weight, pos_row)
+        lo = state.seg_lo if self.sep_id is not None else None
+        for layer, blk in enumerate(self.blocks):
+            x = _block_decode(blk, x, state.k[layer], state.v[layer], lo, t_dev, rope_row, state.window)
+        logits = self.head(self.ln_f(x[:, -1, :].contiguous()))
+        t_dev.add_(1)
+        return logits
+
     @torch.no_grad()
     def decode_step(self, tokens, state: "DecodeState"):
         """Append one token per sequence (tokens (B,), the token AT position state.length) and return the logits
-        (B, V) for the following position — equal to forward(context + token)[0][:, -1]."""
+        (B, V) for the following position — equal to forward(context + token)[0][:, -1].  The step is captured into
+        a CUDA graph on its second call and replayed afterwards (state.use_graph = False keeps it eager)."""
         t = state.length
         if t >= state.max_len or (self.pos_emb is not None and t >= self.block_size):
             raise IndexError(f"decode position {t} exceeds the cache / block size; re-prefill a cropped context "
                              "(the reference crops to the last block_size tokens, generate.py:20-21)")
-        dev = self.tok_emb.weight.device
-        tok = tokens.to(dev).long().reshape(state.batch, 1).contiguous()
-        if self.sep_id is not None:  # a <SEP> opens a new segment at its own position (cumsum(idx == sep), :290)
-            state.seg_lo = torch.where(tok.view(-1) == int(self.sep_id), torch.full_like(state.seg_lo, t), state.seg_lo)
+        state.tok.copy_(tokens.reshape(state.batch, 1), non_blocking=True)
         Fn.reset_side_channel()
-        pos_w = None if self.pos_emb is None else self.pos_emb.weight[t:t + 1]
-        x = Fn.EmbedFn.apply(tok, self.tok_emb.weight, pos_w)
-        lo = state.seg_lo if self.sep_id is not None else None
-        for layer, blk in enumerate(self.blocks):
-            x = _block_decode(blk, x, state.k[layer], state.v[layer], lo, t, state.window)
+        if state.graph is not None:
+            state.graph.replay()
+        elif state.use_graph and getattr(state, "_warm", False) and not self.training:
+            # capture leaves the state untouched: run the step inside the capture, then replay it once for real
+            graph = torch.cuda.CUDAGraph()
+            snap_t, snap_lo = state.t_dev.clone(), state.seg_lo.clone()
+            with torch.cuda.graph(graph):
+                state.logits = self._decode_launch(state)
+            state.t_dev.copy_(snap_t)
+            state.seg_lo.copy_(snap_lo)
+            state.graph = graph
+            graph.replay()
+        else:
+            state.logits = self._decode_launch(state)
+            state._warm = True
         state.length = t + 1
-        return self.head(self.ln_f(x[:, -1, :].contiguous()))
+        return state.logits
 
     def forward_hidden(self, idx, shape_embeddings=None, attention_window: int | None = None):
         final = None

@@ -262,14 +262,16 @@ def attn_probs(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None, dropout_p=
     return att
 
 
-def attn_decode(qkv_new, k_cache, v_cache, lo, t, H, Hk, hd, window=0, scale=None):
-    """One new token per sequence against the (K, V) cache [B, Tmax, Hk*hd]; appends position t. -> bf16 [B, H*hd]."""
+def attn_decode(qkv_new, k_cache, v_cache, lo, t, H, Hk, hd, window=0, scale=None, t_dev=None):
+    """One new token per sequence against the (K, V) cache [B, Tmax, Hk*hd]; appends position t. -> bf16 [B, H*hd].
+    t_dev (int32 device scalar) overrides t: the position is then read on the device (graph replay)."""
     _dev(qkv_new)
     B = qkv_new.shape[0]
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
     out = torch.empty((B, H * hd), dtype=bf16, device=qkv_new.device)
     check(_L().cgpt_attn_decode(qkv_new.data_ptr(), k_cache.data_ptr(), v_cache.data_ptr(), _p(lo), out.data_ptr(), B,
-                                int(t), k_cache.shape[1], H, Hk, hd, int(window or 0), float(scale), _stream()))
+                                int(t), _p(t_dev), k_cache.shape[1], H, Hk, hd, int(window or 0), float(scale),
+                                _stream()))
     return out
 
 

@@ -427,8 +427,10 @@ __global__ void fold_quadrants_add_kernel(const float* __restrict__ s, long long
 __global__ void __launch_bounds__(128)
 attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv_new, __nv_bfloat16* __restrict__ k_cache,
                    __nv_bfloat16* __restrict__ v_cache, const int32_t* __restrict__ lo, __nv_bfloat16* __restrict__ out,
-                   int t, int Tmax, int H, int Hk, int hd, int window, float scale_log2) {
+                   const int32_t* __restrict__ t_dev, int t_host, int Tmax, int H, int Hk, int hd, int window,
+                   float scale_log2) {
   extern __shared__ float dsm[];
+  const int t = t_dev ? min(*t_dev, Tmax - 1) : t_host;  // position of the new token (device-resident under graph replay)
   float* q_s = dsm;                  // [hd]
   float* red = dsm + hd;             // [128 / (hd/8)] x hd partial outputs, also the block reductions
   float* sc = red + 128 * 8;         // [t + 1 - jlo] scores / probabilities
@@ -931,11 +933,12 @@ int cgpt_fold_quadrants_add(const float* s, int64_t lds, float* dst, int64_t ldd
 }
 
 int cgpt_attn_decode(const void* qkv_new, void* k_cache, void* v_cache, const int32_t* lo, void* out, int B, int t,
-                     int Tmax, int H, int Hk, int hd, int window, float scale, cgpt_stream_t stream) {
-  CGPT_REQUIRE(qkv_new && k_cache && v_cache && out && B > 0 && t >= 0 && t < Tmax && H > 0 && Hk > 0 && H % Hk == 0 &&
-                   hd % 16 == 0 && hd <= 128 && window >= 0,
+                     const int32_t* t_dev, int Tmax, int H, int Hk, int hd, int window, float scale,
+                     cgpt_stream_t stream) {
+  CGPT_REQUIRE(qkv_new && k_cache && v_cache && out && B > 0 && (t_dev || (t >= 0 && t < Tmax)) && Tmax > 0 && H > 0 &&
+                   Hk > 0 && H % Hk == 0 && hd % 16 == 0 && hd <= 128 && window >= 0,
                "attn_decode: bad arguments");
-  const size_t smem = (size_t)(hd + 128 * 8 + t + 1) * sizeof(float);
+  const size_t smem = (size_t)(hd + 128 * 8 + (t_dev ? Tmax : t + 1)) * sizeof(float);
   CGPT_REQUIRE(smem <= 200 * 1024, "attn_decode: context too long for the score buffer");
   static size_t configured = 48 * 1024;
   if (smem > configured) {
@@ -944,8 +947,8 @@ int cgpt_attn_decode(const void* qkv_new, void* k_cache, void* v_cache, const in
   }
   attn_decode_kernel<<<B * H, 128, smem, ST(stream)>>>(
       reinterpret_cast<const __nv_bfloat16*>(qkv_new), reinterpret_cast<__nv_bfloat16*>(k_cache),
-      reinterpret_cast<__nv_bfloat16*>(v_cache), lo, reinterpret_cast<__nv_bfloat16*>(out), t, Tmax, H, Hk, hd, window,
-      scale * 1.4426950408889634f);
+      reinterpret_cast<__nv_bfloat16*>(v_cache), lo, reinterpret_cast<__nv_bfloat16*>(out), t_dev, t, Tmax, H, Hk, hd,
+      window, scale * 1.4426950408889634f);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

@@ -171,9 +171,11 @@ int cgpt_attn_probs(const void* qkv, const int32_t* seg_start, float* att, int B
  * loops, which re-run the whole context per generated token (generate.py:14-27, query_model.py:186-213).
  * qkv_new bf16 [B, (H+2Hk)*hd] (RoPE already applied); k_cache / v_cache bf16 [B, Tmax, Hk*hd] hold positions 0..t-1
  * and receive position t; lo[b] (nullable) = first visible position (segment start, model_tiny_gpt.py:283-295);
- * out bf16 [B, H*hd] = softmax(q·K[lo..t]^T·scale)·V[lo..t]. */
+ * out bf16 [B, H*hd] = softmax(q·K[lo..t]^T·scale)·V[lo..t].  With t_dev (nullable, device int32) the position is read
+ * on the device instead of from `t`, so that a captured CUDA graph of the decode step can be replayed for every t. */
 int cgpt_attn_decode(const void* qkv_new, void* k_cache, void* v_cache, const int32_t* lo, void* out, int B, int t,
-                     int Tmax, int H, int Hk, int hd, int window, float scale, cgpt_stream_t stream);
+                     const int32_t* t_dev, int Tmax, int H, int Hk, int hd, int window, float scale,
+                     cgpt_stream_t stream);
 
 /* ---------------------------------------------------------------- LM / aux heads --------- */
 /* out[M,N] = x[M,d]·w[N,d]ᵀ (+bias), fp32 FMA, N <= 128

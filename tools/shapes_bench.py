@@ -105,6 +105,37 @@ def c4():
              model_tflops=B * 512 / ms_last * 1e3 * f / 1e12, argmax_equal_to_full_forward=same)
 
 
+def decode():
+    """C4 model: cached decode (prefill 256 tokens, then 128 decode steps) against the reference's procedure of one
+    full forward per generated token (timed on this repo's own forward at the average context length)."""
+    ctor = dict(vocab_size=68, block_size=512, n_layer=10, n_head=8, n_kv_head=4, n_embd=384, dropout=0.0,
+                label_smoothing=0.05, use_sdpa=True)
+    torch.manual_seed(1337)
+    model = TinyGPT(**ctor)
+    with torch.no_grad():
+        model.tok_emb.weight.mul_(0.02)
+    model = model.to(DEV).eval()
+    T0, n_new = 256, 128
+    for B in (1, 8, 64):
+        seq = synthetic_tokens(B, T0 + n_new, seed=3)[0].to(DEV)
+
+        def run_cached():
+            logits, st = model.prefill(seq[:, :T0])
+            for s in range(n_new):
+                logits = model.decode_step(seq[:, T0 + s], st)
+            return logits
+
+        ms_total = timed(run_cached, reps=3, warmup=1)
+        with torch.no_grad():
+            ms_prefill = timed(lambda: model.prefill(seq[:, :T0]), reps=3, warmup=1)
+            ms_full = timed(lambda: model.next_token_logits(seq[:, :T0 + n_new // 2]), reps=3, warmup=1)
+        ms_step = (ms_total - ms_prefill) / n_new
+        emit(config="C4 bench_b8_gqa4 10L8H kv4 d384", what="KV-cache decode vs one full forward per token", batch=B,
+             prompt=T0, new_tokens=n_new, ms_per_decode_step=ms_step, ms_per_full_forward_at_mean_context=ms_full,
+             tokens_per_s_cached=B / ms_step * 1e3, tokens_per_s_full_forward=B / ms_full * 1e3,
+             speedup=ms_full / ms_step)
+
+
 def c5():
     B, T, H = 8, 4096, 8
     for hd in (48, 64):
@@ -132,4 +163,4 @@ def c5():
 if __name__ == "__main__":
     which = sys.argv[1:] or ["c2", "c4", "c5"]
     for w in which:
-        {"c2": c2, "c4": c4, "c5": c5}[w]()
+        {"c2": c2, "c4": c4, "c5": c5, "decode": decode}[w]()
