@@ -275,6 +275,17 @@ def attn_decode(qkv_new, k_cache, v_cache, lo, t, H, Hk, hd, window=0, scale=Non
     return out
 
 
+def pack_lm_batch(tokens, offsets, lengths, indices, T_out):
+    """(xb, yb) int64 [B, T_out] from the device-resident packed dataset for the sequence `indices` (int64, device)."""
+    _dev(tokens)
+    B = indices.numel()
+    xb = torch.empty((B, T_out), dtype=torch.int64, device=tokens.device)
+    yb = torch.empty((B, T_out), dtype=torch.int64, device=tokens.device)
+    check(_L().cgpt_pack_lm_batch(tokens.data_ptr(), offsets.data_ptr(), lengths.data_ptr(), indices.data_ptr(), B,
+                                  int(T_out), xb.data_ptr(), yb.data_ptr(), _stream()))
+    return xb, yb
+
+
 # ------------------------------------------------------------------ heads / loss
 def skinny_linear_fwd(x2d, w, bias=None):
     _dev(x2d)

@@ -514,6 +514,29 @@ attn_decode_kernel(const __nv_bfloat16* __restrict__ qkv_new, __nv_bfloat16* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------- token feed
+// (xb, yb) of one micro-batch gathered on the device from a resident packed token array:
+// xb[r, c] = seq_r[c], yb[r, c] = seq_r[c + 1] for c < len_r - 1, PAD (0) elsewhere.
+__global__ void pack_lm_batch_kernel(const int32_t* __restrict__ tokens, const long long* __restrict__ offsets,
+                                     const long long* __restrict__ lengths, const long long* __restrict__ indices,
+                                     int B, int T_out, long long* __restrict__ xb, long long* __restrict__ yb) {
+  const long long total = (long long)B * T_out;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int r = (int)(i / T_out), c = (int)(i - (long long)r * T_out);
+    const long long s = indices[r];
+    const long long usable = lengths[s] - 1;
+    long long x = 0, y = 0;
+    if (c < usable) {
+      const int32_t* seq = tokens + offsets[s];
+      x = seq[c];
+      y = seq[c + 1];
+    }
+    xb[i] = x;
+    yb[i] = y;
+  }
+}
+
 // out[n] += sum_m x[m,n]; CTA = 64 columns x a row range; 8 warps stride rows, lanes own column pairs.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
@@ -949,6 +972,18 @@ int cgpt_attn_decode(const void* qkv_new, void* k_cache, void* v_cache, const in
       reinterpret_cast<const __nv_bfloat16*>(qkv_new), reinterpret_cast<__nv_bfloat16*>(k_cache),
       reinterpret_cast<__nv_bfloat16*>(v_cache), lo, reinterpret_cast<__nv_bfloat16*>(out), t_dev, t, Tmax, H, Hk, hd,
       window, scale * 1.4426950408889634f);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_pack_lm_batch(const int32_t* tokens, const int64_t* offsets, const int64_t* lengths, const int64_t* indices,
+                       int B, int T_out, int64_t* xb, int64_t* yb, cgpt_stream_t stream) {
+  CGPT_REQUIRE(tokens && offsets && lengths && indices && xb && yb && B > 0 && T_out > 0, "pack_lm_batch: bad arguments");
+  pack_lm_batch_kernel<<<grid_for((long long)B * T_out, 256), 256, 0, ST(stream)>>>(
+      tokens, reinterpret_cast<const long long*>(offsets), reinterpret_cast<const long long*>(lengths),
+      reinterpret_cast<const long long*>(indices), B, T_out, reinterpret_cast<long long*>(xb),
+      reinterpret_cast<long long*>(yb));
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

@@ -177,6 +177,15 @@ int cgpt_attn_decode(const void* qkv_new, void* k_cache, void* v_cache, const in
                      const int32_t* t_dev, int Tmax, int H, int Hk, int hd, int window, float scale,
                      cgpt_stream_t stream);
 
+/* ---------------------------------------------------------------- token feed -------------- */
+/* One micro-batch (xb, yb) int64 [B, T_out] gathered on the device from a RESIDENT packed dataset — the dynamic
+ * format of the reference (flat token array + per-sequence lengths, data_loading.py:212-225) — for the sequence
+ * indices of a batch: xb[r, c] = seq[c], yb[r, c] = seq[c+1] for c < len-1, PAD = 0 elsewhere; with
+ * T_out = max(len) - 1 this is MmapPackedDataset.fetch_batch (data_loading.py:297-315) without the host gather and
+ * without the H2D copy of the batch (only the B indices travel). */
+int cgpt_pack_lm_batch(const int32_t* tokens, const int64_t* offsets, const int64_t* lengths, const int64_t* indices,
+                       int B, int T_out, int64_t* xb, int64_t* yb, cgpt_stream_t stream);
+
 /* ---------------------------------------------------------------- LM / aux heads --------- */
 /* out[M,N] = x[M,d]·w[N,d]ᵀ (+bias), fp32 FMA, N <= 128
  *                                                   head :217,327; termination_head :220-224,330. */

