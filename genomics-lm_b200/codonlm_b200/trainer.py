@@ -9,6 +9,7 @@ micro-batch: losses stay on the device and are read back only when the caller as
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Iterable, List, Optional, Sequence
 
 import torch
@@ -105,8 +106,12 @@ class GradBuckets:
     """Bucketed bf16 all-reduce of a flat gradient buffer, launched on a side stream as soon as every
     parameter of a bucket has received its gradient."""
 
-    def __init__(self, group: FlatGroup, process_group, bucket_bytes: int = 25 << 20):
+    def __init__(self, group: FlatGroup, process_group, bucket_bytes: int = 25 << 20, overlap: bool = True):
         self.g = group
+        # overlap=False: every bucket is reduced after backward instead of from the gradient-ready hooks.  The NCCL
+        # kernels then never share the SMs with the persistent GEMM / attention kernels (whose grids are sized to all
+        # 148 SMs: a CTA that cannot be placed next to an NCCL CTA runs as a second wave)
+        self.overlap = bool(overlap)
         self.pg = process_group
         self.world = dist.get_world_size(process_group)
         self.on_gpu = group.grad.is_cuda  # CPU tensors only in the gloo tests of this host logic
@@ -144,7 +149,7 @@ class GradBuckets:
             self.contrib_seen[i] += 1
             if self.contrib_need is None:
                 return
-            if self.contrib_seen[i] == self.contrib_need[i]:
+            if self.overlap and self.contrib_seen[i] == self.contrib_need[i]:
                 b = self.bucket_of[i]
                 self.left[b] -= 1
                 if self.left[b] == 0:
@@ -189,7 +194,7 @@ class TrainStep:
 
     def __init__(self, model, lr=3e-4, lr_embedding=None, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  offset_weights: Optional[Dict[int, float]] = None, termination_loss_weight: float = 0.0,
-                 process_group=None, bucket_mb: int = 25):
+                 process_group=None, bucket_mb: int = 25, overlap_allreduce: Optional[bool] = None):
         self.model = model
         self.offset_weights = offset_weights
         self.termination_loss_weight = termination_loss_weight
@@ -205,7 +210,9 @@ class TrainStep:
         if process_group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             pg = process_group if process_group is not None else dist.group.WORLD
             self.world = dist.get_world_size(pg)
-            self.buckets = [GradBuckets(g, pg, bucket_mb << 20) for g in self.groups]
+            if overlap_allreduce is None:
+                overlap_allreduce = os.environ.get("CGPT_DDP_OVERLAP", "1") == "1"
+            self.buckets = [GradBuckets(g, pg, bucket_mb << 20, overlap=overlap_allreduce) for g in self.groups]
         dev = self.groups[0].flat.device
         self._xb = self._yb = None
         self._dev = dev

@@ -1122,10 +1122,16 @@ template <int G>
 __global__ void attn_delta_vec_kernel(const __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ dout,
                                       float* __restrict__ delta, int B, int T, int H,
                                       const int32_t* __restrict__ seg_start, int window, int* __restrict__ qhi_tab,
-                                      int ctr_init) {
+                                      int ctr_init, float4* __restrict__ dq_zero) {
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index
   if (qhi_tab && e < (long long)B * ((T + BKV - 1) / BKV)) fill_qhi_tab((int)e, B, T, seg_start, window, qhi_tab, ctr_init);
   const long long total = (long long)B * T * H * G;
+  // the fp32 dQ workspace has 8 floats per chunk of O: it is cleared here (32 contiguous bytes per thread) instead of
+  // by a separate memset pass in front of the backward kernel
+  if (dq_zero && e < total) {
+    dq_zero[2 * e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    dq_zero[2 * e + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   float s = 0.f;
   if (e < total) {
     const uint4 a = reinterpret_cast<const uint4*>(o)[e];
@@ -2385,7 +2391,8 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     rc = make_tmap_bf16(&tdkv, dqkv, 3, dims, str, box, HD);  // swizzle span = row bytes (64 / 32) or none
     if (rc) return rc;
   }
-  CGPT_CHECK(cudaMemsetAsync(dq_ws, 0, (size_t)B * H * T * HD * sizeof(float), st));
+  constexpr bool kDeltaVec = (HD / 8 == 2 || HD / 8 == 4 || HD / 8 == 8 || HD / 8 == 16);
+  if (!kDeltaVec) CGPT_CHECK(cudaMemsetAsync(dq_ws, 0, (size_t)B * H * T * HD * sizeof(float), st));
   // grid of the warp-specialised kernel = initial value of its work counter (pairs 0..grid-1 are implicit)
   const int ws_pairs = (((T + BKV - 1) / BKV + 1) / 2) * Hk * B;
   const int ws_grid = ws_pairs < num_sms() ? ws_pairs : num_sms();
@@ -2396,7 +2403,8 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     if constexpr (G == 2 || G == 4 || G == 8 || G == 16) {
       const long long chunks = (long long)B * T * H * G;  // >= B * kv tiles, so the table job fits too
       attn_delta_vec_kernel<G><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(po, pd, delta, B, T, H, seg, window,
-                                                                               qhi_tab, ws_grid);
+                                                                               qhi_tab, ws_grid,
+                                                                               reinterpret_cast<float4*>(dq_ws));
     } else {
       const long long warps = (long long)B * T * H;
       attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(po, pd, delta, B, T, H, HD, seg, window, qhi_tab,
