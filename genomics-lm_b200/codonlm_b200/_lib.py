@@ -56,6 +56,8 @@ SIGNATURES = {
     "cgpt_attn_probs": (_i, [_vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _f, C.c_uint64, C.c_uint64, _vp]),
     "cgpt_attn_decode": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _i, _i, _i, _i, _f, _vp]),
     "cgpt_pack_lm_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _vp, _vp]),
+    "cgpt_shape_proj_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
+    "cgpt_shape_proj_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _i64, _i, _vp]),
     "cgpt_dropout": (_i, [_vp, _vp, _vp, _i, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
     "cgpt_skinny_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "cgpt_skinny_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),

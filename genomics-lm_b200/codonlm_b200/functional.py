@@ -135,6 +135,32 @@ class EmbedFn(Function):
         return None, (None if mt is not None else dtok), (None if mp is not None else dpos)
 
 
+class ShapeProjFn(Function):
+    """x + shape_proj(shape_embeddings) — nn.Linear(3, d) on the DNA-shape features added to the embedding
+    (model_tiny_gpt.py:226-229, 310-311).  K = 3 is no tensor-core shape: three small memory-bound kernels."""
+
+    @staticmethod
+    def forward(ctx, x, s, w, b):
+        ctx.save_for_backward(s, w)
+        ctx.masters = (w, b)
+        return ops.shape_proj_fwd(x, s, w.detach(), b.detach())
+
+    @staticmethod
+    def backward(ctx, g):
+        s, w = ctx.saved_tensors
+        wm, bm = ctx.masters
+        g = g.contiguous()
+        mw, mb = _main_grad(wm), _main_grad(bm)
+        dw = mw if mw is not None else torch.zeros_like(w)
+        db = mb if mb is not None else torch.zeros((w.shape[0],), dtype=f32, device=w.device)
+        ds = ops.shape_proj_bwd(g, s, w.detach(), dw, db, ctx.needs_input_grad[1])
+        if mw is not None:
+            _done(wm)
+            _done(bm)
+            return g, ds, None, None
+        return g, ds, dw, db
+
+
 class ResidualLayerNormFn(Function):
     """(x, y) = (x, LN(x)): returning the residual stream through the Function lets backward fuse
     dx = d_residual + LN'(dy) into one kernel (model_tiny_gpt.py:151-152 pre-norm pattern)."""

@@ -621,8 +621,6 @@ class TinyGPT(nn.Module):
         return idx.contiguous()
 
     def _embed(self, idx, shape_embeddings):
-        if shape_embeddings is not None and self.use_shape_guidance:
-            raise NotImplementedError("use_shape_guidance is outside the scope of codonlm_b200 (SURVEY §2.2)")
         B, T = idx.shape
         if _has_hooks(self.tok_emb) or (self.pos_emb is not None and _has_hooks(self.pos_emb)):
             x = self.tok_emb(idx)
@@ -630,6 +628,12 @@ class TinyGPT(nn.Module):
                 x = x + self.pos_emb(torch.arange(0, T, device=idx.device).unsqueeze(0))
         else:
             x = Fn.EmbedFn.apply(idx, self.tok_emb.weight, None if self.pos_emb is None else self.pos_emb.weight)
+        if shape_embeddings is not None and self.use_shape_guidance:  # x + shape_proj(shape_embeddings) (:310-311)
+            if self.n_embd % 4 != 0:
+                raise _lib.CgptError("use_shape_guidance needs n_embd % 4 == 0")
+            s2 = shape_embeddings.to(device=x.device, dtype=f32).reshape(B * T, 3).contiguous()
+            x = Fn.ShapeProjFn.apply(x.reshape(B * T, -1).contiguous(), s2, self.shape_proj.weight,
+                                     self.shape_proj.bias).view(B, T, -1)
         if self.training and self.drop.p > 0.0:  # self.drop(x) (:312)
             x = Fn.DropoutFn.apply(x, None, float(self.drop.p))
         return x

@@ -98,14 +98,15 @@ def termination_aux_loss(termination_logits: torch.Tensor, labels: torch.Tensor,
 def training_loss(model, xb, yb, offset_weights: Optional[Dict[int, float]] = None,
                   termination_loss_weight: float = 0.0, termination_stop_ids=(2,),
                   termination_bucket_edges=(0, 3, 10, 30), termination_class_weights=None,
-                  attention_window=None):
+                  attention_window=None, shape_embeddings=None):
     """total = next + sum_o w_o·loss_o + termination_loss_weight·term  (loop.py:1067-1143, replay excluded).
     Returns (total, parts, logits); no host synchronisation."""
     need_aux = bool(offset_weights) or bool(termination_loss_weight)
     if need_aux:
-        logits, next_loss, aux = model(xb, yb, return_aux=True, attention_window=attention_window)
+        logits, next_loss, aux = model(xb, yb, return_aux=True, attention_window=attention_window,
+                                       shape_embeddings=shape_embeddings)
     else:
-        logits, next_loss = model(xb, yb, attention_window=attention_window)
+        logits, next_loss = model(xb, yb, attention_window=attention_window, shape_embeddings=shape_embeddings)
         aux = {}
     yb = yb.to(logits.device)
     total = next_loss

@@ -286,6 +286,24 @@ def pack_lm_batch(tokens, offsets, lengths, indices, T_out):
     return xb, yb
 
 
+def shape_proj_fwd(x2d, s2d, w, b):
+    """x + shape_embeddings·wᵀ + b  (fp32; x [M, d], shape_embeddings [M, 3], w [d, 3])."""
+    _dev(x2d)
+    M, d = x2d.shape
+    out = torch.empty_like(x2d)
+    check(_L().cgpt_shape_proj_fwd(x2d.data_ptr(), s2d.data_ptr(), w.data_ptr(), b.data_ptr(), out.data_ptr(), M, d,
+                                   _stream()))
+    return out
+
+
+def shape_proj_bwd(dx, s2d, w, dw, db, want_ds):
+    M, d = dx.shape
+    ds = torch.empty((M, 3), dtype=f32, device=dx.device) if want_ds else None
+    check(_L().cgpt_shape_proj_bwd(dx.data_ptr(), s2d.data_ptr(), w.data_ptr(), dw.data_ptr(), db.data_ptr(), _p(ds),
+                                   M, d, _stream()))
+    return ds
+
+
 # ------------------------------------------------------------------ heads / loss
 def skinny_linear_fwd(x2d, w, bias=None):
     _dev(x2d)

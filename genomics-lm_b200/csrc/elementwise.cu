@@ -537,6 +537,88 @@ __global__ void pack_lm_batch_kernel(const int32_t* __restrict__ tokens, const l
   }
 }
 
+// ---------------------------------------------------------------------------------------- shape guidance
+// out[m, c] = x[m, c] + b[c] + sum_k w[c, k] * s[m, k]   (nn.Linear(3, d) on the DNA-shape features, added to the
+// embedding: model_tiny_gpt.py:226-229, 310-311).  One thread per 4 columns.
+__global__ void shape_proj_fwd_kernel(const float* __restrict__ x, const float* __restrict__ s,
+                                      const float* __restrict__ w, const float* __restrict__ b,
+                                      float* __restrict__ out, long long M, int d) {
+  const int d4 = d >> 2;
+  const long long total = M * d4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long m = i / d4;
+    const int c = (int)(i - m * d4) * 4;
+    const float s0 = s[m * 3], s1 = s[m * 3 + 1], s2 = s[m * 3 + 2];
+    float4 v = *reinterpret_cast<const float4*>(x + m * d + c);
+    float* pv = reinterpret_cast<float*>(&v);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float* wr = w + (size_t)(c + e) * 3;
+      pv[e] += b[c + e] + wr[0] * s0 + wr[1] * s1 + wr[2] * s2;
+    }
+    *reinterpret_cast<float4*>(out + m * d + c) = v;
+  }
+}
+
+// dw[c, k] += sum_m dx[m, c] s[m, k], db[c] += sum_m dx[m, c].  CTA = 64 columns x a row range, 4 row lanes.
+__global__ void __launch_bounds__(256)
+shape_proj_wgrad_kernel(const float* __restrict__ dx, const float* __restrict__ s, float* __restrict__ dw,
+                        float* __restrict__ db, long long M, int d, int rows_per_cta) {
+  __shared__ float red[4][64][4];
+  const int cl = threadIdx.x & 63, rl = threadIdx.x >> 6;
+  const int c = blockIdx.x * 64 + cl;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < M ? r0 + rows_per_cta : M;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, ab = 0.f;
+  if (c < d) {
+    for (long long m = r0 + rl; m < r1; m += 4) {
+      const float g = dx[m * d + c];
+      a0 = fmaf(g, s[m * 3], a0);
+      a1 = fmaf(g, s[m * 3 + 1], a1);
+      a2 = fmaf(g, s[m * 3 + 2], a2);
+      ab += g;
+    }
+  }
+  red[rl][cl][0] = a0;
+  red[rl][cl][1] = a1;
+  red[rl][cl][2] = a2;
+  red[rl][cl][3] = ab;
+  __syncthreads();
+  if (rl == 0 && c < d) {
+    float t[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) t[e] = red[0][cl][e] + red[1][cl][e] + red[2][cl][e] + red[3][cl][e];
+    atomicAdd(dw + (size_t)c * 3, t[0]);
+    atomicAdd(dw + (size_t)c * 3 + 1, t[1]);
+    atomicAdd(dw + (size_t)c * 3 + 2, t[2]);
+    atomicAdd(db + c, t[3]);
+  }
+}
+
+// ds[m, k] = sum_c dx[m, c] w[c, k]: one warp per row (only when the shape encoder is trained, loop.py:695)
+__global__ void shape_proj_dgrad_kernel(const float* __restrict__ dx, const float* __restrict__ w,
+                                        float* __restrict__ ds, long long M, int d) {
+  const long long m = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (m >= M) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int c = lane; c < d; c += 32) {
+    const float g = dx[m * d + c];
+    a0 = fmaf(g, w[(size_t)c * 3], a0);
+    a1 = fmaf(g, w[(size_t)c * 3 + 1], a1);
+    a2 = fmaf(g, w[(size_t)c * 3 + 2], a2);
+  }
+  a0 = warp_sum(a0);
+  a1 = warp_sum(a1);
+  a2 = warp_sum(a2);
+  if (lane == 0) {
+    ds[m * 3] = a0;
+    ds[m * 3 + 1] = a1;
+    ds[m * 3 + 2] = a2;
+  }
+}
+
 // out[n] += sum_m x[m,n]; CTA = 64 columns x a row range; 8 warps stride rows, lanes own column pairs.
 __global__ void __launch_bounds__(256)
 colsum_bf16_kernel(const __nv_bfloat16* __restrict__ x, long long ld, float* __restrict__ out, int M, int N,
@@ -986,6 +1068,31 @@ int cgpt_pack_lm_batch(const int32_t* tokens, const int64_t* offsets, const int6
       reinterpret_cast<long long*>(yb));
   count_launch();
   CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_shape_proj_fwd(const float* x, const float* s, const float* w, const float* b, float* out, int64_t M, int d,
+                        cgpt_stream_t stream) {
+  CGPT_REQUIRE(x && s && w && b && out && M > 0 && d > 0 && d % 4 == 0, "shape_proj_fwd: bad arguments");
+  shape_proj_fwd_kernel<<<grid_for(M * (d / 4), 256), 256, 0, ST(stream)>>>(x, s, w, b, out, M, d);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_shape_proj_bwd(const float* dx, const float* s, const float* w, float* dw, float* db, float* ds, int64_t M,
+                        int d, cgpt_stream_t stream) {
+  CGPT_REQUIRE(dx && s && w && dw && db && M > 0 && d > 0, "shape_proj_bwd: bad arguments");
+  const int rows_per_cta = 2048;
+  dim3 grid((d + 63) / 64, (unsigned)((M + rows_per_cta - 1) / rows_per_cta));
+  shape_proj_wgrad_kernel<<<grid, 256, 0, ST(stream)>>>(dx, s, dw, db, M, d, rows_per_cta);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  if (ds) {
+    shape_proj_dgrad_kernel<<<(unsigned)((M * 32 + 255) / 256), 256, 0, ST(stream)>>>(dx, w, ds, M, d);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+  }
   return 0;
 }
 

@@ -177,6 +177,15 @@ int cgpt_attn_decode(const void* qkv_new, void* k_cache, void* v_cache, const in
                      const int32_t* t_dev, int Tmax, int H, int Hk, int hd, int window, float scale,
                      cgpt_stream_t stream);
 
+/* Shape guidance: out = x + nn.Linear(3, d)(shape_embeddings)   model_tiny_gpt.py:226-229, 310-311 (also :377-378).
+ * x, out fp32 [M, d] (d % 4 == 0); s fp32 [M, 3]; w fp32 [d, 3]; b fp32 [d].
+ * Backward: dw [d, 3] += dx^T s, db [d] += column sums of dx, ds [M, 3] = dx w (nullable: only when the shape encoder is
+ * trained, loop.py:695); the gradient of x is dx itself. */
+int cgpt_shape_proj_fwd(const float* x, const float* s, const float* w, const float* b, float* out, int64_t M, int d,
+                        cgpt_stream_t stream);
+int cgpt_shape_proj_bwd(const float* dx, const float* s, const float* w, float* dw, float* db, float* ds, int64_t M,
+                        int d, cgpt_stream_t stream);
+
 /* ---------------------------------------------------------------- token feed -------------- */
 /* One micro-batch (xb, yb) int64 [B, T_out] gathered on the device from a RESIDENT packed dataset — the dynamic
  * format of the reference (flat token array + per-sequence lengths, data_loading.py:212-225) — for the sequence

@@ -61,7 +61,8 @@ def make_cfg(vocab_size, block_size, n_layer=3, n_head=4, n_embd=256, dropout=0.
                 termination_aux=bool(termination_aux),
                 termination_n_classes=int(termination_n_classes),
                 multi_offset_targets=sorted({int(t) for t in multi_offset_targets}) if multi_offset_targets else [],
-                use_swiglu=bool(use_swiglu), use_rope=bool(use_rope))
+                use_swiglu=bool(use_swiglu), use_rope=bool(use_rope),
+                use_shape_guidance=bool(use_shape_guidance))
 
 
 # --------------------------------------------------------------------------
@@ -248,7 +249,8 @@ def _mlp(sd, pre, x, cfg):
 
 def forward(sd: Dict[str, torch.Tensor], cfg: dict, idx: torch.Tensor,
             targets: Optional[torch.Tensor] = None, attention_window: Optional[int] = None,
-            want_hidden: bool = False, want_attn: bool = False) -> dict:
+            want_hidden: bool = False, want_attn: bool = False,
+            shape_embeddings: Optional[torch.Tensor] = None) -> dict:
     """Eval-mode (dropout off) forward of TinyGPT (model_tiny_gpt.py:297-352).
 
     Returns dict(logits, loss|None, termination_logits?, offset_logits?{o:..},
@@ -262,6 +264,8 @@ def forward(sd: Dict[str, torch.Tensor], cfg: dict, idx: torch.Tensor,
         cos = sin = None
     else:
         cos, sin = rope_tables(T, cfg["n_embd"] // cfg["n_head"], device=dev)
+    if shape_embeddings is not None and cfg.get("use_shape_guidance"):  # model_tiny_gpt.py:310-311
+        x = x + linear(shape_embeddings, sd["shape_proj.weight"], sd["shape_proj.bias"])
     m = attention_mask(idx.cpu().numpy(), cfg["sep_id"], attention_window)
     if m is None:
         m = np.tril(np.ones((T, T), dtype=bool))[None, None]
@@ -335,13 +339,13 @@ def termination_aux_loss(term_logits, labels, class_weights=None, ignore_index=-
 
 def training_loss(sd, cfg, idx, targets, offset_weights=None, termination_loss_weight=0.0,
                   termination_stop_ids=(2,), termination_bucket_edges=(0, 3, 10, 30),
-                  termination_class_weights=None, attention_window=None):
+                  termination_class_weights=None, attention_window=None, shape_embeddings=None):
     """Loss composition of the trainer's fwd() (loop.py:1067-1143, replay branch excluded).
 
     total = next + sum_o w_o * loss_o + termination_loss_weight * term
     Returns (total, parts dict, forward-output dict).
     """
-    out = forward(sd, cfg, idx, targets, attention_window=attention_window)
+    out = forward(sd, cfg, idx, targets, attention_window=attention_window, shape_embeddings=shape_embeddings)
     total = out["loss"]
     parts = {"next": out["loss"]}
     if offset_weights:
@@ -436,6 +440,11 @@ def init_state_dict(cfg: dict, seed: int = 1337, emb_scale: float = 1.0) -> Dict
         sd[q + "0.bias"] = 0.02 * torch.randn(d, generator=g)
         sd[q + "2.weight"] = torch.eye(d) + 0.02 * torch.randn(d, d, generator=g)
         sd[q + "2.bias"] = 0.02 * torch.randn(d, generator=g)
+    if cfg.get("use_shape_guidance"):
+        # zero-initialised in the reference (model_tiny_gpt.py:228-229); perturbed so that the branch is visible.
+        # Drawn last: the weights of every other configuration keep their values.
+        sd["shape_proj.weight"] = 0.05 * torch.randn(d, 3, generator=g)
+        sd["shape_proj.bias"] = 0.05 * torch.randn(d, generator=g)
     return sd
 
 

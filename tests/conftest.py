@@ -14,7 +14,7 @@ for p in (ROOT, PKG):
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["gelu_abs_sep", "gelu_default_init", "swiglu_rope_causal", "gqa_untied_weighted",
-                "heads_offsets_term", "window5"]
+                "heads_offsets_term", "window5", "shape_guidance"]
 
 
 def pytest_configure(config):

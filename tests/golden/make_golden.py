@@ -52,6 +52,10 @@ CASES = {
                   multi_offset_targets=[2, 4, 8]),
         B=3, T=64, emb_scale=0.02,
         offset_weights={2: 0.5, 4: 0.25, 8: 0.125}, termination_loss_weight=0.3),
+    "shape_guidance": dict(
+        ctor=dict(vocab_size=68, block_size=48, n_layer=1, n_head=2, n_embd=64, dropout=0.0,
+                  label_smoothing=0.05, sep_id=3, use_sdpa=True, use_shape_guidance=True),
+        B=2, T=40, emb_scale=0.02, shape_guidance=True),
     "window5": dict(
         ctor=dict(vocab_size=68, block_size=32, n_layer=1, n_head=1, n_embd=32, dropout=0.0,
                   label_smoothing=0.0, sep_id=3, use_sdpa=True),
@@ -83,6 +87,8 @@ def build(case):
                 p.add_(0.1 * torch.randn(p.shape, generator=g))
             if name.startswith("offset_projs"):
                 p.add_(0.02 * torch.randn(p.shape, generator=g))
+            if name.startswith("shape_proj"):  # zero-initialised in the reference (:228-229): make it visible
+                p.add_(0.05 * torch.randn(p.shape, generator=g))
     m.eval()
     return m, spec
 
@@ -94,7 +100,10 @@ def main():
         idx, tgt = synthetic_batch(spec["B"], spec["T"], seed=11, realistic=True, vocab_size=V)
         win = spec.get("attention_window")
         out = {}
-        logits, loss, aux = m(idx, tgt, return_aux=True, attention_window=win)
+        shapes = None
+        if spec.get("shape_guidance"):  # stands in for the DNA-shape encoder's output (B, T, 3), loop.py:1070-1077
+            shapes = torch.randn((spec["B"], spec["T"], 3), generator=torch.Generator().manual_seed(5)).requires_grad_(True)
+        logits, loss, aux = m(idx, tgt, return_aux=True, attention_window=win, shape_embeddings=shapes)
         total = loss
         parts = {"next": float(loss.detach())}
         ow = spec.get("offset_weights")
@@ -120,7 +129,11 @@ def main():
         parts["total"] = float(total)
         mask = m.build_attention_mask(idx, win)
         out["attn_mask"] = (mask.numpy() if mask is not None else np.zeros((0,), dtype=bool))
-        hidden = [h.detach().numpy() for _, h in m.iter_hidden_states(idx, attention_window=win)]
+        hidden = [h.detach().numpy() for _, h in m.iter_hidden_states(idx, attention_window=win,
+                                                                      shape_embeddings=shapes)]
+        if shapes is not None:
+            out["shape_embeddings"] = shapes.detach().numpy()
+            out["grad_shape_embeddings"] = shapes.grad.detach().numpy()
         out["hidden_final"] = hidden[-1]
         out["hidden_0"] = hidden[0]
         out["idx"] = idx.numpy()

@@ -66,10 +66,16 @@ def test_golden_reference_vectors(case):
     idx = torch.from_numpy(z["idx"]).to(DEV)
     tgt = torch.from_numpy(z["targets"]).to(DEV)
     ow = {int(k): v for k, v in meta["offset_weights"].items()} or None
+    shapes = None
+    if "shape_embeddings" in z.files:  # shape guidance (model_tiny_gpt.py:310-311): the encoder's output is an input here
+        shapes = torch.from_numpy(z["shape_embeddings"]).to(DEV).requires_grad_(True)
     total, parts, logits = training_loss(model, idx, tgt, offset_weights=ow,
                                          termination_loss_weight=meta["termination_loss_weight"],
-                                         attention_window=meta["attention_window"])
+                                         attention_window=meta["attention_window"], shape_embeddings=shapes)
     total.backward()
+    if shapes is not None:
+        ref = torch.from_numpy(z["grad_shape_embeddings"]).to(DEV)
+        assert ((shapes.grad - ref).norm() / ref.norm()).item() <= GRAD_RTOL
     ref_logits = torch.from_numpy(z["logits"]).to(DEV)
     scale = max(1.0, ref_logits.abs().max().item() / 8.0)  # default-init logits reach |50|: tolerance scales
     err = (logits - ref_logits).abs().max().item()
@@ -91,9 +97,13 @@ def test_golden_reference_vectors(case):
     _grad_check(model, grads)
     # hidden-state iterator (extract_embeddings path)
     with torch.no_grad():
-        stages = list(model.iter_hidden_states(idx, attention_window=meta["attention_window"]))
+        stages = list(model.iter_hidden_states(idx, attention_window=meta["attention_window"],
+                                               shape_embeddings=None if shapes is None else shapes.detach()))
     assert [s for s, _ in stages] == [0] + list(range(1, meta["ctor"]["n_layer"] + 1)) + ["final"]
-    assert torch.equal(stages[0][1].cpu(), torch.from_numpy(z["hidden_0"]))  # embedding gather is exact
+    if shapes is None:
+        assert torch.equal(stages[0][1].cpu(), torch.from_numpy(z["hidden_0"]))  # embedding gather is exact
+    else:
+        assert (stages[0][1].cpu() - torch.from_numpy(z["hidden_0"])).abs().max().item() <= 1e-6
     assert (stages[-1][1].cpu() - torch.from_numpy(z["hidden_final"])).abs().max().item() <= LOGIT_TOL * scale
 
 
@@ -256,6 +266,35 @@ def test_cached_generate_follows_reference_loop_rules():
     assert len(stop) == len(ctx) + 1
     batch = generate_batch(model, torch.tensor([ctx, ctx[::-1]]), max_new=100, topk=2)
     assert batch.shape == (2, 48) and torch.equal(batch[0, : len(ctx)].cpu(), torch.tensor(ctx))
+
+
+def test_shape_guidance_at_scale_against_live_oracle():
+    """use_shape_guidance (model_tiny_gpt.py:226-229, 310-311) at a realistic size: logits, loss, the shape_proj
+    weight / bias gradients and the gradient handed back to the shape encoder against the oracle."""
+    from codonlm_b200 import training_loss
+    ctor = dict(vocab_size=68, block_size=512, n_layer=2, n_head=4, n_embd=256, dropout=0.0, label_smoothing=0.05,
+                use_sdpa=True, use_shape_guidance=True)
+    cfg = O.make_cfg(**ctor)
+    sd = O.init_state_dict(cfg, seed=1337, emb_scale=0.02)
+    idx, tgt = O.synthetic_batch(4, 512, seed=3, realistic=True)
+    model = _build(ctor, sd).train()
+    shapes = torch.randn((4, 512, 3), generator=torch.Generator().manual_seed(2)).to(DEV).requires_grad_(True)
+    total, parts, logits = training_loss(model, idx.to(DEV), tgt.to(DEV), shape_embeddings=shapes)
+    total.backward()
+    sd_dev = {k: v.to(DEV) for k, v in sd.items()}
+    rs = shapes.detach().clone().requires_grad_(True)
+    rtotal, _, rout, rgrads = O.loss_and_grads(sd_dev, cfg, idx.to(DEV), tgt.to(DEV), shape_embeddings=rs)
+    assert (logits - rout["logits"]).abs().max().item() <= LOGIT_TOL
+    assert total.item() == pytest.approx(rtotal.item(), rel=LOSS_RTOL)
+    assert ((shapes.grad - rs.grad).norm() / rs.grad.norm()).item() <= GRAD_RTOL
+    _grad_check(model, {k: v.cpu() for k, v in rgrads.items()})
+    # a model built with the flag but called without shape embeddings behaves like the plain model (:310)
+    with torch.no_grad():
+        a = model(idx.to(DEV))[0]
+    plain = _build(dict(ctor, use_shape_guidance=False), {k: v for k, v in sd.items() if not k.startswith("shape_proj")})
+    with torch.no_grad():
+        b = plain(idx.to(DEV))[0]
+    assert torch.equal(a, b)
 
 
 def test_forward_shapes_and_pad_loss():  # tests/test_models.py:7-27, test_toggles_smoke.py

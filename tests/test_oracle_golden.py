@@ -16,13 +16,16 @@ def test_forward_matches_reference(golden):
     case, z, meta, sd, grads = golden
     cfg = _cfg(meta)
     idx, tgt = torch.from_numpy(z["idx"]), torch.from_numpy(z["targets"])
-    out = O.forward(sd, cfg, idx, tgt, attention_window=meta["attention_window"], want_hidden=True)
+    shapes = torch.from_numpy(z["shape_embeddings"]) if "shape_embeddings" in z.files else None
+    out = O.forward(sd, cfg, idx, tgt, attention_window=meta["attention_window"], want_hidden=True,
+                    shape_embeddings=shapes)
     # fp32 on both sides, different op order (manual softmax vs SDPA): 1e-4 abs at |logit| <~ 50
     scale = max(1.0, float(np.abs(z["logits"]).max()))
     assert np.abs(out["logits"].numpy() - z["logits"]).max() <= 2e-5 * scale
     assert out["loss"].item() == pytest.approx(meta["parts"]["next"], rel=2e-6)
     assert np.array_equal(out["logits"].argmax(-1).numpy(), z["argmax"])
-    assert np.abs(out["hidden"][0].numpy() - z["hidden_0"]).max() == 0.0
+    # the embedding gather is exact; with shape guidance the K=3 projection is added (different summation order)
+    assert np.abs(out["hidden"][0].numpy() - z["hidden_0"]).max() <= (0.0 if shapes is None else 1e-6)
     assert np.abs(out["hidden"][-1].numpy() - z["hidden_final"]).max() <= 2e-5
     if "termination_logits" in z.files:
         assert np.abs(out["termination_logits"].numpy() - z["termination_logits"]).max() <= 2e-5
@@ -44,9 +47,15 @@ def test_losses_and_grads_match_reference(golden):
     cfg = _cfg(meta)
     idx, tgt = torch.from_numpy(z["idx"]), torch.from_numpy(z["targets"])
     ow = {int(k): v for k, v in meta["offset_weights"].items()} or None
+    shapes = None
+    if "shape_embeddings" in z.files:
+        shapes = torch.from_numpy(z["shape_embeddings"]).requires_grad_(True)
     total, parts, out, g = O.loss_and_grads(sd, cfg, idx, tgt, offset_weights=ow,
                                             termination_loss_weight=meta["termination_loss_weight"],
-                                            attention_window=meta["attention_window"])
+                                            attention_window=meta["attention_window"], shape_embeddings=shapes)
+    if shapes is not None:
+        ref = z["grad_shape_embeddings"]
+        assert np.abs(shapes.grad.numpy() - ref).max() <= 2e-5 * np.abs(ref).max()
     assert total.item() == pytest.approx(meta["parts"]["total"], rel=3e-6)
     for o, v in meta["parts"].get("offsets", {}).items():
         assert parts["offsets"][int(o)].item() == pytest.approx(v, rel=3e-6)
