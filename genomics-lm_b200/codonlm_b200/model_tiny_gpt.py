@@ -35,6 +35,30 @@ class MaskSpec:
     window: int = 0                    # 0 = unlimited
 
 
+def mask_spec_from_bool(mask: torch.Tensor, B: int, T: int) -> MaskSpec:
+    """The reference hands its attention a boolean mask tensor (B,1,T,T) / (1,T,T) / (T,T), True = may attend
+    (model_tiny_gpt.py:106-113, built by build_attention_mask :273-295).  Every mask that function can build is a per-row
+    interval [lo_i, i]; it is converted back to that form (first allowed column per row) and checked — one host
+    sync, on this compatibility path only.  Masks that are not causal intervals are refused."""
+    m = mask
+    if m.dim() == 2:
+        m = m[None, None]
+    elif m.dim() == 3:
+        m = m[:, None]
+    if m.dim() != 4 or m.shape[1] != 1 or m.shape[-1] != T or m.shape[-2] != T or m.shape[0] not in (1, B):
+        raise NotImplementedError(f"attention mask of shape {tuple(mask.shape)}: expected (B,1,T,T), (1,T,T) or (T,T)")
+    m = m.to(torch.bool).expand(B, 1, T, T)[:, 0]
+    as_int = m.to(torch.int8)
+    lo = as_int.argmax(dim=-1)
+    hi = (T - 1) - as_int.flip(-1).argmax(dim=-1)
+    rows = torch.arange(T, device=m.device)[None, :]
+    ok = (hi == rows) & (as_int.sum(-1) == rows - lo + 1)
+    if not bool(ok.all()):
+        raise NotImplementedError("codonlm_b200 attention supports causal interval masks (causal / same-segment / "
+                                  "window, as build_attention_mask produces them); this mask is not one")
+    return MaskSpec(lo.to(torch.int32).contiguous(), 0)
+
+
 class _CastBf16(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x):
@@ -327,10 +351,8 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
         Hk = self.n_kv_head if self.n_kv_head is not None else H
         if H % Hk != 0:
             raise ValueError("n_head must be divisible by n_kv_head for GQA")
-        if isinstance(attn_mask, torch.Tensor):
-            raise NotImplementedError(
-                "codonlm_b200 attention takes the mask as a MaskSpec (segment starts + window), see "
-                "TinyGPT.mask_spec(); arbitrary boolean mask tensors are not supported")
+        if isinstance(attn_mask, torch.Tensor):  # the reference's calling convention: a boolean mask tensor
+            attn_mask = mask_spec_from_bool(attn_mask.to(x.device), B, T)
         spec: MaskSpec = attn_mask if attn_mask is not None else MaskSpec(None, 0)
         x2 = x.reshape(B * T, Cdim)
         xb = x2 if x2.dtype == bf16 else _CastBf16.apply(x2.float())

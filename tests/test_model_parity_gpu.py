@@ -297,6 +297,28 @@ def test_shape_guidance_at_scale_against_live_oracle():
     assert torch.equal(a, b)
 
 
+def test_boolean_mask_tensor_is_accepted_like_the_reference():
+    """CausalSelfAttention.forward(x, attn_mask=<bool tensor>) — the reference's calling convention (:106-113) — gives
+    the same output as the interval form for every mask build_attention_mask can produce; other masks are refused."""
+    m = _tiny(n_head=2, n_embd=64, block_size=64, use_sdpa=True)
+    idx, _ = O.synthetic_batch(3, 64, seed=12, realistic=True)
+    idx[:, 20], idx[1, 41] = 3, 3
+    idx = idx.to(DEV)
+    x = torch.randn(3, 64, 64, device=DEV).to(torch.bfloat16)
+    attn = m.blocks[0].attn
+    with torch.no_grad():
+        for window in (None, 7):
+            want = attn(x, attn_mask=m.mask_spec(idx, window))
+            got = attn(x, attn_mask=m.build_attention_mask(idx, window))
+            assert torch.equal(want, got)
+        causal = torch.tril(torch.ones(1, 64, 64, dtype=torch.bool, device=DEV))  # (1,T,T): tests/test_attention_dropout.py:33
+        assert torch.equal(attn(x, attn_mask=causal), attn(x, attn_mask=None))
+        bad = causal.clone()
+        bad[0, 10, 3] = False  # a hole: not an interval
+        with pytest.raises(NotImplementedError):
+            attn(x, attn_mask=bad)
+
+
 def test_forward_shapes_and_pad_loss():  # tests/test_models.py:7-27, test_toggles_smoke.py
     for kw in (dict(), dict(use_sdpa=True), dict(use_swiglu=True), dict(use_rope=True),
                dict(n_head=4, n_kv_head=2, n_embd=64), dict(tie_embeddings=False)):
