@@ -851,19 +851,66 @@ class TinyGPT(nn.Module):
         yield "final", x
 
 
-class _OutOfScope(nn.Module):
-    def __init__(self, *a, **k):
-        raise NotImplementedError(
-            "NoProp variants (model_tiny_gpt.py:391-459) are a different training algorithm and outside the "
-            "hot path this package accelerates (SURVEY §2, §8f-4)")
+class NoPropBlock(Block):
+    """Block + a per-block denoising head (model_tiny_gpt.py:391-416): forward(h, noisy_targets, attn_mask) ->
+    (x, pred_y) with x = block(h + noisy_targets) and pred_y = denoise_head(x).  Same submodule names, creation order
+    (seeded init) and state_dict keys as the reference; the block itself runs on the same kernels as TinyGPT's."""
+
+    def __init__(self, n_embd, n_head, dropout, block_size, n_kv_head: int | None = None, use_sdpa: bool = False):
+        super().__init__(n_embd, n_head, dropout, block_size, n_kv_head=n_kv_head, use_sdpa=use_sdpa)
+        self.denoise_head = Linear(n_embd, n_embd)
+
+    def forward(self, h, noisy_targets=None, attn_mask=None):
+        if noisy_targets is not None:  # x = h + noisy_targets (:407-408), through the residual-add kernel
+            shp = h.shape
+            h2 = h.reshape(-1, shp[-1]).float().contiguous()
+            n2 = noisy_targets.to(h.device).reshape(-1, shp[-1]).float().contiguous()
+            h = Fn.DropoutFn.apply(n2, h2, 0.0).view(shp)
+        x = super().forward(h, attn_mask=attn_mask)
+        return x, self.denoise_head(x)
 
 
-class NoPropBlock(_OutOfScope):
-    pass
+class NoPropTinyGPT(nn.Module):
+    """The reference's NoProp variant (model_tiny_gpt.py:418-459): every block also predicts the clean target
+    embedding; forward(idx, target_embeddings) -> (logits, [pred_y per block]).  Only the module is provided — the
+    NoProp training procedure (src/codonlm/noprop_task.py, train_noprop.py) drives it unchanged."""
 
+    def __init__(self, vocab_size, block_size, n_layer=3, n_head=4, n_embd=256, dropout=0.1, sep_id: int | None = 3,
+                 n_kv_head: int | None = None, use_sdpa: bool = False):
+        super().__init__()
+        self.block_size = block_size
+        self.vocab_size = vocab_size
+        self.n_embd = n_embd
+        self.sep_id = sep_id
+        self.tok_emb = Embedding(vocab_size, n_embd)
+        self.pos_emb = Embedding(block_size, n_embd)
+        self.drop = nn.Dropout(dropout)
+        self.blocks = nn.ModuleList([
+            NoPropBlock(n_embd, n_head, dropout, block_size, n_kv_head=n_kv_head, use_sdpa=use_sdpa)
+            for _ in range(n_layer)
+        ])
+        self.ln_f = LayerNorm(n_embd)
+        self.head = SkinnyLinear(n_embd, vocab_size, bias=False)
+        self.head.weight = self.tok_emb.weight
 
-class NoPropTinyGPT(_OutOfScope):
-    pass
+    def forward(self, idx, target_embeddings=None):
+        _require_cuda(self.tok_emb.weight, "NoPropTinyGPT parameters")
+        dev = self.tok_emb.weight.device
+        idx = idx.to(dev).long().contiguous()
+        B, T = idx.shape
+        if T > self.block_size:
+            raise IndexError(f"sequence length {T} exceeds block_size {self.block_size}")
+        Fn.reset_side_channel()
+        h = Fn.EmbedFn.apply(idx, self.tok_emb.weight, self.pos_emb.weight)
+        if self.training and self.drop.p > 0.0:
+            h = Fn.DropoutFn.apply(h, None, float(self.drop.p))
+        # causal & same-segment (:441-446) in interval form; without sep_id the reference passes no mask (pure causal)
+        spec = MaskSpec(ops.segment_starts(idx, int(self.sep_id)), 0) if self.sep_id is not None else None
+        preds = []
+        for blk in self.blocks:
+            h, pred_y = blk(h, noisy_targets=target_embeddings, attn_mask=spec)
+            preds.append(pred_y)
+        return self.head(self.ln_f(h)), preds
 
 
 __all__ = ["TinyGPT", "NoPropBlock", "NoPropTinyGPT", "DecodeState"]

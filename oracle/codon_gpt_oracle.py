@@ -493,3 +493,32 @@ def fetch_batch_dynamic(flat: np.ndarray, lengths: np.ndarray, indices, pad_id: 
             xb[r, :usable] = seq[:-1]
             yb[r, :usable] = seq[1:]
     return xb, yb
+
+
+# ---------------------------------------------------------------------------------------------------------
+# NoProp variant (reference: model_tiny_gpt.py:391-459)
+# ---------------------------------------------------------------------------------------------------------
+def noprop_forward(sd: Dict[str, torch.Tensor], cfg: dict, idx: torch.Tensor,
+                   target_embeddings: Optional[torch.Tensor] = None):
+    """NoPropTinyGPT.forward (eval mode): (logits, [pred_y per block]).  Every block sees h + target_embeddings
+    (:407-408), runs the usual pre-LN attention + GELU MLP (:412-413) and applies its denoise_head (:415)."""
+    B, T = idx.shape
+    h = sd["tok_emb.weight"][idx] + sd["pos_emb.weight"][:T][None]
+    if cfg["sep_id"] is not None:
+        m = attention_mask(idx.cpu().numpy(), cfg["sep_id"], None)
+    else:
+        m = np.tril(np.ones((T, T), dtype=bool))[None, None]
+    mask_bool = torch.from_numpy(np.ascontiguousarray(m)).to(idx.device)
+    sub = dict(cfg, use_swiglu=False)
+    preds = []
+    for l in range(cfg["n_layer"]):
+        p = f"blocks.{l}."
+        x = h + target_embeddings if target_embeddings is not None else h
+        a, _ = _attention(sd, p + "attn.", layer_norm(x, sd[p + "ln1.weight"], sd[p + "ln1.bias"]), sub, mask_bool,
+                          None, None)
+        x = x + a
+        x = x + _mlp(sd, p + "mlp.", layer_norm(x, sd[p + "ln2.weight"], sd[p + "ln2.bias"]), sub)
+        preds.append(linear(x, sd[p + "denoise_head.weight"], sd[p + "denoise_head.bias"]))
+        h = x
+    h = layer_norm(h, sd["ln_f.weight"], sd["ln_f.bias"])
+    return linear(h, sd["tok_emb.weight"]), preds
