@@ -19,9 +19,11 @@ def generate(model, device, ctx_ids: List[int], max_new: int, temperature: float
     ids = list(ctx_ids)
     max_t = getattr(model, "block_size", None)
     state = None
-    logits = None
+    pending = None  # the last sampled token: appended to the cache only when another token is asked for
     for _ in range(int(max_new)):
-        if state is None or state.length >= state.max_len:
+        if state is not None and pending is not None and state.length < state.max_len:
+            logits = model.decode_step(torch.tensor([pending], device=device), state)
+        else:  # first token, or the context was cropped (every cached position shifted): one pass over the context
             ctx = ids[-max_t:] if max_t is not None else ids
             x = torch.tensor(ctx, dtype=torch.long, device=device).unsqueeze(0)
             logits, state = model.prefill(x, max_len=max_t)
@@ -35,15 +37,12 @@ def generate(model, device, ctx_ids: List[int], max_new: int, temperature: float
         else:
             next_id = int(torch.multinomial(probs, 1).item())
         ids.append(next_id)
+        pending = next_id
         if max_t is not None and len(ids) > max_t:
             ids = ids[-max_t:]
-            state = None  # cropped: every cached position shifts, the next step re-prefills
+            state = None
         if eos_idx is not None and next_id == eos_idx:
             break
-        if state is not None and state.length < state.max_len:
-            logits = model.decode_step(torch.tensor([next_id], device=device), state)
-        else:
-            state = None
     return ids
 
 
