@@ -32,10 +32,23 @@ def _bf16_of(g: torch.Tensor):
     return ops.cast_bf16(g), None
 
 
+class _DirectSum:
+    """Marker in the side channels: the producer kernel has ALREADY added the column sums to `param.main_grad`
+    (no scratch vector, no add kernel).  The consumer only reports the contribution."""
+
+    def __init__(self, param):
+        self.param = param
+
+
 def _bias_grad(gb: torch.Tensor, n: int, master, colsum):
     """Bias gradient = column sums of the output gradient: taken from the producer when it already has them."""
     if colsum is None:
         return _colsum(gb, n, master=master)
+    if isinstance(colsum, _DirectSum):
+        if colsum.param is not master:
+            raise RuntimeError("bias-gradient side channel reached a different layer than the one it was computed for")
+        _done(master)
+        return None
     mg = _main_grad(master)
     if mg is not None:
         mg.add_(colsum)
@@ -166,12 +179,16 @@ class ResidualLayerNormFn(Function):
     dx = d_residual + LN'(dy) into one kernel (model_tiny_gpt.py:151-152 pre-norm pattern)."""
 
     @staticmethod
-    def forward(ctx, x, gamma, beta, want_f32):
+    def forward(ctx, x, gamma, beta, want_f32, colsum_target=None):
+        """colsum_target: the bias Parameter of the residual linear right in front of this LayerNorm (its gradient
+        is the column sum of this node's dx), or None.  With a flat gradient buffer the backward kernel adds straight
+        into its slot."""
         M, d = x.shape
         yb, yf, mean, rstd = ops.layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=want_f32)
         ctx.save_for_backward(x, gamma, mean, rstd)
         ctx.masters = (gamma, beta)
         ctx.want_f32 = want_f32
+        ctx.colsum_target = colsum_target
         if want_f32:
             return x.view_as(x), yb, yf
         return x.view_as(x), yb
@@ -190,18 +207,24 @@ class ResidualLayerNormFn(Function):
         elif gyb is not None:
             dy = gyb
         else:
-            return gx, None, None, None
-        dxsum = torch.zeros_like(gamma)
+            return gx, None, None, None, None
+        tgt = ctx.colsum_target
+        tmg = _main_grad(tgt)
+        if tmg is not None and tmg.numel() == gamma.numel() and tmg.is_contiguous():
+            dxsum, side = tmg, _DirectSum(tgt)  # the kernel accumulates into the bias' gradient slot itself
+        else:
+            dxsum = torch.zeros_like(gamma)
+            side = dxsum
         dx, dxb = ops.layernorm_bwd(dy.contiguous(), x, gamma, mean, rstd, None if gx is None else gx.contiguous(),
                                     dgamma, dbeta, want_bf16=True, dx_colsum=dxsum)
         # the upstream residual GEMM's backward wants dx as a bf16 operand and its column sums as the bias gradient
         _BF16_SIDE.clear()
-        _BF16_SIDE[dx.data_ptr()] = (dxb, dxsum)
+        _BF16_SIDE[dx.data_ptr()] = (dxb, side)
         if mg is not None:
             _done(gam_p)
             _done(bet_p)
-            return dx, None, None, None
-        return dx, dgamma, dbeta, None
+            return dx, None, None, None, None
+        return dx, dgamma, dbeta, None, None
 
 
 class PackedLinearFn(Function):
@@ -255,11 +278,16 @@ class PackedLinearFn(Function):
             b_slots = _packed_slots(ctx.masters[nw:], ctx.rows)
             qsum = _QKV_SIDE.pop(g.data_ptr(), None)
             _QKV_SIDE.clear()
-            if qsum is not None and qsum.numel() != N:
+            direct = isinstance(qsum, _DirectSum)
+            if direct and not (nw > 1 and b_slots is not None and qsum.param is ctx.masters[nw]):
+                raise RuntimeError("bias-gradient side channel of the attention backward reached the wrong linear")
+            if qsum is not None and not direct and qsum.numel() != N:
                 qsum = None
             if nw > 1 and b_slots is not None:
                 packed_b = torch.as_strided(b_slots[0], (N,), (1,))
-                if qsum is not None:
+                if direct:
+                    pass  # the attention backward kernels already added the column sums to these slots
+                elif qsum is not None:
                     packed_b.add_(qsum)
                 else:
                     ops.colsum_bf16(gb, packed_b, N=N, ld=gb.stride(0))
@@ -270,11 +298,15 @@ class PackedLinearFn(Function):
                 for i, (r0, n) in enumerate(ctx.rows):
                     grads.append(_bias_grad(gb, n, ctx.masters[nw + i], qsum[r0:r0 + n]))
             else:
+                if isinstance(gsum, _DirectSum) and nw != 1:
+                    raise RuntimeError("bias-gradient side channel reached a packed linear")
                 for i, (r0, n) in enumerate(ctx.rows):
                     if gsum is not None and nw == 1:
                         grads.append(_bias_grad(gb, n, ctx.masters[nw + i], gsum))
                     else:
                         grads.append(_colsum(gb, n, master=ctx.masters[nw + i], off=r0))
+        elif isinstance(gsum, _DirectSum):
+            raise RuntimeError("bias-gradient side channel reached a linear without bias")
         return (dx, None, None, g if ctx.has_res else None, None, None, *grads)
 
 
@@ -354,7 +386,9 @@ class MlpSwiGLUFn(Function):
         n_out = wd_sh.shape[0]
         g = g.contiguous()
         w_gate, w_up, w_down = ctx.masters
-        gb, _ = _bf16_of(g)
+        gb, gsum = _bf16_of(g)
+        if isinstance(gsum, _DirectSum):
+            raise RuntimeError("bias-gradient side channel reached the bias-free SwiGLU projection")
         dwd = _wgrad(gb, act, n_out, hid, master=w_down)        # [d, hid] (unpadded, odd pitch allowed)
         dact = torch.empty((M, hp), dtype=bf16, device=hin.device)
         ops.gemm(gb, wd_sh, dact, M=M, N=hp, K=n_out, b_mn=True)
@@ -457,7 +491,10 @@ class AttentionFn(Function):
     model_tiny_gpt.py:94-131."""
 
     @staticmethod
-    def forward(ctx, qkv, seg_start, rope, B, T, H, Hk, hd, window, dropout_p=0.0):
+    def forward(ctx, qkv, seg_start, rope, B, T, H, Hk, hd, window, dropout_p=0.0, bias_masters=None):
+        """bias_masters: the (query, key, value) bias Parameters of the packed linear that produced qkv, or None: with
+        adjacent flat gradient slots the backward kernels add the column sums of dqkv straight into them."""
+        ctx.bias_masters = bias_masters
         if rope is not None:
             ops.rope_qk(qkv, rope[0], rope[1], B, T, H, Hk, hd)  # in place: the QKV GEMM output has no other reader
         seed = off = 0
@@ -475,15 +512,29 @@ class AttentionFn(Function):
         seg_start, rope, B, T, H, Hk, hd, window, dropout_p, seed, off = ctx.aux
         # without RoPE dqkv is final here, so the kernels also take its column sums (the q|k|v bias gradients) and
         # hand them to the QKV linear's backward through the side channel
-        csum = torch.zeros(((H + 2 * Hk) * hd,), dtype=f32, device=qkv.device) if rope is None else None
+        csum = side = None
+        if rope is None:
+            bm = ctx.bias_masters
+            slots = None
+            if bm is not None:
+                rows, r = [], 0
+                for p in bm:
+                    rows.append((r, p.shape[0]))
+                    r += p.shape[0]
+                slots = _packed_slots(bm, rows) if r == (H + 2 * Hk) * hd else None
+            if slots is not None:  # the three bias gradients are one contiguous vector of the flat buffer
+                csum = torch.as_strided(slots[0], ((H + 2 * Hk) * hd,), (1,))
+                side = _DirectSum(bm[0])
+            else:
+                csum = side = torch.zeros(((H + 2 * Hk) * hd,), dtype=f32, device=qkv.device)
         dqkv = ops.attn_bwd(qkv, seg_start, out, g.contiguous(), lse, B, T, H, Hk, hd, window=window,
                             dropout_p=dropout_p, seed=seed, offset=off, colsum=csum)
         _QKV_SIDE.clear()
         if rope is not None:
             ops.rope_qk(dqkv, rope[0], rope[1], B, T, H, Hk, hd, inverse=True)
         else:
-            _QKV_SIDE[dqkv.data_ptr()] = csum
-        return dqkv, None, None, None, None, None, None, None, None, None
+            _QKV_SIDE[dqkv.data_ptr()] = side
+        return dqkv, None, None, None, None, None, None, None, None, None, None
 
 
 TC_HEAD_MIN_ROWS = 4096  # below this the fp32 FMA head kernels are used (launch-bound sizes, tests)

@@ -90,16 +90,17 @@ def rotate_half(x):
 # leaf modules (same parameters / keys as nn.LayerNorm, nn.Embedding, nn.Linear)
 # ----------------------------------------------------------------------------------------------
 class LayerNorm(nn.LayerNorm):
-    def forward(self, x):  # public path: fp32 in -> fp32 out (hooks on ln_f see what the reference shows)
+    def forward(self, x, colsum_target=None):  # public path: fp32 in -> fp32 out (hooks on ln_f see what the reference shows)
         _require_cuda(self.weight, "LayerNorm.weight")
         shp = x.shape
         x2 = x.reshape(-1, shp[-1]).float().contiguous()
-        _, _, yf = Fn.ResidualLayerNormFn.apply(x2, self.weight, self.bias, True)
+        _, _, yf = Fn.ResidualLayerNormFn.apply(x2, self.weight, self.bias, True, colsum_target)
         return yf.view(shp)
 
-    def fused(self, x2d):
-        """(residual alias, bf16 normalised) for the pre-norm residual pattern."""
-        return Fn.ResidualLayerNormFn.apply(x2d, self.weight, self.bias, False)
+    def fused(self, x2d, colsum_target=None):
+        """(residual alias, bf16 normalised) for the pre-norm residual pattern.  colsum_target: the bias of the
+        residual linear that produced x2d (its gradient = column sums of this LayerNorm's input gradient)."""
+        return Fn.ResidualLayerNormFn.apply(x2d, self.weight, self.bias, False, colsum_target)
 
 
 class Embedding(nn.Embedding):
@@ -363,7 +364,8 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
                                       self.query.bias, self.key.bias, self.value.bias)
         rope = self.rotary_emb.half_tables(T, x.device) if self.rotary_emb is not None else None
         attn_p = float(self.dropout.p) if self.training else 0.0  # dropout on the probabilities (:104,129)
-        y = Fn.AttentionFn.apply(qkv, spec.seg_start, rope, B, T, H, Hk, hd, int(spec.window or 0), attn_p)
+        y = Fn.AttentionFn.apply(qkv, spec.seg_start, rope, B, T, H, Hk, hd, int(spec.window or 0), attn_p,
+                                 (self.query.bias, self.key.bias, self.value.bias))
         sink = self.__dict__.get("_kv_sink")
         if sink is not None:  # prefill of the incremental-decode cache: the (rotated) key / value column blocks
             q3 = qkv.view(B, T, -1)
@@ -413,7 +415,16 @@ class Block(nn.Module):
         self.ln2 = LayerNorm(n_embd)
         self.mlp = SwiGLU(n_embd, dropout) if use_swiglu else GeluMLP(n_embd, dropout)
 
-    def forward(self, x, attn_mask=None):
+    def residual_bias(self):
+        """The bias added right before this block's output joins the residual stream (fc2 of a GELU MLP), when that
+        add is fused into the GEMM and nothing (dropout, hooks) sits behind it: the next LayerNorm's backward then adds
+        its column sums straight into this bias' gradient slot.  None otherwise."""
+        mlp = self.mlp
+        if not isinstance(mlp, GeluMLP) or _has_hooks(mlp) or (self.training and mlp[3].p > 0.0):
+            return None
+        return mlp[2].bias
+
+    def forward(self, x, attn_mask=None, prev_bias=None):
         B, T, d = x.shape
         x2 = x.reshape(B * T, d)
         if x2.dtype != f32:
@@ -423,15 +434,17 @@ class Block(nn.Module):
         if _has_hooks(self.ln1):
             h = _CastBf16.apply(self.ln1(x2))
         else:
-            x2, h = self.ln1.fused(x2.contiguous())
+            x2, h = self.ln1.fused(x2.contiguous(), prev_bias)
         if _has_hooks(self.attn):
             x2 = x2 + self.attn(h.view(B, T, d), attn_mask=attn_mask).reshape(B * T, d)
+            proj_bias = None
         else:
             x2 = self.attn(h.view(B, T, d), attn_mask=attn_mask, residual=x2).reshape(B * T, d)
+            proj_bias = self.attn.proj.bias
         if _has_hooks(self.ln2):
             h = _CastBf16.apply(self.ln2(x2))
         else:
-            x2, h = self.ln2.fused(x2.contiguous())
+            x2, h = self.ln2.fused(x2.contiguous(), proj_bias)
         if _has_hooks(self.mlp):
             x2 = x2 + self.mlp(h.view(B, T, d)).reshape(B * T, d)
         else:
@@ -719,9 +732,11 @@ class TinyGPT(nn.Module):
         Fn.reset_side_channel()
         x = self._embed(idx, shape_embeddings)
         spec = self.mask_spec(idx, attention_window)
+        prev_bias = None  # bias of the residual linear in front of the next LayerNorm (Block.residual_bias)
         for blk in self.blocks:
-            x = blk(x, attn_mask=spec)
-        x = self.ln_f(x)
+            x = blk(x, attn_mask=spec, prev_bias=prev_bias)
+            prev_bias = None if _has_hooks(blk) else blk.residual_bias()
+        x = self.ln_f(x, colsum_target=prev_bias)
         logits, aux = self._heads(x, B, T)
         loss = None
         if targets is not None:
