@@ -68,3 +68,36 @@ def test_cpu_forward_fails_loudly():
     m = TinyGPT(68, 8, n_layer=1, n_head=1, n_embd=16, dropout=0.0)
     with pytest.raises(_lib.CgptError, match="no CPU implementation"):
         m(torch.zeros((1, 4), dtype=torch.long))
+
+
+def test_boolean_masks_convert_to_interval_starts():
+    """mask_spec_from_bool (the reference's boolean-mask calling convention, model_tiny_gpt.py:106-113): every mask the
+    oracle's build_attention_mask restatement produces maps to first-visible-column = max(segment start, i-window+1);
+    masks that are not causal intervals are refused.  Pure index logic: runs on the CPU."""
+    import numpy as np
+    import torch
+    from codonlm_b200.model_tiny_gpt import mask_spec_from_bool
+    from oracle import codon_gpt_oracle as O
+    idx, _ = O.synthetic_batch(3, 50, seed=8, realistic=True)
+    idx[:, 13], idx[2, 31] = 3, 3
+    for window in (None, 1, 6):
+        m = torch.from_numpy(np.ascontiguousarray(O.attention_mask(idx.numpy(), 3, window)))
+        spec = mask_spec_from_bool(m, 3, 50)
+        seg_start = torch.zeros_like(idx)
+        for b in range(3):
+            last = 0
+            for t in range(50):
+                if int(idx[b, t]) == 3:
+                    last = t
+                seg_start[b, t] = last
+        want = seg_start if window is None else torch.maximum(seg_start, torch.arange(50)[None] - window + 1)
+        assert spec.window == 0 and torch.equal(spec.seg_start.long(), want)
+    tri = torch.tril(torch.ones(50, 50, dtype=torch.bool))
+    assert torch.equal(mask_spec_from_bool(tri, 3, 50).seg_start, torch.zeros((3, 50), dtype=torch.int32))
+    assert torch.equal(mask_spec_from_bool(tri[None], 3, 50).seg_start, torch.zeros((3, 50), dtype=torch.int32))
+    holed = tri.clone()
+    holed[9, 4] = False
+    full = torch.ones(50, 50, dtype=torch.bool)  # not causal
+    for bad in (holed, full, tri[None, None].expand(3, 2, 50, 50)):
+        with pytest.raises(NotImplementedError):
+            mask_spec_from_bool(bad, 3, 50)
