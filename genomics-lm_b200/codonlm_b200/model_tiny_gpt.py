@@ -826,6 +826,10 @@ class TinyGPT(nn.Module):
                              "(the reference crops to the last block_size tokens, generate.py:20-21)")
         state.tok.copy_(tokens.reshape(state.batch, 1), non_blocking=True)
         Fn.reset_side_channel()
+        # a captured step holds pointers to the bf16 weight copies it was captured with: drop it when a master changed
+        wkey = (_SHADOW_GEN[0],) + tuple(p._version for p in self.parameters())
+        if state.graph is not None and state.__dict__.get("_wkey") != wkey:
+            state.graph = None
         if state.graph is not None:
             state.graph.replay()
         elif state.use_graph and getattr(state, "_warm", False) and not self.training:
@@ -837,6 +841,7 @@ class TinyGPT(nn.Module):
             state.t_dev.copy_(snap_t)
             state.seg_lo.copy_(snap_lo)
             state.graph = graph
+            state._wkey = wkey
             graph.replay()
         else:
             state.logits = self._decode_launch(state)

@@ -238,6 +238,16 @@ def test_kv_cache_decode_equals_full_forward(name, window):
         logits = model.decode_step(seq[:, T0 + s], state)
     assert state.length == T0 + n_new
     print(f"{name} window={window}: worst cached-vs-full logit difference {worst:.2e}")
+    if window is None:  # a weight change invalidates the captured step: the next steps must follow the new weights
+        assert state.graph is not None
+        with torch.no_grad():
+            model.blocks[0].attn.proj.weight.mul_(1.5)  # a GEMM weight: its bf16 copy is what the graph points to
+        logits, state = model.prefill(seq[:, :T0], state=state)
+        for s in range(3):
+            logits = model.decode_step(seq[:, T0 + s], state)
+        with torch.no_grad():
+            full = model(seq[:, :T0 + 3])[0][:, -1]
+        assert (logits - full).abs().max().item() <= 1e-2
 
 
 def test_cached_generate_follows_reference_loop_rules():
