@@ -81,3 +81,39 @@ def test_param_groups_follow_reference_rule():
     assert back[-1] == "tok_emb.weight" and back[0].startswith("ln_f")  # reverse execution order
     n_total = sum(p.numel() for p in m.parameters())
     assert sum(p.numel() for _, p in g["head"] + g["backbone"]) == n_total
+
+
+def test_flat_buffers_keep_packed_operands_adjacent():
+    """FlatGroup on the trainer's parameter order: the query|key|value weights (and biases) of every block must lie
+    back to back in the flat master / gradient / shadow buffers — that is what lets one GEMM, one weight-gradient GEMM
+    and the attention backward's fused bias sums treat them as ONE packed operand (functional._packed_slots)."""
+    from codonlm_b200 import TinyGPT
+    from codonlm_b200.functional import _packed_slots
+    from codonlm_b200.model_tiny_gpt import _adjacent
+    from codonlm_b200.trainer import FlatGroup, split_param_groups
+    for kw in (dict(), dict(n_kv_head=2), dict(use_swiglu=True, use_rope=True)):
+        m = TinyGPT(68, 32, n_layer=3, n_head=4, n_embd=64, dropout=0.0, termination_aux=True,
+                    multi_offset_targets=[2, 4], **kw)
+        g = split_param_groups(m)
+        fg = FlatGroup(g["backbone"], lr=1e-3, weight_decay=0.0)
+        assert fg.flat.numel() == fg.grad.numel() == fg.shadow.numel()
+        for blk in m.blocks:
+            a = blk.attn
+            ws = (a.query.weight, a.key.weight, a.value.weight)
+            bs = (a.query.bias, a.key.bias, a.value.bias)
+            assert _adjacent([p.data for p in ws]) and _adjacent([p.main_grad for p in ws])
+            assert _adjacent([p._cgpt_shadow for p in ws])
+            rows, r = [], 0
+            for p in ws:
+                rows.append((r, p.shape[0]))
+                r += p.shape[0]
+            assert _packed_slots(ws, rows) is not None
+            assert _packed_slots((a.key.weight, a.query.weight, a.value.weight), rows) is None  # wrong order
+            # every slot starts on a 256-byte boundary: a bias shorter than 64 floats (GQA with a narrow kv width) leaves
+            # a gap, and the module then falls back to per-bias column sums / a private packed copy
+            tight = all(p.numel() % 64 == 0 for p in bs)
+            assert _adjacent([p.data for p in bs]) == tight
+            assert (_packed_slots(bs, rows) is not None) == tight
+        # every parameter is a view of the flat buffer and keeps its values
+        for n, p in g["backbone"]:
+            assert p.data.data_ptr() >= fg.flat.data_ptr() and p.main_grad.shape == p.shape
