@@ -1,0 +1,50 @@
+"""Pins the oracle at the BASELINE.json shapes themselves (C1 'tiny 2L4H d128 seq 256 fp32 forward+loss on CPU', C2
+'stage2.5 6L4H d256 RoPE+SwiGLU seq 512'), where full weight dumps would be megabytes: the weights come from the oracle's
+own deterministic initialiser (so the test can rebuild them), are loaded STRICTLY into the unmodified reference model, and
+only the reference's outputs are stored — loss, every 97th logit, the argmax map, hidden-state checksums.
+
+    python tests/golden/make_baseline_shape_golden.py      (build container only: needs /root/reference)
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.environ.get("CGPT_REFERENCE", "/root/reference"))
+from src.codonlm.model_tiny_gpt import TinyGPT  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", ".."))
+from oracle import codon_gpt_oracle as O  # noqa: E402  (weights + tokens only; the numbers below come from the reference)
+
+CASES = {
+    "C1": (dict(vocab_size=68, block_size=256, n_layer=2, n_head=4, n_embd=128, dropout=0.0, label_smoothing=0.05,
+                use_sdpa=True), 8, 256),
+    "C2": (dict(vocab_size=68, block_size=512, n_layer=6, n_head=4, n_embd=256, dropout=0.0, label_smoothing=0.05,
+                use_sdpa=True, use_rope=True, use_swiglu=True), 2, 512),
+}
+out = {}
+for name, (ctor, B, T) in CASES.items():
+    cfg = O.make_cfg(**ctor)
+    sd = O.init_state_dict(cfg, seed=1337, emb_scale=0.02)
+    m = TinyGPT(**ctor).eval()
+    full = dict(sd)
+    for l in range(ctor["n_layer"]):
+        full[f"blocks.{l}.attn.mask"] = m.blocks[l].attn.mask
+    missing = m.load_state_dict(full, strict=True)
+    idx, tgt = O.synthetic_batch(B, T, seed=1337, realistic=True)
+    with torch.no_grad():
+        logits, loss = m(idx, tgt)
+        hidden = m.forward_hidden(idx)
+    flat = logits.reshape(-1)
+    out[name + ".loss"] = np.array(float(loss), dtype=np.float64)
+    out[name + ".logit_samples"] = flat[::97].numpy()
+    out[name + ".argmax"] = logits.argmax(-1).numpy().astype(np.int8)
+    out[name + ".logits_abs_mean"] = np.array(float(flat.abs().mean()), dtype=np.float64)
+    out[name + ".hidden_row_norms"] = hidden.norm(dim=-1).numpy()
+    out[name + ".meta"] = np.array(json.dumps(dict(ctor=ctor, B=B, T=T, torch=torch.__version__)))
+    print(name, "loss", float(loss), "logits", tuple(logits.shape))
+np.savez_compressed(os.path.join(HERE, "baseline_shapes.npz"), **out)
+print("wrote baseline_shapes.npz", os.path.getsize(os.path.join(HERE, "baseline_shapes.npz")) // 1024, "KiB")

@@ -137,3 +137,27 @@ def test_causality_and_segment_isolation():  # reference tests/test_embedding_ex
     hc = O.forward(sd, cfg, c, want_hidden=True)["hidden"][-1]
     # tokens after the separator only differ through... nothing: pos-emb and own segment are unchanged
     assert torch.allclose(ha[:, 5:], hc[:, 5:], atol=0, rtol=0)
+
+
+@pytest.mark.parametrize("name", ["C1", "C2"])
+def test_oracle_at_baseline_shapes_matches_reference(name):
+    """BASELINE.json configs[0] ('tiny 2L4H d128, seq 256, fp32 forward+loss on CPU') and configs[1] (6L4H d256
+    RoPE+SwiGLU, seq 512) at full shape: the oracle rebuilds the weights the unmodified reference was run on
+    (tests/golden/make_baseline_shape_golden.py) and must reproduce its loss, sampled logits, argmax map and
+    hidden-state row norms."""
+    import json
+    import os
+    from conftest import ROOT
+    z = np.load(os.path.join(ROOT, "tests", "golden", "baseline_shapes.npz"))
+    meta = json.loads(str(z[name + ".meta"]))
+    cfg = O.make_cfg(**meta["ctor"])
+    sd = O.init_state_dict(cfg, seed=1337, emb_scale=0.02)
+    idx, tgt = O.synthetic_batch(meta["B"], meta["T"], seed=1337, realistic=True)
+    out = O.forward(sd, cfg, idx, tgt, want_hidden=True)
+    assert out["loss"].item() == pytest.approx(float(z[name + ".loss"]), rel=3e-6)
+    flat = out["logits"].reshape(-1)
+    assert np.abs(flat[::97].numpy() - z[name + ".logit_samples"]).max() <= 3e-5
+    assert float(flat.abs().mean()) == pytest.approx(float(z[name + ".logits_abs_mean"]), rel=1e-5)
+    assert np.array_equal(out["logits"].argmax(-1).numpy().astype(np.int8), z[name + ".argmax"])
+    norms = out["hidden"][-1].norm(dim=-1).numpy()
+    assert np.abs(norms - z[name + ".hidden_row_norms"]).max() <= 1e-4 * np.abs(norms).max()
