@@ -24,7 +24,14 @@ CASES = {
                 use_sdpa=True), 8, 256),
     "C2": (dict(vocab_size=68, block_size=512, n_layer=6, n_head=4, n_embd=256, dropout=0.0, label_smoothing=0.05,
                 use_sdpa=True, use_rope=True, use_swiglu=True), 2, 512),
+    # C3: 12L8H d512, separate / multi-offset heads + termination head, seq 1024 (one sequence: forward + all losses)
+    "C3": (dict(vocab_size=68, block_size=1024, n_layer=12, n_head=8, n_embd=512, dropout=0.0, label_smoothing=0.05,
+                use_sdpa=True, termination_aux=True, multi_offset_targets=[2, 4, 8, 16, 32]), 1, 1024),
+    # C4: bench_b8_gqa4 (10L8H, 4 kv heads, d384), seq 512
+    "C4": (dict(vocab_size=68, block_size=512, n_layer=10, n_head=8, n_kv_head=4, n_embd=384, dropout=0.0,
+                label_smoothing=0.05, use_sdpa=True), 2, 512),
 }
+from src.codonlm.training import objectives as RO  # noqa: E402
 out = {}
 for name, (ctor, B, T) in CASES.items():
     cfg = O.make_cfg(**ctor)
@@ -36,8 +43,16 @@ for name, (ctor, B, T) in CASES.items():
     missing = m.load_state_dict(full, strict=True)
     idx, tgt = O.synthetic_batch(B, T, seed=1337, realistic=True)
     with torch.no_grad():
-        logits, loss = m(idx, tgt)
+        logits, loss, aux = m(idx, tgt, return_aux=True)
         hidden = m.forward_hidden(idx)
+        if ctor.get("multi_offset_targets"):
+            ow = {o: 0.2 for o in ctor["multi_offset_targets"]}
+            off_total, off_losses = RO.multi_offset_lm_loss(aux["offset_logits"], tgt, ow,
+                                                            label_smoothing=ctor["label_smoothing"], loss_weights=None)
+            out[name + ".offset_losses"] = np.array([float(off_losses[o]) for o in ctor["multi_offset_targets"]])
+            labels = RO.termination_distance_bucket_labels(tgt, stop_ids=(2,), bucket_edges=(0, 3, 10, 30))
+            out[name + ".termination_loss"] = np.array(float(RO.termination_aux_loss(aux["termination_logits"], labels)))
+            out[name + ".offset32_logit_samples"] = aux["offset_logits"][32].reshape(-1)[::97].numpy()
     flat = logits.reshape(-1)
     out[name + ".loss"] = np.array(float(loss), dtype=np.float64)
     out[name + ".logit_samples"] = flat[::97].numpy()

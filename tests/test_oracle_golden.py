@@ -139,12 +139,13 @@ def test_causality_and_segment_isolation():  # reference tests/test_embedding_ex
     assert torch.allclose(ha[:, 5:], hc[:, 5:], atol=0, rtol=0)
 
 
-@pytest.mark.parametrize("name", ["C1", "C2"])
+@pytest.mark.parametrize("name", ["C1", "C2", "C3", "C4"])
 def test_oracle_at_baseline_shapes_matches_reference(name):
-    """BASELINE.json configs[0] ('tiny 2L4H d128, seq 256, fp32 forward+loss on CPU') and configs[1] (6L4H d256
-    RoPE+SwiGLU, seq 512) at full shape: the oracle rebuilds the weights the unmodified reference was run on
-    (tests/golden/make_baseline_shape_golden.py) and must reproduce its loss, sampled logits, argmax map and
-    hidden-state row norms."""
+    """BASELINE.json configs[0] ('tiny 2L4H d128, seq 256, fp32 forward+loss on CPU'), configs[1] (6L4H d256
+    RoPE+SwiGLU, seq 512), configs[2] (12L8H d512 with the multi-offset and termination heads, seq 1024) and configs[3]
+    (bench_b8_gqa4) at full shape: the oracle rebuilds the weights the unmodified reference was run on
+    (tests/golden/make_baseline_shape_golden.py) and must reproduce its loss, sampled logits, argmax map,
+    hidden-state row norms and — for C3 — the offset and termination losses of the reference's objectives."""
     import json
     import os
     from conftest import ROOT
@@ -161,3 +162,12 @@ def test_oracle_at_baseline_shapes_matches_reference(name):
     assert np.array_equal(out["logits"].argmax(-1).numpy().astype(np.int8), z[name + ".argmax"])
     norms = out["hidden"][-1].norm(dim=-1).numpy()
     assert np.abs(norms - z[name + ".hidden_row_norms"]).max() <= 1e-4 * np.abs(norms).max()
+    if name + ".offset_losses" in z.files:
+        offs = meta["ctor"]["multi_offset_targets"]
+        total, parts, _ = O.training_loss(sd, cfg, idx, tgt, offset_weights={o: 0.2 for o in offs},
+                                          termination_loss_weight=0.1)
+        got = np.array([parts["offsets"][o].item() for o in offs])
+        assert np.abs(got - z[name + ".offset_losses"]).max() <= 3e-6 * np.abs(got).max()
+        assert parts["termination"].item() == pytest.approx(float(z[name + ".termination_loss"]), rel=3e-6)
+        o32 = out["offset_logits"][32].reshape(-1)[::97].numpy()
+        assert np.abs(o32 - z[name + ".offset32_logit_samples"]).max() <= 3e-5
