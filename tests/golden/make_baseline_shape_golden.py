@@ -53,6 +53,21 @@ for name, (ctor, B, T) in CASES.items():
             labels = RO.termination_distance_bucket_labels(tgt, stop_ids=(2,), bucket_edges=(0, 3, 10, 30))
             out[name + ".termination_loss"] = np.array(float(RO.termination_aux_loss(aux["termination_logits"], labels)))
             out[name + ".offset32_logit_samples"] = aux["offset_logits"][32].reshape(-1)[::97].numpy()
+    # gradients of the trainer's total loss (loop.py:1067-1143): per-parameter norms and every 997th entry
+    m.zero_grad()
+    lg, ls, ax = m(idx, tgt, return_aux=True)
+    total = ls
+    if ctor.get("multi_offset_targets"):
+        ot, _ = RO.multi_offset_lm_loss(ax["offset_logits"], tgt, {o: 0.2 for o in ctor["multi_offset_targets"]},
+                                        label_smoothing=ctor["label_smoothing"], loss_weights=None)
+        lb = RO.termination_distance_bucket_labels(tgt, stop_ids=(2,), bucket_edges=(0, 3, 10, 30))
+        total = total + ot + 0.1 * RO.termination_aux_loss(ax["termination_logits"], lb)
+    total.backward()
+    names = [k for k, p in m.named_parameters() if p.grad is not None]
+    out[name + ".grad_names"] = np.array(json.dumps(names))
+    out[name + ".grad_norms"] = np.array([float(dict(m.named_parameters())[k].grad.norm()) for k in names])
+    out[name + ".grad_samples"] = torch.cat([dict(m.named_parameters())[k].grad.reshape(-1)[::997] for k in names]).numpy()
+    out[name + ".total_loss"] = np.array(float(total))
     flat = logits.reshape(-1)
     out[name + ".loss"] = np.array(float(loss), dtype=np.float64)
     out[name + ".logit_samples"] = flat[::97].numpy()

@@ -162,6 +162,18 @@ def test_oracle_at_baseline_shapes_matches_reference(name):
     assert np.array_equal(out["logits"].argmax(-1).numpy().astype(np.int8), z[name + ".argmax"])
     norms = out["hidden"][-1].norm(dim=-1).numpy()
     assert np.abs(norms - z[name + ".hidden_row_norms"]).max() <= 1e-4 * np.abs(norms).max()
+    # backward: per-parameter gradient norms and sampled entries of the trainer's total loss
+    names = json.loads(str(z[name + ".grad_names"]))
+    offs_all = meta["ctor"].get("multi_offset_targets")
+    kw = dict(offset_weights={o: 0.2 for o in offs_all}, termination_loss_weight=0.1) if offs_all else {}
+    total, _, _, grads = O.loss_and_grads(sd, cfg, idx, tgt, **kw)
+    assert total.item() == pytest.approx(float(z[name + ".total_loss"]), rel=3e-6)
+    assert set(names) == set(grads)
+    ref_norms = z[name + ".grad_norms"]
+    got_norms = np.array([grads[k].norm().item() for k in names])
+    assert np.abs(got_norms - ref_norms).max() <= 3e-5 * ref_norms.max()
+    samples = torch.cat([grads[k].reshape(-1)[::997] for k in names]).numpy()
+    assert np.abs(samples - z[name + ".grad_samples"]).max() <= 3e-5 * np.abs(z[name + ".grad_samples"]).max()
     if name + ".offset_losses" in z.files:
         offs = meta["ctor"]["multi_offset_targets"]
         total, parts, _ = O.training_loss(sd, cfg, idx, tgt, offset_weights={o: 0.2 for o in offs},
