@@ -117,3 +117,64 @@ def test_flat_buffers_keep_packed_operands_adjacent():
         # every parameter is a view of the flat buffer and keeps its values
         for n, p in g["backbone"]:
             assert p.data.data_ptr() >= fg.flat.data_ptr() and p.main_grad.shape == p.shape
+
+
+def _nonfinite_worker(rank, world, port, out):
+    import math
+    sys.path.insert(0, PKG)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from codonlm_b200.trainer import AccumulationHealth, run_accumulation_groups
+
+    class FakeStep:
+        def __init__(self):
+            self.grad, self.steps, self.discards = 0.0, [], 0
+
+        def zero_grad(self):
+            self.grad = 0.0
+
+        def arm_collectives(self, armed):
+            pass
+
+        def forward_backward(self, xb, yb):
+            self.grad += 0.0 if math.isnan(xb) else xb
+            loss = torch.tensor(float(xb))
+            return loss, {"next": loss}
+
+        def optimizer_step(self, lr_scale=1.0, micro_batches=1):
+            self.steps.append((self.grad, micro_batches))
+
+        def discard_gradients(self):
+            self.discards += 1
+            self.grad = 0.0
+
+    # only rank 1 sees a non-finite loss (its 4th micro-batch): BOTH ranks must abort that group and regroup alike
+    vals = [1.0, 2.0, 3.0, float("nan") if rank == 1 else 4.0, 5.0, 6.0, 7.0]
+    step, health = FakeStep(), AccumulationHealth()
+    recs = list(run_accumulation_groups(step, [(v, None) for v in vals], 2, health, max_nonfinite_groups=3))
+    torch.save(dict(steps=step.steps, discards=step.discards, health=health.metrics_dict(),
+                    sizes=[r["group_size"] for r in recs]), f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_nonfinite_flag_is_shared_across_ranks(tmp_path):
+    """run_accumulation_groups max-reduces the per-micro-batch non-finite flags over the ranks: a NaN seen
+    by one rank aborts the accumulation group on every rank, so the replicas keep taking the same optimiser steps."""
+    import socket
+    out = str(tmp_path / "nf.pt")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    try:
+        mp.spawn(_nonfinite_worker, args=(2, port, out), nprocs=2, join=True)
+    except mp.ProcessExitedException:
+        if not (os.path.exists(out + ".0") and os.path.exists(out + ".1")):
+            raise
+    r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    # groups: [1,2] step | [3,(4|nan)] aborted on both | [5,6] step | [7] trailing step
+    assert r0["sizes"] == r1["sizes"] == [2, 2, 1]
+    assert r0["discards"] == r1["discards"] == 1
+    assert r0["health"] == r1["health"] == {"active_microbatches": 0, "nonfinite_microbatches": 1, "aborted_groups": 1,
+                                            "discarded_finite_microbatches": 1}
+    assert [s[0] for s in r0["steps"]] == [3.0, 11.0, 7.0] and [s[0] for s in r1["steps"]] == [3.0, 11.0, 7.0]
