@@ -459,13 +459,17 @@ def test_trainstep_flat_buffers_match_plain_autograd_and_torch_adamw(batch):
         a, b = p.main_grad, grads1[n]
         assert torch.allclose(a, b, rtol=2e-3, atol=1e-6 + 2e-3 * b.abs().max().item()), n  # atomics reorder sums
     ts.optimizer_step()
+    gmax_all = max(g.abs().max().item() for g in grads1.values())
     for (n, p1), (_, p2) in zip(m1.named_parameters(), m2.named_parameters()):
         # the first Adam step moves every element by ~lr*sign(g): elements whose gradient sits at the summation-order
-        # noise floor (reduce-add atomics) may take opposite signs in the two runs, so they are gated on the mean only
+        # noise floor (reduce-add atomics) may take opposite signs in the two runs, so they are gated on the mean only;
+        # a tensor whose whole gradient is analytically zero (key.bias: softmax shift invariance) is pure noise: skipped
         g1 = grads1[n]
-        solid = g1.abs() > 1e-3 * g1.abs().max()
+        solid = g1.abs() > max(1e-3 * g1.abs().max().item(), 1e-6 * gmax_all)
+        if not bool(solid.any()):
+            continue
         assert torch.allclose(p1[solid], p2[solid], rtol=1e-4, atol=2e-5), n
-        assert (p1 - p2).abs().mean().item() <= 1e-4, n
+        assert (p1 - p2).abs().mean().item() <= 1e-4 + 6e-3 * (1.0 - solid.float().mean().item()), n
     # a second step runs on refreshed bf16 shadows and keeps training
     l0 = ts.step(idx, tgt).item()
     for _ in range(5):
