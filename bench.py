@@ -35,24 +35,38 @@ OFFSET_W = {o: 0.2 for o in OFFSETS}
 TERM_W = 0.1
 
 
-def workload_ctor(n_layer=12, seq=1024):
-    return dict(vocab_size=68, block_size=seq, n_layer=n_layer, n_head=8, n_embd=512, dropout=0.0,
+def workload_ctor(n_layer=12, seq=1024, dropout=0.0):
+    return dict(vocab_size=68, block_size=seq, n_layer=n_layer, n_head=8, n_embd=512, dropout=dropout,
                 label_smoothing=0.05, sep_id=3, use_sdpa=True, termination_aux=True, multi_offset_targets=OFFSETS)
 
 
-def train_flops_per_token(n_layer, d, T, V=68, n_off=5):
-    """Algorithmic FLOPs (causal attention counted exactly as 2dT per layer), train = 3 x fwd."""
-    fwd = n_layer * (24 * d * d + 2 * d * T) + 2 * d * V + n_off * (4 * d * d + 2 * d * V)
+def train_flops_per_token(n_layer, d, T, V=68, n_off=5, visible_keys_per_token=None):
+    """Algorithmic FLOPs per token, train = 3 x fwd.  Attention is credited for the (query, key) pairs the mask makes
+    visible: 4·d FLOPs per pair per layer forward (QKᵀ + PV over all heads).  Fully causal sequences have (T+1)/2
+    visible keys per token, i.e. SURVEY §8's 2dT; a segmented stream has fewer and is credited for fewer."""
+    vis = (T + 1) / 2.0 if visible_keys_per_token is None else float(visible_keys_per_token)
+    fwd = n_layer * (24 * d * d + 4 * d * vis) + 2 * d * V + n_off * (4 * d * d + 2 * d * V)
     return 3 * fwd
 
 
-def synthetic_tokens(B, T, seed, vocab=68):
-    """Codon ids U{4..67}; BOS first; EOS(2)+SEP(3) every U{100..400}; PAD(0) tails on half the rows
-    (SURVEY §8d 'realistic' variant: exercises segment masks, offset boundary masks, termination labels).
-    targets = ids shifted left, last column PAD."""
+def visible_keys_per_token(idx, sep_id=3):
+    """Mean number of keys a query may attend to under the reference's mask (causal AND same segment, where
+    seg = cumsum(idx == sep), model_tiny_gpt.py:273-295): i - start(i) + 1 with start(i) = last <SEP> at or before i."""
+    x = idx.numpy()
+    B, T = x.shape
+    pos = np.broadcast_to(np.arange(T), (B, T))
+    start = np.maximum.accumulate(np.where(x == sep_id, pos, 0), axis=1)
+    return float((pos - start + 1).mean())
+
+
+def synthetic_tokens(B, T, seed, vocab=68, kind="random"):
+    """kind="random" (the headline, north_star's "synthetic random-codon batches"): codon ids U{4..67},
+    no <SEP> — every sequence is one segment, attention is fully causal.  kind="realistic" (second line): BOS first;
+    EOS(2)+SEP(3) every U{100..400}; PAD(0) tails on half the rows (exercises segment masks, offset boundary masks,
+    termination labels).  targets = ids shifted left, last column PAD."""
     rng = np.random.default_rng(seed)
     idx = rng.integers(4, vocab, size=(B, T), dtype=np.int64)
-    for b in range(B):
+    for b in range(B if kind == "realistic" else 0):
         idx[b, 0] = 1
         t = int(rng.integers(100, 401))
         while t + 1 < T:
@@ -117,7 +131,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # reference arm / CPU baseline: the oracle port of the reference's PyTorch fp32 CPU path
 # ------------------------------------------------------------------------------------------------
-def cpu_reference_steps(n_layer, seq, steps, warmup, budget_s, batch=2):
+def cpu_reference_steps(n_layer, seq, steps, warmup, budget_s, batch=2, tokens="random"):
     from oracle import codon_gpt_oracle as O  # the one place bench.py touches oracle/ (CPU baseline legs)
     torch.set_num_threads(os.cpu_count() or 1)
     cores = torch.get_num_threads()
@@ -130,7 +144,7 @@ def cpu_reference_steps(n_layer, seq, steps, warmup, budget_s, batch=2):
     leaves["head.weight"] = leaves["tok_emb.weight"]
     params = [v for k, v in leaves.items() if isinstance(v, torch.Tensor) and v.requires_grad and k != "head.weight"]
     opt = torch.optim.AdamW(params, lr=3e-4, weight_decay=0.05)
-    idx, tgt = synthetic_tokens(batch, seq, seed=1337)
+    idx, tgt = synthetic_tokens(batch, seq, seed=1337, kind=tokens)
     times = []
     t_begin = time.perf_counter()
     for i in range(warmup + steps):
@@ -154,7 +168,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_reference_steps(args.layers, args.seq, args.steps, max(1, min(args.warmup, 2)), budget_s=240)
+    base = cpu_reference_steps(args.layers, args.seq, args.steps, max(1, min(args.warmup, 2)), budget_s=240,
+                               tokens=args.tokens)
     line = {"metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": base["steps"],
             "warmup": max(1, min(args.warmup, 2)), "ms_per_step": base["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
@@ -169,7 +184,10 @@ def config_dict(args, world, note=None):
     c = {"workload": f"C3 codon-GPT {args.layers}L8H d512 (MHA hd64, GELU 2048) + offset heads {OFFSETS} + "
                      f"termination head, train step fwd+bwd+AdamW, seq {args.seq}",
          "per_gpu_batch": args.batch, "seq_len": args.seq, "global_batch": args.batch * world,
-         "parallelism": f"dp{world}", "tokens": "realistic synthetic (BOS, EOS+SEP every U{100..400}, PAD tails)",
+         "parallelism": f"dp{world}",
+         "tokens": ("random codons U{4..67}, one segment per sequence (full causal attention)" if args.tokens == "random"
+                    else "realistic synthetic (BOS, EOS+SEP every U{100..400}, PAD tails on half the rows)"),
+         "dropout": args.dropout,
          "l2": "per-step working set (~14 GB of activations) is far larger than the 126 MB L2; no explicit flush"}
     if note:
         c["note"] = note
@@ -189,14 +207,12 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if "CGPT_KEEP_NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "WARN"  # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     from codonlm_b200 import TinyGPT, ops
     from codonlm_b200.trainer import TrainStep
 
     torch.manual_seed(1337)
-    model = TinyGPT(**workload_ctor(args.layers, args.seq))
+    model = TinyGPT(**workload_ctor(args.layers, args.seq, args.dropout))
     with torch.no_grad():  # trained-scale embeddings: keeps the loss in a realistic range
         model.tok_emb.weight.mul_(0.02)
         model.pos_emb.weight.mul_(0.02)
@@ -205,7 +221,8 @@ def run_ours(args):
                      termination_loss_weight=TERM_W)
     B, T = args.batch, args.seq
     n_host = 4
-    host = [synthetic_tokens(B, T, seed=1337 + 1000 * rank + i) for i in range(n_host)]
+    host = [synthetic_tokens(B, T, seed=1337 + 1000 * rank + i, kind=args.tokens) for i in range(n_host)]
+    vis = float(np.mean([visible_keys_per_token(x) for x, _ in host]))
     pinned = [(x.pin_memory(), y.pin_memory()) for x, y in host]
     resident = [(x.to(dev), y.to(dev)) for x, y in host]
 
@@ -317,7 +334,8 @@ def run_ours(args):
         peaks, peak_src = measured_peaks()
         toks_step = B * T * world
         value = toks_step * args.steps / (ms_total / 1e3)
-        fpt = train_flops_per_token(args.layers, 512, T)
+        fpt = train_flops_per_token(args.layers, 512, T, visible_keys_per_token=vis)
+        fpt_causal = train_flops_per_token(args.layers, 512, T)
         gemm_ms = sum(ev[0].elapsed_time(ev[1]) for ev in gemm_events)
         gemm_flops = sum(ev[2] for ev in gemm_events)
         gemm_bytes = sum(ev[3] for ev in gemm_events)
@@ -353,11 +371,15 @@ def run_ours(args):
                                       f"({roof_ms_total / args.steps:.2f} ms/step); the timed region replays a CUDA graph"
                                       if use_graph else "the timed region itself")},
             "step_flops": {"train_flops_per_token": fpt, "model_tflops": value / world * fpt / 1e12,
-                           "frac_of_bf16_burst_peak": value / world * fpt / 1e12 / peaks["bf16_tflops"]},
+                           "frac_of_bf16_burst_peak": value / world * fpt / 1e12 / peaks["bf16_tflops"],
+                           "frac_of_bf16_sustained_peak": value / world * fpt / 1e12 / peaks["bf16_tflops_sustained"],
+                           "attention_visible_keys_per_token": vis, "full_causal_keys_per_token": (T + 1) / 2.0,
+                           "note": "attention FLOPs credited for the (query, key) pairs the mask makes visible "
+                                   "(executed work); full-causal credit would be %.4g FLOPs/token" % fpt_causal},
             "loss": {"first": first_loss, "last": last_loss},
         }
         if world == 1 and not args.no_cpu_baseline:
-            base = cpu_reference_steps(args.layers, args.seq, steps=8, warmup=1, budget_s=25)
+            base = cpu_reference_steps(args.layers, args.seq, steps=8, warmup=1, budget_s=25, tokens=args.tokens)
             line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
         _emit(line)
     if world > 1:
@@ -438,6 +460,9 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="sequences per GPU per step")
     ap.add_argument("--seq", type=int, default=1024)
     ap.add_argument("--layers", type=int, default=12)
+    ap.add_argument("--tokens", default="random", choices=["random", "realistic"],
+                    help="random = north_star's random-codon batches (headline); realistic = segmented stream with PAD tails")
+    ap.add_argument("--dropout", type=float, default=0.0, help="dropout probability of the model (reference configs: 0.1)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="run the timed region eagerly (default: CUDA graph at N=1)")
     ap.add_argument("--breakdown", default=None, help="write a per-op CUDA-event breakdown of one step to this file")

@@ -192,6 +192,8 @@ class GradBuckets:
 class TrainStep:
     """One optimiser step = forward + backward (+ all-reduce) + AdamW on a (B,T) batch of codon ids."""
 
+    HYPER_RING = 8  # pinned staging rows for the per-step AdamW scalars
+
     def __init__(self, model, lr=3e-4, lr_embedding=None, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  offset_weights: Optional[Dict[int, float]] = None, termination_loss_weight: float = 0.0,
                  process_group=None, bucket_mb: int = 25, overlap_allreduce: Optional[bool] = None):
@@ -201,9 +203,15 @@ class TrainStep:
         self.betas, self.eps = betas, eps
         groups = split_param_groups(model)
         self.groups: List[FlatGroup] = []
+        # a group exists only when it has parameters (loop.py:712-726 `if embedding_params:` / `if backbone_params:`):
+        # with freeze_backbone (loop.py:656-667) only the aux heads train and the backbone group is empty
         if groups["head"]:
             self.groups.append(FlatGroup(groups["head"], lr_embedding if lr_embedding is not None else lr, 0.0))
-        self.groups.append(FlatGroup(groups["backbone"], lr, weight_decay))
+        if groups["backbone"]:
+            self.groups.append(FlatGroup(groups["backbone"], lr, weight_decay))
+        if not self.groups:
+            raise ValueError("TrainStep: the model has no trainable parameters")
+        self.group_kinds = [k for k in ("head", "backbone") if groups[k]]
         self.step_count = 0
         self.world = 1
         self.buckets: List[GradBuckets] = []
@@ -218,9 +226,14 @@ class TrainStep:
         self._dev = dev
         # step-dependent AdamW scalars on the device, one row per group: [lr, 1-b1^t, sqrt(1-b2^t)] (graph replay)
         self._hyper = torch.zeros((len(self.groups), 3), dtype=torch.float32, device=dev)
-        self._hyper_host = torch.zeros((len(self.groups), 3), dtype=torch.float32).pin_memory() if dev.type == "cuda" \
-            else torch.zeros((len(self.groups), 3))
+        # The host runs ahead of the stream (nothing in step() synchronises), so ONE pinned staging row would be
+        # overwritten for step N+k before the async copy of step N has read it.  A ring of pinned rows, each guarded by
+        # an event recorded right after its copy: a slot is rewritten only once its copy has executed.
+        self._hyper_ring = [(torch.zeros((len(self.groups), 3), dtype=torch.float32).pin_memory() if dev.type == "cuda"
+                             else torch.zeros((len(self.groups), 3)), None) for _ in range(self.HYPER_RING)]
+        self._hyper_slot = 0
         self._graph = None
+        self.last_lr_scale = 1.0
 
     # ------------------------------------------------------------------ pieces
     def zero_grad(self):
@@ -244,9 +257,13 @@ class TrainStep:
             bk.finish()
         self.zero_grad()
 
-    def optimizer_step(self, lr_scale: float = 1.0, micro_batches: int = 1):
+    def optimizer_step(self, lr_scale: float = 1.0, micro_batches: int = 1, global_micro_batches: Optional[int] = None):
+        """AdamW on the summed gradients divided by the number of micro-batches that produced them (loop.py:145-150):
+        `micro_batches` local ones on each of `world` ranks, or — when the ranks hold different numbers (a ragged
+        trailing group) — `global_micro_batches`, the sum over the ranks, which every rank must pass identically."""
         self.step_count += 1
-        gscale = 1.0 / (micro_batches * self.world)  # mean over micro-batches and ranks (loop.py:145-150)
+        n_global = int(global_micro_batches) if global_micro_batches is not None else micro_batches * self.world
+        gscale = 1.0 / max(1, n_global)
         for bk in self.buckets:
             bk.finish()
         self._push_hyper(lr_scale)
@@ -258,11 +275,127 @@ class TrainStep:
 
     def _push_hyper(self, lr_scale: float):
         t = self.step_count
+        slot = self._hyper_slot
+        self._hyper_slot = (slot + 1) % self.HYPER_RING
+        row, ev = self._hyper_ring[slot]
+        if ev is not None:
+            ev.synchronize()  # the copy that last read this row has executed (HYPER_RING steps ago: never waits in practice)
         for gi, g in enumerate(self.groups):
-            self._hyper_host[gi, 0] = g.lr * lr_scale
-            self._hyper_host[gi, 1] = 1.0 - self.betas[0] ** t
-            self._hyper_host[gi, 2] = math.sqrt(1.0 - self.betas[1] ** t)
-        self._hyper.copy_(self._hyper_host, non_blocking=True)
+            row[gi, 0] = g.lr * lr_scale
+            row[gi, 1] = 1.0 - self.betas[0] ** t
+            row[gi, 2] = math.sqrt(1.0 - self.betas[1] ** t)
+        self._hyper.copy_(row, non_blocking=True)
+        if self._hyper.is_cuda:
+            ev = torch.cuda.Event()
+            ev.record()
+            self._hyper_ring[slot] = (row, ev)
+        self.last_lr_scale = float(lr_scale)
+
+    # ------------------------------------------------------------------ optimiser state in torch.optim.AdamW layout
+    def reference_param_groups(self):
+        """The reference's optimiser param groups (loop.py:681-726) over this model's parameters: 'embedding' group
+        (aux heads: lr_embedding, no decay) first when non-empty, then the backbone, each in named_parameters() order
+        — the order that fixes the integer parameter ids of torch's optimizer.state_dict()."""
+        fast, slow, seen = [], [], set()
+        for name, p in self.model.named_parameters():
+            if id(p) in seen or not p.requires_grad:
+                continue
+            seen.add(id(p))
+            (fast if any(m in name for m in HEAD_GROUP_MARKERS) else slow).append(p)
+        out = []
+        by_kind = dict(zip(self.group_kinds, self.groups))
+        if fast:
+            g = by_kind["head"]
+            out.append({"params": fast, "lr": g.lr, "weight_decay": g.weight_decay})
+        if slow:
+            g = by_kind["backbone"]
+            out.append({"params": slow, "lr": g.lr, "weight_decay": g.weight_decay})
+        return out
+
+    def _slot(self, p):
+        for g in self.groups:
+            for q, o in zip(g.params, g.offsets):
+                if q is p:
+                    return g, o
+        raise KeyError("parameter is not owned by this TrainStep")
+
+    def _shell_optimizer(self):
+        """A torch.optim.AdamW over the same parameters and groups, used ONLY as the (de)serialiser of its own
+        state_dict layout (it never steps): whatever keys this torch version writes / validates are produced / checked
+        by torch itself."""
+        opt = torch.optim.AdamW(self.reference_param_groups(), betas=self.betas, eps=self.eps)
+        for pg in opt.param_groups:
+            pg.setdefault("initial_lr", pg["lr"])  # what LambdaLR adds on construction (loop.py:780)
+        return opt
+
+    def state_dict(self, lr_scale_fn=None) -> dict:
+        """Optimiser state as `torch.optim.AdamW.state_dict()` of the reference's optimiser would hold it
+        (`payload["optimizer"]`, loop.py:962): per-parameter `step`, `exp_avg`, `exp_avg_sq` sliced out of the flat
+        m / v buffers, param groups with the current (scheduled) lr.  A reference `last.pt` therefore resumes here and
+        a checkpoint written here resumes in the reference (loop.py:891-893).  With `lr_scale_fn` (the LambdaLR lambda)
+        the stored lr is the one the reference's scheduler has already set for the NEXT step (it steps right after the
+        optimiser, loop.py:1181-1182); without it, the scale of the last step taken."""
+        opt = self._shell_optimizer()
+        if self.step_count > 0:
+            for pg in opt.param_groups:
+                for p in pg["params"]:
+                    g, o = self._slot(p)
+                    n = p.numel()
+                    opt.state[p] = {"step": torch.tensor(float(self.step_count)),
+                                    "exp_avg": g.m[o:o + n].view_as(p).clone(),
+                                    "exp_avg_sq": g.v[o:o + n].view_as(p).clone()}
+        scale = float(lr_scale_fn(self.step_count)) if lr_scale_fn is not None else self.last_lr_scale
+        for pg in opt.param_groups:
+            pg["lr"] = pg["initial_lr"] * scale
+        return opt.state_dict()
+
+    def load_state_dict(self, state: dict):
+        """Accepts `torch.optim.AdamW.state_dict()` of the reference's optimiser (same two groups, same order)."""
+        opt = self._shell_optimizer()
+        opt.load_state_dict(state)  # torch validates group count and sizes and casts / moves the state tensors
+        steps = set()
+        with torch.no_grad():
+            for pg in opt.param_groups:
+                for p in pg["params"]:
+                    st = opt.state.get(p)
+                    g, o = self._slot(p)
+                    n = p.numel()
+                    if not st:
+                        g.m[o:o + n].zero_()
+                        g.v[o:o + n].zero_()
+                        continue
+                    g.m[o:o + n].copy_(st["exp_avg"].reshape(-1))
+                    g.v[o:o + n].copy_(st["exp_avg_sq"].reshape(-1))
+                    steps.add(int(round(float(st["step"]))))
+        if len(steps) > 1:
+            raise ValueError(f"optimizer state holds different step counts per parameter {sorted(steps)}: the fused "
+                             "AdamW keeps one step counter (the reference steps all parameters together)")
+        self.step_count = steps.pop() if steps else 0
+        by_kind = dict(zip(self.group_kinds, self.groups))
+        kinds = [k for k in ("head", "backbone") if k in by_kind]
+        for kind, pg in zip(kinds, opt.param_groups):
+            g = by_kind[kind]
+            g.weight_decay = float(pg["weight_decay"])
+            base = float(pg.get("initial_lr", pg["lr"]))
+            g.lr = base
+            self.last_lr_scale = float(pg["lr"]) / base if base > 0 else 1.0
+        if opt.param_groups:
+            self.betas = tuple(opt.param_groups[0]["betas"])
+            self.eps = float(opt.param_groups[0]["eps"])
+        if self._graph is not None:  # group scalars are baked into a captured step
+            self._graph = None
+
+    def scheduler_state_dict(self, lr_scale_fn=None) -> dict:
+        """`payload["scheduler"]` of the reference (LambdaLR.state_dict(), loop.py:963) after `step_count` optimiser
+        steps: produced by a real LambdaLR over the shell optimiser so the key set is torch's own."""
+        opt = self._shell_optimizer()
+        fn = lr_scale_fn if lr_scale_fn is not None else (lambda i: 1.0)
+        sched = torch.optim.lr_scheduler.LambdaLR(opt, fn)
+        sd = sched.state_dict()
+        sd["last_epoch"] = int(self.step_count)
+        sd["_step_count"] = int(self.step_count) + 1
+        sd["_last_lr"] = [pg["initial_lr"] * float(fn(self.step_count)) for pg in opt.param_groups]
+        return sd
 
     # ------------------------------------------------------------------ the step
     def _eager_step(self, xb, yb, lr_scale: float = 1.0):
@@ -437,6 +570,8 @@ def run_accumulation_groups(step, microbatches: Iterable, grad_accum_steps: int,
     Yields one dict per optimiser step: {"step", "group_size", "total_loss_sum", "next_loss_sum", "lr_scale"}."""
     gacc = max(1, int(grad_accum_steps))
     step_idx = int(first_step_idx)
+    distributed = process_group is not None or (dist.is_available() and dist.is_initialized()
+                                                and dist.get_world_size() > 1)
     queue: List[tuple] = []
     it = iter(microbatches)
     exhausted = False
@@ -446,36 +581,56 @@ def run_accumulation_groups(step, microbatches: Iterable, grad_accum_steps: int,
                 queue.append(next(it))
             except StopIteration:
                 exhausted = True
-        if not queue:
-            return
         group = queue[:gacc]
+        # The ranks agree on the composition of the group BEFORE running it: a rank-sharded stream whose length is not
+        # a multiple of gacc x world leaves the ranks with different numbers of local micro-batches in the trailing
+        # group (possibly none).  n_global (sum over ranks) is what the gradient mean divides by on EVERY rank, and a
+        # rank without local micro-batches still joins the group's collectives (with zero gradients).
+        n_local = len(group)
+        n_global = n_local
+        dev = getattr(step, "_dev", None) or torch.device("cpu")
+        if distributed:
+            cnt = torch.tensor([float(n_local)], device=dev)
+            dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=process_group)
+            n_global = int(round(cnt.item()))
+        if n_global == 0:
+            return
         step.zero_grad()
         losses, nexts = [], []
         for k, (xb, yb) in enumerate(group):
-            step.arm_collectives(k == len(group) - 1)
+            step.arm_collectives(k == n_local - 1)
             loss, parts = step.forward_backward(xb, yb)
             losses.append(loss.detach().reshape(1).float())
             nexts.append(parts["next"].detach().reshape(1).float())
-        stacked = torch.cat(losses + nexts)
-        bad = (~torch.isfinite(stacked[: len(group)])).float()
-        if process_group is not None or (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+        if n_local == 0:
+            step.arm_collectives(True)  # nothing to launch from: optimizer_step() reduces every bucket (zeros from here)
+        # fixed-length vectors (gacc slots; empty slots are finite zeros) so that every rank reduces the same shape
+        pad = [torch.zeros(1, device=dev)] * (gacc - n_local)
+        stacked = torch.cat([t.to(dev) for t in losses] + pad + [t.to(dev) for t in nexts] + pad)
+        bad = (~torch.isfinite(stacked[:gacc])).float()
+        if distributed:
             dist.all_reduce(bad, op=dist.ReduceOp.MAX, group=process_group)
         host = torch.cat([bad, stacked]).cpu()  # the group's only host sync
-        bad_h = host[: len(group)].tolist()
+        bad_h = host[:gacc].tolist()
         first_bad = next((k for k, b in enumerate(bad_h) if b > 0), None)
         if first_bad is None:
             for _ in group:
                 health.record_finite_microbatch()
             scale = 1.0 if lr_scale_fn is None else float(lr_scale_fn(step_idx))
-            step.optimizer_step(lr_scale=scale, micro_batches=len(group))
-            health.complete_group()
-            vals = host[len(group):].tolist()
-            yield {"step": step_idx, "group_size": len(group), "total_loss_sum": sum(vals[: len(group)]),
-                   "next_loss_sum": sum(vals[len(group):]), "lr_scale": scale}
+            if distributed:
+                step.optimizer_step(lr_scale=scale, micro_batches=max(1, n_local), global_micro_batches=n_global)
+            else:
+                step.optimizer_step(lr_scale=scale, micro_batches=n_local)
+            if n_local:
+                health.complete_group()
+            vals = host[gacc:].tolist()
+            yield {"step": step_idx, "group_size": n_local, "global_group_size": n_global,
+                   "total_loss_sum": sum(vals[:n_local]), "next_loss_sum": sum(vals[gacc:gacc + n_local]),
+                   "lr_scale": scale}
             step_idx += 1
-            queue = queue[len(group):]
+            queue = queue[n_local:]
         else:
-            for _ in range(first_bad):
+            for _ in range(min(first_bad, n_local)):
                 health.record_finite_microbatch()
             health.abort_group()
             step.discard_gradients()

@@ -4,6 +4,7 @@ sum of the two ranks' gradients (to bf16 rounding) and both ranks must end up wi
 import os
 import sys
 
+import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
@@ -141,7 +142,7 @@ def _nonfinite_worker(rank, world, port, out):
             loss = torch.tensor(float(xb))
             return loss, {"next": loss}
 
-        def optimizer_step(self, lr_scale=1.0, micro_batches=1):
+        def optimizer_step(self, lr_scale=1.0, micro_batches=1, global_micro_batches=None):
             self.steps.append((self.grad, micro_batches))
 
         def discard_gradients(self):
@@ -178,3 +179,75 @@ def test_nonfinite_flag_is_shared_across_ranks(tmp_path):
     assert r0["health"] == r1["health"] == {"active_microbatches": 0, "nonfinite_microbatches": 1, "aborted_groups": 1,
                                             "discarded_finite_microbatches": 1}
     assert [s[0] for s in r0["steps"]] == [3.0, 11.0, 7.0] and [s[0] for s in r1["steps"]] == [3.0, 11.0, 7.0]
+
+
+def _ragged_worker(rank, world, port, out):
+    sys.path.insert(0, PKG)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from codonlm_b200.token_feed import rank_microbatches
+    from codonlm_b200.trainer import AccumulationHealth, run_accumulation_groups
+
+    class SumStep:
+        """'Gradient' = sum of local micro-batch values; optimizer_step all-reduces it like the gradient buckets do and
+        records the mean the fused AdamW would see (sum over ranks x 1/global count)."""
+
+        def __init__(self):
+            self.grad, self.means, self.calls = torch.zeros(1), [], []
+
+        def zero_grad(self):
+            self.grad.zero_()
+
+        def arm_collectives(self, armed):
+            pass
+
+        def forward_backward(self, xb, yb):
+            self.grad += xb
+            loss = torch.tensor(float(xb))
+            return loss, {"next": loss}
+
+        def optimizer_step(self, lr_scale=1.0, micro_batches=1, global_micro_batches=None):
+            g = self.grad.clone()
+            dist.all_reduce(g)
+            self.means.append(g.item() / global_micro_batches)
+            self.calls.append((micro_batches, global_micro_batches))
+
+        def discard_gradients(self):
+            self.grad.zero_()
+
+    # 11 micro-batches, global accumulation 4, world 2: groups [0..3] [4..7] [8,9,10]; the last one gives rank 0 two
+    # micro-batches (8, 10) and rank 1 one (9) — ADVICE r1: ranks must agree on the group and divide by the GLOBAL count
+    vals = [float(v) for v in range(1, 12)]
+    mine = list(rank_microbatches([(v, None) for v in vals], rank, world, 4))
+    step, health = SumStep(), AccumulationHealth()
+    recs = list(run_accumulation_groups(step, mine, 4 // world, health))
+    # 9 micro-batches: the trailing group is [9] and only rank 0 holds it — rank 1 must still join its collectives
+    vals2 = [float(v) for v in range(1, 10)]
+    mine2 = list(rank_microbatches([(v, None) for v in vals2], rank, world, 4))
+    step2 = SumStep()
+    recs2 = list(run_accumulation_groups(step2, mine2, 4 // world, AccumulationHealth()))
+    torch.save(dict(means=step.means, calls=step.calls, sizes=[(r["group_size"], r["global_group_size"]) for r in recs],
+                    means2=step2.means, sizes2=[(r["group_size"], r["global_group_size"]) for r in recs2]),
+               f"{out}.{rank}")
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_ragged_trailing_group_is_agreed_on_by_all_ranks(tmp_path):
+    import socket
+    out = str(tmp_path / "rg.pt")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    try:
+        mp.spawn(_ragged_worker, args=(2, port, out), nprocs=2, join=True)
+    except mp.ProcessExitedException:
+        if not (os.path.exists(out + ".0") and os.path.exists(out + ".1")):
+            raise
+    r0, r1 = torch.load(out + ".0"), torch.load(out + ".1")
+    want = [sum(range(1, 5)) / 4, sum(range(5, 9)) / 4, sum(range(9, 12)) / 3]  # the single-process reference's means
+    assert r0["means"] == pytest.approx(want) and r1["means"] == pytest.approx(want)
+    assert r0["sizes"] == [(2, 4), (2, 4), (2, 3)] and r1["sizes"] == [(2, 4), (2, 4), (1, 3)]
+    want2 = [sum(range(1, 5)) / 4, sum(range(5, 9)) / 4, 9.0]
+    assert r0["means2"] == pytest.approx(want2) and r1["means2"] == pytest.approx(want2)
+    assert r0["sizes2"][-1] == (1, 1) and r1["sizes2"][-1] == (0, 1)

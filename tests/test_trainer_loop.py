@@ -31,7 +31,7 @@ class FakeStep:
         loss = torch.tensor(float(xb))
         return loss, {"next": loss * 0.5}
 
-    def optimizer_step(self, lr_scale=1.0, micro_batches=1):
+    def optimizer_step(self, lr_scale=1.0, micro_batches=1, global_micro_batches=None):
         self.steps.append((self.grad / micro_batches, micro_batches, lr_scale))
 
     def discard_gradients(self):
@@ -149,3 +149,94 @@ def test_resolve_warmup_steps_rules():
             resolve_warmup_steps(bad, 1000)
     with pytest.raises(ValueError):
         resolve_warmup_steps({}, 0)
+
+
+# ---- optimiser state in the reference's checkpoint layout (loop.py:891-893, 962-963) -------------------------------
+def _small_model(**kw):
+    from codonlm_b200 import TinyGPT
+    torch.manual_seed(11)
+    base = dict(vocab_size=68, block_size=16, n_layer=2, n_head=2, n_embd=32, dropout=0.0, termination_aux=True,
+                multi_offset_targets=[2, 4])
+    base.update(kw)
+    return TinyGPT(**base)
+
+
+def _reference_adamw(model, lr, lr_embedding, wd):
+    """The reference's optimiser construction (loop.py:681-731), restated."""
+    fast, slow = [], []
+    for name, p in model.named_parameters():
+        if not p.requires_grad:
+            continue
+        (fast if ("transformer.wte" in name or "shape_proj" in name or "offset_projs" in name
+                  or "termination_head" in name) else slow).append(p)
+    groups = []
+    if fast:
+        groups.append({"params": fast, "lr": lr_embedding, "weight_decay": 0.0})
+    if slow:
+        groups.append({"params": slow, "lr": lr, "weight_decay": wd})
+    return torch.optim.AdamW(groups)
+
+
+def test_optimizer_state_round_trips_with_torch_adamw():
+    """TrainStep.state_dict() must be loadable by the reference's torch.optim.AdamW (same groups, same parameter ids)
+    and carry m / v / step exactly; a state_dict written by that AdamW must load into the flat buffers."""
+    import copy
+    from codonlm_b200.trainer import TrainStep, cosine_lr_scale
+    m_ref = _small_model()
+    m_ours = copy.deepcopy(m_ref)
+    opt = _reference_adamw(m_ref, 3e-3, 1e-3, 0.05)
+    sched_fn = lambda i: cosine_lr_scale(i, 2, 10, 0.1)  # noqa: E731
+    sched = torch.optim.lr_scheduler.LambdaLR(opt, sched_fn)
+    for _ in range(3):  # three real AdamW steps on CPU with synthetic gradients
+        for p in m_ref.parameters():
+            p.grad = torch.randn_like(p)
+        opt.step()
+        sched.step()
+    ts = TrainStep(m_ours, lr=3e-3, lr_embedding=1e-3, weight_decay=0.05)
+    ts.load_state_dict(copy.deepcopy(opt.state_dict()))
+    assert ts.step_count == 3
+    named_ref = dict(m_ref.named_parameters())
+    for name, p in m_ours.named_parameters():
+        g, o = ts._slot(p)
+        st = opt.state[named_ref[name]]
+        assert torch.equal(g.m[o:o + p.numel()].view_as(p), st["exp_avg"]), name
+        assert torch.equal(g.v[o:o + p.numel()].view_as(p), st["exp_avg_sq"]), name
+    assert [g.lr for g in ts.groups] == [1e-3, 3e-3] and [g.weight_decay for g in ts.groups] == [0.0, 0.05]
+    # and back: what TrainStep writes is what torch wrote (ids, tensors, hyper-parameters, scheduled lr)
+    back = ts.state_dict(lr_scale_fn=sched_fn)
+    want = opt.state_dict()
+    assert [pg["params"] for pg in back["param_groups"]] == [pg["params"] for pg in want["param_groups"]]
+    for a, b in zip(back["param_groups"], want["param_groups"]):
+        assert set(a) == set(b)
+        for k in ("weight_decay", "betas", "eps", "initial_lr", "amsgrad"):
+            assert a[k] == b[k], k
+        assert a["lr"] == pytest.approx(b["lr"], rel=1e-12)
+    assert set(back["state"]) == set(want["state"])
+    for k in want["state"]:
+        for f in ("step", "exp_avg", "exp_avg_sq"):
+            assert torch.equal(back["state"][k][f].float(), want["state"][k][f].float()), (k, f)
+    fresh = _reference_adamw(copy.deepcopy(m_ref), 3e-3, 1e-3, 0.05)
+    fresh.load_state_dict(back)  # the reference's resume path (loop.py:891-893) accepts it
+    ssd = ts.scheduler_state_dict(sched_fn)
+    assert set(ssd) == set(sched.state_dict()) and ssd["last_epoch"] == 3
+    assert ssd["_last_lr"] == pytest.approx(sched.state_dict()["_last_lr"])
+    torch.optim.lr_scheduler.LambdaLR(fresh, sched_fn).load_state_dict(ssd)
+    # an untouched TrainStep writes an empty state, like a fresh torch optimiser
+    assert TrainStep(_small_model()).state_dict()["state"] == {}
+
+
+def test_frozen_backbone_builds_only_the_head_group():
+    """freeze_backbone (loop.py:656-667): only offset_projs / termination_head train; the backbone group is empty and
+    must simply not exist (the reference guards with `if backbone_params:`)."""
+    from codonlm_b200.trainer import TrainStep
+    m = _small_model()
+    for name, p in m.named_parameters():
+        p.requires_grad = ("offset_projs" in name) or ("termination_head" in name)
+    ts = TrainStep(m, lr=1e-3, lr_embedding=5e-4)
+    assert ts.group_kinds == ["head"] and len(ts.groups) == 1 and ts.groups[0].lr == 5e-4
+    assert all(("offset_projs" in n) or ("termination_head" in n) for n in ts.groups[0].names)
+    assert len(ts.state_dict()["param_groups"]) == 1
+    for p in m.parameters():
+        p.requires_grad = False
+    with pytest.raises(ValueError):
+        TrainStep(m)
