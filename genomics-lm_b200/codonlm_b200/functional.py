@@ -16,39 +16,63 @@ from .ops import EPI_GELU, EPI_MUL_AUX, EPI_NONE, bf16, f32
 
 _SMS = 148
 
-# Side channel from LayerNorm backward to the backward of the residual linear right before it: the bf16 copy
-# and the column sums of the fp32 gradient tensor dx, produced by the same kernel that wrote dx.  It holds at
-# most ONE entry (the consumer runs before the next LayerNorm backward) and the entry is dropped when it is
-# used or replaced, so a recycled device address can never be matched against a stale entry.
-_BF16_SIDE = {}
-_QKV_SIDE = {}  # dqkv.data_ptr() -> column sums of dqkv taken inside the attention backward kernels
+# By-products of a backward kernel that the NEXT backward node wants (LayerNorm backward -> the residual linear in
+# front of it: the bf16 copy and the column sums of dx; attention backward -> the QKV linear: the column sums of dqkv)
+# travel ON the gradient tensor itself, as a Python attribute: autograd hands the same tensor object to the next node,
+# and when it does not (a hook, an accumulation, a clone in between) the attribute is simply gone and the consumer
+# recomputes.  Nothing is keyed by device address, nothing is module-global: two models, retain_graph or a second
+# backward in flight cannot cross wires.
+_SIDE_ATTR = "_cgpt_side"
+
+
+def _attach(g: torch.Tensor, bf16_copy, colsum):
+    setattr(g, _SIDE_ATTR, (bf16_copy, colsum))
+
+
+def _detach_side(g: torch.Tensor):
+    hit = getattr(g, _SIDE_ATTR, None)
+    if hit is not None:
+        delattr(g, _SIDE_ATTR)
+    return hit
 
 
 def _bf16_of(g: torch.Tensor):
     """(bf16 copy of g, column sums of g or None)."""
-    hit = _BF16_SIDE.pop(g.data_ptr(), None)
-    if hit is not None and hit[0].shape == g.shape:
+    hit = _detach_side(g)
+    if hit is not None and hit[0] is not None and hit[0].shape == g.shape:
         return hit
     return ops.cast_bf16(g), None
 
 
-class _DirectSum:
-    """Marker in the side channels: the producer kernel has ALREADY added the column sums to `param.main_grad`
-    (no scratch vector, no add kernel).  The consumer only reports the contribution."""
+# When the producer kernel has ALREADY added the column sums to `param.main_grad` (no scratch vector, no add kernel)
+# it leaves a credit on the Parameter object; the consumer that owns that bias takes the credit instead of computing
+# the sums.  Credits and debits balance within every backward pass (the producer always runs before its consumer);
+# trainer.TrainStep.zero_grad() clears leftovers of an interrupted backward.
+def _credit(param):
+    param._cgpt_direct = getattr(param, "_cgpt_direct", 0) + 1
 
-    def __init__(self, param):
-        self.param = param
+
+def _take_credit(param) -> bool:
+    n = getattr(param, "_cgpt_direct", 0) if param is not None else 0
+    if n > 0:
+        param._cgpt_direct = n - 1
+        return True
+    return False
 
 
-def _bias_grad(gb: torch.Tensor, n: int, master, colsum):
+def clear_credits(params):
+    for p in params:
+        if getattr(p, "_cgpt_direct", 0):
+            p._cgpt_direct = 0
+
+
+def _bias_grad(gb: torch.Tensor, n: int, master, colsum, off: int = 0):
     """Bias gradient = column sums of the output gradient: taken from the producer when it already has them."""
-    if colsum is None:
-        return _colsum(gb, n, master=master)
-    if isinstance(colsum, _DirectSum):
-        if colsum.param is not master:
-            raise RuntimeError("bias-gradient side channel reached a different layer than the one it was computed for")
+    if _take_credit(master):  # the producer kernel added them to master.main_grad itself
         _done(master)
         return None
+    if colsum is None:
+        return _colsum(gb, n, master=master, off=off)
     mg = _main_grad(master)
     if mg is not None:
         mg.add_(colsum)
@@ -210,16 +234,16 @@ class ResidualLayerNormFn(Function):
             return gx, None, None, None, None
         tgt = ctx.colsum_target
         tmg = _main_grad(tgt)
-        if tmg is not None and tmg.numel() == gamma.numel() and tmg.is_contiguous():
-            dxsum, side = tmg, _DirectSum(tgt)  # the kernel accumulates into the bias' gradient slot itself
-        else:
-            dxsum = torch.zeros_like(gamma)
-            side = dxsum
+        direct = tmg is not None and tmg.numel() == gamma.numel() and tmg.is_contiguous()
+        dxsum = tmg if direct else torch.zeros_like(gamma)  # direct: the kernel adds into the bias' gradient slot itself
         dx, dxb = ops.layernorm_bwd(dy.contiguous(), x, gamma, mean, rstd, None if gx is None else gx.contiguous(),
                                     dgamma, dbeta, want_bf16=True, dx_colsum=dxsum)
         # the upstream residual GEMM's backward wants dx as a bf16 operand and its column sums as the bias gradient
-        _BF16_SIDE.clear()
-        _BF16_SIDE[dx.data_ptr()] = (dxb, side)
+        if direct:
+            _credit(tgt)
+            _attach(dx, dxb, None)
+        else:
+            _attach(dx, dxb, dxsum)
         if mg is not None:
             _done(gam_p)
             _done(bet_p)
@@ -255,7 +279,11 @@ class PackedLinearFn(Function):
         M, K = x.shape
         N = w_sh.shape[0]
         g = g.contiguous()
-        gb, gsum = _bf16_of(g) if g.dtype == f32 else (g, None)
+        if g.dtype == f32:
+            gb, gsum = _bf16_of(g)
+        else:  # bf16 gradient (dqkv from the attention backward): its column sums may ride along
+            hit = _detach_side(g)
+            gb, gsum = g, (None if hit is None else hit[1])
         dx = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty((M, K), dtype=bf16, device=x.device)
@@ -276,37 +304,23 @@ class PackedLinearFn(Function):
                 grads.append(_wgrad(gb, x, n, k_in, dy_off=r0, master=ctx.masters[i]))
         if ctx.has_bias:
             b_slots = _packed_slots(ctx.masters[nw:], ctx.rows)
-            qsum = _QKV_SIDE.pop(g.data_ptr(), None)
-            _QKV_SIDE.clear()
-            direct = isinstance(qsum, _DirectSum)
-            if direct and not (nw > 1 and b_slots is not None and qsum.param is ctx.masters[nw]):
-                raise RuntimeError("bias-gradient side channel of the attention backward reached the wrong linear")
-            if qsum is not None and not direct and qsum.numel() != N:
-                qsum = None
             if nw > 1 and b_slots is not None:
                 packed_b = torch.as_strided(b_slots[0], (N,), (1,))
-                if direct:
-                    pass  # the attention backward kernels already added the column sums to these slots
-                elif qsum is not None:
-                    packed_b.add_(qsum)
+                if _take_credit(ctx.masters[nw]):
+                    pass  # the attention backward kernels already added the column sums of dqkv to these slots
+                elif gsum is not None and gsum.numel() == N:
+                    packed_b.add_(gsum)
                 else:
                     ops.colsum_bf16(gb, packed_b, N=N, ld=gb.stride(0))
                 for m in ctx.masters[nw:]:
                     _done(m)
                 grads.extend([None] * nw)
-            elif qsum is not None:
-                for i, (r0, n) in enumerate(ctx.rows):
-                    grads.append(_bias_grad(gb, n, ctx.masters[nw + i], qsum[r0:r0 + n]))
             else:
-                if isinstance(gsum, _DirectSum) and nw != 1:
-                    raise RuntimeError("bias-gradient side channel reached a packed linear")
+                if gsum is not None and gsum.numel() != N:
+                    gsum = None
                 for i, (r0, n) in enumerate(ctx.rows):
-                    if gsum is not None and nw == 1:
-                        grads.append(_bias_grad(gb, n, ctx.masters[nw + i], gsum))
-                    else:
-                        grads.append(_colsum(gb, n, master=ctx.masters[nw + i], off=r0))
-        elif isinstance(gsum, _DirectSum):
-            raise RuntimeError("bias-gradient side channel reached a linear without bias")
+                    grads.append(_bias_grad(gb, n, ctx.masters[nw + i], None if gsum is None else gsum[r0:r0 + n],
+                                            off=r0))
         return (dx, None, None, g if ctx.has_res else None, None, None, *grads)
 
 
@@ -386,9 +400,7 @@ class MlpSwiGLUFn(Function):
         n_out = wd_sh.shape[0]
         g = g.contiguous()
         w_gate, w_up, w_down = ctx.masters
-        gb, gsum = _bf16_of(g)
-        if isinstance(gsum, _DirectSum):
-            raise RuntimeError("bias-gradient side channel reached the bias-free SwiGLU projection")
+        gb, _ = _bf16_of(g)
         dwd = _wgrad(gb, act, n_out, hid, master=w_down)        # [d, hid] (unpadded, odd pitch allowed)
         dact = torch.empty((M, hp), dtype=bf16, device=hin.device)
         ops.gemm(gb, wd_sh, dact, M=M, N=hp, K=n_out, b_mn=True)
@@ -456,8 +468,6 @@ class OffsetHeadFn(Function):
 
 
 def reset_side_channel():
-    _BF16_SIDE.clear()
-    _QKV_SIDE.clear()
     _HEAD_W_CACHE.clear()
 
 
@@ -482,7 +492,7 @@ class DropoutFn(Function):
     def backward(ctx, g):
         seed, off, p = ctx.rng
         g = g.contiguous()
-        _BF16_SIDE.clear()  # g's side data describes g, not dropout(g)
+        _detach_side(g)  # by-products describe g, not dropout(g); the residual path has no consumer for them
         return ops.dropout(g, None, p, seed, off), (g if ctx.has_res else None), None
 
 
@@ -512,7 +522,8 @@ class AttentionFn(Function):
         seg_start, rope, B, T, H, Hk, hd, window, dropout_p, seed, off = ctx.aux
         # without RoPE dqkv is final here, so the kernels also take its column sums (the q|k|v bias gradients) and
         # hand them to the QKV linear's backward through the side channel
-        csum = side = None
+        csum = None
+        direct = False
         if rope is None:
             bm = ctx.bias_masters
             slots = None
@@ -524,16 +535,17 @@ class AttentionFn(Function):
                 slots = _packed_slots(bm, rows) if r == (H + 2 * Hk) * hd else None
             if slots is not None:  # the three bias gradients are one contiguous vector of the flat buffer
                 csum = torch.as_strided(slots[0], ((H + 2 * Hk) * hd,), (1,))
-                side = _DirectSum(bm[0])
+                direct = True
             else:
-                csum = side = torch.zeros(((H + 2 * Hk) * hd,), dtype=f32, device=qkv.device)
+                csum = torch.zeros(((H + 2 * Hk) * hd,), dtype=f32, device=qkv.device)
         dqkv = ops.attn_bwd(qkv, seg_start, out, g.contiguous(), lse, B, T, H, Hk, hd, window=window,
                             dropout_p=dropout_p, seed=seed, offset=off, colsum=csum)
-        _QKV_SIDE.clear()
         if rope is not None:
             ops.rope_qk(dqkv, rope[0], rope[1], B, T, H, Hk, hd, inverse=True)
+        elif direct:
+            _credit(bm[0])
         else:
-            _QKV_SIDE[dqkv.data_ptr()] = side
+            _attach(dqkv, None, csum)
         return dqkv, None, None, None, None, None, None, None, None, None, None
 
 

@@ -80,6 +80,85 @@ def _require_cuda(t: torch.Tensor, what: str):
             "inputs to a B200 (model.to('cuda'))")
 
 
+# ----------------------------------------------------------------------------------------------
+# host staging (SURVEY hard part 6): reference callers that keep the model on the CPU
+# ----------------------------------------------------------------------------------------------
+_HOOK_TABLES = ("_forward_hooks", "_forward_pre_hooks", "_forward_hooks_with_kwargs",
+                "_forward_pre_hooks_with_kwargs", "_forward_hooks_always_called")
+
+
+def _staging_device() -> torch.device:
+    if not torch.cuda.is_available():
+        raise _lib.CgptError(
+            "codonlm_b200 has no CPU implementation and no CUDA device is visible: the model's parameters are on the "
+            "host, and staging them needs a B200")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _device_twin(mod: nn.Module) -> nn.Module:
+    """CUDA replica of a CPU-resident module.  The reference's inference callers pick their device as
+    `mps if available else cpu` (scripts/query_model.py:29-34, src/codonlm/score_mutations.py:29-31) and therefore keep
+    the model and its inputs on the host; the replica lets them run unchanged: it is built on first use, refreshed
+    when a host parameter / buffer changes (load_state_dict, in-place edits: tensor._version), shares the host
+    module's forward-hook tables (hooks registered on the host modules fire, with device tensors), and mirrors
+    train / eval flags and `use_sdpa`.  Results are copied back to the caller's device by the call sites."""
+    import copy
+    dev = _staging_device()
+    tensors = list(mod.parameters()) + list(mod.buffers())
+    key = tuple(t._version for t in tensors) + tuple(id(t) for t in tensors)
+    twin = mod.__dict__.get("_cgpt_twin")
+    if twin is None or mod.__dict__.get("_cgpt_twin_dev") != dev:
+        saved = {k: mod.__dict__.pop(k) for k in ("_cgpt_twin", "_cgpt_twin_key", "_cgpt_twin_dev") if k in mod.__dict__}
+        try:
+            twin = copy.deepcopy(mod).to(dev)
+        finally:
+            mod.__dict__.update(saved)
+        for a, b in zip(mod.modules(), twin.modules()):
+            for name in _HOOK_TABLES:
+                if name in a.__dict__:
+                    b.__dict__[name] = a.__dict__[name]  # the SAME tables: later (de)registrations are seen
+        mod.__dict__["_cgpt_twin"], mod.__dict__["_cgpt_twin_dev"] = twin, dev
+        mod.__dict__["_cgpt_twin_key"] = key
+    elif mod.__dict__.get("_cgpt_twin_key") != key:
+        with torch.no_grad():
+            for src, dst in zip(tensors, list(twin.parameters()) + list(twin.buffers())):
+                dst.copy_(src)
+        mod.__dict__["_cgpt_twin_key"] = key
+    for a, b in zip(mod.modules(), twin.modules()):
+        b.training = a.training
+        if hasattr(a, "use_sdpa"):
+            b.use_sdpa = a.use_sdpa
+    return twin
+
+
+def _to_device(obj, dev):
+    if isinstance(obj, torch.Tensor):
+        return obj.to(dev)
+    if isinstance(obj, dict):
+        return {k: _to_device(v, dev) for k, v in obj.items()}
+    if isinstance(obj, (tuple, list)):
+        return type(obj)(_to_device(v, dev) for v in obj)
+    return obj
+
+
+def _host_call(mod: nn.Module, method: str, args, kwargs, home: torch.device):
+    """Run `mod.<method>` on the CUDA replica of a host-resident module and bring the results home.  Inference only:
+    a host-resident model cannot be TRAINED through the replica (its gradients would live on another module)."""
+    if torch.is_grad_enabled() and mod.training and any(p.requires_grad for p in mod.parameters()):
+        raise _lib.CgptError(
+            "training a host-resident model: move it to the GPU first (model.to('cuda')), as the reference trainer does "
+            "(loop.py:486-579); host staging serves inference callers only")
+    twin = _device_twin(mod)
+    dev = next(twin.parameters()).device
+    with torch.no_grad():
+        out = getattr(twin, method)(*_to_device(args, dev), **_to_device(kwargs, dev))
+    for a, b in zip(mod.modules(), twin.modules()):
+        if isinstance(a, CausalSelfAttention):
+            la = b.last_attn
+            a.last_attn = None if la is None else la.to(home)
+    return _to_device(out, home)
+
+
 def rotate_half(x):
     x1 = x[..., : x.shape[-1] // 2]
     x2 = x[..., x.shape[-1] // 2:]
@@ -345,7 +424,8 @@ class CausalSelfAttention(nn.Module, _ShadowMixin):
         return self._get_shadow("attn", (q.weight, k.weight, v.weight, q.bias, k.bias, v.bias, self.proj.weight), build)
 
     def forward(self, x, attn_mask=None, residual=None):
-        _require_cuda(self.query.weight, "attention weights")
+        if not self.query.weight.is_cuda:  # host-resident module called directly (tests/test_attention_dropout.py:33-59)
+            return _host_call(self, "forward", (x,), dict(attn_mask=attn_mask, residual=residual), x.device)
         B, T, Cdim = x.size()
         H = self.n_head
         hd = Cdim // H
@@ -727,6 +807,10 @@ class TinyGPT(nn.Module):
     def forward(self, idx, targets=None, return_aux: bool = False, shape_embeddings=None,
                 attention_window: int | None = None):
         in_dev = idx.device
+        if not self.tok_emb.weight.is_cuda:  # host-resident model (the reference's inference callers): stage it
+            return _host_call(self, "forward", (idx,), dict(targets=targets, return_aux=return_aux,
+                                                             shape_embeddings=shape_embeddings,
+                                                             attention_window=attention_window), in_dev)
         idx = self._prep_idx(idx)
         B, T = idx.shape
         Fn.reset_side_channel()
@@ -755,6 +839,8 @@ class TinyGPT(nn.Module):
         full forward (src/codonlm/generate.py:14-27 `_next_token_logits`, scripts/query_model.py `next_token`),
         for a whole batch of contexts: the final LayerNorm and the fp32 head run on B rows instead of B·T."""
         in_dev = idx.device
+        if not self.tok_emb.weight.is_cuda:
+            return _host_call(self, "next_token_logits", (idx,), dict(attention_window=attention_window), in_dev)
         idx = self._prep_idx(idx)
         Fn.reset_side_channel()
         x = self._embed(idx, None)
@@ -860,6 +946,18 @@ class TinyGPT(nn.Module):
 
     def iter_hidden_states(self, idx, shape_embeddings=None, attention_window: int | None = None):
         """Yield canonical causal states at embedding, block, and final-norm stages (:368-389)."""
+        if not self.tok_emb.weight.is_cuda:  # host-resident model (scripts/extract_embeddings.py:273-274): stage it
+            home = idx.device
+            if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
+                raise _lib.CgptError("training a host-resident model: move it to the GPU first (model.to('cuda'))")
+            twin = _device_twin(self)
+            dev = next(twin.parameters()).device
+            with torch.no_grad():
+                for stage, hidden in twin.iter_hidden_states(_to_device(idx, dev),
+                                                             shape_embeddings=_to_device(shape_embeddings, dev),
+                                                             attention_window=attention_window):
+                    yield stage, hidden.to(home)
+            return
         idx = self._prep_idx(idx)
         x = self._embed(idx, shape_embeddings)
         spec = self.mask_spec(idx, attention_window)

@@ -98,9 +98,12 @@ def termination_aux_loss(termination_logits: torch.Tensor, labels: torch.Tensor,
 def training_loss(model, xb, yb, offset_weights: Optional[Dict[int, float]] = None,
                   termination_loss_weight: float = 0.0, termination_stop_ids=(2,),
                   termination_bucket_edges=(0, 3, 10, 30), termination_class_weights=None,
-                  attention_window=None, shape_embeddings=None):
-    """total = next + sum_o w_o·loss_o + termination_loss_weight·term  (loop.py:1067-1143, replay excluded).
-    Returns (total, parts, logits); no host synchronisation."""
+                  attention_window=None, shape_embeddings=None, replay=None, replay_loss_weight: float = 0.1,
+                  replay_class_weights=None, replay_shape_embeddings=None):
+    """total = next + sum_o w_o·loss_o + termination_loss_weight·term + replay_loss_weight·replay
+    (the trainer's fwd(), loop.py:1067-1143).  `replay = (replay_x, replay_labels)` is the generated-state replay batch
+    of this micro-batch (loop.py:1113-1141): a second forward whose termination logits are scored against sparse labels
+    (-100 = unsupervised).  Returns (total, parts, logits); no host synchronisation."""
     need_aux = bool(offset_weights) or bool(termination_loss_weight)
     if need_aux:
         logits, next_loss, aux = model(xb, yb, return_aux=True, attention_window=attention_window,
@@ -125,4 +128,13 @@ def training_loss(model, xb, yb, offset_weights: Optional[Dict[int, float]] = No
         tl = termination_aux_loss(term_logits, labels, termination_class_weights)
         total = total + termination_loss_weight * tl
         parts["termination"] = tl
+    if replay is not None:
+        replay_x, replay_labels = replay
+        _, _, replay_aux = model(replay_x, return_aux=True, shape_embeddings=replay_shape_embeddings)
+        replay_logits = replay_aux.get("termination_logits")
+        if replay_logits is None:
+            raise RuntimeError("replay_loss_enabled=true but model returned no termination logits")
+        rl = termination_aux_loss(replay_logits, replay_labels.to(replay_logits.device), replay_class_weights)
+        total = total + replay_loss_weight * rl
+        parts["replay"] = rl
     return total, parts, logits

@@ -15,6 +15,7 @@ from typing import Dict, Iterable, List, Optional, Sequence
 import torch
 import torch.distributed as dist
 
+from . import functional as Fn
 from . import ops
 from .model_tiny_gpt import bump_shadow_generation
 from .objectives import training_loss
@@ -239,6 +240,7 @@ class TrainStep:
     def zero_grad(self):
         for g in self.groups:
             g.grad.zero_()
+            Fn.clear_credits(g.params)  # leftovers of an interrupted backward (functional._credit)
 
     def forward_backward(self, xb, yb):
         total, parts, _ = training_loss(self.model, xb, yb, offset_weights=self.offset_weights,

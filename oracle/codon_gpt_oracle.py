@@ -339,10 +339,13 @@ def termination_aux_loss(term_logits, labels, class_weights=None, ignore_index=-
 
 def training_loss(sd, cfg, idx, targets, offset_weights=None, termination_loss_weight=0.0,
                   termination_stop_ids=(2,), termination_bucket_edges=(0, 3, 10, 30),
-                  termination_class_weights=None, attention_window=None, shape_embeddings=None):
-    """Loss composition of the trainer's fwd() (loop.py:1067-1143, replay branch excluded).
+                  termination_class_weights=None, attention_window=None, shape_embeddings=None,
+                  replay=None, replay_loss_weight=0.1, replay_class_weights=None):
+    """Loss composition of the trainer's fwd() (loop.py:1067-1143).
 
-    total = next + sum_o w_o * loss_o + termination_loss_weight * term
+    total = next + sum_o w_o * loss_o + termination_loss_weight * term + replay_loss_weight * replay
+    where replay (loop.py:1113-1141) is the termination-head loss of a SECOND forward over a batch of generated
+    contexts `replay = (replay_x, replay_labels)` (labels -100 except the supervised generated states).
     Returns (total, parts dict, forward-output dict).
     """
     out = forward(sd, cfg, idx, targets, attention_window=attention_window, shape_embeddings=shape_embeddings)
@@ -361,6 +364,12 @@ def training_loss(sd, cfg, idx, targets, offset_weights=None, termination_loss_w
         tl = termination_aux_loss(out["termination_logits"], labels, termination_class_weights)
         total = total + termination_loss_weight * tl
         parts["termination"] = tl
+    if replay is not None:
+        replay_x, replay_labels = replay
+        rout = forward(sd, cfg, replay_x, None)  # model(replay_x, return_aux=True): no targets, no shape guidance here
+        rl = termination_aux_loss(rout["termination_logits"], replay_labels, replay_class_weights)
+        total = total + replay_loss_weight * rl
+        parts["replay"] = rl
     return total, parts, out
 
 

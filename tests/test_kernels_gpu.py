@@ -388,6 +388,37 @@ def test_attention_fwd_bwd(ops, case):
         assert rel <= 2e-2, f"{name} rel-norm err {rel}"
 
 
+@pytest.mark.parametrize("hd", [64, 32])
+def test_attention_forward_reference_maximum_is_moved_when_scores_grow(ops, hd):
+    """The forward keeps the row maximum of the FIRST visible kv tile as the softmax reference and moves it only when a
+    later tile overshoots it by ~2^40 (attn_fwd_w3_kernel).  Scores that grow by hundreds of nats along the key axis
+    force that path on most tiles; scores that shrink exercise the opposite side (late tiles underflow to exact
+    zeros).  Output and LSE must match the fp32 reference either way, and the backward must accept that LSE."""
+    B, T, H = 2, 640, 2
+    g = torch.Generator().manual_seed(3)
+    u = torch.nn.functional.normalize(torch.randn(hd, generator=g), dim=0)
+    pos = torch.arange(T, dtype=torch.float32) / T
+    for direction in (+1.0, -1.0):
+        q = (u * 8.0)[None, :].repeat(T, 1) + 0.05 * torch.randn(T, hd, generator=g)
+        k = (direction * 300.0 * pos)[:, None] * u[None, :] + 0.05 * torch.randn(T, hd, generator=g)
+        v = torch.randn(T, hd, generator=g)
+        row = torch.cat([q.repeat(1, H), k.repeat(1, H), v.repeat(1, H)], dim=1)
+        qkv = row.repeat(B, 1).to(torch.bfloat16).to(DEV)
+        idx = torch.full((B, T), 5, dtype=torch.long, device=DEV)
+        out, lse = ops.attn_fwd(qkv, None, B, T, H, H, hd)
+        q32 = qkv.float().requires_grad_(True)
+        ry, rlse, _ = _attn_ref(q32, idx, B, T, H, H, hd, None, None)
+        assert torch.isfinite(out.float()).all() and torch.isfinite(lse).all()
+        assert (out.float() - ry).abs().max().item() <= 3e-2
+        assert torch.allclose(lse, rlse, rtol=1e-3, atol=5e-3)
+        dout = torch.randn(B * T, H * hd, generator=g).to(torch.bfloat16).to(DEV)
+        ry.backward(dout.float())
+        dqkv = ops.attn_bwd(qkv, None, out, dout, lse, B, T, H, H, hd)
+        dv = dqkv.float()[:, 2 * H * hd:]
+        rdv = q32.grad[:, 2 * H * hd:]
+        assert ((dv - rdv).norm() / rdv.norm()).item() <= 2e-2
+
+
 def test_split_head_on_tensor_cores_is_fp32_accurate(ops):
     """hi/lo bf16 split head (tcgen05) vs float64: forward, dx, dW, db — errors must sit at the 1e-5 level,
     two orders below a plain bf16 GEMM."""

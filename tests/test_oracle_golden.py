@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 import torch
 
-from conftest import GOLDEN_DIR
+from conftest import GOLDEN_DIR, load_golden
 from oracle import codon_gpt_oracle as O
 
 
@@ -183,3 +183,24 @@ def test_oracle_at_baseline_shapes_matches_reference(name):
         assert parts["termination"].item() == pytest.approx(float(z[name + ".termination_loss"]), rel=3e-6)
         o32 = out["offset_logits"][32].reshape(-1)[::97].numpy()
         assert np.abs(o32 - z[name + ".offset32_logit_samples"]).max() <= 3e-5
+
+
+def test_replay_term_of_the_trainer_loss_matches_reference():
+    """The replay branch of fwd() (loop.py:1113-1141): second forward over generated contexts, termination-head CE on
+    sparse labels with replay_class_weights, added with replay_loss_weight.  Golden from the unmodified reference
+    (tests/golden/make_replay_golden.py, replay batch built by its GeneratedTerminationReplayDataset)."""
+    z, meta, sd, grads = load_golden("replay_term")
+    cfg = O.make_cfg(**meta["ctor"])
+    idx, tgt = torch.from_numpy(z["idx"]), torch.from_numpy(z["targets"])
+    replay = (torch.from_numpy(z["replay_x"]), torch.from_numpy(z["replay_labels"]))
+    assert (replay[1] != -100).sum().item() > 0 and (replay[1] == -100).sum().item() > 0
+    ow = {int(k): v for k, v in meta["offset_weights"].items()}
+    total, parts, out, got = O.loss_and_grads(sd, cfg, idx, tgt, offset_weights=ow,
+                                              termination_loss_weight=meta["termination_loss_weight"], replay=replay,
+                                              replay_loss_weight=meta["replay_loss_weight"],
+                                              replay_class_weights=torch.tensor(meta["replay_class_weights"]))
+    assert parts["replay"].item() == pytest.approx(meta["parts"]["replay"], rel=3e-6)
+    assert total.item() == pytest.approx(meta["parts"]["total"], rel=3e-6)
+    gmax = max(v.norm().item() for v in grads.values())
+    for k, ref in grads.items():  # key.bias gradients are analytically zero (pure rounding noise): absolute floor
+        assert (got[k] - ref).norm().item() <= 2e-5 * max(ref.norm().item(), 1e-3 * gmax), k

@@ -11,10 +11,10 @@ from codonlm_b200 import ops  # noqa: E402
 B, T, H, Hk, hd = (int(os.environ.get(k, v)) for k, v in (("AB", 64), ("AT", 1024), ("AH", 8), ("AHK", 8), ("AHD", 64)))
 dev = "cuda"
 qkv = torch.randn(B * T, (H + 2 * Hk) * hd, device=dev).to(torch.bfloat16)
-if os.environ.get("AREAL", "1") == "1":  # the bench's token stream: SEP every U{100..400} tokens
-    sys.path.insert(0, ROOT)
+if os.environ.get("AREAL", "1") == "1":  # the bench's token streams: ATOK=random (headline: one segment per sequence,
+    sys.path.insert(0, ROOT)             # full causal) or ATOK=realistic (SEP every U{100..400} tokens)
     from bench import synthetic_tokens  # noqa: E402
-    idx = synthetic_tokens(B, T, 1234)[0].to(dev)
+    idx = synthetic_tokens(B, T, 1234, kind=os.environ.get("ATOK", "random"))[0].to(dev)
 else:
     idx = torch.randint(4, 68, (B, T), device=dev)
     idx[:, 300] = 3
