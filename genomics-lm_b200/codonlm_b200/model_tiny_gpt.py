@@ -144,6 +144,7 @@ def _to_device(obj, dev):
 def _host_call(mod: nn.Module, method: str, args, kwargs, home: torch.device):
     """Run `mod.<method>` on the CUDA replica of a host-resident module and bring the results home.  Inference only:
     a host-resident model cannot be TRAINED through the replica (its gradients would live on another module)."""
+    _staging_device()  # fails loudly without a CUDA device: there is no CPU path
     if torch.is_grad_enabled() and mod.training and any(p.requires_grad for p in mod.parameters()):
         raise _lib.CgptError(
             "training a host-resident model: move it to the GPU first (model.to('cuda')), as the reference trainer does "
@@ -948,6 +949,7 @@ class TinyGPT(nn.Module):
         """Yield canonical causal states at embedding, block, and final-norm stages (:368-389)."""
         if not self.tok_emb.weight.is_cuda:  # host-resident model (scripts/extract_embeddings.py:273-274): stage it
             home = idx.device
+            _staging_device()
             if torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters()):
                 raise _lib.CgptError("training a host-resident model: move it to the GPU first (model.to('cuda'))")
             twin = _device_twin(self)

@@ -213,9 +213,61 @@ def swiglu_bwd(gu, dact, hp):
 
 
 # ------------------------------------------------------------------ attention
+class DeviceGenerator:
+    """Dropout generator state that lives on the device: {seed, base offset} as two int64 in HBM
+    (cgpt_set_philox_state).  Kernels add the base to their by-value offset themselves, so a CUDA graph that
+    captured a training step with dropout draws new masks on every replay; `advance()` (one launch, captured with
+    the step) moves the base past everything the step consumed.  Seeded from torch's CUDA generator, so
+    torch.manual_seed still governs the masks (reference tests/test_attention_dropout.py:62-78)."""
+
+    def __init__(self, device: torch.device):
+        gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
+        seed = gen.initial_seed() & 0x7FFFFFFFFFFFFFFF
+        self.state = torch.tensor([seed, gen.get_offset()], dtype=torch.int64, device=device)
+        self.consumed = 0  # by-value offsets handed out since the last advance()
+
+    def draw(self, n_random: int):
+        off = self.consumed
+        self.consumed += (int(n_random) + 3) // 4 * 4
+        return 0, off
+
+    def advance(self):
+        """Move the base offset past the draws made since the previous advance (device-side add)."""
+        if self.consumed:
+            check(_L().cgpt_philox_advance(self.state.data_ptr(), self.consumed, _stream()))
+        inc, self.consumed = self.consumed, 0
+        return inc
+
+
+_ACTIVE_GEN = [None]
+
+
+class device_generator:
+    """Context: dropout kernels launched inside read seed / base offset from `gen.state` (forward AND the backward
+    kernels that autograd launches from its own thread: the switch is process-wide)."""
+
+    def __init__(self, gen: Optional["DeviceGenerator"]):
+        self.gen = gen
+
+    def __enter__(self):
+        self.prev = _ACTIVE_GEN[0]
+        _ACTIVE_GEN[0] = self.gen
+        check(_L().cgpt_set_philox_state(None if self.gen is None else self.gen.state.data_ptr()))
+        return self.gen
+
+    def __exit__(self, *exc):
+        _ACTIVE_GEN[0] = self.prev
+        check(_L().cgpt_set_philox_state(None if self.prev is None else self.prev.state.data_ptr()))
+        return False
+
+
 def philox_state(device: torch.device, n_random: int):
-    """(seed, offset) from torch's CUDA generator, advanced by n_random: torch.manual_seed governs dropout
-    (reference tests/test_attention_dropout.py:62-78) without any kernel launch or host sync."""
+    """(seed, offset) for a dropout kernel.  Default: torch's CUDA generator, advanced by n_random on the host —
+    torch.manual_seed governs dropout (reference tests/test_attention_dropout.py:62-78) without any kernel launch or
+    host sync.  Inside a `device_generator` scope: (0, offset within the step); the kernels add the device-resident
+    seed and base offset."""
+    if _ACTIVE_GEN[0] is not None:
+        return _ACTIVE_GEN[0].draw(n_random)
     gen = torch.cuda.default_generators[device.index if device.index is not None else torch.cuda.current_device()]
     seed, off = gen.initial_seed(), gen.get_offset()
     gen.set_offset(off + (int(n_random) + 3) // 4 * 4)

@@ -197,10 +197,13 @@ class TrainStep:
 
     def __init__(self, model, lr=3e-4, lr_embedding=None, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  offset_weights: Optional[Dict[int, float]] = None, termination_loss_weight: float = 0.0,
-                 process_group=None, bucket_mb: int = 25, overlap_allreduce: Optional[bool] = None):
+                 process_group=None, bucket_mb: int = 25, overlap_allreduce: Optional[bool] = None,
+                 replay_loss_weight: float = 0.1, replay_class_weights=None):
         self.model = model
         self.offset_weights = offset_weights
         self.termination_loss_weight = termination_loss_weight
+        self.replay_loss_weight = replay_loss_weight
+        self.replay_class_weights = replay_class_weights
         self.betas, self.eps = betas, eps
         groups = split_param_groups(model)
         self.groups: List[FlatGroup] = []
@@ -235,6 +238,12 @@ class TrainStep:
         self._hyper_slot = 0
         self._graph = None
         self.last_lr_scale = 1.0
+        # dropout masks: generator state on the device, so that a captured step draws fresh masks on every replay
+        self._gen = None
+        if dev.type == "cuda" and getattr(model, "dropout_p", 0.0) > 0.0:
+            self._gen = ops.DeviceGenerator(dev)
+            if dist.is_available() and dist.is_initialized():  # different masks on different ranks
+                self._gen.state[1] += dist.get_rank() << 40
 
     # ------------------------------------------------------------------ pieces
     def zero_grad(self):
@@ -242,10 +251,15 @@ class TrainStep:
             g.grad.zero_()
             Fn.clear_credits(g.params)  # leftovers of an interrupted backward (functional._credit)
 
-    def forward_backward(self, xb, yb):
-        total, parts, _ = training_loss(self.model, xb, yb, offset_weights=self.offset_weights,
-                                        termination_loss_weight=self.termination_loss_weight)
-        total.backward()
+    def forward_backward(self, xb, yb, replay=None):
+        with ops.device_generator(self._gen):  # no-op scope without dropout
+            total, parts, _ = training_loss(self.model, xb, yb, offset_weights=self.offset_weights,
+                                            termination_loss_weight=self.termination_loss_weight, replay=replay,
+                                            replay_loss_weight=self.replay_loss_weight,
+                                            replay_class_weights=self.replay_class_weights)
+            total.backward()
+            if self._gen is not None:
+                self._gen.advance()  # device-side: the next micro-batch (or graph replay) draws new masks
         return total.detach(), parts
 
     def arm_collectives(self, armed: bool):
@@ -408,18 +422,19 @@ class TrainStep:
 
     def capture(self, B: int, T: int, warmup: int = 3, allow_collectives: bool = False):
         """Capture forward + backward (+ bucketed all-reduce) + AdamW for a fixed (B, T) into one CUDA graph
-        (dropout off): removes every launch gap and all Python work from the step.  step() then replays it.
+        : removes every launch gap and all Python work from the step.  step() then replays it.  Dropout works
+        under the graph: the Philox seed / base offset live in device memory (ops.DeviceGenerator) and the captured
+        step ends with the kernel that advances the base, so every replay draws new masks.
         With more than one rank the NCCL all-reduces and the side stream they run on are part of the graph
         (allow_collectives=True; every rank must capture, and replay, in lock step)."""
         if self.world > 1 and not allow_collectives:
             raise RuntimeError("capture(): pass allow_collectives=True to capture the bucketed all-reduce as well")
-        if self.model.training and getattr(self.model, "dropout_p", 0.0) > 0.0:
-            raise RuntimeError("capture(): dropout draws its Philox offset on the host; run eagerly")
         self._gx = torch.zeros((B, T), dtype=torch.int64, device=self._dev)
         self._gy = torch.zeros((B, T), dtype=torch.int64, device=self._dev)
         self._gx[:, :] = 4
         self._gy[:, :-1] = 4
         snap = [(g.flat.clone(), g.m.clone(), g.v.clone()) for g in self.groups]
+        gen_snap = None if self._gen is None else self._gen.state.clone()
         count = self.step_count
         side = torch.cuda.Stream()
         side.wait_stream(torch.cuda.current_stream())
@@ -447,6 +462,8 @@ class TrainStep:
             g.m.copy_(m)
             g.v.copy_(v)
             g.shadow.copy_(f)
+        if gen_snap is not None:
+            self._gen.state.copy_(gen_snap)
         self.step_count = count
         bump_shadow_generation()
         self._graph = graph

@@ -122,7 +122,8 @@ template <int HD>
 __global__ void __launch_bounds__(256, FwdSmem<HD>::kTwoCtas ? 2 : 1)
 attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restrict__ seg_start,
                 __nv_bfloat16* __restrict__ out, float* __restrict__ lse, int T, int H, int Hk, int window,
-                float scale_log2, int smem_bytes, const DropoutCfg drop) {
+                float scale_log2, int smem_bytes, const DropoutCfg drop_in) {
+  const DropoutCfg drop = resolve_dropout(drop_in);
   using C = HeadCfg<HD>;
   using S = FwdSmem<HD>;
   constexpr int TMEM_COLS = 256;
@@ -443,7 +444,8 @@ template <int HD>
 __global__ void __launch_bounds__(320, 1)
 attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out,
                    const int32_t* __restrict__ seg_start, float* __restrict__ lse, int Bsz, int T, int H, int Hk,
-                   int window, float scale_log2, const DropoutCfg drop, int smem_bytes) {
+                   int window, float scale_log2, const DropoutCfg drop_in, int smem_bytes) {
+  const DropoutCfg drop = resolve_dropout(drop_in);
   using C = HeadCfg<HD>;
   using S = FwdWsSmem<HD>;
   constexpr int NS = S::kStages;
@@ -792,7 +794,8 @@ template <int HD>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_w2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out,
                    const int32_t* __restrict__ seg_start, float* __restrict__ lse, int Bsz, int T, int H, int Hk,
-                   int window, float scale_log2, const DropoutCfg drop, int smem_bytes) {
+                   int window, float scale_log2, const DropoutCfg drop_in, int smem_bytes) {
+  const DropoutCfg drop = resolve_dropout(drop_in);
   using C = HeadCfg<HD>;
   using S = FwdW2Smem<HD>;
   constexpr int NS = S::kStages;
@@ -1105,7 +1108,8 @@ template <int HD, bool DROP>
 __global__ void __launch_bounds__(384, 1)
 attn_fwd_w3_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out,
                    const int32_t* __restrict__ seg_start, float* __restrict__ lse, int Bsz, int T, int H, int Hk,
-                   int window, float scale_log2, const DropoutCfg drop, int smem_bytes) {
+                   int window, float scale_log2, const DropoutCfg drop_in, int smem_bytes) {
+  const DropoutCfg drop = resolve_dropout(drop_in);
   using C = HeadCfg<HD>;
   using S = FwdW2Smem<HD>;
   constexpr int NS = S::kStages;
@@ -1576,7 +1580,8 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
                 const __grid_constant__ CUtensorMap tm_dq, const int32_t* __restrict__ seg_start,
                 const float* __restrict__ lse, const float* __restrict__ delta, __nv_bfloat16* __restrict__ dqkv,
                 float* __restrict__ dq_ws, int Bsz, int T, int H, int Hk, int window, float scale,
-                const DropoutCfg drop) {
+                const DropoutCfg drop_in) {
+  const DropoutCfg drop = resolve_dropout(drop_in);
   using C = HeadCfg<HD>;
   using S = BwdSmem<HD>;
   constexpr int TMEM_COLS = 512;
@@ -2000,7 +2005,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                    const int32_t* __restrict__ seg_start,
                    int* __restrict__ qhi_tab, const float* __restrict__ lse, const float* __restrict__ delta,
                    __nv_bfloat16* __restrict__ dqkv, float* __restrict__ dq_ws, float* __restrict__ dqkv_colsum,
-                   int Bsz, int T, int H, int Hk, int window, float scale, const DropoutCfg drop, int smem_bytes) {
+                   int Bsz, int T, int H, int Hk, int window, float scale, const DropoutCfg drop_in, int smem_bytes) {
+  const DropoutCfg drop = resolve_dropout(drop_in);
   using C = HeadCfg<HD>;
   using S = BwdWsSmem<HD>;
   constexpr int TMEM_COLS = 512;
@@ -2592,7 +2598,8 @@ attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfloat16* __restric
 // (b, h, i) row, SIMT dot products.  O(T^2 hd) and not tuned: never on the training path.
 __global__ void attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const int32_t* __restrict__ seg,
                                   float* __restrict__ att, int B, int T, int H, int Hk, int hd, int window,
-                                  float scale, const DropoutCfg drop) {
+                                  float scale, const DropoutCfg drop_in) {
+  const DropoutCfg drop = resolve_dropout(drop_in);
   const int lane = threadIdx.x & 31;
   const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (w >= (long long)B * H * T) return;

@@ -355,7 +355,15 @@ struct DropoutCfg {
   float inv_keep;   // 1 / (1 - p)
   uint2 key;        // seed
   uint32_t off_lo, off_hi;  // generator offset: separates successive calls under the same seed
+  // Device-resident generator state {seed, base offset} (cgpt_set_philox_state), or nullptr.  When set, the seed is
+  // read from it and the base offset is ADDED to the by-value offset inside the kernel: a CUDA graph that captured
+  // the launch draws fresh masks on every replay (the base is advanced on the device, cgpt_philox_advance).
+  const unsigned long long* dev_state;
 };
+}  // namespace cgpt
+// defined in core.cu; process-wide on purpose: backward kernels are launched from autograd's worker thread
+extern const unsigned long long* volatile cgpt_philox_dev_state;
+namespace cgpt {
 __host__ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset) {
   DropoutCfg d;
   const double t = (double)p * 4294967296.0;
@@ -364,6 +372,18 @@ __host__ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset)
   d.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   d.off_lo = (uint32_t)offset;
   d.off_hi = (uint32_t)(offset >> 32);
+  d.dev_state = d.thresh ? cgpt_philox_dev_state : nullptr;
+  return d;
+}
+// the configuration a kernel works with: seed / offset resolved against the device-resident state, if any
+__device__ __forceinline__ DropoutCfg resolve_dropout(DropoutCfg d) {
+  if (d.dev_state != nullptr) {
+    const unsigned long long seed = d.dev_state[0];
+    const unsigned long long off = d.dev_state[1] + ((static_cast<unsigned long long>(d.off_hi) << 32) | d.off_lo);
+    d.key = make_uint2(static_cast<uint32_t>(seed), static_cast<uint32_t>(seed >> 32));
+    d.off_lo = static_cast<uint32_t>(off);
+    d.off_hi = static_cast<uint32_t>(off >> 32);
+  }
   return d;
 }
 // attention-probability mask for 4 consecutive key positions j4*4..j4*4+3 of query row i, head bh

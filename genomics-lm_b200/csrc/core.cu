@@ -6,7 +6,11 @@
 
 #include "common.cuh"
 
+const unsigned long long* volatile cgpt_philox_dev_state = nullptr;
+
 namespace cgpt {
+
+__global__ void philox_advance_kernel(unsigned long long* state, unsigned long long inc) { state[1] += inc; }
 
 static thread_local char g_err[512] = "";
 static std::atomic<int64_t> g_launches{0};
@@ -123,6 +127,22 @@ int cgpt_set_device(int device) {
   cudaError_t e = cudaSetDevice(device);
   if (e != cudaSuccess) return cgpt::check_cuda(e, "cudaSetDevice");
   return 0;
+}
+
+int cgpt_set_philox_state(const uint64_t* dev_state) {
+  cgpt_philox_dev_state = reinterpret_cast<const unsigned long long*>(dev_state);
+  return 0;
+}
+
+int cgpt_philox_advance(uint64_t* dev_state, uint64_t increment, cgpt_stream_t stream) {
+  if (dev_state == nullptr) {
+    cgpt::set_error("cgpt_philox_advance: null state");
+    return CGPT_ERR_INVALID;
+  }
+  cgpt::philox_advance_kernel<<<1, 1, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<unsigned long long*>(dev_state), static_cast<unsigned long long>(increment));
+  cgpt::count_launch(1);
+  return cgpt::check_cuda(cudaGetLastError(), "philox_advance_kernel");
 }
 
 int cgpt_device_ok(int device) {

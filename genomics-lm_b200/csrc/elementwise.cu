@@ -778,7 +778,8 @@ __global__ void swiglu_bwd_kernel(const __nv_bfloat16* __restrict__ gu, long lon
 // out = (residual) + x * mask / (1-p); x fp32; out fp32 or bf16.  4 elements per Philox call.
 template <bool OUT_BF16>
 __global__ void dropout_kernel(const float4* __restrict__ x, const float4* __restrict__ residual, void* __restrict__ out,
-                               long long n4, DropoutCfg d) {
+                               long long n4, DropoutCfg d_in) {
+  const DropoutCfg d = resolve_dropout(d_in);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
     const uint4 r = philox4x32_10(d.key, make_uint4((uint32_t)i + d.off_lo, (uint32_t)(i >> 32) + d.off_hi, 0u, 0x656c7700u));
     float4 v = x[i];

@@ -224,6 +224,15 @@ int cgpt_ce_bwd(const float* logits, const float* row_lse, const int64_t* target
 int cgpt_dropout(const float* x, const float* residual /*nullable*/, void* out, int out_bf16, int64_t n, float p,
                  uint64_t seed, uint64_t offset, cgpt_stream_t stream);
 
+/* Device-resident dropout generator state (reference: torch's CUDA generator drives nn.Dropout / SDPA dropout_p,
+ * model_tiny_gpt.py:104,147,312; tests/test_attention_dropout.py:62-78).  dev_state = {seed, base offset} (2 x u64 in
+ * device memory) or NULL.  While set, every kernel that takes (seed, offset) reads the seed from dev_state[0] and adds
+ * dev_state[1] to its by-value offset ON THE DEVICE, so a captured CUDA graph of a training step draws fresh masks on
+ * every replay; cgpt_philox_advance adds `increment` to the base offset (one launch, part of the graph).
+ * Process-wide (backward kernels are launched from autograd's thread); NULL restores by-value seeds. */
+int cgpt_set_philox_state(const uint64_t* dev_state /*nullable*/);
+int cgpt_philox_advance(uint64_t* dev_state, uint64_t increment, cgpt_stream_t stream);
+
 /* ---------------------------------------------------------------- optimiser -------------- */
 /* torch.optim.AdamW step on a flat fp32 buffer (loop.py:681-731 param groups are separate calls);
  * g is multiplied by grad_scale first (grad-accum / DDP mean, loop.py:145-150); optional bf16 shadow. */

@@ -749,3 +749,49 @@ def test_use_checkpoint_flag_trains_identically():
     assert (outs[1][0] - rout["logits"]).abs().max().item() <= LOGIT_TOL
     assert outs[1][1].item() == pytest.approx(rtotal.item(), rel=LOSS_RTOL)
     _grad_check(outs[1][3], {k: v.cpu() for k, v in rgrads.items()})
+
+
+def test_trainstep_graph_capture_with_dropout_draws_fresh_masks():
+    """dropout 0.1 (every shipped reference config) under the CUDA-graph step: the Philox seed / base offset live in
+    device memory (ops.DeviceGenerator), the captured step ends by advancing the base, so (1) a replayed step equals the
+    eager step from the same generator state, (2) successive replays on the SAME batch draw different masks, (3)
+    torch.manual_seed still governs the masks, (4) training reduces the loss."""
+    import copy
+    from codonlm_b200 import TinyGPT
+    from codonlm_b200.trainer import TrainStep
+    kw = dict(vocab_size=68, block_size=64, n_layer=2, n_head=2, n_embd=64, dropout=0.1, label_smoothing=0.05,
+              termination_aux=True, multi_offset_targets=[2, 4], use_sdpa=True)
+    torch.manual_seed(3)
+    base = TinyGPT(**kw).to(DEV).train()
+    idx, tgt = O.synthetic_batch(64, 64, seed=9, realistic=True)
+    idx, tgt = idx.to(DEV), tgt.to(DEV)
+    ow = {2: 0.5, 4: 0.25}
+
+    def run(graph, seed):
+        torch.manual_seed(seed)
+        ts = TrainStep(copy.deepcopy(base), lr=1e-3, offset_weights=ow, termination_loss_weight=0.1)
+        assert ts._gen is not None
+        if graph:
+            ts.capture(64, 64)
+        return [ts.step(idx, tgt).item() for _ in range(4)], ts
+
+    eager, _ = run(False, 11)
+    graph, ts = run(True, 11)
+    other, _ = run(True, 12)
+    assert ts._graph is not None
+    # first step: same weights, same masks (the summation order of fp32 atomics is the only difference)
+    assert graph[0] == pytest.approx(eager[0], rel=1e-5)
+    assert graph[1] == pytest.approx(eager[1], rel=2e-3) and graph[3] == pytest.approx(eager[3], rel=5e-3)
+    assert other[0] != graph[0]                                   # another seed, other masks
+    model = ts.model.eval()
+    with torch.no_grad():
+        e1, _ = model(idx)
+        e2, _ = model(idx)
+    assert torch.equal(e1, e2)                                    # eval: no dropout, deterministic
+    # fresh masks per replay: freeze the weights (lr 0) and replay the same batch
+    torch.manual_seed(5)
+    ts0 = TrainStep(copy.deepcopy(base), lr=0.0, weight_decay=0.0, offset_weights=ow, termination_loss_weight=0.1)
+    ts0.capture(64, 64)
+    same_batch = [ts0.step(idx, tgt).item() for _ in range(3)]
+    assert len(set(same_batch)) == 3, same_batch
+    assert graph[3] < graph[0] + 0.05                             # and it trains

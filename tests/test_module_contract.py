@@ -68,6 +68,13 @@ def test_cpu_forward_fails_loudly():
     m = TinyGPT(68, 8, n_layer=1, n_head=1, n_embd=16, dropout=0.0)
     with pytest.raises(_lib.CgptError, match="no CPU implementation"):
         m(torch.zeros((1, 4), dtype=torch.long))
+    m.eval()  # host-resident inference callers are staged to a B200 — which this box does not have: still loud
+    with torch.no_grad(), pytest.raises(_lib.CgptError, match="no CPU implementation"):
+        m(torch.zeros((1, 4), dtype=torch.long))
+    with torch.no_grad(), pytest.raises(_lib.CgptError, match="no CPU implementation"):
+        m.forward_hidden(torch.zeros((1, 4), dtype=torch.long))
+    with torch.no_grad(), pytest.raises(_lib.CgptError, match="no CPU implementation"):
+        m.blocks[0].attn(torch.zeros((1, 4, 16)))
 
 
 def test_boolean_masks_convert_to_interval_starts():
