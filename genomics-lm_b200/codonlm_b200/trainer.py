@@ -198,8 +198,12 @@ class TrainStep:
     def __init__(self, model, lr=3e-4, lr_embedding=None, weight_decay=0.05, betas=(0.9, 0.999), eps=1e-8,
                  offset_weights: Optional[Dict[int, float]] = None, termination_loss_weight: float = 0.0,
                  process_group=None, bucket_mb: int = 25, overlap_allreduce: Optional[bool] = None,
-                 replay_loss_weight: float = 0.1, replay_class_weights=None):
+                 replay_loss_weight: float = 0.1, replay_class_weights=None, termination_stop_ids=(2,),
+                 termination_bucket_edges=(0, 3, 10, 30), termination_class_weights=None):
         self.model = model
+        self.termination_kwargs = dict(termination_stop_ids=tuple(termination_stop_ids),
+                                       termination_bucket_edges=tuple(termination_bucket_edges),
+                                       termination_class_weights=termination_class_weights)
         self.offset_weights = offset_weights
         self.termination_loss_weight = termination_loss_weight
         self.replay_loss_weight = replay_loss_weight
@@ -256,7 +260,7 @@ class TrainStep:
             total, parts, _ = training_loss(self.model, xb, yb, offset_weights=self.offset_weights,
                                             termination_loss_weight=self.termination_loss_weight, replay=replay,
                                             replay_loss_weight=self.replay_loss_weight,
-                                            replay_class_weights=self.replay_class_weights)
+                                            replay_class_weights=self.replay_class_weights, **self.termination_kwargs)
             total.backward()
             if self._gen is not None:
                 self._gen.advance()  # device-side: the next micro-batch (or graph replay) draws new masks
