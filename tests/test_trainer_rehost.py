@@ -104,12 +104,12 @@ def test_three_epochs_follow_the_reference_trainer(tmp_path):
     assert seen == [w["token_sum"] for w in want]                       # the same micro-batches, in the same order
     rel = [abs(a / w["loss"] - 1) for a, w in zip(got, want)]
     assert got[0] == pytest.approx(want[0]["loss"], rel=3e-3)            # first micro-batch: same weights, bf16 forward
-    assert max(rel) <= 3e-2, f"worst micro-batch loss deviation {max(rel):.3e}"
+    assert max(rel) <= 5e-3, f"worst micro-batch loss deviation {max(rel):.3e}"  # measured 2.7e-4
     assert out["step"] == g["counters"]["step"] == 18
     hist = out["history"]
     assert len(hist) == 3
-    assert hist[-1]["train_loss"] == pytest.approx(g["losses"]["train_loss"], rel=2e-2)
-    assert hist[-1]["val_loss"] == pytest.approx(g["losses"]["val_loss"], rel=2e-2)
+    assert hist[-1]["train_loss"] == pytest.approx(g["losses"]["train_loss"], rel=5e-3)
+    assert hist[-1]["val_loss"] == pytest.approx(g["losses"]["val_loss"], rel=5e-3)
     assert out["best_epoch"] == g["counters"]["best_epoch"]
     print(f"\n[trainer re-host] worst micro-batch loss deviation {max(rel):.2e}; final train "
           f"{hist[-1]['train_loss']:.4f} vs {g['losses']['train_loss']:.4f}, val {hist[-1]['val_loss']:.4f} vs "
@@ -171,6 +171,6 @@ def test_reference_checkpoint_resumes_here(tmp_path):
     want = [w["loss"] for w in g["resumed_microbatches"]]
     assert len(got) == len(want) == 11
     assert got[0] == pytest.approx(want[0], rel=3e-3)  # same weights, same optimiser state, same micro-batch
-    assert max(abs(a / b - 1) for a, b in zip(got, want)) <= 2e-2
+    assert max(abs(a / b - 1) for a, b in zip(got, want)) <= 5e-3
     assert out["step"] == g["resumed_counters"]["step"] == 18
     assert out["history"][-1]["val_loss"] == pytest.approx(g["resumed_losses"]["val_loss"], rel=1e-2)
