@@ -283,9 +283,34 @@ def dropout(x: torch.Tensor, residual: Optional[torch.Tensor], p: float, seed: i
     return out
 
 
+def _pad_heads(x, n_heads, hd, hdp):
+    """[M, n_heads*hd] -> [M, n_heads*hdp], zeros in the extra columns of every head."""
+    M = x.shape[0]
+    out = torch.zeros((M, n_heads, hdp), dtype=x.dtype, device=x.device)
+    out[:, :, :hd] = x.reshape(M, n_heads, hd)
+    return out.view(M, n_heads * hdp)
+
+
+def _unpad_heads(x, n_heads, hd, hdp):
+    return x.view(x.shape[0], n_heads, hdp)[:, :, :hd].reshape(x.shape[0], n_heads * hd).contiguous()
+
+
+def _padded_hd(hd):
+    """Head sizes the tensor-core kernels do not tile (not a multiple of 16: the reference's own unit tests use
+    n_embd 8 / 16 with 2 heads, tests/test_attention_dropout.py:11-12, test_embedding_extraction_contract.py:18-19) run
+    on zero-padded heads: zero q/k columns add nothing to QKᵀ, zero v columns give zero output columns, and the
+    softmax scale stays 1/sqrt(hd) of the TRUE width.  A compatibility path for toy models, not a hot path."""
+    return hd if hd % 16 == 0 else (hd + 15) // 16 * 16
+
+
 def attn_fwd(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None, dropout_p=0.0, seed=0, offset=0):
     _dev(qkv)
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
+    hdp = _padded_hd(hd)
+    if hdp != hd:
+        out, lse = attn_fwd(_pad_heads(qkv, H + 2 * Hk, hd, hdp), seg_start, B, T, H, Hk, hdp, window, scale, dropout_p,
+                            seed, offset)
+        return _unpad_heads(out, H, hd, hdp), lse
     out = torch.empty((B * T, H * hd), dtype=bf16, device=qkv.device)
     lse = torch.empty((B, H, T), dtype=f32, device=qkv.device)
     check(_L().cgpt_attn_fwd(qkv.data_ptr(), _p(seg_start), out.data_ptr(), lse.data_ptr(), B, T, H, Hk, hd,
@@ -297,6 +322,14 @@ def attn_bwd(qkv, seg_start, out, dout, lse, B, T, H, Hk, hd, window=0, scale=No
              colsum=None):
     """dqkv; `colsum` (fp32 [(H+2Hk)*hd], accumulated) also receives the column sums of dqkv (q|k|v bias grads)."""
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
+    hdp = _padded_hd(hd)
+    if hdp != hd:
+        dq = attn_bwd(_pad_heads(qkv, H + 2 * Hk, hd, hdp), seg_start, _pad_heads(out, H, hd, hdp),
+                      _pad_heads(dout, H, hd, hdp), lse, B, T, H, Hk, hdp, window, scale, dropout_p, seed, offset)
+        dq = _unpad_heads(dq, H + 2 * Hk, hd, hdp)
+        if colsum is not None:
+            colsum.add_(dq.float().sum(0))
+        return dq
     dqkv = torch.empty_like(qkv)
     nbytes = _L().cgpt_attn_bwd_workspace(B, T, H, Hk, hd)
     ws = torch.empty((nbytes // 4,), dtype=f32, device=qkv.device)
@@ -308,6 +341,10 @@ def attn_bwd(qkv, seg_start, out, dout, lse, B, T, H, Hk, hd, window=0, scale=No
 
 def attn_probs(qkv, seg_start, B, T, H, Hk, hd, window=0, scale=None, dropout_p=0.0, seed=0, offset=0):
     scale = 1.0 / math.sqrt(hd) if scale is None else scale
+    hdp = _padded_hd(hd)
+    if hdp != hd:
+        return attn_probs(_pad_heads(qkv, H + 2 * Hk, hd, hdp), seg_start, B, T, H, Hk, hdp, window, scale, dropout_p,
+                          seed, offset)
     att = torch.empty((B, H, T, T), dtype=f32, device=qkv.device)
     check(_L().cgpt_attn_probs(qkv.data_ptr(), _p(seg_start), att.data_ptr(), B, T, H, Hk, hd, int(window or 0),
                                float(scale), float(dropout_p), seed, offset, _stream()))

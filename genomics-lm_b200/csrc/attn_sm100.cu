@@ -279,14 +279,9 @@ attn_fwd_kernel(const __grid_constant__ CUtensorMap tm, const int32_t* __restric
         }
       }
       if (drop.thresh) {  // dropout on the (still unnormalised) probabilities; the row sum stays undropped (:104,129)
+        const uint32_t keep = attn_keep_mask32(drop, b * H + h, i, kv0 + c4 * 32);
 #pragma unroll
-        for (int j4 = 0; j4 < 8; ++j4) {
-          const uint4 rb = attn_dropout_bits(drop, b * H + h, i, (kv0 + c4 * 32) / 4 + j4);
-          p[4 * j4 + 0] = rb.x >= drop.thresh ? p[4 * j4 + 0] * drop.inv_keep : 0.f;
-          p[4 * j4 + 1] = rb.y >= drop.thresh ? p[4 * j4 + 1] * drop.inv_keep : 0.f;
-          p[4 * j4 + 2] = rb.z >= drop.thresh ? p[4 * j4 + 2] * drop.inv_keep : 0.f;
-          p[4 * j4 + 3] = rb.w >= drop.thresh ? p[4 * j4 + 3] * drop.inv_keep : 0.f;
-        }
+        for (int j = 0; j < 32; ++j) p[j] = ((keep >> j) & 1u) ? p[j] * drop.inv_keep16 : 0.f;
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -696,14 +691,9 @@ attn_fwd_ws_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             }
           }
           if (drop.thresh) {  // dropout on the (still unnormalised) probabilities; the row sum stays undropped (:104,129)
+            const uint32_t keep = attn_keep_mask32(drop, b * H + h, i, kv0 + c4 * 32);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const uint4 rb = attn_dropout_bits(drop, b * H + h, i, (kv0 + c4 * 32) / 4 + j4);
-              p[4 * j4 + 0] = rb.x >= drop.thresh ? p[4 * j4 + 0] * drop.inv_keep : 0.f;
-              p[4 * j4 + 1] = rb.y >= drop.thresh ? p[4 * j4 + 1] * drop.inv_keep : 0.f;
-              p[4 * j4 + 2] = rb.z >= drop.thresh ? p[4 * j4 + 2] * drop.inv_keep : 0.f;
-              p[4 * j4 + 3] = rb.w >= drop.thresh ? p[4 * j4 + 3] * drop.inv_keep : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) p[j] = ((keep >> j) & 1u) ? p[j] * drop.inv_keep16 : 0.f;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -1037,14 +1027,9 @@ attn_fwd_w2_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
             ls1 += p[j + 1];
           }
           if (drop.thresh) {  // dropout on the (still unnormalised) probabilities; the row sum stays undropped (:104,129)
+            const uint32_t keep = attn_keep_mask32(drop, b * H + h, i, kv0 + c4 * 32);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const uint4 rb = attn_dropout_bits(drop, b * H + h, i, (kv0 + c4 * 32) / 4 + j4);
-              p[4 * j4 + 0] = rb.x >= drop.thresh ? p[4 * j4 + 0] * drop.inv_keep : 0.f;
-              p[4 * j4 + 1] = rb.y >= drop.thresh ? p[4 * j4 + 1] * drop.inv_keep : 0.f;
-              p[4 * j4 + 2] = rb.z >= drop.thresh ? p[4 * j4 + 2] * drop.inv_keep : 0.f;
-              p[4 * j4 + 3] = rb.w >= drop.thresh ? p[4 * j4 + 3] * drop.inv_keep : 0.f;
-            }
+            for (int j = 0; j < 32; ++j) p[j] = ((keep >> j) & 1u) ? p[j] * drop.inv_keep16 : 0.f;
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -1364,14 +1349,9 @@ attn_fwd_w3_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
               ls1 += p[j + 1];
             }
             if constexpr (DROP) {  // dropout on the (still unnormalised) probabilities; the row sum stays undropped (:104,129)
+              const uint32_t keep = attn_keep_mask32(drop, b * H + h, i, kv0 + c4 * 32);
 #pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                const uint4 rbits = attn_dropout_bits(drop, b * H + h, i, (kv0 + c4 * 32) / 4 + j4);
-                p[4 * j4 + 0] = rbits.x >= drop.thresh ? p[4 * j4 + 0] * drop.inv_keep : 0.f;
-                p[4 * j4 + 1] = rbits.y >= drop.thresh ? p[4 * j4 + 1] * drop.inv_keep : 0.f;
-                p[4 * j4 + 2] = rbits.z >= drop.thresh ? p[4 * j4 + 2] * drop.inv_keep : 0.f;
-                p[4 * j4 + 3] = rbits.w >= drop.thresh ? p[4 * j4 + 3] * drop.inv_keep : 0.f;
-              }
+              for (int j = 0; j < 32; ++j) p[j] = ((keep >> j) & 1u) ? p[j] * drop.inv_keep16 : 0.f;
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -1788,18 +1768,13 @@ attn_bwd_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_constan
           }
         }
         if (drop.thresh) {  // P feeds dV as dropout(P); dS = P * (dP * mask/(1-p) - delta)
+          const uint32_t keep = attn_keep_mask32(drop, b * H + hq, i, kv0 + c4 * 32);
 #pragma unroll
-          for (int j4 = 0; j4 < 8; ++j4) {
-            const uint4 rb = attn_dropout_bits(drop, b * H + hq, i, (kv0 + c4 * 32) / 4 + j4);
-            const uint32_t bits[4] = {rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const int j = 4 * j4 + e;
-              const float mk = bits[e] >= drop.thresh ? drop.inv_keep : 0.f;
+          for (int j = 0; j < 32; ++j) {
+            const float mk = ((keep >> j) & 1u) ? drop.inv_keep16 : 0.f;
               const float pj = p[j];
               ds[j] = pj * (__uint_as_float(rp[j]) * mk - dl);
               p[j] = pj * mk;
-            }
           }
         }
 #pragma unroll
@@ -2425,18 +2400,13 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             }
           }
           if (drop.thresh) {
+            const uint32_t keep = attn_keep_mask32(drop, b * H + hq, i, kv0 + c4 * 32);
 #pragma unroll
-            for (int j4 = 0; j4 < 8; ++j4) {
-              const uint4 rb = attn_dropout_bits(drop, b * H + hq, i, (kv0 + c4 * 32) / 4 + j4);
-              const uint32_t bits[4] = {rb.x, rb.y, rb.z, rb.w};
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const int j = 4 * j4 + e;
-                const float mk = bits[e] >= drop.thresh ? drop.inv_keep : 0.f;
+            for (int j = 0; j < 32; ++j) {
+              const float mk = ((keep >> j) & 1u) ? drop.inv_keep16 : 0.f;
                 const float pj = p[j];
                 ds[j] = pj * (__uint_as_float(rp[j]) * mk - dl);
                 p[j] = pj * mk;
-              }
             }
           }
           // the single P buffer: the dV MMAs of the previous tile must have retired (they were issued right behind
@@ -2640,9 +2610,7 @@ __global__ void attn_probs_kernel(const __nv_bfloat16* __restrict__ qkv, const i
   for (int j = lane; j < T; j += 32) {
     float v = row[j] * inv;
     if (drop.thresh) {
-      const uint4 rb = attn_dropout_bits(drop, b * H + h, i, j >> 2);
-      const uint32_t bit = (j & 3) == 0 ? rb.x : ((j & 3) == 1 ? rb.y : ((j & 3) == 2 ? rb.z : rb.w));
-      v = bit >= drop.thresh ? v * drop.inv_keep : 0.f;
+      v = attn_keep(drop, b * H + h, i, j) ? v * drop.inv_keep16 : 0.f;
     }
     row[j] = v;
   }

@@ -339,9 +339,10 @@ __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- Philox4x32-10 (counter-based RNG for dropout: the mask is recomputed in backward, never stored)
-__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
+template <int ROUNDS>
+__device__ __forceinline__ uint4 philox4x32(uint2 key, uint4 ctr) {
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     const uint32_t hi0 = __umulhi(0xD2511F53u, ctr.x), lo0 = 0xD2511F53u * ctr.x;
     const uint32_t hi1 = __umulhi(0xCD9E8D57u, ctr.z), lo1 = 0xCD9E8D57u * ctr.z;
     ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
@@ -350,11 +351,16 @@ __device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
   }
   return ctr;
 }
+__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) { return philox4x32<10>(key, ctr); }
 struct DropoutCfg {
   uint32_t thresh;  // keep iff random u32 >= thresh  (thresh = p * 2^32); 0 = dropout off
   float inv_keep;   // 1 / (1 - p)
   uint2 key;        // seed
   uint32_t off_lo, off_hi;  // generator offset: separates successive calls under the same seed
+  // attention-probability masks use 16 random bits per element (8 elements per Philox call): keep iff u16 >= thresh16,
+  // scaled by inv_keep16 = 1 / (1 - thresh16 / 65536) so that the mask stays exactly unbiased
+  uint32_t thresh16;
+  float inv_keep16;
   // Device-resident generator state {seed, base offset} (cgpt_set_philox_state), or nullptr.  When set, the seed is
   // read from it and the base offset is ADDED to the by-value offset inside the kernel: a CUDA graph that captured
   // the launch draws fresh masks on every replay (the base is advanced on the device, cgpt_philox_advance).
@@ -372,6 +378,8 @@ __host__ inline DropoutCfg make_dropout(float p, uint64_t seed, uint64_t offset)
   d.key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
   d.off_lo = (uint32_t)offset;
   d.off_hi = (uint32_t)(offset >> 32);
+  d.thresh16 = d.thresh >> 16;
+  d.inv_keep16 = 65536.f / (65536.f - (float)d.thresh16);
   d.dev_state = d.thresh ? cgpt_philox_dev_state : nullptr;
   return d;
 }
@@ -386,9 +394,26 @@ __device__ __forceinline__ DropoutCfg resolve_dropout(DropoutCfg d) {
   }
   return d;
 }
-// attention-probability mask for 4 consecutive key positions j4*4..j4*4+3 of query row i, head bh
-__device__ __forceinline__ uint4 attn_dropout_bits(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t j4) {
-  return philox4x32_10(make_uint2(d.key.x ^ d.off_lo, d.key.y ^ d.off_hi), make_uint4(j4, i, bh, 0x61747400u));
+// Attention-probability dropout: keep-mask of the 32 consecutive key positions jb .. jb+31 (jb % 32 == 0) of query
+// row i, head bh; bit e set = keep position jb+e.  Four Philox4x32-7 calls (7 rounds pass BigCrush; cuRAND's 10 are a
+// safety margin that costs 40 % more integer multiplies here), 16 bits per position.  Forward, backward and the dense
+// probability kernel all go through these two functions, so they see the same mask.
+__device__ __forceinline__ uint4 attn_dropout_octet(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t j8) {
+  return philox4x32<7>(make_uint2(d.key.x ^ d.off_lo, d.key.y ^ d.off_hi), make_uint4(j8, i, bh, 0x61747400u));
+}
+__device__ __forceinline__ uint32_t keep_bits8(const uint4 r, uint32_t t) {
+  return (uint32_t)((r.x & 0xffffu) >= t) | ((uint32_t)((r.x >> 16) >= t) << 1) | ((uint32_t)((r.y & 0xffffu) >= t) << 2) |
+         ((uint32_t)((r.y >> 16) >= t) << 3) | ((uint32_t)((r.z & 0xffffu) >= t) << 4) | ((uint32_t)((r.z >> 16) >= t) << 5) |
+         ((uint32_t)((r.w & 0xffffu) >= t) << 6) | ((uint32_t)((r.w >> 16) >= t) << 7);
+}
+__device__ __forceinline__ uint32_t attn_keep_mask32(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t jb) {
+  uint32_t m = 0;
+#pragma unroll
+  for (uint32_t q = 0; q < 4; ++q) m |= keep_bits8(attn_dropout_octet(d, bh, i, (jb >> 3) + q), d.thresh16) << (8 * q);
+  return m;
+}
+__device__ __forceinline__ bool attn_keep(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t j) {
+  return (keep_bits8(attn_dropout_octet(d, bh, i, j >> 3), d.thresh16) >> (j & 7u)) & 1u;
 }
 
 // ---- small math

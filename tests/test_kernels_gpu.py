@@ -502,7 +502,10 @@ def test_attention_dropout_matches_masked_reference(ops, case):
     mask = torch.where(vis, pr1 / pr0.clamp_min(1e-30), torch.zeros_like(pr0))       # 0 or 1/(1-p)
     kept = (mask[vis] > 0).float().mean().item()
     assert abs(kept - (1 - p)) < 2e-2
-    assert torch.allclose(mask[vis & (mask > 0)], torch.tensor(1 / (1 - p), device=DEV), rtol=1e-5)
+    # attention masks draw 16 bits per element: the effective drop probability is floor(p 2^32) >> 16 over 2^16, and
+    # the kept probabilities are scaled by exactly 1 / (1 - that), so the mask stays unbiased
+    t16 = int(p * 2 ** 32) >> 16
+    assert torch.allclose(mask[vis & (mask > 0)], torch.tensor(65536.0 / (65536 - t16), device=DEV), rtol=1e-5)
     out, lse = ops.attn_fwd(qkv, ss, B, T, H, Hk, hd, dropout_p=p, seed=seed, offset=off, **kw)
     out2, _ = ops.attn_fwd(qkv, ss, B, T, H, Hk, hd, dropout_p=p, seed=seed, offset=off, **kw)
     assert torch.equal(out, out2)

@@ -125,6 +125,14 @@ ORACLE_CASES = {
                                  {2: 0.2, 4: 0.2, 8: 0.2, 16: 0.2, 32: 0.2}, 0.1),
     "C4_gqa4_d384_hd48_2L": (dict(vocab_size=68, block_size=512, n_layer=2, n_head=8, n_kv_head=4, n_embd=384,
                                   dropout=0.0, label_smoothing=0.05, use_sdpa=True), 2, 512, None, 0.0),
+    # the widths of the reference's own unit tests (tests/test_attention_dropout.py:11-12 n_embd 8 / 2 heads,
+    # test_embedding_extraction_contract.py:18-19 n_embd 16 / 2 heads): head sizes 4 and 8 run on zero-padded heads
+    "toy_hd4": (dict(vocab_size=69, block_size=16, n_layer=2, n_head=2, n_embd=8, dropout=0.0, use_sdpa=True), 4, 16,
+                None, 0.0),
+    "toy_hd8_manual_gqa": (dict(vocab_size=69, block_size=32, n_layer=1, n_head=2, n_kv_head=1, n_embd=16, dropout=0.0,
+                                use_sdpa=False), 3, 32, None, 0.0),
+    "toy_hd8_rope_swiglu": (dict(vocab_size=69, block_size=32, n_layer=1, n_head=2, n_embd=16, dropout=0.0,
+                                 use_sdpa=True, use_rope=True, use_swiglu=True), 3, 32, None, 0.0),
     "ragged_T_333": (dict(vocab_size=69, block_size=512, n_layer=1, n_head=2, n_embd=128, dropout=0.0,
                           label_smoothing=0.0, use_sdpa=True, tie_embeddings=False), 3, 333, None, 0.0),
 }
