@@ -66,6 +66,7 @@ SIGNATURES = {
     "cgpt_set_philox_state": (_i, [_vp]),
     "cgpt_philox_advance": (_i, [_vp, C.c_uint64, _vp]),
     "cgpt_adamw": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
+    "cgpt_adamw_bf16grad": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),
 }
 
 

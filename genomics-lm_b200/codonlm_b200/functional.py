@@ -30,9 +30,17 @@ def _attach(g: torch.Tensor, bf16_copy, colsum):
 
 
 def _detach_side(g: torch.Tensor):
+    """By-products attached to `g` — or to the tensor `g` is a full, contiguous view of: between two blocks the residual
+    stream passes reshape nodes ((B,T,d) <-> (B*T,d)), whose backward hands on a VIEW of the producer's tensor."""
     hit = getattr(g, _SIDE_ATTR, None)
     if hit is not None:
         delattr(g, _SIDE_ATTR)
+        return hit
+    base = g._base
+    if base is not None and base.data_ptr() == g.data_ptr() and base.numel() == g.numel() and g.is_contiguous():
+        hit = getattr(base, _SIDE_ATTR, None)
+        if hit is not None:
+            delattr(base, _SIDE_ATTR)
     return hit
 
 

@@ -435,7 +435,9 @@ def ce_bwd(logits2d, row_lse, targets, sums, gscale, B, T, *, coef=1.0, shift=0,
 
 # ------------------------------------------------------------------ optimiser
 def adamw(p, g, m, v, shadow, lr, beta1, beta2, eps, wd, step, grad_scale=1.0, dev_hyper=None):
-    check(_L().cgpt_adamw(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow), p.numel(), float(lr),
+    """Fused AdamW on flat buffers; `g` fp32, or bf16 (the all-reduced gradient buckets, consumed in place)."""
+    fn = _L().cgpt_adamw_bf16grad if g.dtype == bf16 else _L().cgpt_adamw
+    check(fn(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), _p(shadow), p.numel(), float(lr),
                           float(beta1), float(beta2), float(eps), float(wd), int(step), float(grad_scale),
                           _p(dev_hyper), _stream()))
 

@@ -107,8 +107,12 @@ class GradBuckets:
     """Bucketed bf16 all-reduce of a flat gradient buffer, launched on a side stream as soon as every
     parameter of a bucket has received its gradient."""
 
-    def __init__(self, group: FlatGroup, process_group, bucket_bytes: int = 25 << 20, overlap: bool = True):
+    def __init__(self, group: FlatGroup, process_group, bucket_bytes: int = 25 << 20, overlap: bool = True,
+                 copy_back: bool = True):
         self.g = group
+        # copy_back=False: finish() leaves the reduced gradient in the bf16 staging buffer (`reduced`) and the fused
+        # AdamW reads it from there (cgpt_adamw_bf16grad): one pass over the gradients less per step
+        self.copy_back = bool(copy_back)
         # overlap=False: every bucket is reduced after backward instead of from the gradient-ready hooks.  The NCCL
         # kernels then never share the SMs with the persistent GEMM / attention kernels (whose grids are sized to all
         # 148 SMs: a CTA that cannot be placed next to an NCCL CTA runs as a second wave)
@@ -131,7 +135,8 @@ class GradBuckets:
                 self.need.append(count)
                 start, count = end, 0
         self.left = list(self.need)
-        self.staging = [torch.empty(e - s, dtype=torch.bfloat16, device=group.grad.device) for s, e in self.bounds]
+        self.reduced = torch.zeros(group.numel, dtype=torch.bfloat16, device=group.grad.device)  # all buckets, flat
+        self.staging = [self.reduced[s:e] for s, e in self.bounds]
         self.pending = []
         # A parameter can receive several contributions per backward (tied head/tok_emb, offset heads sharing
         # the head).  The first step counts them (no overlap: everything is reduced in finish()); later steps
@@ -184,8 +189,9 @@ class GradBuckets:
         self.contrib_seen = [0] * len(self.contrib_seen)
         for b, work in self.pending:
             work.wait()  # the compute stream now waits for that bucket's all-reduce
-            s, e = self.bounds[b]
-            self.g.grad[s:e].copy_(self.staging[b])
+            if self.copy_back:
+                s, e = self.bounds[b]
+                self.g.grad[s:e].copy_(self.staging[b])
         self.pending.clear()
         self.left = list(self.need)
 
@@ -228,7 +234,9 @@ class TrainStep:
             self.world = dist.get_world_size(pg)
             if overlap_allreduce is None:
                 overlap_allreduce = os.environ.get("CGPT_DDP_OVERLAP", "1") == "1"
-            self.buckets = [GradBuckets(g, pg, bucket_mb << 20, overlap=overlap_allreduce) for g in self.groups]
+            on_gpu = self.groups[0].grad.is_cuda
+            self.buckets = [GradBuckets(g, pg, bucket_mb << 20, overlap=overlap_allreduce, copy_back=not on_gpu)
+                            for g in self.groups]
         dev = self.groups[0].flat.device
         self._xb = self._yb = None
         self._dev = dev
@@ -288,10 +296,17 @@ class TrainStep:
             bk.finish()
         self._push_hyper(lr_scale)
         for gi, g in enumerate(self.groups):
-            ops.adamw(g.flat, g.grad, g.m, g.v, g.shadow if g.shadow.is_cuda else None, g.lr * lr_scale, self.betas[0],
-                      self.betas[1], self.eps, g.weight_decay, self.step_count, gscale, dev_hyper=self._hyper[gi])
+            ops.adamw(g.flat, self._grad_source(gi), g.m, g.v, g.shadow if g.shadow.is_cuda else None, g.lr * lr_scale,
+                      self.betas[0], self.betas[1], self.eps, g.weight_decay, self.step_count, gscale,
+                      dev_hyper=self._hyper[gi])
         # the kernel wrote the masters behind autograd's back: invalidate the bf16 shadow caches
         bump_shadow_generation()
+
+    def _grad_source(self, gi: int):
+        """What AdamW reads: the flat fp32 gradient, or — data-parallel on the GPU — the all-reduced bf16 buckets."""
+        if self.buckets and not self.buckets[gi].copy_back:
+            return self.buckets[gi].reduced
+        return self.groups[gi].grad
 
     def _push_hyper(self, lr_scale: float):
         t = self.step_count
@@ -457,7 +472,7 @@ class TrainStep:
                 bk.finish()
             gscale = 1.0 / self.world
             for gi, g in enumerate(self.groups):
-                ops.adamw(g.flat, g.grad, g.m, g.v, g.shadow, g.lr, self.betas[0], self.betas[1], self.eps,
+                ops.adamw(g.flat, self._grad_source(gi), g.m, g.v, g.shadow, g.lr, self.betas[0], self.betas[1], self.eps,
                           g.weight_decay, 1, gscale, dev_hyper=self._hyper[gi])
             self._gloss = loss
         # undo the warm-up / capture-time updates: capture must not change the training state
@@ -474,7 +489,9 @@ class TrainStep:
         self._graph_shape = (B, T)
 
     def step(self, xb, yb, lr_scale: float = 1.0):
-        """Device-resident inputs; returns the total loss as a 0-dim device tensor (no host sync)."""
+        """Device-resident inputs; returns the total loss as a 0-dim device tensor (no host sync).  Under a captured
+        graph the returned tensor is the graph's OWN output buffer: every replay overwrites it, so a caller that
+        collects losses over several steps must `.clone()` (or `.item()`) each one before the next step."""
         if self._graph is not None and tuple(xb.shape) == self._graph_shape:
             self._gx.copy_(xb, non_blocking=True)
             self._gy.copy_(yb, non_blocking=True)

@@ -103,8 +103,12 @@ __global__ void embed_fwd_kernel(const int64_t* __restrict__ idx, const float4* 
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     const size_t m = i / d4;
     const int c = (int)(i - m * d4);
-    int64_t v = idx[m];
-    v = v < 0 ? 0 : (v >= vocab ? vocab - 1 : v);
+    const int64_t v = idx[m];
+    if (v < 0 || v >= vocab) {  // F.embedding raises for such an id; here the row is NaN: loud downstream, no OOB read
+      const float q = __int_as_float(0x7fc00000);
+      x[i] = make_float4(q, q, q, q);
+      continue;
+    }
     float4 a = __ldg(tok + (size_t)v * d4 + c);
     if (pos) {
       const float4 p = __ldg(pos + (size_t)(m % T) * d4 + c);
@@ -802,7 +806,8 @@ __global__ void dropout_kernel(const float4* __restrict__ x, const float4* __res
 }
 
 // ============================================================ AdamW (torch.optim.AdamW semantics)
-__global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+template <typename GradT>
+__global__ void adamw_kernel(float* __restrict__ p, const GradT* __restrict__ g, float* __restrict__ m,
                              float* __restrict__ v, __nv_bfloat16* __restrict__ shadow, long long n, float lr,
                              float b1, float b2, float eps, float wd, float bc1, float bc2_sqrt, float gscale,
                              const float* __restrict__ hyper) {
@@ -812,7 +817,8 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     bc2_sqrt = hyper[2];
   }
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gr = g[i] * gscale;
+    float gr;
+    if constexpr (sizeof(GradT) == 2) gr = __bfloat162float(g[i]) * gscale; else gr = g[i] * gscale;
     float pv = p[i] * (1.f - lr * wd);
     const float mv = b1 * m[i] + (1.f - b1) * gr;
     const float vv = b2 * v[i] + (1.f - b2) * gr * gr;
@@ -1180,8 +1186,22 @@ int cgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16, 
   CGPT_REQUIRE(p && g && m && v && n > 0 && step >= 1, "adamw: bad arguments");
   const float bc1 = 1.f - powf(beta1, (float)step);
   const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
-  adamw_kernel<<<grid_for(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n,
-                                                         lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale, dev_hyper);
+  adamw_kernel<float><<<grid_for(n, 256), 256, 0, ST(stream)>>>(p, g, m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n,
+                                                                lr, beta1, beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale, dev_hyper);
+  count_launch();
+  CGPT_LAUNCH_CHECK();
+  return 0;
+}
+
+int cgpt_adamw_bf16grad(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16, int64_t n, float lr,
+                        float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                        const float* dev_hyper, cgpt_stream_t stream) {
+  CGPT_REQUIRE(p && g_bf16 && m && v && n > 0 && step >= 1, "adamw_bf16grad: bad arguments");
+  const float bc1 = 1.f - powf(beta1, (float)step);
+  const float bc2_sqrt = sqrtf(1.f - powf(beta2, (float)step));
+  adamw_kernel<__nv_bfloat16><<<grid_for(n, 256), 256, 0, ST(stream)>>>(
+      p, reinterpret_cast<const __nv_bfloat16*>(g_bf16), m, v, reinterpret_cast<__nv_bfloat16*>(shadow_bf16), n, lr, beta1,
+      beta2, eps, weight_decay, bc1, bc2_sqrt, grad_scale, dev_hyper);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

@@ -184,20 +184,28 @@ skinny_dw_kernel(const float* __restrict__ dout, const float* __restrict__ x, fl
 
 // ------------------------------------------------------------------ cross entropy (one warp per row, V <= 128)
 struct RowInfo {
-  bool keep;
+  bool keep, bad;
   int64_t target;
 };
 
+// `bad`: a kept row whose label lies outside [0, V).  F.cross_entropy raises for such a label; a kernel cannot, and
+// must neither read logits / class weights out of bounds nor return a plausible-looking number: the row's loss term is
+// NaN (the total loss turns NaN, which the trainer's non-finite policy reports and aborts on) and its gradient row 0.
 __device__ __forceinline__ RowInfo ce_row_info(const int64_t* targets, const int32_t* next_boundary, int row, int T,
-                                               int shift, int64_t ignore_index) {
+                                               int shift, int64_t ignore_index, int V) {
   RowInfo ri;
   const int b = row / T, t = row - b * T;
   ri.keep = false;
+  ri.bad = false;
   ri.target = 0;
   if (t + shift < T) {
     const int64_t tg = targets[(size_t)b * T + t + shift];
     ri.target = tg;
     ri.keep = (tg != ignore_index) && (next_boundary == nullptr || next_boundary[row] >= t + shift);
+    if (ri.keep && (tg < 0 || tg >= V)) {
+      ri.bad = true;
+      ri.keep = false;
+    }
   }
   return ri;
 }
@@ -232,7 +240,7 @@ ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targ
   }
   se = warp_sum(se);
   const float lse = mx + logf(se);
-  const RowInfo ri = ce_row_info(targets, next_boundary, row, T, shift, ignore_index);
+  const RowInfo ri = ce_row_info(targets, next_boundary, row, T, shift, ignore_index, V);
   float loss = 0.f, wt = 0.f;
   if (ri.keep) {
     swz = warp_sum(swz);
@@ -242,6 +250,9 @@ ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targ
     loss = (1.f - smoothing) * wy * (lse - z[tg]);
     if (smoothing > 0.f) loss += (smoothing / V) * (sw * lse - swz);
     wt = wy;
+  } else if (ri.bad) {
+    loss = __int_as_float(0x7fc00000);  // label out of range: poison the loss, do not dereference
+    wt = 1.f;
   }
   if (lane == 0) {
     row_lse[row] = lse;
@@ -283,7 +294,7 @@ ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ row_ls
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
-  const RowInfo ri = ce_row_info(targets, next_boundary, row, T, shift, ignore_index);
+  const RowInfo ri = ce_row_info(targets, next_boundary, row, T, shift, ignore_index, V);
   float* o = dlogits + (size_t)row * V;
   if (!ri.keep) {
     for (int c = lane; c < V; c += 32) o[c] = 0.f;

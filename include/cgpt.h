@@ -241,6 +241,11 @@ int cgpt_philox_advance(uint64_t* dev_state, uint64_t increment, cgpt_stream_t s
 int cgpt_adamw(float* p, const float* g, float* m, float* v, void* shadow_bf16 /*nullable*/, int64_t n,
                float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
                const float* dev_hyper, cgpt_stream_t stream);
+/* The same step with the gradient read as bf16: the data-parallel trainer all-reduces bf16 gradient buckets (SURVEY
+ * §8e) and the optimiser consumes the reduced buckets in place — no fp32 copy-back pass over the gradients. */
+int cgpt_adamw_bf16grad(float* p, const void* g_bf16, float* m, float* v, void* shadow_bf16 /*nullable*/, int64_t n,
+                        float lr, float beta1, float beta2, float eps, float weight_decay, int step, float grad_scale,
+                        const float* dev_hyper, cgpt_stream_t stream);
 
 #ifdef __cplusplus
 }

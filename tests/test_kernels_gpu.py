@@ -522,3 +522,21 @@ def test_attention_dropout_matches_masked_reference(ops, case):
         a, r = dqkv.float()[:, sl], q32.grad[:, sl]
         rel = ((a - r).norm() / r.norm()).item()
         assert rel <= 3e-2, f"{name} rel-norm err {rel}"
+
+
+def test_cross_entropy_out_of_range_label_poisons_the_loss(ops):
+    """A label outside [0, V) that is not ignore_index: F.cross_entropy raises; the kernels must not read out of bounds
+    and must not return a finite loss — the loss is NaN (the trainer's non-finite policy takes it from there), the
+    gradient of that row is zero, every other row is unaffected."""
+    from codonlm_b200 import functional as Fn
+    g = torch.Generator().manual_seed(2)
+    B, T, V = 2, 16, 68
+    logits = torch.randn(B * T, V, generator=g).to(DEV).requires_grad_(True)
+    tgt = torch.randint(1, V, (B, T), generator=g).to(DEV)
+    good, _ = Fn.CrossEntropyFn.apply(logits, tgt, None, None, B, T, 0, 0.05, 0, False)
+    assert torch.isfinite(good)
+    bad_t = tgt.clone()
+    bad_t[1, 3] = V + 5
+    bad_t[0, 7] = -7
+    loss, _ = Fn.CrossEntropyFn.apply(logits, bad_t, None, None, B, T, 0, 0.05, 0, False)
+    assert torch.isnan(loss)
