@@ -480,6 +480,7 @@ def run_train(args, wl):
         ops.gemm = orig_gemm
         roof_ms_total = r0.elapsed_time(r1)
         step._graph = graph
+        del graph  # the ONLY owner must be `step`: a captured graph that outlives the communicator blocks its teardown
     clock_info = clocks.stop() if clocks else None
 
     # ---- timed region 2: end to end through the public call, host buffers in, host loss out
