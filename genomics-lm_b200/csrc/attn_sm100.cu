@@ -1997,7 +1997,8 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   uint64_t* g_bar = bars + 7;       // [2] dV, dK, dQ MMAs of a tile have retired
   uint64_t* dkv_bar = bars + 9;     // the math warps have drained dK/dV of an item from TMEM
   uint64_t* pfree_bar = bars + 10;  // the dV MMAs of a tile have retired: the P buffer may be rewritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+  uint64_t* sfree_bar = bars + 11;  // the math warps hold S, dP of a tile in registers: the TMEM tiles may be rewritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
   uint64_t* sched_bar = bars + 16;                                 // [8] a pair descriptor has been published
   int4* sched = reinterpret_cast<int4*>(bars + 24);                // [8] {pair slot kk, kv head, batch, valid}
 
@@ -2022,6 +2023,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
     mbar_init(&kv_bar[0], 1);
     mbar_init(&kv_bar[1], 1);
     mbar_init(pfree_bar, 1);
+    mbar_init(sfree_bar, 8);
     for (int i = 0; i < 8; ++i) mbar_init(&sched_bar[i], 1);
     mbar_init(&q_bar[0], 1);
     mbar_init(&q_bar[1], 1);
@@ -2201,12 +2203,17 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
           else
             load_q(g + 1, nkvh * rep, nkvb, nb_);
         }
-        mbar_wait(&p_bar[buf], (g >> 1) & 1);  // P, dS of tile g are in smem; S/dP TMEM is free
+        // Within an item the next tile's scores are issued as soon as the math warps have pulled S / dP of this tile
+        // into registers (sfree_bar: a few hundred cycles into their work), so S(g+1), dP(g+1) are computed WHILE P, dS
+        // of tile g are being made.  After an item's LAST tile the math warps first need the gradients (dQ write-out,
+        // dK/dV epilogue), so there the scores of the next item follow the gradient MMAs.
+        if (has_next && !last) {
+          mbar_wait(sfree_bar, g & 1);
+          tc_fence_after();
+          issue_scores(g + 1, n_it);
+        }
+        mbar_wait(&p_bar[buf], (g >> 1) & 1);  // P, dS of tile g are in smem
         tc_fence_after();
-        // Within an item the next tile's scores go first, so that the math warps can start on it while the
-        // gradient MMAs run.  After an item's LAST tile the math warps first need those gradients (dQ write-out,
-        // dK/dV epilogue), so there the order is reversed.
-        if (has_next && !last) issue_scores(g + 1, n_it);
         if (it == 0 && n_it > 0) {  // dK/dV accumulators still hold the previous item until the math warps drain them
           mbar_wait(dkv_bar, (n_it - 1) & 1);
           tc_fence_after();
@@ -2361,6 +2368,11 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         tc_fence_after();
         uint8_t* sP = smem + S::kP;
         uint8_t* sdS = smem + S::kdS + buf * kPTileBytes;
+        auto release_sdp = [&]() {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sfree_bar);
+        };
 #pragma unroll 1
         for (int cc = 0; cc < 2; ++cc) {
           const int c4 = half * 2 + cc;
@@ -2377,12 +2389,14 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
               ptile_store(sP, row, c4 * 4 + q, make_uint4(0u, 0u, 0u, 0u));
               ptile_store(sdS, row, c4 * 4 + q, make_uint4(0u, 0u, 0u, 0u));
             }
+            if (cc == 1) release_sdp();
             continue;
           }
           uint32_t rs[32], rp[32];
           tmem_ld32(tS + lane_base + c4 * 32, rs);
           tmem_ld32(tdP + lane_base + c4 * 32, rp);
           tmem_ld_wait();
+          if (cc == 1) release_sdp();  // S, dP of the tile are consumed: the next tile's scores may be computed
           float p[32], ds[32];
           if (!w_full) {
             const unsigned span = static_cast<unsigned>(i - jlo);
