@@ -513,7 +513,7 @@ def run_train(args, wl):
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
         peak = peaks["bf16_tflops_sustained"]
         traffic = traffic_src = None
-        tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")  # from the committed ncu launch list
+        tpath = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")  # from the committed ncu launch list
         if os.path.exists(tpath) and args.workload == "c3":
             with open(tpath) as f:
                 tj = json.load(f)
