@@ -65,16 +65,6 @@ __device__ __forceinline__ void ptile_store(uint8_t* base, int row, int chunk, u
                : "memory");
 }
 
-__device__ __forceinline__ uint4 ptile_load(uint8_t* base, int row, int chunk) {
-  const int atom = chunk >> 3, c = chunk & 7;
-  uint4 v;
-  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
-               : "r"(smem_u32(base) + atom * 16384 + row * 128 + ((c ^ (row & 7)) << 4))
-               : "memory");
-  return v;
-}
-
 template <int HD>
 __device__ __forceinline__ void tma_tile(uint8_t* dst, const CUtensorMap* tm, uint64_t* bar, int col, int row, int b) {
   using C = HeadCfg<HD>;
@@ -1450,392 +1440,6 @@ attn_fwd_w3_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
   }
 }
 
-// The w3 forward with the S tile released EARLY: S is streamed through registers in four pipelined chunks, so it is free
-// as soon as the last chunk has been loaded (sfree_bar) and the MMA warp computes S(t+1) during the rest of the softmax
-// of tile t.  The reference maximum is maintained per CHUNK from registers (a chunk whose exponentials overshoot — or the
-// first visible chunk of a row — raises the reference, rescales l, O (TMEM) and the P chunks already written, and is
-// recomputed from its registers), so S is never re-read and the first tile of an item needs no separate maximum pass.
-template <int HD, bool DROP>
-__global__ void __launch_bounds__(384, 1)
-attn_fwd_w4_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant__ CUtensorMap tm_out,
-                   const int32_t* __restrict__ seg_start, float* __restrict__ lse, int Bsz, int T, int H, int Hk,
-                   int window, float scale_log2, const DropoutCfg drop_in, int smem_bytes) {
-  const DropoutCfg drop = resolve_dropout(drop_in);
-  using C = HeadCfg<HD>;
-  using S = FwdW2Smem<HD>;
-  constexpr int NS = S::kStages;
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem0 = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  if (static_cast<int>(smem0 - smem_raw) + S::kTotal > smem_bytes) __trap();
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int strm = warp < 8 ? (warp >> 2) : (warp & 1);  // softmax warps 0-3 | 4-7, MMA warps 8 | 9, TMA warps 10 | 11
-  uint8_t* smem = smem0 + strm * S::kStream;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::kBar);
-  uint64_t* q_full = bars;             // Q of the item has landed
-  uint64_t* q_empty = bars + 1;        // every S MMA of the item has retired
-  uint64_t* kv_full = bars + 2;        // [NS]
-  uint64_t* kv_empty = bars + 2 + NS;  // [NS] the P·V MMA that read the stage has retired
-  uint64_t* s_bar = bars + 2 + 2 * NS; // S of a tile is in TMEM (and the previous P·V has retired: P is free)
-  uint64_t* p_bar = s_bar + 1;         // P of a tile is in smem, its S has been consumed
-  uint64_t* pv_bar = p_bar + 1;        // P·V of a tile has retired: P may be rewritten, O is quiescent / complete
-  uint64_t* sfree_bar = pv_bar + 1;    // the softmax warps hold the last chunk of S in registers: S may be rewritten
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem0 + S::kBar) + 32;  // shared by both streams (behind stream 0's barriers)
-
-  const int rep = H / Hk;
-  const int vcta = blockIdx.x * 2 + strm, vgrid = gridDim.x * 2;
-  const int nqb = (T + BQ - 1) / BQ;
-
-  if (tid == 0 || tid == 128) {  // one thread of each stream initialises that stream's barriers
-    tma_prefetch_desc(&tm);
-    tma_prefetch_desc(&tm_out);
-    mbar_init(q_full, 1);
-    mbar_init(q_empty, 1);
-    mbar_init(s_bar, 1);
-    mbar_init(p_bar, 4);
-    mbar_init(pv_bar, 1);
-    mbar_init(sfree_bar, 4);
-    for (int i = 0; i < NS; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
-    }
-    fence_mbar_init();
-  }
-  if (warp == 0) {
-    __syncwarp();
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-  const uint32_t tS = tmem_base + strm * 256, tO = tS + 128;  // S: 128 columns, O: HD columns (accumulated over an item)
-
-  auto kv_lo_of = [&](int qb, int b) { return row_jlo(seg_start ? seg_start + (size_t)b * T : nullptr, qb * BQ, T, window) / BKV; };
-
-  if (warp >= 10) {
-    // ================================================================= TMA producer
-    const bool leader = elect_one();
-    PairCursor cur;
-    cur.begin(vcta, vgrid, nqb, H, Bsz, true);
-    int nx_lo = cur.valid ? kv_lo_of(cur.k, cur.b) : 0;
-    uint32_t t = 0;
-    for (int n_it = 0; cur.valid; ++n_it) {
-      const int qb = cur.k, h = cur.head, b = cur.b, kv_lo = nx_lo;
-      const int kvh = h / rep;
-      cur.next();
-      if (cur.valid) nx_lo = kv_lo_of(cur.k, cur.b);
-      mbar_wait(q_empty, (n_it & 1) ^ 1);
-      if (leader) {
-        mbar_expect_tx(q_full, C::TILE_BYTES);
-        tma_tile<HD>(smem + S::kQ, &tm, q_full, h * HD, qb * BQ, b);
-      }
-      for (int kvb = kv_lo; kvb <= qb; ++kvb, ++t) {
-        const int st = t % NS;
-        mbar_wait(&kv_empty[st], ((t / NS) & 1) ^ 1);
-        if (leader) {
-          mbar_expect_tx(&kv_full[st], 2 * C::TILE_BYTES);
-          tma_tile<HD>(smem + S::kK + st * C::TILE_BYTES, &tm, &kv_full[st], (H + kvh) * HD, kvb * BKV, b);
-          tma_tile<HD>(smem + S::kV + st * C::TILE_BYTES, &tm, &kv_full[st], (H + Hk + kvh) * HD, kvb * BKV, b);
-        }
-      }
-    }
-  } else if (warp >= 8) {
-    // ================================================================= MMA issuer
-    const bool leader = elect_one();
-    constexpr uint32_t idesc_s = umma_idesc_bf16(128, 128, false, false);
-    constexpr uint32_t idesc_o = umma_idesc_bf16(128, HD, false, true);
-    const uint32_t sQ_u = smem_u32(smem + S::kQ), sK_u = smem_u32(smem + S::kK), sV_u = smem_u32(smem + S::kV);
-    const uint32_t sP_u = smem_u32(smem + S::kP);
-    // O (TMEM) += P(tt) V(tt); `first` = first tile of its item (overwrite)
-    auto issue_pv = [&](uint32_t tt, bool first) {
-      const uint32_t st = tt % NS;
-      mbar_wait(p_bar, tt & 1);
-      tc_fence_after();
-      if (leader) {
-#pragma unroll
-        for (int ks = 0; ks < BKV / 16; ++ks)
-          umma_bf16(tO, ptile_kmajor(sP_u, ks), C::mnmajor(sV_u + st * C::TILE_BYTES, ks), idesc_o, ks > 0 || !first);
-        umma_commit(pv_bar);
-        umma_commit(&kv_empty[st]);
-      }
-      __syncwarp();
-    };
-    PairCursor cur;
-    cur.begin(vcta, vgrid, nqb, H, Bsz, true);
-    int nx_lo = cur.valid ? kv_lo_of(cur.k, cur.b) : 0;
-    uint32_t t = 0;
-    bool pv_first = false;  // tile t-1 was the first of its item
-    for (int n_it = 0; cur.valid; ++n_it) {
-      const int qb = cur.k, kv_lo = nx_lo;
-      cur.next();
-      if (cur.valid) nx_lo = kv_lo_of(cur.k, cur.b);
-      for (int kvb = kv_lo; kvb <= qb; ++kvb, ++t) {
-        // S(t) goes first: it only needs the S tile back (the softmax warps pulled the last chunk of S(t-1) into
-        // registers), not P(t-1) — the scores of the next tile are computed while the softmax of this one finishes
-        if (t >= 1) {
-          mbar_wait(sfree_bar, (t - 1) & 1);
-          tc_fence_after();
-        }
-        if (kvb == kv_lo) mbar_wait(q_full, n_it & 1);
-        const uint32_t st = t % NS;
-        mbar_wait(&kv_full[st], (t / NS) & 1);
-        tc_fence_after();
-        if (leader) {
-#pragma unroll
-          for (int ks = 0; ks < HD / 16; ++ks)
-            umma_bf16(tS, C::kmajor(sQ_u, ks), C::kmajor(sK_u + st * C::TILE_BYTES, ks), idesc_s, ks > 0);
-          umma_commit(s_bar);
-          if (kvb == qb) umma_commit(q_empty);  // last S MMA of the item: the Q buffer is free after this
-        }
-        __syncwarp();
-        if (t >= 1) issue_pv(t - 1, pv_first);
-        pv_first = kvb == kv_lo;
-      }
-    }
-    if (t >= 1) {
-      issue_pv(t - 1, pv_first);
-      mbar_wait(&kv_empty[(t - 1) % NS], ((t - 1) / NS) & 1);  // every MMA has retired before the CTA tears down
-    }
-  } else {
-    // ================================================================= softmax warps: thread = query row
-    const int row = tid & 127;
-    const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
-    PairCursor cur;
-    cur.begin(vcta, vgrid, nqb, H, Bsz, true);
-    int nx_ss = 0, nx_ss0 = 0;
-    auto prefetch_item = [&](const PairCursor& c) {
-      const int i0 = c.k * BQ;
-      nx_ss0 = seg_start ? seg_start[(size_t)c.b * T + i0] : 0;
-      nx_ss = (seg_start && i0 + row < T) ? seg_start[(size_t)c.b * T + i0 + row] : 0;
-    };
-    if (cur.valid) prefetch_item(cur);
-    uint32_t t = 0;
-    int n_item = 0;
-    uint8_t* sP = smem + S::kP;
-    constexpr float kLagSum = 1099511627776.f;  // 2^40: the sum of a 32-column chunk whose maximum overshoots m_ref by ~2^35..2^40
-    while (cur.valid) {
-      const int qb = cur.k, h = cur.head, b = cur.b;
-      const int q0 = qb * BQ, i = q0 + row;
-      const bool row_valid = i < T;
-      int jlo = row_valid ? nx_ss : 0x3fffffff, jlo0 = nx_ss0;
-      if (window > 0) {
-        jlo = row_valid ? max(jlo, i - window + 1) : jlo;
-        jlo0 = max(jlo0, q0 - window + 1);
-      }
-      const int kv_lo = jlo0 / BKV;
-      cur.next();
-      if (cur.valid) prefetch_item(cur);
-      const unsigned span = static_cast<unsigned>(i - jlo);
-      // Softmax is shift invariant: any reference r with |r - rowmax| < ~100 (log2 units) gives the same P (bf16 keeps
-      // the fp32 exponent range) and the same O / l up to an exact power of two.  m_ref is the exact maximum of the
-      // row's FIRST visible tile and is only moved when a later tile overshoots it by 2^kLag (checked on the row sum):
-      // one pass over S per tile, and O never leaves TMEM (the P·V MMAs accumulate into it; no per-tile fold).
-      float m_ref = -INFINITY, l_run = 0.f;
-      for (int kvb = kv_lo; kvb <= qb; ++kvb, ++t) {
-        const int kv0 = kvb * BKV;
-        // per 32-column chunk the warp (32 consecutive rows) votes: visible to every row / to none / mixed
-        unsigned cls_bits = 0;  // 2 bits per chunk: 0 = all visible, 1 = none, 2 = mixed
-        unsigned sees_bits = 0; // bit c: this ROW has a visible entry in chunk c
-#pragma unroll
-        for (int c4 = 0; c4 < 4; ++c4) {
-          const int jb = kv0 + c4 * 32;
-          const bool full = row_valid && jb >= jlo && jb + 31 <= i;
-          const bool none = !row_valid || jb > i || jb + 31 < jlo;
-          sees_bits |= (none ? 0u : 1u) << c4;
-          cls_bits |= (__all_sync(0xffffffffu, full) ? 0u : (__all_sync(0xffffffffu, none) ? 1u : 2u)) << (2 * c4);
-        }
-        mbar_wait(s_bar, t & 1);  // S(t) is in TMEM
-        tc_fence_after();
-        // the previous item's output was staged in this warp's rows of the P buffer: its bulk store has read them
-        bulk_wait_read0();
-        __syncwarp();
-        float ls0 = 0.f, ls1 = 0.f;
-        bool p_free = false;  // P·V(t-1) has retired: the P buffer may be rewritten, O may be rescaled
-        auto need_pv = [&]() {
-          if (!p_free) {
-            if (t >= 1) {
-              mbar_wait(pv_bar, (t - 1) & 1);
-              tc_fence_after();
-            }
-            p_free = true;
-          }
-        };
-        uint32_t ra[32], rb[32];
-        auto chunk = [&](const int c4, const uint32_t (&r)[32]) {
-          const unsigned cl = (cls_bits >> (2 * c4)) & 3u;
-          if (cl == 1u) {  // nothing visible: the P chunk is zero
-            need_pv();
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ptile_store(sP, row, c4 * 4 + q, make_uint4(0u, 0u, 0u, 0u));
-            return;
-          }
-          const int jb = kv0 + c4 * 32;
-          float p[32];
-          float cs = 0.f;
-          // a row whose reference is still unset and that sees something here must take the exact path first
-          bool fix = __any_sync(0xffffffffu, m_ref == -INFINITY && ((sees_bits >> c4) & 1u));
-#pragma unroll 1
-          for (int attempt = 0; attempt < 2; ++attempt) {
-            if (fix) {  // exact masked maximum of the chunk -> new reference; l, the tile's partial sums, O and the P
-                        // chunks already written follow by 2^(old - new)
-              float mraw = -INFINITY;
-              if (cl == 2u) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  mraw = fmaxf(mraw, (row_valid && visible(jb + j, jlo, span)) ? __uint_as_float(r[j]) : -INFINITY);
-              } else {
-#pragma unroll
-                for (int j = 0; j < 32; ++j) mraw = fmaxf(mraw, __uint_as_float(r[j]));
-              }
-              const float m_new = fmaxf(m_ref, mraw * scale_log2);
-              const float m_safe = (m_new == -INFINITY) ? 0.f : m_new;
-              const float alpha = fast_exp2(m_ref - m_safe);  // 0 for a row that had seen nothing yet, 1 if unchanged
-              if (__any_sync(0xffffffffu, alpha != 1.f)) {
-                l_run *= alpha;
-                ls0 *= alpha;
-                ls1 *= alpha;
-                need_pv();
-                if (kvb > kv_lo) {  // O *= alpha (rows of this warp only)
-#pragma unroll
-                  for (int c0 = 0; c0 < HD; c0 += 16) {
-                    uint32_t ro[16];
-                    tmem_ld16(tO + lane_base + c0, ro);
-                    tmem_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 16; ++c) ro[c] = __float_as_uint(__uint_as_float(ro[c]) * alpha);
-                    tmem_st16(tO + lane_base + c0, ro);
-                  }
-                  tmem_st_wait();
-                }
-                for (int q = 0; q < c4 * 4; ++q) {  // P chunks of this tile written under the old reference
-                  uint4 v = ptile_load(sP, row, q);
-                  uint32_t* w = reinterpret_cast<uint32_t*>(&v);
-#pragma unroll
-                  for (int e = 0; e < 4; ++e) {
-                    const float2 f = unpack_bf16(w[e]);
-                    w[e] = pack_bf16(f.x * alpha, f.y * alpha);
-                  }
-                  ptile_store(sP, row, q, v);
-                }
-              }
-              m_ref = m_new;
-            }
-            const float neg_m = (m_ref == -INFINITY) ? 0.f : -m_ref;  // rows that see nothing: every p is masked to 0
-            if (cl == 2u) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float pv = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2, neg_m));
-                p[j] = (row_valid && visible(jb + j, jlo, span)) ? pv : 0.f;
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) p[j] = fast_exp2(fmaf(__uint_as_float(r[j]), scale_log2, neg_m));
-            }
-            float c0s = 0.f, c1s = 0.f;
-#pragma unroll
-            for (int j = 0; j < 32; j += 2) {
-              c0s += p[j];
-              c1s += p[j + 1];
-            }
-            cs = c0s + c1s;
-            // a chunk that overshoots the reference by more than ~2^35 (or produced inf / nan): raise it, redo
-            fix = __any_sync(0xffffffffu, !(cs <= kLagSum));
-            if (!fix) break;
-          }
-          ls0 += cs;
-          if constexpr (DROP) {  // dropout on the (still unnormalised) probabilities; the row sum stays undropped (:104,129)
-            const uint32_t keep = attn_keep_mask32(drop, b * H + h, i, kv0 + c4 * 32);
-#pragma unroll
-            for (int j = 0; j < 32; ++j) p[j] = ((keep >> j) & 1u) ? p[j] * drop.inv_keep16 : 0.f;
-          }
-          need_pv();
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            uint4 v;
-            v.x = pack_bf16(p[q * 8 + 0], p[q * 8 + 1]);
-            v.y = pack_bf16(p[q * 8 + 2], p[q * 8 + 3]);
-            v.z = pack_bf16(p[q * 8 + 4], p[q * 8 + 5]);
-            v.w = pack_bf16(p[q * 8 + 6], p[q * 8 + 7]);
-            ptile_store(sP, row, c4 * 4 + q, v);
-          }
-        };
-        auto load = [&](int c4, uint32_t (&r)[32]) {
-          if (((cls_bits >> (2 * c4)) & 3u) != 1u) tmem_ld32(tS + lane_base + c4 * 32, r);
-        };
-        load(0, ra);
-        tmem_ld_wait();
-        load(1, rb);
-        chunk(0, ra);
-        tmem_ld_wait();
-        load(2, ra);
-        chunk(1, rb);
-        tmem_ld_wait();
-        load(3, rb);
-        chunk(2, ra);
-        tmem_ld_wait();
-        // the whole of S(t) has passed through registers: the MMA warp may compute S(t+1) into the tile
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(sfree_bar);
-        chunk(3, rb);
-        l_run += ls0 + ls1;
-        fence_proxy_async_smem();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(p_bar);
-      }
-      // last tile of the item: its P·V (and with it the whole accumulation) has retired
-      mbar_wait(pv_bar, (t - 1) & 1);
-      ++n_item;
-      tc_fence_after();
-      float o_acc[HD];
-#pragma unroll
-      for (int c0 = 0; c0 < HD; c0 += 16) {
-        uint32_t r[16];
-        tmem_ld16(tO + lane_base + c0, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 16; ++c) o_acc[c0 + c] = __uint_as_float(r[c]);
-      }
-      tc_fence_before();
-      const float m_run = m_ref;
-      {
-        const float inv = 1.f / l_run;
-        // output rows -> bf16, staged in this warp's rows of the P buffer (first atom), one TMA store per warp
-        constexpr int ROWB = HD * 2;
-        uint8_t* stg = smem + S::kP + (warp & 3) * 4096;
-        const int sw = ROWB == 128 ? (lane & 7) : (ROWB == 64 ? ((lane >> 1) & 3) : (ROWB == 32 ? ((lane >> 2) & 1) : 0));
-        const uint32_t rowp = smem_u32(stg + lane * ROWB);
-#pragma unroll
-        for (int c0 = 0; c0 < HD; c0 += 8) {
-          const uint32_t off = static_cast<uint32_t>(((c0 >> 3) ^ sw) << 4);
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(rowp + off),
-                       "r"(pack_bf16(o_acc[c0 + 0] * inv, o_acc[c0 + 1] * inv)),
-                       "r"(pack_bf16(o_acc[c0 + 2] * inv, o_acc[c0 + 3] * inv)),
-                       "r"(pack_bf16(o_acc[c0 + 4] * inv, o_acc[c0 + 5] * inv)),
-                       "r"(pack_bf16(o_acc[c0 + 6] * inv, o_acc[c0 + 7] * inv))
-                       : "memory");
-        }
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-          tma_store_3d(&tm_out, smem_u32(stg), h * HD, q0 + (warp & 3) * 32, b);
-          bulk_commit();
-        }
-        if (row_valid) lse[((size_t)b * H + h) * T + i] = (m_run + log2f(l_run)) * kLn2;
-      }
-    }
-    bulk_wait_read0();
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
 // last query tile that can see each (batch, kv tile): the warp-specialised backward reads this table instead of
 // searching seg_start itself.  Side job of the first threads of the delta kernels.
 __device__ __forceinline__ int qhi_ctr_index(int B, int T) { return (B * ((T + BKV - 1) / BKV) + 63) / 64 * 64; }
@@ -3055,8 +2659,7 @@ int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B
     static const int variant = [] {  // CGPT_ATTN_FWD=ws selects the one-CTA-per-SM kernel (probe / fallback)
       const char* e = getenv("CGPT_ATTN_FWD");
       if (e && e[0] == 'w' && e[1] == 's') return 0;
-      if (e && e[0] == 'w' && e[1] == '2') return 1;  // w2: two-pass / register-folded O
-      return (e && e[0] == 'w' && e[1] == '3') ? 2 : 3;  // w3: whole-tile reference; default: attn_fwd_w4_kernel
+      return (e && e[0] == 'w' && e[1] == '2') ? 1 : 2;  // w2: two-pass / register-folded O; default: attn_fwd_w3_kernel
     }();
     if (variant >= 1) {
       using S2 = FwdW2Smem<HD>;
@@ -3064,16 +2667,13 @@ int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B
       const uint32_t box2[3] = {(uint32_t)HD, 32u, 1u};
       rc = make_tmap_bf16(&to2, out, 3, dims, str, box2, 2 * HD);  // swizzle span = row bytes (128 / 64 / 32) or none
       if (rc) return rc;
-      auto k2 = variant == 3 ? (drop.thresh ? attn_fwd_w4_kernel<HD, true> : attn_fwd_w4_kernel<HD, false>)
-              : variant == 2 ? (drop.thresh ? attn_fwd_w3_kernel<HD, true> : attn_fwd_w3_kernel<HD, false>)
+      auto k2 = variant == 2 ? (drop.thresh ? attn_fwd_w3_kernel<HD, true> : attn_fwd_w3_kernel<HD, false>)
                              : attn_fwd_w2_kernel<HD>;
       static bool configured2 = false;
       if (!configured2) {
         CGPT_CHECK(cudaFuncSetAttribute(attn_fwd_w2_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::kDynamic));
         CGPT_CHECK(cudaFuncSetAttribute(attn_fwd_w3_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::kDynamic));
         CGPT_CHECK(cudaFuncSetAttribute(attn_fwd_w3_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::kDynamic));
-        CGPT_CHECK(cudaFuncSetAttribute(attn_fwd_w4_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::kDynamic));
-        CGPT_CHECK(cudaFuncSetAttribute(attn_fwd_w4_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, S2::kDynamic));
         configured2 = true;
       }
       const int half_pairs = (n_pairs + 1) / 2;  // two item streams per CTA
