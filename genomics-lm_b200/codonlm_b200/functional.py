@@ -420,12 +420,12 @@ class MlpSwiGLUFn(Function):
         return dh, (g if ctx.has_res else None), None, None, dwg, dwu, dwd
 
 
-def _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd=True):
+def _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd=True, out_dtype=f32):
     M, d = xb.shape
     dact = torch.empty((M, d), dtype=bf16, device=xb.device) if need_bwd else None
     act = torch.empty((M, d), dtype=bf16, device=xb.device)
     ops.gemm(xb, w1_sh, act, M=M, N=d, K=d, bias=b1, epilogue=EPI_GELU, aux_out=dact, ldaux=d)
-    out = torch.empty((M, d), dtype=f32, device=xb.device)
+    out = torch.empty((M, d), dtype=out_dtype, device=xb.device)
     ops.gemm(act, w2_sh, out, M=M, N=d, K=d, bias=b2)
     return out, act, dact
 
@@ -622,6 +622,35 @@ def _split_head_bwd(g, x3, w3, wk, wm, bm, dims, need_dx, dx_dtype=f32, dw_into=
     return dx, (None if dw_into is not None else dw), db
 
 
+def _plain_head_fwd(hb, w3, V):
+    """logits_o = bf16(h_o) · bf16(E)ᵀ with fp32 accumulation, for the OFFSET branches (model_tiny_gpt.py:336).  h_o is
+    itself the output of a bf16-operand GEMM (relative error ~2^-9), so the hi/lo split that makes the MAIN head
+    fp32-accurate (argmax parity) would only resolve rounding noise here: the shared head is applied to the bf16 h_o
+    with the hi part of the split head weight (w3[:, :d], row pitch 3d) — no split pass over h_o, K = d instead of 3d."""
+    M, d = hb.shape
+    out = torch.empty((M, V), dtype=f32, device=hb.device)
+    ops.gemm(hb, w3, out, M=M, N=V, K=d, ldb=w3.stride(0))
+    return out
+
+
+def _plain_head_bwd(g, hb, wk, wm, dims, dw_into=None):
+    """-> dh (bf16 [M, d]); the head-weight gradient gᵀ·h_o is accumulated into main_grad / `dw_into` (fp32 [V, d])."""
+    M, d, V = dims
+    Vp = (V + 7) // 8 * 8
+    gb = ops.cast_bf16(g.contiguous(), ld_out=Vp)            # [M, Vp], pad columns zero
+    dh = torch.empty((M, d), dtype=bf16, device=g.device)
+    ops.gemm(gb, wk, dh, M=M, N=d, K=Vp, b_mn=True)           # wk[0:Vp] = hi rows of the head weight (zero-padded)
+    mw = _main_grad(wm)
+    dw = mw if mw is not None else dw_into
+    tiles = ((V + 127) // 128) * ((d + 255) // 256)
+    split = ops.pick_split_k(tiles, (M + 63) // 64, _SMS)
+    ops.gemm(gb, hb, dw, M=V, N=d, K=M, a_mn=True, b_mn=True, lda=Vp, ldb=hb.stride(0), ldc=d, accumulate=True,
+             split_k=split)
+    if mw is not None:
+        _done(wm)
+    return dh
+
+
 class HeadsFn(Function):
     """Everything that reads the final hidden state, as ONE autograd node (model_tiny_gpt.py:326-337): LM head,
     termination head and the offset heads (MLP + shared LM head).  The hidden state is split into bf16 hi|lo|hi
@@ -645,10 +674,9 @@ class HeadsFn(Function):
         saved = [x, x3, w3, wk]
         for o in range(n_off):
             w1_sh, b1, w2_sh, b2, w1, w2 = off[6 * o:6 * o + 6]
-            h, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd)
-            lo, h3, _, _ = _split_head_fwd(h, head_w, None)
-            outs.append(lo)
-            saved += [dact, act, w1_sh, w2_sh, h3]
+            hb, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd, out_dtype=bf16)
+            outs.append(_plain_head_fwd(hb, w3, head_w.shape[0]))
+            saved += [dact, act, w1_sh, w2_sh, hb]
         if need_bwd:
             ctx.save_for_backward(*saved)
         ctx.masters = (head_w, term_w, term_b) + tuple(off)
@@ -687,12 +715,12 @@ class HeadsFn(Function):
                 dtw = dtb = None
         grads = []
         for o in range(ctx.n_off):
-            dact, act, w1_sh, w2_sh, h3 = saved[4 + 5 * o:9 + 5 * o]
+            dact, act, w1_sh, w2_sh, hb = saved[4 + 5 * o:9 + 5 * o]
             _, b1, _, b2, w1, w2 = off[6 * o:6 * o + 6]
             if g_off[o] is None:
                 grads += [None] * 6
                 continue
-            gb, _, _ = _split_head_bwd(g_off[o], h3, w3, wk, head_w, None, (M, d, V), True, bf16, dw_into=dhw)
+            gb = _plain_head_bwd(g_off[o], hb, wk, head_w, (M, d, V), dw_into=dhw)
             _, db1, db2, dw1, dw2 = _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2, dx_into=dx)
             grads += [None, db1, None, db2, dw1, dw2]
         return (dx, dhw, dtw, dtb, *grads)

@@ -210,64 +210,108 @@ __device__ __forceinline__ RowInfo ce_row_info(const int64_t* targets, const int
   return ri;
 }
 
+// One warp handles kCeRows consecutive rows at a time: the logits of all of them (and their targets / boundary
+// entries) are requested before anything is used, so a warp has kCeRows independent chains of global latency in
+// flight instead of three dependent ones; the target logit comes from the lane that already holds it (shuffle), not
+// from memory.  A CTA (8 warps) covers 8*kCeRows rows and writes ONE partial (loss, weight) pair, summed in a fixed
+// order: the final reduction reads M / (8*kCeRows) pairs instead of M.
+constexpr int kCeRows = 4;
+constexpr int kCeRowsPerCta = 8 * kCeRows;
+
 __global__ void __launch_bounds__(256)
 ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
-              const int32_t* __restrict__ next_boundary, const float* __restrict__ class_w, float* __restrict__ row_ws,
-              float* __restrict__ row_lse, int M, int T, int V, int shift, float smoothing, int64_t ignore_index) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const float* z = logits + (size_t)row * V;
-  float v[4];
-  float mx = -INFINITY;
+              const int32_t* __restrict__ next_boundary, const float* __restrict__ class_w, float* __restrict__ part,
+              float* __restrict__ row_lse, int M, int T, int V, int shift, float smoothing, int64_t ignore_index,
+              int n_part) {
+  __shared__ float red[2][8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = (blockIdx.x * 8 + warp) * kCeRows;
+  float v[kCeRows][4];
+  RowInfo ri[kCeRows];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = lane + 32 * k;
-    v[k] = c < V ? z[c] : -INFINITY;
-    mx = fmaxf(mx, v[k]);
-  }
-  mx = warp_max(mx);
-  float se = 0.f, swz = 0.f, sw = 0.f;
+  for (int r = 0; r < kCeRows; ++r) {
+    const int row = row0 + r;
+    const float* z = logits + (size_t)(row < M ? row : 0) * V;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = lane + 32 * k;
-    if (c < V) {
-      se += expf(v[k] - mx);
-      const float wc = class_w ? __ldg(class_w + c) : 1.f;
-      swz += wc * v[k];
-      sw += wc;
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane + 32 * k;
+      v[r][k] = (row < M && c < V) ? z[c] : -INFINITY;
+    }
+    if (row < M) {
+      ri[r] = ce_row_info(targets, next_boundary, row, T, shift, ignore_index, V);
+    } else {
+      ri[r].keep = ri[r].bad = false;
+      ri[r].target = 0;
     }
   }
-  se = warp_sum(se);
-  const float lse = mx + logf(se);
-  const RowInfo ri = ce_row_info(targets, next_boundary, row, T, shift, ignore_index, V);
-  float loss = 0.f, wt = 0.f;
-  if (ri.keep) {
-    swz = warp_sum(swz);
-    sw = warp_sum(sw);
-    const int tg = (int)ri.target;
-    const float wy = class_w ? __ldg(class_w + tg) : 1.f;
-    loss = (1.f - smoothing) * wy * (lse - z[tg]);
-    if (smoothing > 0.f) loss += (smoothing / V) * (sw * lse - swz);
-    wt = wy;
-  } else if (ri.bad) {
-    loss = __int_as_float(0x7fc00000);  // label out of range: poison the loss, do not dereference
-    wt = 1.f;
+  float wc[4], sw = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    wc[k] = c < V ? (class_w ? __ldg(class_w + c) : 1.f) : 0.f;
+    sw += wc[k];
+  }
+  sw = warp_sum(sw);
+  float loss_acc = 0.f, wt_acc = 0.f;
+#pragma unroll
+  for (int r = 0; r < kCeRows; ++r) {
+    const int row = row0 + r;
+    float mx = fmaxf(fmaxf(v[r][0], v[r][1]), fmaxf(v[r][2], v[r][3]));
+    mx = warp_max(mx);
+    float se = 0.f, swz = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (lane + 32 * k < V) {
+        se += expf(v[r][k] - mx);
+        swz += wc[k] * v[r][k];
+      }
+    }
+    se = warp_sum(se);
+    const float lse = mx + logf(se);
+    float loss = 0.f, wt = 0.f;
+    if (ri[r].keep) {  // warp-uniform: every lane computed the same RowInfo
+      swz = warp_sum(swz);
+      const int tg = (int)ri[r].target;
+      const int tk = tg >> 5;
+      const float zsel = tk == 0 ? v[r][0] : (tk == 1 ? v[r][1] : (tk == 2 ? v[r][2] : v[r][3]));
+      const float wsel = tk == 0 ? wc[0] : (tk == 1 ? wc[1] : (tk == 2 ? wc[2] : wc[3]));
+      const float ztg = __shfl_sync(0xffffffffu, zsel, tg & 31);
+      const float wy = __shfl_sync(0xffffffffu, wsel, tg & 31);
+      loss = (1.f - smoothing) * wy * (lse - ztg);
+      if (smoothing > 0.f) loss += (smoothing / V) * (sw * lse - swz);
+      wt = wy;
+    } else if (ri[r].bad) {
+      loss = __int_as_float(0x7fc00000);  // label out of range: poison the loss, do not dereference
+      wt = 1.f;
+    }
+    if (lane == 0 && row < M) row_lse[row] = lse;
+    loss_acc += loss;  // fixed order: rows of the warp, then warps of the CTA, then CTAs
+    wt_acc += wt;
   }
   if (lane == 0) {
-    row_lse[row] = lse;
-    row_ws[row] = loss;
-    row_ws[M + row] = wt;
+    red[0][warp] = loss_acc;
+    red[1][warp] = wt_acc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      a += red[0][w];
+      b2 += red[1][w];
+    }
+    part[blockIdx.x] = a;
+    part[n_part + blockIdx.x] = b2;
   }
 }
 
-// deterministic (fixed-order) reduction of the per-row terms into sums[0..1]
-__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ row_ws, float* __restrict__ sums, int M) {
+// deterministic (fixed-order) reduction of the per-CTA partial sums into sums[0..1]
+__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ part, float* __restrict__ sums, int n) {
   __shared__ float red[2][32];
   float a = 0.f, b = 0.f;
-  for (int i = threadIdx.x; i < M; i += 1024) {
-    a += row_ws[i];
-    b += row_ws[M + i];
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    a += part[i];
+    b += part[n + i];
   }
   a = warp_sum(a);
   b = warp_sum(b);
@@ -291,29 +335,59 @@ ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ row_ls
               const int32_t* __restrict__ next_boundary, const float* __restrict__ class_w,
               const float* __restrict__ sums, const float* __restrict__ gscale, float coef, float* __restrict__ dlogits,
               int M, int T, int V, int shift, float smoothing, int64_t ignore_index) {
-  const int lane = threadIdx.x & 31;
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= M) return;
-  const RowInfo ri = ce_row_info(targets, next_boundary, row, T, shift, ignore_index, V);
-  float* o = dlogits + (size_t)row * V;
-  if (!ri.keep) {
-    for (int c = lane; c < V; c += 32) o[c] = 0.f;
-    return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int row0 = (blockIdx.x * 8 + warp) * kCeRows;
+  float v[kCeRows][4], lse[kCeRows];
+  RowInfo ri[kCeRows];
+#pragma unroll
+  for (int r = 0; r < kCeRows; ++r) {
+    const int row = row0 + r;
+    if (row < M) {
+      ri[r] = ce_row_info(targets, next_boundary, row, T, shift, ignore_index, V);
+    } else {
+      ri[r].keep = ri[r].bad = false;
+      ri[r].target = 0;
+    }
+    lse[r] = row < M ? row_lse[row] : 0.f;
+    const float* z = logits + (size_t)(row < M ? row : 0) * V;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane + 32 * k;
+      v[r][k] = (row < M && c < V && ri[r].keep) ? z[c] : 0.f;
+    }
   }
-  const float* z = logits + (size_t)row * V;
-  const float lse = row_lse[row];
   const float scale = coef * (gscale ? *gscale : 1.f) / sums[1];
-  float sw = 0.f;
-  for (int c = lane; c < V; c += 32) sw += class_w ? __ldg(class_w + c) : 1.f;
+  float wc[4], sw = 0.f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int c = lane + 32 * k;
+    wc[k] = c < V ? (class_w ? __ldg(class_w + c) : 1.f) : 0.f;
+    sw += wc[k];
+  }
   sw = warp_sum(sw);
-  const int tg = (int)ri.target;
-  const float wy = class_w ? __ldg(class_w + tg) : 1.f;
-  for (int c = lane; c < V; c += 32) {
-    const float p = expf(z[c] - lse);
-    const float wc = class_w ? __ldg(class_w + c) : 1.f;
-    float g = (1.f - smoothing) * wy * (p - (c == tg ? 1.f : 0.f));
-    if (smoothing > 0.f) g += (smoothing / V) * (p * sw - wc);
-    o[c] = g * scale;
+#pragma unroll
+  for (int r = 0; r < kCeRows; ++r) {
+    const int row = row0 + r;
+    if (row >= M) break;
+    float* o = dlogits + (size_t)row * V;
+    if (!ri[r].keep) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (lane + 32 * k < V) o[lane + 32 * k] = 0.f;
+      continue;
+    }
+    const int tg = (int)ri[r].target;
+    const float wy = class_w ? __ldg(class_w + tg) : 1.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = lane + 32 * k;
+      if (c < V) {
+        const float p = expf(v[r][k] - lse[r]);
+        float g = (1.f - smoothing) * wy * (p - (c == tg ? 1.f : 0.f));
+        if (smoothing > 0.f) g += (smoothing / V) * (p * sw - wc[k]);
+        o[c] = g * scale;
+      }
+    }
   }
 }
 
@@ -384,11 +458,12 @@ int cgpt_ce_fwd(const float* logits, const int64_t* targets, const int32_t* next
   CGPT_REQUIRE(V >= 1 && V <= 128, "ce: V=%d must be in [1,128]", V);
   CGPT_REQUIRE(shift >= 0, "ce: shift must be >= 0");
   const int M = B * T;
-  ce_fwd_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, targets, next_boundary, class_w, row_ws, row_lse, M, T, V,
-                                                     shift, smoothing, ignore_index);
+  const int n_part = (M + kCeRowsPerCta - 1) / kCeRowsPerCta;  // per-CTA partial pairs live in row_ws (2*M floats >= 2*n_part)
+  ce_fwd_kernel<<<n_part, 256, 0, ST(stream)>>>(logits, targets, next_boundary, class_w, row_ws, row_lse, M, T, V, shift,
+                                                smoothing, ignore_index, n_part);
   count_launch();
   CGPT_LAUNCH_CHECK();
-  ce_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_ws, sums, M);
+  ce_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_ws, sums, n_part);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;
@@ -400,7 +475,7 @@ int cgpt_ce_bwd(const float* logits, const float* row_lse, const int64_t* target
   CGPT_REQUIRE(logits && row_lse && targets && sums && dlogits && B > 0 && T > 0, "ce_bwd: bad arguments");
   CGPT_REQUIRE(V >= 1 && V <= 128, "ce: V=%d must be in [1,128]", V);
   const int M = B * T;
-  ce_bwd_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(logits, row_lse, targets, next_boundary, class_w, sums, gscale,
+  ce_bwd_kernel<<<(M + kCeRowsPerCta - 1) / kCeRowsPerCta, 256, 0, ST(stream)>>>(logits, row_lse, targets, next_boundary, class_w, sums, gscale,
                                                      coef, dlogits, M, T, V, shift, smoothing, ignore_index);
   count_launch();
   CGPT_LAUNCH_CHECK();

@@ -207,7 +207,7 @@ int cgpt_skinny_linear_bwd(const float* dout, const float* x, const float* w, fl
  * Row r=(b,t) uses target tgt[b, t+shift]; it is kept iff t+shift < T, target != ignore_index and
  * (next_boundary==NULL || next_boundary[b,t] >= t+shift)   (offset_target_mask, objectives.py:13-23).
  * sums[0] += sum of weighted losses, sums[1] += sum of w[target] (fixed-order, deterministic);
- * row_lse[M] is saved for backward; row_ws is a [2*M] fp32 scratch (per-row loss | weight). */
+ * row_lse[M] is saved for backward; row_ws is a [2*M] fp32 scratch (per-CTA partial loss | weight sums, fixed order). */
 int cgpt_ce_fwd(const float* logits, const int64_t* targets, const int32_t* next_boundary /*nullable*/,
                 const float* class_w /*nullable*/, float* sums, float* row_lse, float* row_ws, int B, int T,
                 int V, int shift, float smoothing, int64_t ignore_index, cgpt_stream_t stream);
