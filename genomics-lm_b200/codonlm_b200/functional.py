@@ -143,6 +143,14 @@ def _packed_slots(masters, rows):
     return slots
 
 
+def _adjacent_tensors(tensors) -> bool:
+    """True when the tensors sit back to back in memory (same dtype), i.e. form one packed row-major matrix."""
+    for a, b in zip(tensors[:-1], tensors[1:]):
+        if a.dtype != b.dtype or a.data_ptr() + a.numel() * a.element_size() != b.data_ptr():
+            return False
+    return True
+
+
 def _colsum(dy: torch.Tensor, n: int, master=None, off: int = 0):
     mg = _main_grad(master)
     out = mg if mg is not None else torch.zeros((n,), dtype=f32, device=dy.device)
@@ -430,17 +438,18 @@ def _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd=True, out_dtype=f32):
     return out, act, dact
 
 
-def _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2, dx_into=None):
+def _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2, dx_into=None, act_ld=None, dact_ld=None):
     """gb: bf16 gradient of the MLP output -> (dx bf16, db1, db2, dw1, dw2), None where accumulated in place.
-    With `dx_into` (fp32 [M, d]) the input gradient is ADDED to it by the GEMM instead (returns dx None)."""
+    With `dx_into` (fp32 [M, d]) the input gradient is ADDED to it by the GEMM instead (returns dx None).
+    act / dact may be column slices of a wider buffer (row pitch act_ld / dact_ld)."""
     M, d = xb.shape
-    dw2 = _wgrad(gb, act, d, d, master=w2)
+    dw2 = _wgrad(gb, act, d, d, master=w2, x_ld=act_ld)
     db2 = _colsum(gb, d, master=b2)
     dpre = torch.empty((M, d), dtype=bf16, device=xb.device)
     fuse = (d % 8 == 0)
     mb1 = _main_grad(b1)
     db1 = (mb1 if mb1 is not None else torch.zeros((d,), dtype=f32, device=xb.device)) if fuse else None
-    ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=d, colsum=db1)
+    ops.gemm(gb, w2_sh, dpre, M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX, aux=dact, ldaux=dact_ld or d, colsum=db1)
     dw1 = _wgrad(dpre, xb, d, d, master=w1)
     if not fuse:
         db1 = _colsum(dpre, d, master=b1)
@@ -672,9 +681,30 @@ class HeadsFn(Function):
             outs.append(ops.skinny_linear_fwd(x, term_w, term_b))
         xb = x3[:, :d]  # bf16(x): row pitch 3d
         saved = [x, x3, w3, wk]
+        # All offset MLPs read the same xb.  When their first linears sit back to back in the trainer's flat buffers
+        # (TinyGPT.packed_param_groups -> trainer._packed_order) they ARE one [n_off*d, d] operand: one fc1 GEMM here,
+        # one fc1 input-gradient GEMM (K = n_off*d, instead of n_off read-modify-write passes over dx) and one fc1
+        # weight-gradient GEMM in backward.
+        packed = n_off > 1 and _adjacent_tensors([off[6 * o] for o in range(n_off)]) and \
+            _adjacent_tensors([off[6 * o + 1].data for o in range(n_off)]) and all(
+                off[6 * o].shape == (d, d) for o in range(n_off))
+        ctx.packed = bool(packed)
+        if packed:
+            nd = n_off * d
+            w1_all = torch.as_strided(off[0], (nd, d), (d, 1))
+            b1_all = torch.as_strided(off[1].data, (nd,), (1,))
+            dact_all = torch.empty((M, nd), dtype=bf16, device=x.device) if need_bwd else None
+            act_all = torch.empty((M, nd), dtype=bf16, device=x.device)
+            ops.gemm(xb, w1_all, act_all, M=M, N=nd, K=d, bias=b1_all, epilogue=EPI_GELU, aux_out=dact_all, ldaux=nd)
         for o in range(n_off):
             w1_sh, b1, w2_sh, b2, w1, w2 = off[6 * o:6 * o + 6]
-            hb, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd, out_dtype=bf16)
+            if packed:
+                act = act_all[:, o * d:(o + 1) * d]
+                dact = None if dact_all is None else dact_all[:, o * d:(o + 1) * d]
+                hb = torch.empty((M, d), dtype=bf16, device=x.device)
+                ops.gemm(act, w2_sh, hb, M=M, N=d, K=d, bias=b2)
+            else:
+                hb, act, dact = _offset_mlp_fwd(xb, w1_sh, b1, w2_sh, b2, need_bwd, out_dtype=bf16)
             outs.append(_plain_head_fwd(hb, w3, head_w.shape[0]))
             saved += [dact, act, w1_sh, w2_sh, hb]
         if need_bwd:
@@ -714,14 +744,43 @@ class HeadsFn(Function):
                     _done(term_b)
                 dtw = dtb = None
         grads = []
-        for o in range(ctx.n_off):
+        n_off = ctx.n_off
+        w1_masters = [off[6 * o + 4] for o in range(n_off)]
+        b1_masters = [off[6 * o + 1] for o in range(n_off)]
+        rows = [(o * d, d) for o in range(n_off)]
+        w1_slots = _packed_slots(w1_masters, rows) if ctx.packed else None
+        packed = (ctx.packed and w1_slots is not None and all(g is not None for g in g_off)
+                  and all(_main_grad(b) is not None for b in b1_masters))
+        if packed:
+            # second linears and shared head per offset; the pre-activation gradients of ALL offsets land in one
+            # [M, n_off*d] buffer, which then feeds ONE fc1 weight-gradient and ONE fc1 input-gradient GEMM
+            nd = n_off * d
+            dpre_all = torch.empty((M, nd), dtype=bf16, device=x.device)
+            for o in range(n_off):
+                dact, act, w1_sh, w2_sh, hb = saved[4 + 5 * o:9 + 5 * o]
+                _, b1, _, b2, w1, w2 = off[6 * o:6 * o + 6]
+                gb = _plain_head_bwd(g_off[o], hb, wk, head_w, (M, d, V), dw_into=dhw)
+                dw2 = _wgrad(gb, act, d, d, master=w2)
+                db2 = _colsum(gb, d, master=b2)
+                ops.gemm(gb, w2_sh, dpre_all[:, o * d:(o + 1) * d], M=M, N=d, K=d, b_mn=True, epilogue=EPI_MUL_AUX,
+                         aux=dact, ldaux=nd, ldc=nd, colsum=_main_grad(b1))
+                _done(b1)
+                grads += [None, None, None, db2, None, dw2]
+            w1_first = saved[4 + 2]  # w1_sh of offset 0: the packed [n_off*d, d] shadow starts there
+            _wgrad_into(dpre_all, xb, nd, d, torch.as_strided(w1_slots[0], (nd, d), (d, 1)))
+            for m in w1_masters:
+                _done(m)
+            ops.gemm(dpre_all, torch.as_strided(w1_first, (nd, d), (d, 1)), dx, M=M, N=d, K=nd, b_mn=True, accumulate=True)
+            return (dx, dhw, dtw, dtb, *grads)
+        for o in range(n_off):
             dact, act, w1_sh, w2_sh, hb = saved[4 + 5 * o:9 + 5 * o]
             _, b1, _, b2, w1, w2 = off[6 * o:6 * o + 6]
             if g_off[o] is None:
                 grads += [None] * 6
                 continue
             gb = _plain_head_bwd(g_off[o], hb, wk, head_w, (M, d, V), dw_into=dhw)
-            _, db1, db2, dw1, dw2 = _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2, dx_into=dx)
+            _, db1, db2, dw1, dw2 = _offset_mlp_bwd(gb, xb, dact, act, w1_sh, w2_sh, b1, b2, w1, w2, dx_into=dx,
+                                                    act_ld=act.stride(0), dact_ld=None if dact is None else dact.stride(0))
             grads += [None, db1, None, db2, dw1, dw2]
         return (dx, dhw, dtw, dtb, *grads)
 

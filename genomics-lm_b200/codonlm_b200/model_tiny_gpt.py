@@ -676,6 +676,14 @@ class TinyGPT(nn.Module):
             self.register_buffer("loss_weights", torch.ones(vocab_size, dtype=torch.float32))
         self._lw_cache = None
 
+    def packed_param_groups(self):
+        """The first linears of the offset MLPs all read the final hidden state: made neighbours in the trainer's flat
+        buffers (trainer._packed_order) they are one [n_off*d, d] operand (functional.HeadsFn)."""
+        mlps = [self.offset_projs[str(o)] for o in self.multi_offset_targets]
+        if len(mlps) < 2:
+            return []
+        return [tuple(m[0].weight for m in mlps), tuple(m[0].bias for m in mlps)]
+
     # ------------------------------------------------------------------ reference API
     def to_dict(self) -> dict:
         return {
