@@ -182,6 +182,83 @@ skinny_dw_kernel(const float* __restrict__ dout, const float* __restrict__ x, fl
   }
 }
 
+// dw += doutᵀ·x for heads with N <= 8 outputs (the 5-class termination head): the generic kernel keeps 11 of its 16
+// output lanes idle there and stages x through shared memory.  Here a thread owns 4 consecutive columns of x for ALL N
+// outputs (N x 4 fp32 accumulators), the CTA's 256 threads are (d/4) column owners x several row groups, rows are walked
+// with 4 loads in flight per thread and the row's N gradients come as broadcast loads: x is read once, coalesced, at HBM
+// rate.  Row groups are combined through shared memory, then one atomic per accumulator and CTA.
+__global__ void __launch_bounds__(256)
+skinny_dw_small_kernel(const float* __restrict__ dout, const float* __restrict__ x, float* __restrict__ dw,
+                       float* __restrict__ dbias, int M, int N, int d, int rows_per_cta) {
+  extern __shared__ float red[];  // [groups-1][8][d]
+  const int d4 = d >> 2;
+  const int groups = 256 / d4;          // row groups inside the CTA (d = 512: 2)
+  const int tid = threadIdx.x;
+  const int grp = tid / d4, c4 = tid - grp * d4;
+  const bool active = grp < groups;
+  const int r_begin = blockIdx.x * rows_per_cta;
+  const int r_end = min(M, r_begin + rows_per_cta);
+  float acc[8][4];
+  float bacc[8];
+#pragma unroll
+  for (int n = 0; n < 8; ++n) {
+    bacc[n] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) acc[n][i] = 0.f;
+  }
+  if (active) {
+    const float4* xp = reinterpret_cast<const float4*>(x) + c4;
+    for (int r0 = r_begin + grp * 4; r0 < r_end; r0 += groups * 4) {
+      float4 xv[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        xv[k] = (r0 + k < r_end) ? __ldg(xp + (size_t)(r0 + k) * d4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        if (r0 + k >= r_end) break;
+        const float* g = dout + (size_t)(r0 + k) * N;
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+          if (n < N) {
+            const float a = __ldg(g + n);
+            acc[n][0] += a * xv[k].x;
+            acc[n][1] += a * xv[k].y;
+            acc[n][2] += a * xv[k].z;
+            acc[n][3] += a * xv[k].w;
+            bacc[n] += a;
+          }
+        }
+      }
+    }
+  }
+  if (active && grp > 0) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) red[((grp - 1) * 8 + n) * d + c4 * 4 + i] = acc[n][i];
+  }
+  __syncthreads();
+  if (active && grp == 0) {
+    for (int gq = 1; gq < groups; ++gq)
+#pragma unroll
+      for (int n = 0; n < 8; ++n)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[n][i] += red[((gq - 1) * 8 + n) * d + c4 * 4 + i];
+#pragma unroll
+    for (int n = 0; n < 8; ++n) {
+      if (n >= N) break;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) atomicAdd(dw + (size_t)n * d + c4 * 4 + i, acc[n][i]);
+    }
+  }
+  // bias gradient: every row group of column owner 0 has summed its rows' gradients
+  if (dbias && active && c4 == 0) {
+#pragma unroll
+    for (int n = 0; n < 8; ++n)
+      if (n < N) atomicAdd(dbias + n, bacc[n]);
+  }
+}
+
 // ------------------------------------------------------------------ cross entropy (one warp per row, V <= 128)
 struct RowInfo {
   bool keep, bad;
@@ -439,7 +516,16 @@ int cgpt_skinny_linear_bwd(const float* dout, const float* x, const float* w, fl
     rows = (rows + 31) / 32 * 32;
     row_ctas = (M + rows - 1) / rows;
     dim3 grid(col_tiles, row_ctas);
-    if (N <= 16)
+    const int d4 = d / 4;
+    if (N <= 8 && d4 <= 256 && 256 % d4 == 0 && (size_t)(256 / d4 - 1) * 8 * d * 4 <= 48 * 1024) {
+      // small-head kernel: 2 CTAs per SM worth of row slices, each a multiple of the 4-row step of every row group
+      const int groups = 256 / d4;
+      int ctas = 2 * num_sms();
+      int rpc = (M + ctas - 1) / ctas;
+      rpc = (rpc + groups * 4 - 1) / (groups * 4) * (groups * 4);
+      ctas = (M + rpc - 1) / rpc;
+      skinny_dw_small_kernel<<<ctas, 256, (size_t)(groups - 1) * 8 * d * 4, ST(stream)>>>(dout, x, dw, dbias, M, N, d, rpc);
+    } else if (N <= 16)
       skinny_dw_kernel<1><<<grid, 256, 0, ST(stream)>>>(dout, x, dw, dbias, M, N, d, rows);
     else if (N <= 80)
       skinny_dw_kernel<5><<<grid, 256, 0, ST(stream)>>>(dout, x, dw, dbias, M, N, d, rows);

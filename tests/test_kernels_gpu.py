@@ -272,7 +272,7 @@ def test_cast_colsum_rope_swiglu_adamw(ops):
 # ------------------------------------------------------------------------------------------ heads / CE
 def test_skinny_linear_and_ce(ops):
     g = torch.Generator().manual_seed(6)
-    for (B, T, d, V) in [(2, 33, 32, 68), (4, 256, 512, 68), (3, 100, 384, 69), (2, 64, 64, 5)]:
+    for (B, T, d, V) in [(2, 33, 32, 68), (4, 256, 512, 68), (3, 100, 384, 69), (2, 64, 64, 5), (9, 333, 512, 5), (2, 50, 384, 8)]:
         M = B * T
         x = torch.randn(M, d, generator=g).to(DEV)
         w = (torch.randn(V, d, generator=g) * 0.2).to(DEV)
