@@ -143,6 +143,7 @@ class GradBuckets:
         # launch a bucket as soon as all contributions of all its parameters have arrived.
         self.contrib_seen = [0] * len(group.params)
         self.contrib_need = None
+        self.last_order = None  # bucket launch order of the last complete step
         self.armed = True  # False while accumulating the non-final micro-batches of a group: nothing is launched
         for i, p in enumerate(group.params):
             p._cgpt_grad_ready = self._make_hook(i)
@@ -181,9 +182,15 @@ class GradBuckets:
     def finish(self):
         """Wait for all buckets and write the reduced gradients (sum over ranks) back as fp32."""
         launched = {b for b, _ in self.pending}
-        for b in range(len(self.bounds)):  # first step, or parameters that got no gradient this step
+        # Buckets not launched from the hooks (first step; parameters without a gradient this step; a rank that held
+        # no micro-batch of a ragged accumulation group) are launched here.  Collectives must be issued in the SAME
+        # order on every rank: the order the hooks produced in the last complete step, when there is one.
+        order = self.last_order if (self.last_order is not None and not launched) else range(len(self.bounds))
+        for b in order:
             if b not in launched:
                 self._launch(b)
+        if len(self.pending) == len(self.bounds):
+            self.last_order = [b for b, _ in self.pending]
         if self.contrib_need is None:
             self.contrib_need = [max(1, c) for c in self.contrib_seen]
         self.contrib_seen = [0] * len(self.contrib_seen)

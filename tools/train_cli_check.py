@@ -17,7 +17,7 @@ PKG = os.path.join(ROOT, "genomics-lm_b200")
 
 
 def main():
-    work = sys.argv[1] if len(sys.argv) > 1 else tempfile.mkdtemp(prefix="cgpt_train_")
+    work = os.path.abspath(sys.argv[1] if len(sys.argv) > 1 else tempfile.mkdtemp(prefix="cgpt_train_"))
     os.makedirs(work, exist_ok=True)
     with open(os.path.join(ROOT, "tests", "golden", "trainer_golden.json")) as f:
         g = json.load(f)
