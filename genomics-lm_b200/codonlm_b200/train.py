@@ -413,7 +413,9 @@ def _worker(rank: int, world: int, port: int, cfg: dict, args):
         os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
                           LOCAL_RANK=str(rank))
         torch.cuda.set_device(rank)
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+        import datetime
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank),
+                                timeout=datetime.timedelta(seconds=int(cfg.get("collective_timeout_s", 600))))
         pg = dist.group.WORLD
     dev = torch.device("cuda", rank)
     train = StaticTokenSet.from_npz(args.train_npz, dev)

@@ -144,6 +144,7 @@ class GradBuckets:
         self.contrib_seen = [0] * len(group.params)
         self.contrib_need = None
         self.last_order = None  # bucket launch order of the last complete step
+        self.last_hook_order = None  # ... and the part of it that the gradient-ready hooks launched during backward
         self.armed = True  # False while accumulating the non-final micro-batches of a group: nothing is launched
         for i, p in enumerate(group.params):
             p._cgpt_grad_ready = self._make_hook(i)
@@ -179,13 +180,24 @@ class GradBuckets:
             work = dist.all_reduce(stg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
             self.pending.append((b, work))
 
+    def join_without_backward(self):
+        """A rank that holds no micro-batch of an accumulation group (ragged tail) still has to issue the group's
+        collectives, and in the order its peers do: they launch buckets from their gradient-ready hooks DURING backward,
+        i.e. before anything the caller all-reduces after backward (the non-finite flags).  Launch the same buckets, in
+        the same order, now (the gradients are zero here); finish() adds the rest."""
+        if self.last_hook_order and not self.pending:
+            for b in self.last_hook_order:
+                self._launch(b)
+
     def finish(self):
         """Wait for all buckets and write the reduced gradients (sum over ranks) back as fp32."""
         launched = {b for b, _ in self.pending}
+        if self.contrib_need is not None and self.armed:
+            self.last_hook_order = [b for b, _ in self.pending]  # what the gradient-ready hooks launched, in order
         # Buckets not launched from the hooks (first step; parameters without a gradient this step; a rank that held
         # no micro-batch of a ragged accumulation group) are launched here.  Collectives must be issued in the SAME
         # order on every rank: the order the hooks produced in the last complete step, when there is one.
-        order = self.last_order if (self.last_order is not None and not launched) else range(len(self.bounds))
+        order = self.last_order if self.last_order is not None else range(len(self.bounds))
         for b in order:
             if b not in launched:
                 self._launch(b)
@@ -285,6 +297,10 @@ class TrainStep:
         """Gradient buckets are all-reduced only from the backward of a group's LAST micro-batch."""
         for bk in self.buckets:
             bk.armed = bool(armed)
+
+    def join_collectives_without_backward(self):
+        for bk in self.buckets:
+            bk.join_without_backward()
 
     def discard_gradients(self):
         """Drop an aborted accumulation group: pending bucket reductions are drained, gradients zeroed."""
@@ -650,7 +666,10 @@ def run_accumulation_groups(step, microbatches: Iterable, grad_accum_steps: int,
             losses.append(loss.detach().reshape(1).float())
             nexts.append(parts["next"].detach().reshape(1).float())
         if n_local == 0:
-            step.arm_collectives(True)  # nothing to launch from: optimizer_step() reduces every bucket (zeros from here)
+            step.arm_collectives(True)
+            join = getattr(step, "join_collectives_without_backward", None)
+            if join is not None:
+                join()  # the peers' hooks launch their buckets during backward, BEFORE the flag all-reduce below
         # fixed-length vectors (gacc slots; empty slots are finite zeros) so that every rank reduces the same shape
         pad = [torch.zeros(1, device=dev)] * (gacc - n_local)
         stacked = torch.cat([t.to(dev) for t in losses] + pad + [t.to(dev) for t in nexts] + pad)

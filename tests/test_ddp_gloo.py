@@ -251,3 +251,64 @@ def test_ragged_trailing_group_is_agreed_on_by_all_ranks(tmp_path):
     want2 = [sum(range(1, 5)) / 4, sum(range(5, 9)) / 4, 9.0]
     assert r0["means2"] == pytest.approx(want2) and r1["means2"] == pytest.approx(want2)
     assert r0["sizes2"][-1] == (1, 1) and r1["sizes2"][-1] == (0, 1)
+
+
+def _empty_rank_worker(rank, world, port, out):
+    sys.path.insert(0, PKG)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import datetime
+    dist.init_process_group("gloo", rank=rank, world_size=world, timeout=datetime.timedelta(seconds=60))
+    from codonlm_b200.trainer import FlatGroup, GradBuckets
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 64), torch.nn.GELU(), torch.nn.Linear(64, 48), torch.nn.GELU(),
+                              torch.nn.Linear(48, 8))
+    named = list(net.named_parameters())
+    named.reverse()
+    group = FlatGroup(named, lr=1e-3, weight_decay=0.0)
+    buckets = GradBuckets(group, dist.group.WORLD, bucket_bytes=1024)  # several buckets of DIFFERENT sizes
+    assert len({e - s for s, e in buckets.bounds}) > 1
+
+    def backward(seed):
+        group.grad.zero_()
+        for p_ in group.params:
+            p_.grad = p_.main_grad
+        torch.manual_seed(seed)
+        net(torch.randn(32, 16)).square().mean().backward()
+
+    flags = []
+    for it in range(3):  # step 0 counts contributions, step 1 launches from the hooks on both ranks
+        if it < 2 or rank == 0:
+            backward(100 + rank + 10 * it)
+        else:  # step 2: rank 1 holds no micro-batch of this (ragged) group
+            group.grad.zero_()
+            buckets.join_without_backward()
+        flag = torch.tensor([float(rank == 0 and it == 2)])
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)  # what run_accumulation_groups reduces right after backward
+        flags.append(flag.item())
+        local = group.grad.clone()
+        buckets.finish()
+        gathered = [torch.zeros_like(local) for _ in range(world)]
+        dist.all_gather(gathered, local)
+        expect = sum(g.to(torch.bfloat16).float() for g in gathered)
+        assert (group.grad - expect).abs().max().item() <= 2 ** -7 * max(1e-6, expect.abs().max().item())
+    if rank == 0:
+        torch.save(flags, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_rank_without_microbatch_issues_collectives_in_peer_order(tmp_path):
+    """A rank that holds no micro-batch of a ragged accumulation group must issue the bucket all-reduces where its
+    peers' gradient-ready hooks do — before the flag all-reduce that follows backward — or the collectives pair up
+    wrongly (found on 2 GPUs: the trainer CLI dead-locked in the trailing group of an epoch)."""
+    import socket
+    out = str(tmp_path / "er.pt")
+    with socket.socket() as sk:
+        sk.bind(("127.0.0.1", 0))
+        port = sk.getsockname()[1]
+    try:
+        mp.spawn(_empty_rank_worker, args=(2, port, out), nprocs=2, join=True)
+    except mp.ProcessExitedException:
+        if not os.path.exists(out):
+            raise
+    assert torch.load(out) == [0.0, 0.0, 1.0]

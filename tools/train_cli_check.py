@@ -27,6 +27,7 @@ def main():
     cfg = dict(g["cfg"])
     cfg.pop("device", None)
     cfg["runs_dir"] = os.path.join(work, "runs")
+    cfg["collective_timeout_s"] = 60  # a mismatched collective must fail the check quickly
     with open(os.path.join(work, "config.yaml"), "w") as f:
         yaml.safe_dump(cfg, f)
     env = dict(os.environ, PYTHONPATH=PKG + os.pathsep + os.environ.get("PYTHONPATH", ""))
@@ -35,7 +36,7 @@ def main():
         run_id = f"cli_{gpus}gpu"
         cmd = [sys.executable, "-m", "codonlm_b200.train", "--config", os.path.join(work, "config.yaml"), "--run_id", run_id,
                "--train_npz", os.path.join(work, "train.npz"), "--val_npz", os.path.join(work, "val.npz"), "--gpus", str(gpus)]
-        res = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=work, timeout=900)
+        res = subprocess.run(cmd, capture_output=True, text=True, env=env, cwd=work, timeout=300)
         print(res.stdout[-1500:])
         if res.returncode != 0:
             print(res.stderr[-3000:])
