@@ -284,6 +284,10 @@ class Trainer:
             total_sum += rec["total_loss_sum"]
             next_sum += rec["next_loss_sum"]
             n += rec["group_size"]
+        if self.world > 1:  # the logged epoch means cover every rank's micro-batches
+            t = torch.tensor([total_sum, next_sum, float(n)], dtype=torch.float64, device=self.device)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.pg)
+            total_sum, next_sum, n = float(t[0]), float(t[1]), int(round(float(t[2])))
         return total_sum / max(n, 1), next_sum / max(n, 1)
 
     @torch.no_grad()

@@ -55,6 +55,7 @@ def main():
         # single micro-batch of an epoch is held by rank 0 alone (ragged group, agreed on by both ranks)
         assert results[2][0] == results[1][0], results
         assert abs(results[2][2] / results[1][2] - 1) < 1e-2, results
+        assert abs(results[2][3] / results[1][3] - 1) < 1e-2, results  # epoch mean over BOTH ranks' micro-batches
     print("[train_cli_check] ok")
 
 
