@@ -238,6 +238,13 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, uint32_t
                "r"(src_smem), "r"(c0), "r"(c1)
                : "memory");
 }
+// 1-D bulk copy global -> shared (no tensor map; 16-byte aligned addresses, size a multiple of 16), completion on
+// an mbarrier.  The streaming kernels (LayerNorm) keep whole rows in flight with it instead of per-thread loads.
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_smem),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }

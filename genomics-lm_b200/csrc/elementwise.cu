@@ -1,6 +1,8 @@
 // Memory-bound kernels of the codon-GPT step: integer scans, embedding gather / scatter-add,
 // LayerNorm fwd/bwd, casts, column sums, RoPE, SwiGLU gate, AdamW.  All HBM-bound: vectorised,
 // coalesced accesses, warp-shuffle reductions, grids sized in multiples of the SM count.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace cgpt {
@@ -214,7 +216,7 @@ template <int VPT>
 __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ yb, float* __restrict__ yf, float* __restrict__ mean,
-                     float* __restrict__ rstd, int M, int d, float eps) {
+                     float* __restrict__ rstd, int M, int d, float eps, int rev) {
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = d >> 2;
@@ -226,7 +228,8 @@ layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
     bt[k] = c < nvec ? __ldg(reinterpret_cast<const float4*>(beta) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float inv_d = 1.f / d;
-  for (int row = blockIdx.x * wpb + (threadIdx.x >> 5); row < M; row += gridDim.x * wpb) {
+  for (int rowi = blockIdx.x * wpb + (threadIdx.x >> 5); rowi < M; rowi += gridDim.x * wpb) {
+    const int row = rev ? M - 1 - rowi : rowi;  // rev: last rows first (the producer's newest lines are still in L2)
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
     float4 v[VPT];
     float s = 0.f;
@@ -271,7 +274,7 @@ __global__ void __launch_bounds__(256, (VPT <= 4) ? 2 : 1)
 layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, const float* __restrict__ gamma,
                      const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ dres,
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dgamma,
-                     float* __restrict__ dbeta, float* __restrict__ dxsum, int M, int d) {
+                     float* __restrict__ dbeta, float* __restrict__ dxsum, int M, int d, int rev) {
   __shared__ float red[8][VPT * 128];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -285,7 +288,8 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
     gm[k] = c < nvec ? __ldg(reinterpret_cast<const float4*>(gamma) + c) : make_float4(0.f, 0.f, 0.f, 0.f);
     ag[k] = ab[k] = ax[k] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
-  for (int row = blockIdx.x * wpb + warp; row < M; row += gridDim.x * wpb) {
+  for (int rowi = blockIdx.x * wpb + warp; rowi < M; rowi += gridDim.x * wpb) {
+    const int row = rev ? M - 1 - rowi : rowi;
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + (size_t)row * d);
     float4 xh[VPT], dyv[VPT], rv[VPT];
@@ -370,6 +374,259 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
       float t = 0.f;
 #pragma unroll
       for (int w2 = 0; w2 < 8; ++w2) t += red[w2][c];
+      atomicAdd(dst + c, t);
+    }
+  }
+}
+
+// ---- streaming variants (d = 128 * VPT exactly, 16-byte aligned rows): every warp owns a ring of row slots in shared
+// memory that the bulk-copy engine fills (cp.async.bulk, one mbarrier per slot), so whole rows stay in flight while the
+// warp computes on the previous one — the per-thread-load kernels above expose one HBM round trip per row and warp
+// (their loads are only in flight between the issue and the first use).  Same arithmetic, same column ownership.
+constexpr int kLnWarps = 8;
+
+template <int VPT, int SLOTS>
+struct LnFwdStream {
+  static constexpr int kRowBytes = VPT * 128 * 4;
+  static constexpr int kBarOff = kLnWarps * SLOTS * kRowBytes;
+  static constexpr int kSmem = kBarOff + kLnWarps * SLOTS * 8;
+};
+
+template <int VPT, int SLOTS>
+__global__ void __launch_bounds__(kLnWarps * 32, 3)
+layernorm_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                            __nv_bfloat16* __restrict__ yb, float* __restrict__ yf, float* __restrict__ mean,
+                            float* __restrict__ rstd, int M, float eps, int rev) {
+  using L = LnFwdStream<VPT, SLOTS>;
+  constexpr int D = VPT * 128;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* ring = ln_smem + warp * SLOTS * L::kRowBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + L::kBarOff) + warp * SLOTS;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  __syncwarp();
+  const int stride = gridDim.x * kLnWarps;
+  const int row0 = blockIdx.x * kLnWarps + warp;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const long long r = row0 + (long long)s * stride;
+      if (r < M) {
+        mbar_expect_tx(&bars[s], L::kRowBytes);
+        bulk_load_1d(smem_u32(ring + s * L::kRowBytes), x + (size_t)(rev ? M - 1 - r : r) * D, L::kRowBytes, &bars[s]);
+      }
+    }
+  }
+  float4 g[VPT], bt[VPT];
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    g[k] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * k);
+    bt[k] = __ldg(reinterpret_cast<const float4*>(beta) + lane + 32 * k);
+  }
+  constexpr float inv_d = 1.f / D;
+  int it = 0;
+  for (long long rowi = row0; rowi < M; rowi += stride, ++it) {
+    const long long row = rev ? M - 1 - rowi : rowi;
+    const int slot = it % SLOTS;
+    mbar_wait(&bars[slot], (it / SLOTS) & 1);
+    const float4* xr = reinterpret_cast<const float4*>(ring + slot * L::kRowBytes);
+    float4 v[VPT];
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      v[k] = xr[lane + 32 * k];
+      s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
+    }
+    __syncwarp();  // every lane has its part of the row in registers: the slot can be refilled
+    if (lane == 0) {
+      const long long rn = rowi + (long long)SLOTS * stride;
+      if (rn < M) {
+        mbar_expect_tx(&bars[slot], L::kRowBytes);
+        bulk_load_1d(smem_u32(ring + slot * L::kRowBytes), x + (size_t)(rev ? M - 1 - rn : rn) * D, L::kRowBytes,
+                     &bars[slot]);
+      }
+    }
+    const float mu = warp_sum(s) * inv_d;
+    float q = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const float a = v[k].x - mu, b = v[k].y - mu, e = v[k].z - mu, f = v[k].w - mu;
+      q += (a * a + b * b) + (e * e + f * f);
+    }
+    const float rs = rsqrtf(warp_sum(q) * inv_d + eps);
+    if (lane == 0) {
+      mean[row] = mu;
+      rstd[row] = rs;
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int c = lane + 32 * k;
+      float4 o;
+      o.x = (v[k].x - mu) * rs * g[k].x + bt[k].x;
+      o.y = (v[k].y - mu) * rs * g[k].y + bt[k].y;
+      o.z = (v[k].z - mu) * rs * g[k].z + bt[k].z;
+      o.w = (v[k].w - mu) * rs * g[k].w + bt[k].w;
+      if (yf) reinterpret_cast<float4*>(yf + (size_t)row * D)[c] = o;
+      if (yb) reinterpret_cast<uint2*>(yb + (size_t)row * D)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+    }
+  }
+}
+
+template <int VPT, int SLOTS>
+struct LnBwdStream {
+  static constexpr int D = VPT * 128;
+  static constexpr int kXOff = 0, kResOff = D * 4, kDyOff = D * 8;
+  static constexpr int kRowBytes = D * 10;  // x fp32 | dres fp32 | dy bf16
+  static constexpr int kBarOff = kLnWarps * SLOTS * kRowBytes;
+  static constexpr int kSmem = kBarOff + kLnWarps * SLOTS * 8;
+  static_assert(kLnWarps * SLOTS * kRowBytes >= kLnWarps * D * 4, "the column reduction reuses the ring");
+};
+
+template <int VPT, int SLOTS>
+__global__ void __launch_bounds__(kLnWarps * 32, 2)
+layernorm_bwd_stream_kernel(const __nv_bfloat16* __restrict__ dy, const float* __restrict__ x,
+                            const float* __restrict__ gamma, const float* __restrict__ mean,
+                            const float* __restrict__ rstd, const float* __restrict__ dres, float* __restrict__ dx,
+                            __nv_bfloat16* __restrict__ dxb, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                            float* __restrict__ dxsum, int M, int rev) {
+  using L = LnBwdStream<VPT, SLOTS>;
+  constexpr int D = L::D;
+  extern __shared__ __align__(128) uint8_t ln_smem[];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  uint8_t* ring = ln_smem + warp * SLOTS * L::kRowBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + L::kBarOff) + warp * SLOTS;
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) mbar_init(&bars[s], 1);
+    fence_mbar_init();
+    fence_proxy_async_smem();
+  }
+  __syncwarp();
+  const int stride = gridDim.x * kLnWarps;
+  const int row0 = blockIdx.x * kLnWarps + warp;
+  const uint32_t row_tx = dres ? L::kRowBytes : D * 6;
+  auto issue = [&](int slot, long long ri) {  // lane 0 only
+    const long long r = rev ? M - 1 - ri : ri;
+    uint8_t* sb = ring + slot * L::kRowBytes;
+    mbar_expect_tx(&bars[slot], row_tx);
+    bulk_load_1d(smem_u32(sb + L::kXOff), x + (size_t)r * D, D * 4, &bars[slot]);
+    bulk_load_1d(smem_u32(sb + L::kDyOff), dy + (size_t)r * D, D * 2, &bars[slot]);
+    if (dres) bulk_load_1d(smem_u32(sb + L::kResOff), dres + (size_t)r * D, D * 4, &bars[slot]);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < SLOTS; ++s) {
+      const long long r = row0 + (long long)s * stride;
+      if (r < M) issue(s, r);
+    }
+  }
+  constexpr float inv_d = 1.f / D;
+  float4 gm[VPT], ag[VPT], ab[VPT], ax[VPT];  // ax: column sums of dx (bias gradient of the upstream linear)
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    gm[k] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * k);
+    ag[k] = ab[k] = ax[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  float mu_n = 0.f, rs_n = 0.f;
+  if (row0 < M) {
+    mu_n = mean[rev ? M - 1 - row0 : row0];
+    rs_n = rstd[rev ? M - 1 - row0 : row0];
+  }
+  int it = 0;
+  for (long long rowi = row0; rowi < M; rowi += stride, ++it) {
+    const long long row = rev ? M - 1 - rowi : rowi;
+    const int slot = it % SLOTS;
+    const float mu = mu_n, rs = rs_n;
+    if (rowi + stride < M) {  // the next row's statistics travel under this row's math
+      const long long rn = rev ? M - 1 - (rowi + stride) : rowi + stride;
+      mu_n = mean[rn];
+      rs_n = rstd[rn];
+    }
+    mbar_wait(&bars[slot], (it / SLOTS) & 1);
+    const uint8_t* sb = ring + slot * L::kRowBytes;
+    const float4* xr = reinterpret_cast<const float4*>(sb + L::kXOff);
+    const uint2* dyr = reinterpret_cast<const uint2*>(sb + L::kDyOff);
+    const float4* rr = reinterpret_cast<const float4*>(sb + L::kResOff);
+    float4 xh[VPT], dyv[VPT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const uint2 u = dyr[lane + 32 * k];
+      const float2 lo = unpack_bf16(u.x), hi = unpack_bf16(u.y);
+      dyv[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+      const float4 xv = xr[lane + 32 * k];
+      xh[k] = make_float4((xv.x - mu) * rs, (xv.y - mu) * rs, (xv.z - mu) * rs, (xv.w - mu) * rs);
+    }
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const float gx = dyv[k].x * gm[k].x, gy = dyv[k].y * gm[k].y, gz = dyv[k].z * gm[k].z, gw = dyv[k].w * gm[k].w;
+      s1 += (gx + gy) + (gz + gw);
+      s2 += (gx * xh[k].x + gy * xh[k].y) + (gz * xh[k].z + gw * xh[k].w);
+      ag[k].x += dyv[k].x * xh[k].x;
+      ag[k].y += dyv[k].y * xh[k].y;
+      ag[k].z += dyv[k].z * xh[k].z;
+      ag[k].w += dyv[k].w * xh[k].w;
+      ab[k].x += dyv[k].x;
+      ab[k].y += dyv[k].y;
+      ab[k].z += dyv[k].z;
+      ab[k].w += dyv[k].w;
+    }
+    const float m1 = warp_sum(s1) * inv_d, m2 = warp_sum(s2) * inv_d;
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const int c = lane + 32 * k;
+      float4 o;
+      o.x = rs * (dyv[k].x * gm[k].x - m1 - xh[k].x * m2);
+      o.y = rs * (dyv[k].y * gm[k].y - m1 - xh[k].y * m2);
+      o.z = rs * (dyv[k].z * gm[k].z - m1 - xh[k].z * m2);
+      o.w = rs * (dyv[k].w * gm[k].w - m1 - xh[k].w * m2);
+      if (dres) {
+        const float4 rv = rr[c];
+        o.x += rv.x;
+        o.y += rv.y;
+        o.z += rv.z;
+        o.w += rv.w;
+      }
+      reinterpret_cast<float4*>(dx + (size_t)row * D)[c] = o;
+      if (dxb) reinterpret_cast<uint2*>(dxb + (size_t)row * D)[c] = make_uint2(pack_bf16(o.x, o.y), pack_bf16(o.z, o.w));
+      if (dxsum) {
+        ax[k].x += o.x;
+        ax[k].y += o.y;
+        ax[k].z += o.z;
+        ax[k].w += o.w;
+      }
+    }
+    __syncwarp();  // every lane is done with the slot: refill it with the row SLOTS iterations ahead
+    if (lane == 0) {
+      const long long rn = rowi + (long long)SLOTS * stride;
+      if (rn < M) issue(slot, rn);
+    }
+  }
+  // per-CTA reduction of the column partials over its 8 warps (the ring is idle now: every copy that was issued has
+  // been waited for), then one atomic per column
+  float* red = reinterpret_cast<float*>(ln_smem);
+#pragma unroll
+  for (int pass = 0; pass < 3; ++pass) {
+    if (pass == 2 && dxsum == nullptr) break;
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < VPT; ++k) {
+      const float4 val = pass == 0 ? ag[k] : (pass == 1 ? ab[k] : ax[k]);
+      *reinterpret_cast<float4*>(&red[warp * D + (lane + 32 * k) * 4]) = val;
+    }
+    __syncthreads();
+    float* dst = pass == 0 ? dgamma : (pass == 1 ? dbeta : dxsum);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) {
+      float t = 0.f;
+#pragma unroll
+      for (int w2 = 0; w2 < kLnWarps; ++w2) t += red[w2 * D + c];
       atomicAdd(dst + c, t);
     }
   }
@@ -831,6 +1088,26 @@ __global__ void adamw_kernel(float* __restrict__ p, const GradT* __restrict__ g,
   }
 }
 
+// CGPT_LN_STREAM: 0 = per-thread-load LayerNorm kernels, 1 (default) = streaming backward, 2 = streaming forward too
+// (measured slower than the per-thread-load forward: 41.0 vs 38.9 us at 65536 x 512); read once
+inline int ln_stream_enabled() {
+  static const int on = [] {
+    const char* e = getenv("CGPT_LN_STREAM");
+    return e ? atoi(e) : 1;
+  }();
+  return on;
+}
+// CGPT_LN_REVERSE=0: rows in ascending order.  Default: LAST rows first — the GEMM in front of a LayerNorm produces its
+// rows in ascending order, so its newest lines are still in L2 when the LayerNorm starts, and the LayerNorm ends on
+// the rows the next GEMM reads first.
+inline bool ln_reverse_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CGPT_LN_REVERSE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 inline int grid_for(long long work_items, int threads, int max_waves = 8) {
   long long g = (work_items + threads - 1) / threads;
   const long long cap = (long long)num_sms() * max_waves;
@@ -972,10 +1249,24 @@ int cgpt_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
   CGPT_REQUIRE(x && gamma && beta && mean && rstd && (y_bf16 || y_f32) && M > 0, "layernorm_fwd: bad arguments");
   CGPT_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
                128 * kLnMaxVec);
-  const int grid = grid_for((long long)M * 32, 256, 4);
   const int vpt = (d / 4 + 31) / 32;
+  const int rev = ln_reverse_enabled() ? 1 : 0;
   __nv_bfloat16* yb = reinterpret_cast<__nv_bfloat16*>(y_bf16);
-#define LN_FWD(V) layernorm_fwd_kernel<V><<<grid, 256, 0, ST(stream)>>>(x, gamma, beta, yb, y_f32, mean, rstd, M, d, eps)
+  if (d == 512 && ln_stream_enabled() > 1 && M >= 1024 && ((reinterpret_cast<uintptr_t>(x) & 15) == 0)) {
+    using L = LnFwdStream<4, 4>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CGPT_CHECK(cudaFuncSetAttribute(layernorm_fwd_stream_kernel<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));
+      attr_set = true;
+    }
+    const int grid = grid_for((long long)M * 32, kLnWarps * 32, 3);
+    layernorm_fwd_stream_kernel<4, 4><<<grid, kLnWarps * 32, L::kSmem, ST(stream)>>>(x, gamma, beta, yb, y_f32, mean, rstd, M, eps, rev);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+    return 0;
+  }
+  const int grid = grid_for((long long)M * 32, 256, 4);
+#define LN_FWD(V) layernorm_fwd_kernel<V><<<grid, 256, 0, ST(stream)>>>(x, gamma, beta, yb, y_f32, mean, rstd, M, d, eps, rev)
   if (vpt <= 1) LN_FWD(1); else if (vpt <= 2) LN_FWD(2); else if (vpt <= 4) LN_FWD(4); else LN_FWD(8);
 #undef LN_FWD
   count_launch();
@@ -990,9 +1281,25 @@ int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const floa
   CGPT_REQUIRE(d % 4 == 0 && d <= 128 * kLnMaxVec, "layernorm: d=%d must be a multiple of 4 and <= %d", d,
                128 * kLnMaxVec);
   const int vpt = (d / 4 + 31) / 32;
-  const int grid = grid_for((long long)M * 32, 256, vpt <= 4 ? 2 : 1);
+  const int rev = ln_reverse_enabled() ? 1 : 0;
   __nv_bfloat16* dxb = reinterpret_cast<__nv_bfloat16*>(dx_bf16);
-#define LN_BWD(V, F) layernorm_bwd_kernel<V, F><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, d)
+  if (d == 512 && !dy_is_f32 && ln_stream_enabled() > 0 && M >= 1024 &&
+      (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(dres)) & 15) == 0)) {
+    using L = LnBwdStream<4, 2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+      CGPT_CHECK(cudaFuncSetAttribute(layernorm_bwd_stream_kernel<4, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::kSmem));
+      attr_set = true;
+    }
+    const int grid = grid_for((long long)M * 32, kLnWarps * 32, 2);
+    layernorm_bwd_stream_kernel<4, 2><<<grid, kLnWarps * 32, L::kSmem, ST(stream)>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, rev);
+    count_launch();
+    CGPT_LAUNCH_CHECK();
+    return 0;
+  }
+  const int grid = grid_for((long long)M * 32, 256, vpt <= 4 ? 2 : 1);
+#define LN_BWD(V, F) layernorm_bwd_kernel<V, F><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, d, rev)
   if (dy_is_f32) {
     if (vpt <= 1) LN_BWD(1, true); else if (vpt <= 2) LN_BWD(2, true); else if (vpt <= 4) LN_BWD(4, true); else LN_BWD(8, true);
   } else {

@@ -756,12 +756,30 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int acc = it & 1;
       // this tile's bias slice -> smem (zeros when there is none), before the accumulator is even ready.
       // Double-buffered by accumulator parity; the barrier below also orders the reuse two tiles later.
+      // Every warp fetches the entries of ITS column chunks into registers now and stores them once the accumulator
+      // is ready (the four warps of a column group store identical values to the same words; a warp only ever reads
+      // what it stored itself), so no CTA-wide barrier sits between tiles and the epilogue warps drift apart instead
+      // of hitting the FMA / MUFU / shared-memory pipes in lock step.
       const uint32_t bias_tile = smem_u32(smem + L::kBiasOff) + acc * BN * 4;
-      if (ew * 32 < BN) {
-        const int cb = n_blk * BN + ew * 32 + lane;
-        float bv = 0.f;
-        if (p.bias != nullptr && ks == 0 && cb < p.N) bv = __ldg(p.bias + cb);
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_tile + (ew * 32 + lane) * 4), "f"(bv) : "memory");
+      const bool legacy_sync = (p.debug & 8) != 0;
+      int bcol[2];
+      float bval[2] = {0.f, 0.f};
+      if (legacy_sync) {
+        if (ew * 32 < BN) {
+          const int cb = n_blk * BN + ew * 32 + lane;
+          float bv = 0.f;
+          if (p.bias != nullptr && ks == 0 && cb < p.N) bv = __ldg(p.bias + cb);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_tile + (ew * 32 + lane) * 4), "f"(bv) : "memory");
+        }
+      } else {
+        const bool chunk32 = bf16_rowmath || (tma_io && !p.out_f32);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          const int i = lane + 32 * h;
+          bcol[h] = chunk32 ? (grp + 4 * h) * 32 + lane : (grp + 4 * (i >> 4)) * 16 + (i & 15);
+          const int cb = n_blk * BN + bcol[h];
+          if (bcol[h] < BN && p.bias != nullptr && ks == 0 && cb < p.N) bval[h] = __ldg(p.bias + cb);
+        }
       }
       const int row0 = m_blk * BM + q * 32;
       if constexpr (L::kAuxPrefetch) {
@@ -805,9 +823,17 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           __syncwarp();
         }
       }
-      named_bar_sync(1, kEpiWarps * 32);
+      if (legacy_sync) named_bar_sync(1, kEpiWarps * 32);
       mbar_wait(&tfull_bar[acc], (it >> 1) & 1);
       tc_fence_after();
+      if (!legacy_sync) {
+        // safe only now: this accumulator parity's bias words were last read two tiles ago, and the MMA warp could
+        // not start this tile before all sixteen warps had handed that accumulator back
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+          if (bcol[h] < BN) asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_tile + bcol[h] * 4), "f"(bval[h]) : "memory");
+        __syncwarp();
+      }
       const uint32_t tbase = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + acc * BN;
       if (p.debug & 4) {
       } else if (L::kResPrefetch && tma_io && p.out_f32 && p.residual != nullptr) {

@@ -15,6 +15,7 @@ SHAPES = {
     "qkv_fwd": (M, 1536, 512, False, False, torch.bfloat16, ops.EPI_NONE, False, 1),
     "fc1_fwd_gelu": (M, 2048, 512, False, False, torch.bfloat16, ops.EPI_GELU, False, 1),
     "fc2_dgrad_mulaux": (M, 2048, 512, False, True, torch.bfloat16, ops.EPI_MUL_AUX, False, 1),
+    "fc2_dgrad_mulaux_colsum": (M, 2048, 512, False, True, torch.bfloat16, ops.EPI_MUL_AUX, False, 1),
     "proj_fwd_res": (M, 512, 512, False, False, torch.float32, ops.EPI_NONE, True, 1),
     "fc2_fwd_res": (M, 512, 2048, False, False, torch.float32, ops.EPI_NONE, True, 1),
     "fc1_dgrad": (M, 512, 2048, False, True, torch.bfloat16, ops.EPI_NONE, False, 1),
@@ -38,6 +39,8 @@ def run(name, iters=10):
         kw.update(aux_out=aux, ldaux=n)
     elif epi == ops.EPI_MUL_AUX:
         kw.update(aux=aux, ldaux=n)
+        if name.endswith("_colsum"):
+            kw.update(colsum=torch.zeros(n, device=dev))
     flush = torch.empty(64 << 20, dtype=torch.float32, device=dev)  # 256 MB > L2
     for _ in range(2):
         ops.gemm(a, b, out, **kw)
