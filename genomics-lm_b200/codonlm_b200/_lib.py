@@ -61,8 +61,8 @@ SIGNATURES = {
     "cgpt_dropout": (_i, [_vp, _vp, _vp, _i, _i64, _f, C.c_uint64, C.c_uint64, _vp]),
     "cgpt_skinny_linear_fwd": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "cgpt_skinny_linear_bwd": (_i, [_vp, _vp, _vp, _vp, _i, _vp, _vp, _i, _i, _i, _vp]),
-    "cgpt_ce_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i64, _vp]),
-    "cgpt_ce_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _i, _i, _i, _i, _f, _i64, _vp]),
+    "cgpt_ce_fwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _f, _i64, _i, _vp]),
+    "cgpt_ce_bwd": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _f, _vp, _vp, _i, _i64, _i, _i, _i, _i, _f, _i64, _vp]),
     "cgpt_set_philox_state": (_i, [_vp]),
     "cgpt_philox_advance": (_i, [_vp, C.c_uint64, _vp]),
     "cgpt_adamw": (_i, [_vp, _vp, _vp, _vp, _vp, _i64, _f, _f, _f, _f, _f, _i, _f, _vp, _vp]),

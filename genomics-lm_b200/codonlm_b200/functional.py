@@ -44,6 +44,15 @@ def _detach_side(g: torch.Tensor):
     return hit
 
 
+def _grad_form_of(g: torch.Tensor, shape):
+    """bf16 form of the logit gradient `g` left by the cross-entropy backward (padded copy or hi|lo|hi split), if it
+    travelled with `g` and has the wanted shape."""
+    hit = _detach_side(g)
+    if hit is not None and hit[0] is not None and tuple(hit[0].shape) == tuple(shape):
+        return hit[0]
+    return None
+
+
 def _bf16_of(g: torch.Tensor):
     """(bf16 copy of g, column sums of g or None)."""
     hit = _detach_side(g)
@@ -602,7 +611,9 @@ def _split_head_bwd(g, x3, w3, wk, wm, bm, dims, need_dx, dx_dtype=f32, dw_into=
     """-> (dx or None, dw or None, db or None); dw/db are None when accumulated into main_grad (or `dw_into`)."""
     M, d, V = dims
     Vp = (V + 7) // 8 * 8
-    g3 = ops.split3(g.contiguous(), cols_pad=Vp)  # [M, 3Vp]  hi|lo|hi
+    g3 = _grad_form_of(g, (M, 3 * Vp))
+    if g3 is None:
+        g3 = ops.split3(g.contiguous(), cols_pad=Vp)  # [M, 3Vp]  hi|lo|hi
     dx = None
     if need_dx:
         # dx = g·w: reduction over the (tripled, padded) vocabulary; w as [hi; hi; lo] stacked along K
@@ -646,7 +657,9 @@ def _plain_head_bwd(g, hb, wk, wm, dims, dw_into=None):
     """-> dh (bf16 [M, d]); the head-weight gradient gᵀ·h_o is accumulated into main_grad / `dw_into` (fp32 [V, d])."""
     M, d, V = dims
     Vp = (V + 7) // 8 * 8
-    gb = ops.cast_bf16(g.contiguous(), ld_out=Vp)            # [M, Vp], pad columns zero
+    gb = _grad_form_of(g, (M, Vp))                           # written by the CE backward kernel itself, or:
+    if gb is None:
+        gb = ops.cast_bf16(g.contiguous(), ld_out=Vp)        # [M, Vp], pad columns zero
     dh = torch.empty((M, d), dtype=bf16, device=g.device)
     ops.gemm(gb, wk, dh, M=M, N=d, K=Vp, b_mn=True)           # wk[0:Vp] = hi rows of the head weight (zero-padded)
     mw = _main_grad(wm)
@@ -841,22 +854,30 @@ class CrossEntropyFn(Function):
     (model_tiny_gpt.py:343-349; objectives.py:39-57, 94-105).  Returns (loss, kept_weight)."""
 
     @staticmethod
-    def forward(ctx, logits2d, targets, next_boundary, class_w, B, T, shift, smoothing, ignore_index, zero_if_empty):
-        sums, row_lse = ops.ce_fwd(logits2d, targets, B, T, shift=shift, next_boundary=next_boundary, class_w=class_w,
-                                   smoothing=smoothing, ignore_index=ignore_index)
+    def forward(ctx, logits2d, targets, next_boundary, class_w, B, T, shift, smoothing, ignore_index, zero_if_empty,
+                grad_form=0):
+        # the kernel's last CTA also forms the mean (0 instead of NaN for an empty selection when asked): no torch
+        # arithmetic on the sums
+        sums, row_lse, loss = ops.ce_fwd(logits2d, targets, B, T, shift=shift, next_boundary=next_boundary,
+                                         class_w=class_w, smoothing=smoothing, ignore_index=ignore_index,
+                                         zero_if_empty=zero_if_empty)
         ctx.save_for_backward(logits2d, row_lse, targets, sums)
-        ctx.aux = (next_boundary, class_w, B, T, shift, smoothing, ignore_index)
-        loss = sums[0] / sums[1]
-        if zero_if_empty:
-            loss = torch.where(sums[1] > 0, loss, torch.zeros_like(loss))
+        ctx.aux = (next_boundary, class_w, B, T, shift, smoothing, ignore_index, grad_form)
         ctx.mark_non_differentiable(sums)
         return loss, sums
 
     @staticmethod
     def backward(ctx, g, _gs):
         logits2d, row_lse, targets, sums = ctx.saved_tensors
-        next_boundary, class_w, B, T, shift, smoothing, ignore_index = ctx.aux
+        next_boundary, class_w, B, T, shift, smoothing, ignore_index, grad_form = ctx.aux
         gs = g.reshape(1).to(f32).contiguous()
-        dl = ops.ce_bwd(logits2d, row_lse, targets, sums, gs, B, T, shift=shift, next_boundary=next_boundary,
-                        class_w=class_w, smoothing=smoothing, ignore_index=ignore_index)
-        return dl, None, None, None, None, None, None, None, None, None
+        # grad_form: the bf16 form of the logit gradient that the head's backward GEMMs read (1 = padded bf16 copy,
+        # 2 = hi|lo|hi split), written by the same kernel and handed on ON the gradient tensor (_attach)
+        res = ops.ce_bwd(logits2d, row_lse, targets, sums, gs, B, T, shift=shift, next_boundary=next_boundary,
+                         class_w=class_w, smoothing=smoothing, ignore_index=ignore_index, bf16_mode=grad_form)
+        if grad_form:
+            dl, side = res
+            _attach(dl, side, None)
+        else:
+            dl = res
+        return dl, None, None, None, None, None, None, None, None, None, None

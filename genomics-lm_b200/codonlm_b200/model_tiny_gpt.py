@@ -795,12 +795,17 @@ class TinyGPT(nn.Module):
             outs = Fn.HeadsFn.apply(x2, self.head.weight, None if th is None else th.weight,
                                     None if th is None else th.bias, *args)
             logits = outs[0].view(B, T, -1)
+            # which bf16 form of the logit gradient this node's backward GEMMs read (Fn.CrossEntropyFn writes it from
+            # the same kernel as the fp32 gradient): 2 = hi|lo|hi split (fp32-accurate main head), 1 = padded bf16 copy
+            logits._cgpt_grad_form = 2
             k = 1
             if th is not None:
                 aux["termination_logits"] = outs[1].view(B, T, -1)
                 k = 2
             if len(self.offset_projs) > 0:
                 aux["offset_logits"] = {o: outs[k + i].view(B, T, -1) for i, o in enumerate(self.multi_offset_targets)}
+                for lg in aux["offset_logits"].values():
+                    lg._cgpt_grad_form = 1
             return logits, aux
         logits = self.head(x)
         if self.termination_head is not None:
@@ -835,7 +840,7 @@ class TinyGPT(nn.Module):
         if targets is not None:
             tg = targets.to(idx.device).long().contiguous()
             loss, _ = Fn.CrossEntropyFn.apply(logits.view(B * T, -1), tg, None, self.class_weights(), B, T, 0,
-                                              self.label_smoothing, 0, False)
+                                              self.label_smoothing, 0, False, getattr(logits, "_cgpt_grad_form", 0))
         if in_dev != idx.device:  # callers that keep their tensors on the host get host results back
             logits = logits.to(in_dev)
         if return_aux:

@@ -60,7 +60,7 @@ def multi_offset_lm_loss(logits, yb: torch.Tensor, offset_weights: Dict[int, flo
         if lg2.dtype != torch.float32 or not lg2.is_contiguous():
             lg2 = lg2.float().contiguous()
         loss, sums = Fn.CrossEntropyFn.apply(lg2, yb, nb, loss_weights, B, T, offset - 1, float(label_smoothing),
-                                             PAD_ID, True)
+                                             PAD_ID, True, getattr(lg, "_cgpt_grad_form", 0))
         losses[offset] = loss
         counts[offset] = sums[1]
         total = total + float(weight) * loss

@@ -410,27 +410,36 @@ def skinny_linear_bwd(dout, x2d, w, dx, dx_accumulate, dw, dbias):
                                       _p(dw), _p(dbias), M, N, d, _stream()))
 
 
-def ce_fwd(logits2d, targets, B, T, *, shift=0, next_boundary=None, class_w=None, smoothing=0.0, ignore_index=0):
-    """Returns (sums[2] = (loss_sum, weight_sum), row_lse[M])."""
+def ce_fwd(logits2d, targets, B, T, *, shift=0, next_boundary=None, class_w=None, smoothing=0.0, ignore_index=0,
+           zero_if_empty=False):
+    """Returns (sums[2] = (loss_sum, weight_sum), row_lse[M], mean loss (0-dim)); the mean is 0 instead of NaN for an
+    empty selection when `zero_if_empty`."""
     _dev(logits2d)
     M, V = logits2d.shape
-    sums = torch.zeros((2,), dtype=f32, device=logits2d.device)
+    sums = torch.empty((2,), dtype=f32, device=logits2d.device)
+    mean = torch.empty((), dtype=f32, device=logits2d.device)
     row_lse = torch.empty((M,), dtype=f32, device=logits2d.device)
     row_ws = torch.empty((2 * M,), dtype=f32, device=logits2d.device)
     check(_L().cgpt_ce_fwd(logits2d.data_ptr(), targets.data_ptr(), _p(next_boundary), _p(class_w), sums.data_ptr(),
-                           row_lse.data_ptr(), row_ws.data_ptr(), B, T, V, int(shift), float(smoothing),
-                           int(ignore_index), _stream()))
-    return sums, row_lse
+                           mean.data_ptr(), row_lse.data_ptr(), row_ws.data_ptr(), B, T, V, int(shift), float(smoothing),
+                           int(ignore_index), int(bool(zero_if_empty)), _stream()))
+    return sums, row_lse, mean
 
 
 def ce_bwd(logits2d, row_lse, targets, sums, gscale, B, T, *, coef=1.0, shift=0, next_boundary=None, class_w=None,
-           smoothing=0.0, ignore_index=0):
+           smoothing=0.0, ignore_index=0, bf16_mode=0):
+    """-> dlogits (fp32), or (dlogits, by-product) when bf16_mode != 0: 1 = bf16 [M, Vp] copy (pad columns zero),
+    2 = bf16 [M, 3*Vp] hi|lo|hi split, Vp = V rounded up to 8 — what the head GEMMs of the backward pass read."""
     M, V = logits2d.shape
     dlogits = torch.empty((M, V), dtype=f32, device=logits2d.device)
+    Vp = (V + 7) // 8 * 8
+    side = None
+    if bf16_mode:
+        side = torch.empty((M, (3 if bf16_mode == 2 else 1) * Vp), dtype=bf16, device=logits2d.device)
     check(_L().cgpt_ce_bwd(logits2d.data_ptr(), row_lse.data_ptr(), targets.data_ptr(), _p(next_boundary), _p(class_w),
-                           sums.data_ptr(), _p(gscale), float(coef), dlogits.data_ptr(), B, T, V, int(shift),
-                           float(smoothing), int(ignore_index), _stream()))
-    return dlogits
+                           sums.data_ptr(), _p(gscale), float(coef), dlogits.data_ptr(), _p(side), int(bf16_mode), Vp,
+                           B, T, V, int(shift), float(smoothing), int(ignore_index), _stream()))
+    return dlogits if not bf16_mode else (dlogits, side)
 
 
 # ------------------------------------------------------------------ optimiser

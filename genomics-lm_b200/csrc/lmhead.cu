@@ -259,7 +259,7 @@ skinny_dw_small_kernel(const float* __restrict__ dout, const float* __restrict__
   }
 }
 
-// ------------------------------------------------------------------ cross entropy (one warp per row, V <= 128)
+// ------------------------------------------------------------------ cross entropy (one THREAD per row, V <= 128)
 struct RowInfo {
   bool keep, bad;
   int64_t target;
@@ -287,183 +287,274 @@ __device__ __forceinline__ RowInfo ce_row_info(const int64_t* targets, const int
   return ri;
 }
 
-// One warp handles kCeRows consecutive rows at a time: the logits of all of them (and their targets / boundary
-// entries) are requested before anything is used, so a warp has kCeRows independent chains of global latency in
-// flight instead of three dependent ones; the target logit comes from the lane that already holds it (shuffle), not
-// from memory.  A CTA (8 warps) covers 8*kCeRows rows and writes ONE partial (loss, weight) pair, summed in a fixed
-// order: the final reduction reads M / (8*kCeRows) pairs instead of M.
-constexpr int kCeRows = 4;
-constexpr int kCeRowsPerCta = 8 * kCeRows;
+// A CTA of 128 threads owns 128 consecutive rows: their logits (one contiguous block of 128*V floats) are copied to
+// shared memory with coalesced 16-byte loads, then every thread walks ITS row from shared memory (odd row pitch in
+// 16-byte cells / words: conflict-free).  The per-row scalar work (row info, max, log-sum-exp, target pick) is done
+// once per row instead of once per lane of a warp-per-row kernel, which is what bound the V = 68 heads: ~11
+// warp-instructions per row instead of ~150.  The CTA writes ONE partial (loss, weight) pair; the last CTA to finish
+// (ticket counter) adds the partials up in index order, so the sums do not depend on the order of arrival.
+constexpr int kCeThreads = 128;
+constexpr int kCeCounters = 64;
+__device__ unsigned int g_ce_tickets[kCeCounters];  // zero at load; the last CTA of a launch re-arms its counter
 
-__global__ void __launch_bounds__(256)
-ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
-              const int32_t* __restrict__ next_boundary, const float* __restrict__ class_w, float* __restrict__ part,
-              float* __restrict__ row_lse, int M, int T, int V, int shift, float smoothing, int64_t ignore_index,
-              int n_part) {
-  __shared__ float red[2][8];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row0 = (blockIdx.x * 8 + warp) * kCeRows;
-  float v[kCeRows][4];
-  RowInfo ri[kCeRows];
-#pragma unroll
-  for (int r = 0; r < kCeRows; ++r) {
-    const int row = row0 + r;
-    const float* z = logits + (size_t)(row < M ? row : 0) * V;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = lane + 32 * k;
-      v[r][k] = (row < M && c < V) ? z[c] : -INFINITY;
-    }
-    if (row < M) {
-      ri[r] = ce_row_info(targets, next_boundary, row, T, shift, ignore_index, V);
-    } else {
-      ri[r].keep = ri[r].bad = false;
-      ri[r].target = 0;
-    }
-  }
-  float wc[4], sw = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = lane + 32 * k;
-    wc[k] = c < V ? (class_w ? __ldg(class_w + c) : 1.f) : 0.f;
-    sw += wc[k];
-  }
-  sw = warp_sum(sw);
-  float loss_acc = 0.f, wt_acc = 0.f;
-#pragma unroll
-  for (int r = 0; r < kCeRows; ++r) {
-    const int row = row0 + r;
-    float mx = fmaxf(fmaxf(v[r][0], v[r][1]), fmaxf(v[r][2], v[r][3]));
-    mx = warp_max(mx);
-    float se = 0.f, swz = 0.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      if (lane + 32 * k < V) {
-        se += expf(v[r][k] - mx);
-        swz += wc[k] * v[r][k];
+// smem row pitch in floats: rows of 16-byte cells with an odd cell count (V % 4 == 0), else an odd word count
+__host__ __device__ inline int ce_pitch(int V) {
+  if ((V & 3) == 0) return ((V >> 2) & 1) ? V : V + 4;
+  return (V & 1) ? V : V + 1;
+}
+
+// global [rows, V] block -> smem rows of pitch Vs (VEC: 16-byte pieces; a piece never straddles rows)
+template <bool VEC>
+__device__ __forceinline__ void ce_stage_rows(const float* __restrict__ src, float* z, int rows, int V, int Vs) {
+  const int tid = threadIdx.x;
+  if constexpr (VEC) {
+    const int V4 = V >> 2, n4 = rows * V4;
+    int r = tid / V4, c = tid - r * V4;
+    const int dr = kCeThreads / V4, dc = kCeThreads - dr * V4;
+#pragma unroll 4
+    for (int i = tid; i < n4; i += kCeThreads) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(src) + i);
+      *reinterpret_cast<float4*>(z + r * Vs + c * 4) = v;
+      r += dr;
+      c += dc;
+      if (c >= V4) {
+        c -= V4;
+        ++r;
       }
     }
-    se = warp_sum(se);
+  } else {
+    const int n = rows * V;
+    int r = tid / V, c = tid - r * V;
+    const int dr = kCeThreads / V, dc = kCeThreads - dr * V;
+#pragma unroll 4
+    for (int i = tid; i < n; i += kCeThreads) {
+      z[r * Vs + c] = __ldg(src + i);
+      r += dr;
+      c += dc;
+      if (c >= V) {
+        c -= V;
+        ++r;
+      }
+    }
+  }
+}
+
+template <bool VEC>
+__global__ void __launch_bounds__(kCeThreads)
+ce_fwd_kernel(const float* __restrict__ logits, const int64_t* __restrict__ targets,
+              const int32_t* __restrict__ next_boundary, const float* __restrict__ class_w, float* __restrict__ part,
+              float* __restrict__ row_lse, float* __restrict__ sums, float* __restrict__ mean_out, int M, int T, int V,
+              int Vs, int shift,
+              float smoothing, int64_t ignore_index, int zero_if_empty, unsigned int* __restrict__ ticket) {
+  extern __shared__ __align__(16) float ce_smem[];
+  __shared__ float red[2][kCeThreads / 32];
+  __shared__ bool is_last;
+  float* z = ce_smem;                    // [128][Vs]
+  float* wcs = ce_smem + kCeThreads * Vs;  // [V] class weights (1 when there are none)
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row_base = blockIdx.x * kCeThreads;
+  const int rows = min(kCeThreads, M - row_base);
+  const int n_part = gridDim.x;
+  for (int c = tid; c < V; c += kCeThreads) wcs[c] = class_w ? __ldg(class_w + c) : 1.f;
+  ce_stage_rows<VEC>(logits + (size_t)row_base * V, z, rows, V, Vs);
+  RowInfo ri;
+  ri.keep = ri.bad = false;
+  ri.target = 0;
+  if (tid < rows) ri = ce_row_info(targets, next_boundary, row_base + tid, T, shift, ignore_index, V);
+  __syncthreads();
+  float loss = 0.f, wt = 0.f;
+  if (tid < rows) {
+    const float* zr = z + tid * Vs;
+    float mx = -INFINITY;
+    if constexpr (VEC) {
+      for (int c = 0; c < V; c += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(zr + c);
+        mx = fmaxf(fmaxf(mx, fmaxf(q.x, q.y)), fmaxf(q.z, q.w));
+      }
+    } else {
+      for (int c = 0; c < V; ++c) mx = fmaxf(mx, zr[c]);
+    }
+    float se = 0.f, swz = 0.f, sw = 0.f;
+    const bool smooth = smoothing > 0.f && ri.keep;
+    if constexpr (VEC) {
+      for (int c = 0; c < V; c += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(zr + c);
+        se += (expf(q.x - mx) + expf(q.y - mx)) + (expf(q.z - mx) + expf(q.w - mx));
+        if (smooth) {
+          const float4 w4 = *reinterpret_cast<const float4*>(wcs + c);
+          swz += (w4.x * q.x + w4.y * q.y) + (w4.z * q.z + w4.w * q.w);
+          sw += (w4.x + w4.y) + (w4.z + w4.w);
+        }
+      }
+    } else {
+      for (int c = 0; c < V; ++c) {
+        const float q = zr[c];
+        se += expf(q - mx);
+        if (smooth) {
+          swz += wcs[c] * q;
+          sw += wcs[c];
+        }
+      }
+    }
     const float lse = mx + logf(se);
-    float loss = 0.f, wt = 0.f;
-    if (ri[r].keep) {  // warp-uniform: every lane computed the same RowInfo
-      swz = warp_sum(swz);
-      const int tg = (int)ri[r].target;
-      const int tk = tg >> 5;
-      const float zsel = tk == 0 ? v[r][0] : (tk == 1 ? v[r][1] : (tk == 2 ? v[r][2] : v[r][3]));
-      const float wsel = tk == 0 ? wc[0] : (tk == 1 ? wc[1] : (tk == 2 ? wc[2] : wc[3]));
-      const float ztg = __shfl_sync(0xffffffffu, zsel, tg & 31);
-      const float wy = __shfl_sync(0xffffffffu, wsel, tg & 31);
-      loss = (1.f - smoothing) * wy * (lse - ztg);
+    row_lse[row_base + tid] = lse;
+    if (ri.keep) {
+      const int tg = (int)ri.target;
+      const float wy = wcs[tg];
+      loss = (1.f - smoothing) * wy * (lse - zr[tg]);
       if (smoothing > 0.f) loss += (smoothing / V) * (sw * lse - swz);
       wt = wy;
-    } else if (ri[r].bad) {
+    } else if (ri.bad) {
       loss = __int_as_float(0x7fc00000);  // label out of range: poison the loss, do not dereference
       wt = 1.f;
     }
-    if (lane == 0 && row < M) row_lse[row] = lse;
-    loss_acc += loss;  // fixed order: rows of the warp, then warps of the CTA, then CTAs
-    wt_acc += wt;
   }
+  // fixed order: lanes of a warp (shuffle tree), warps of the CTA, then CTAs (below)
+  loss = warp_sum(loss);
+  wt = warp_sum(wt);
   if (lane == 0) {
-    red[0][warp] = loss_acc;
-    red[1][warp] = wt_acc;
+    red[0][warp] = loss;
+    red[1][warp] = wt;
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (tid == 0) {
     float a = 0.f, b2 = 0.f;
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
+    for (int w = 0; w < kCeThreads / 32; ++w) {
       a += red[0][w];
       b2 += red[1][w];
     }
     part[blockIdx.x] = a;
     part[n_part + blockIdx.x] = b2;
-  }
-}
-
-// deterministic (fixed-order) reduction of the per-CTA partial sums into sums[0..1]
-__global__ void __launch_bounds__(1024) ce_reduce_kernel(const float* __restrict__ part, float* __restrict__ sums, int n) {
-  __shared__ float red[2][32];
-  float a = 0.f, b = 0.f;
-  for (int i = threadIdx.x; i < n; i += 1024) {
-    a += part[i];
-    b += part[n + i];
-  }
-  a = warp_sum(a);
-  b = warp_sum(b);
-  if ((threadIdx.x & 31) == 0) {
-    red[0][threadIdx.x >> 5] = a;
-    red[1][threadIdx.x >> 5] = b;
+    __threadfence();
+    is_last = atomicAdd(ticket, 1u) == (unsigned)(n_part - 1);
   }
   __syncthreads();
-  if (threadIdx.x < 32) {
-    a = warp_sum(red[0][threadIdx.x]);
-    b = warp_sum(red[1][threadIdx.x]);
-    if (threadIdx.x == 0) {
-      sums[0] += a;
-      sums[1] += b;
+  if (!is_last) return;
+  __threadfence();
+  float a = 0.f, b2 = 0.f;
+  for (int i = tid; i < n_part; i += kCeThreads) {
+    a += __ldcg(part + i);
+    b2 += __ldcg(part + n_part + i);
+  }
+  a = warp_sum(a);
+  b2 = warp_sum(b2);
+  __syncthreads();  // red[] of the first reduction has been read
+  if (lane == 0) {
+    red[0][warp] = a;
+    red[1][warp] = b2;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    a = b2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < kCeThreads / 32; ++w) {
+      a += red[0][w];
+      b2 += red[1][w];
     }
+    sums[0] = a;
+    sums[1] = b2;
+    if (mean_out) *mean_out = (zero_if_empty && !(b2 > 0.f)) ? 0.f : a / b2;
+    *ticket = 0u;
   }
 }
 
-__global__ void __launch_bounds__(256)
+// bf16 by-products of the logit gradient for the GEMMs that consume it (the head's input- and weight-gradient GEMMs
+// read bf16 operands): mode 1 = [M, ld] bf16(g) with zero pad columns; mode 2 = [M, 3*ld] hi | lo | hi (the split
+// operand of the fp32-accurate head), pads zero.  Written from the staged fp32 rows, 4 bytes per thread, coalesced.
+template <bool VEC>
+__global__ void __launch_bounds__(kCeThreads)
 ce_bwd_kernel(const float* __restrict__ logits, const float* __restrict__ row_lse, const int64_t* __restrict__ targets,
               const int32_t* __restrict__ next_boundary, const float* __restrict__ class_w,
               const float* __restrict__ sums, const float* __restrict__ gscale, float coef, float* __restrict__ dlogits,
-              int M, int T, int V, int shift, float smoothing, int64_t ignore_index) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int row0 = (blockIdx.x * 8 + warp) * kCeRows;
-  float v[kCeRows][4], lse[kCeRows];
-  RowInfo ri[kCeRows];
-#pragma unroll
-  for (int r = 0; r < kCeRows; ++r) {
-    const int row = row0 + r;
-    if (row < M) {
-      ri[r] = ce_row_info(targets, next_boundary, row, T, shift, ignore_index, V);
-    } else {
-      ri[r].keep = ri[r].bad = false;
-      ri[r].target = 0;
-    }
-    lse[r] = row < M ? row_lse[row] : 0.f;
-    const float* z = logits + (size_t)(row < M ? row : 0) * V;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = lane + 32 * k;
-      v[r][k] = (row < M && c < V && ri[r].keep) ? z[c] : 0.f;
-    }
+              uint32_t* __restrict__ dl_bf16, int bf16_mode, int ld_bf16, int M, int T, int V, int Vs, int shift,
+              float smoothing, int64_t ignore_index) {
+  extern __shared__ __align__(16) float ce_smem[];
+  float* z = ce_smem;
+  float* wcs = ce_smem + kCeThreads * Vs;
+  const int tid = threadIdx.x;
+  const int row_base = blockIdx.x * kCeThreads;
+  const int rows = min(kCeThreads, M - row_base);
+  for (int c = tid; c < V; c += kCeThreads) wcs[c] = class_w ? __ldg(class_w + c) : 1.f;
+  ce_stage_rows<VEC>(logits + (size_t)row_base * V, z, rows, V, Vs);
+  RowInfo ri;
+  ri.keep = ri.bad = false;
+  ri.target = 0;
+  float lse = 0.f;
+  if (tid < rows) {
+    ri = ce_row_info(targets, next_boundary, row_base + tid, T, shift, ignore_index, V);
+    lse = row_lse[row_base + tid];
   }
   const float scale = coef * (gscale ? *gscale : 1.f) / sums[1];
-  float wc[4], sw = 0.f;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int c = lane + 32 * k;
-    wc[k] = c < V ? (class_w ? __ldg(class_w + c) : 1.f) : 0.f;
-    sw += wc[k];
-  }
-  sw = warp_sum(sw);
-#pragma unroll
-  for (int r = 0; r < kCeRows; ++r) {
-    const int row = row0 + r;
-    if (row >= M) break;
-    float* o = dlogits + (size_t)row * V;
-    if (!ri[r].keep) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k)
-        if (lane + 32 * k < V) o[lane + 32 * k] = 0.f;
-      continue;
-    }
-    const int tg = (int)ri[r].target;
-    const float wy = class_w ? __ldg(class_w + tg) : 1.f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int c = lane + 32 * k;
-      if (c < V) {
-        const float p = expf(v[r][k] - lse[r]);
-        float g = (1.f - smoothing) * wy * (p - (c == tg ? 1.f : 0.f));
-        if (smoothing > 0.f) g += (smoothing / V) * (p * sw - wc[k]);
-        o[c] = g * scale;
+  __syncthreads();
+  if (tid < rows) {
+    float* zr = z + tid * Vs;
+    if (!ri.keep) {
+      for (int c = 0; c < V; ++c) zr[c] = 0.f;
+    } else {
+      const int tg = (int)ri.target;
+      const float wy = wcs[tg];
+      const float a = (1.f - smoothing) * wy * scale;
+      float sw = 0.f;
+      if (smoothing > 0.f)
+        for (int c = 0; c < V; ++c) sw += wcs[c];
+      const float bsm = smoothing > 0.f ? (smoothing / V) * scale : 0.f;
+      // g = scale * ((1-s) wy (p - onehot) + s/V (p sw - w_c))
+      for (int c = 0; c < V; ++c) {
+        const float p = expf(zr[c] - lse);
+        float g = a * (p - (c == tg ? 1.f : 0.f));
+        if (smoothing > 0.f) g += bsm * (p * sw - wcs[c]);
+        zr[c] = g;
       }
+    }
+  }
+  __syncthreads();
+  // smem rows -> dlogits (same piece mapping as the staging), then the bf16 by-product
+  {
+    float* dst = dlogits + (size_t)row_base * V;
+    if constexpr (VEC) {
+      const int V4 = V >> 2, n4 = rows * V4;
+      int r = tid / V4, c = tid - r * V4;
+      const int dr = kCeThreads / V4, dc = kCeThreads - dr * V4;
+      for (int i = tid; i < n4; i += kCeThreads) {
+        reinterpret_cast<float4*>(dst)[i] = *reinterpret_cast<const float4*>(z + r * Vs + c * 4);
+        r += dr;
+        c += dc;
+        if (c >= V4) {
+          c -= V4;
+          ++r;
+        }
+      }
+    } else {
+      const int n = rows * V;
+      int r = tid / V, c = tid - r * V;
+      const int dr = kCeThreads / V, dc = kCeThreads - dr * V;
+      for (int i = tid; i < n; i += kCeThreads) {
+        dst[i] = z[r * Vs + c];
+        r += dr;
+        c += dc;
+        if (c >= V) {
+          c -= V;
+          ++r;
+        }
+      }
+    }
+  }
+  if (bf16_mode != 0) {
+    const int wpr1 = ld_bf16 >> 1;                       // 4-byte words per section of a row
+    const int wpr = bf16_mode == 2 ? 3 * wpr1 : wpr1;    // words per output row
+    uint32_t* dst = dl_bf16 + (size_t)row_base * wpr;
+    const int n = rows * wpr;
+    for (int i = tid; i < n; i += kCeThreads) {
+      const int r = i / wpr, w = i - r * wpr;
+      const int sec = w / wpr1, c = (w - sec * wpr1) * 2;
+      const float v0 = c < V ? z[r * Vs + c] : 0.f, v1 = c + 1 < V ? z[r * Vs + c + 1] : 0.f;
+      uint32_t o = pack_bf16(v0, v1);
+      if (sec == 1) {  // lo = bf16(v - hi)
+        const float2 hi = unpack_bf16(o);
+        o = pack_bf16(v0 - hi.x, v1 - hi.y);
+      }
+      dst[i] = o;
     }
   }
 }
@@ -538,31 +629,72 @@ int cgpt_skinny_linear_bwd(const float* dout, const float* x, const float* w, fl
 }
 
 int cgpt_ce_fwd(const float* logits, const int64_t* targets, const int32_t* next_boundary, const float* class_w,
-                float* sums, float* row_lse, float* row_ws, int B, int T, int V, int shift, float smoothing,
-                int64_t ignore_index, cgpt_stream_t stream) {
+                float* sums, float* mean_out, float* row_lse, float* row_ws, int B, int T, int V, int shift,
+                float smoothing, int64_t ignore_index, int zero_if_empty, cgpt_stream_t stream) {
   CGPT_REQUIRE(logits && targets && sums && row_lse && row_ws && B > 0 && T > 0, "ce_fwd: bad arguments");
   CGPT_REQUIRE(V >= 1 && V <= 128, "ce: V=%d must be in [1,128]", V);
   CGPT_REQUIRE(shift >= 0, "ce: shift must be >= 0");
   const int M = B * T;
-  const int n_part = (M + kCeRowsPerCta - 1) / kCeRowsPerCta;  // per-CTA partial pairs live in row_ws (2*M floats >= 2*n_part)
-  ce_fwd_kernel<<<n_part, 256, 0, ST(stream)>>>(logits, targets, next_boundary, class_w, row_ws, row_lse, M, T, V, shift,
-                                                smoothing, ignore_index, n_part);
-  count_launch();
-  CGPT_LAUNCH_CHECK();
-  ce_reduce_kernel<<<1, 1024, 0, ST(stream)>>>(row_ws, sums, n_part);
+  const int n_part = (M + kCeThreads - 1) / kCeThreads;  // per-CTA partial pairs live in row_ws (2*M floats >= 2*n_part)
+  const int Vs = ce_pitch(V);
+  const size_t smem = (size_t)(kCeThreads * Vs + V) * 4;
+  const bool vec = (V % 4 == 0) && ((reinterpret_cast<uintptr_t>(logits) & 15) == 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGPT_CHECK(cudaFuncSetAttribute(ce_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CGPT_CHECK(cudaFuncSetAttribute(ce_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CGPT_CHECK(cudaFuncSetAttribute(ce_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CGPT_CHECK(cudaFuncSetAttribute(ce_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    attr_set = true;
+  }
+  // one ticket counter per launch in flight: launches on one stream are ordered anyway; launches on different streams
+  // get different counters unless 64 other CE launches were issued in between
+  static unsigned int next_ticket = 0;
+  unsigned int* tickets = nullptr;
+  CGPT_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_ce_tickets));
+  unsigned int* ticket = tickets + (next_ticket++ % kCeCounters);
+  if (vec)
+    ce_fwd_kernel<true><<<n_part, kCeThreads, smem, ST(stream)>>>(logits, targets, next_boundary, class_w, row_ws, row_lse,
+                                                                  sums, mean_out, M, T, V, Vs, shift, smoothing, ignore_index,
+                                                                  zero_if_empty, ticket);
+  else
+    ce_fwd_kernel<false><<<n_part, kCeThreads, smem, ST(stream)>>>(logits, targets, next_boundary, class_w, row_ws, row_lse,
+                                                                   sums, mean_out, M, T, V, Vs, shift, smoothing, ignore_index,
+                                                                   zero_if_empty, ticket);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;
 }
 
 int cgpt_ce_bwd(const float* logits, const float* row_lse, const int64_t* targets, const int32_t* next_boundary,
-                const float* class_w, const float* sums, const float* gscale, float coef, float* dlogits, int B, int T,
-                int V, int shift, float smoothing, int64_t ignore_index, cgpt_stream_t stream) {
+                const float* class_w, const float* sums, const float* gscale, float coef, float* dlogits,
+                void* dl_bf16, int bf16_mode, int64_t ld_bf16, int B, int T, int V, int shift, float smoothing,
+                int64_t ignore_index, cgpt_stream_t stream) {
   CGPT_REQUIRE(logits && row_lse && targets && sums && dlogits && B > 0 && T > 0, "ce_bwd: bad arguments");
   CGPT_REQUIRE(V >= 1 && V <= 128, "ce: V=%d must be in [1,128]", V);
+  CGPT_REQUIRE(bf16_mode == 0 || (dl_bf16 && (bf16_mode == 1 || bf16_mode == 2) && ld_bf16 >= V && ld_bf16 % 2 == 0 &&
+                                  ld_bf16 <= 256 && (reinterpret_cast<uintptr_t>(dl_bf16) & 3) == 0),
+               "ce_bwd: bf16 by-product needs mode 1|2, an even pitch >= V and a 4-byte aligned buffer");
   const int M = B * T;
-  ce_bwd_kernel<<<(M + kCeRowsPerCta - 1) / kCeRowsPerCta, 256, 0, ST(stream)>>>(logits, row_lse, targets, next_boundary, class_w, sums, gscale,
-                                                     coef, dlogits, M, T, V, shift, smoothing, ignore_index);
+  const int Vs = ce_pitch(V);
+  const size_t smem = (size_t)(kCeThreads * Vs + V) * 4;
+  const bool vec = (V % 4 == 0) && (((reinterpret_cast<uintptr_t>(logits) | reinterpret_cast<uintptr_t>(dlogits)) & 15) == 0);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CGPT_CHECK(cudaFuncSetAttribute(ce_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    CGPT_CHECK(cudaFuncSetAttribute(ce_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 72 * 1024));
+    attr_set = true;
+  }
+  const int grid = (M + kCeThreads - 1) / kCeThreads;
+  uint32_t* ob = reinterpret_cast<uint32_t*>(dl_bf16);
+  if (vec)
+    ce_bwd_kernel<true><<<grid, kCeThreads, smem, ST(stream)>>>(logits, row_lse, targets, next_boundary, class_w, sums, gscale,
+                                                                coef, dlogits, ob, bf16_mode, (int)ld_bf16, M, T, V, Vs, shift,
+                                                                smoothing, ignore_index);
+  else
+    ce_bwd_kernel<false><<<grid, kCeThreads, smem, ST(stream)>>>(logits, row_lse, targets, next_boundary, class_w, sums, gscale,
+                                                                 coef, dlogits, ob, bf16_mode, (int)ld_bf16, M, T, V, Vs, shift,
+                                                                 smoothing, ignore_index);
   count_launch();
   CGPT_LAUNCH_CHECK();
   return 0;

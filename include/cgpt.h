@@ -206,16 +206,23 @@ int cgpt_skinny_linear_bwd(const float* dout, const float* x, const float* w, fl
 /* Cross entropy, mean over kept rows               model_tiny_gpt.py:343-349; objectives.py:39-57,100-105.
  * Row r=(b,t) uses target tgt[b, t+shift]; it is kept iff t+shift < T, target != ignore_index and
  * (next_boundary==NULL || next_boundary[b,t] >= t+shift)   (offset_target_mask, objectives.py:13-23).
- * sums[0] += sum of weighted losses, sums[1] += sum of w[target] (fixed-order, deterministic);
- * row_lse[M] is saved for backward; row_ws is a [2*M] fp32 scratch (per-CTA partial loss | weight sums, fixed order). */
+ * sums[0] = sum of weighted losses, sums[1] = sum of w[target] (fixed-order, deterministic: per-CTA partials, added up
+ * in index order by the last CTA to finish); *mean_out (nullable) = sums[0] / sums[1] — the mean loss — or 0 when no
+ * row is kept and zero_if_empty != 0 (objectives.py:100-105).  All three are WRITTEN, not accumulated.
+ * row_lse[M] is saved for backward; row_ws is a [2*M] fp32 scratch (the per-CTA partial loss | weight sums). */
 int cgpt_ce_fwd(const float* logits, const int64_t* targets, const int32_t* next_boundary /*nullable*/,
-                const float* class_w /*nullable*/, float* sums, float* row_lse, float* row_ws, int B, int T,
-                int V, int shift, float smoothing, int64_t ignore_index, cgpt_stream_t stream);
-/* dlogits = coef * (*gscale) / sums[1] * dL_row/dlogits   (zero rows for dropped targets). */
+                const float* class_w /*nullable*/, float* sums, float* mean_out, float* row_lse, float* row_ws,
+                int B, int T, int V, int shift, float smoothing, int64_t ignore_index, int zero_if_empty,
+                cgpt_stream_t stream);
+/* dlogits = coef * (*gscale) / sums[1] * dL_row/dlogits   (zero rows for dropped targets).
+ * Optional bf16 by-product for the GEMMs that consume the gradient (nullable / bf16_mode 0 = none):
+ * bf16_mode 1: dl_bf16[M, ld_bf16] = bf16(dlogits), pad columns zero; bf16_mode 2: dl_bf16[M, 3*ld_bf16] =
+ * hi | lo | hi with hi = bf16(g), lo = bf16(g - hi) (the split operand of the fp32-accurate head). */
 int cgpt_ce_bwd(const float* logits, const float* row_lse, const int64_t* targets,
                 const int32_t* next_boundary, const float* class_w, const float* sums,
-                const float* gscale /*device scalar, nullable = 1*/, float coef, float* dlogits, int B, int T,
-                int V, int shift, float smoothing, int64_t ignore_index, cgpt_stream_t stream);
+                const float* gscale /*device scalar, nullable = 1*/, float coef, float* dlogits,
+                void* dl_bf16 /*nullable*/, int bf16_mode, int64_t ld_bf16, int B, int T, int V, int shift,
+                float smoothing, int64_t ignore_index, cgpt_stream_t stream);
 
 /* ---------------------------------------------------------------- dropout ---------------- */
 /* out = (residual) + x * mask / (1-p)   nn.Dropout on the embedding (:312) and the MLP output (:57,147).

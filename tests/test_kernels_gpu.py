@@ -280,7 +280,7 @@ def test_cast_colsum_rope_swiglu_adamw(ops):
 # ------------------------------------------------------------------------------------------ heads / CE
 def test_skinny_linear_and_ce(ops):
     g = torch.Generator().manual_seed(6)
-    for (B, T, d, V) in [(2, 33, 32, 68), (4, 256, 512, 68), (3, 100, 384, 69), (2, 64, 64, 5), (9, 333, 512, 5), (2, 50, 384, 8)]:
+    for (B, T, d, V) in [(2, 33, 32, 68), (4, 256, 512, 68), (3, 100, 384, 69), (2, 64, 64, 5), (9, 333, 512, 5), (2, 50, 384, 8), (8, 300, 64, 128), (2, 70, 64, 64)]:
         M = B * T
         x = torch.randn(M, d, generator=g).to(DEV)
         w = (torch.randn(V, d, generator=g) * 0.2).to(DEV)
@@ -302,13 +302,20 @@ def test_skinny_linear_and_ce(ops):
         cw = (torch.rand(V, generator=g) + 0.5).to(DEV)
         for eps, cwt in ((0.0, None), (0.05, None), (0.1, cw)):
             lg = (out * 3).contiguous()
-            sums, lse = ops.ce_fwd(lg, tgt, B, T, class_w=cwt, smoothing=eps, ignore_index=0)
+            sums, lse, mean = ops.ce_fwd(lg, tgt, B, T, class_w=cwt, smoothing=eps, ignore_index=0)
+            assert mean.item() == (sums[0] / sums[1]).item()
             l32 = lg.clone().requires_grad_(True)
             rl = torch.nn.functional.cross_entropy(l32, tgt.view(-1), ignore_index=0, label_smoothing=eps, weight=cwt)
             assert (sums[0] / sums[1]).item() == pytest.approx(rl.item(), rel=2e-6)
             rl.backward()
             dl = ops.ce_bwd(lg, lse, tgt, sums, None, B, T, class_w=cwt, smoothing=eps, ignore_index=0)
             assert torch.allclose(dl, l32.grad, rtol=1e-4, atol=1e-7)
+            # bf16 by-products of the same kernel: padded copy, and the hi|lo|hi split (== the stand-alone kernels)
+            Vp = (V + 7) // 8 * 8
+            dl1, cp = ops.ce_bwd(lg, lse, tgt, sums, None, B, T, class_w=cwt, smoothing=eps, ignore_index=0, bf16_mode=1)
+            assert torch.equal(dl1, dl) and torch.equal(cp, ops.cast_bf16(dl, ld_out=Vp))
+            dl2, sp = ops.ce_bwd(lg, lse, tgt, sums, None, B, T, class_w=cwt, smoothing=eps, ignore_index=0, bf16_mode=2)
+            assert torch.equal(dl2, dl) and torch.equal(sp, ops.split3(dl, cols_pad=Vp))
 
 
 def test_ce_offset_mask_matches_oracle(ops):
@@ -319,12 +326,13 @@ def test_ce_offset_mask_matches_oracle(ops):
     logits = torch.randn(B, T, V, generator=g).to(DEV)
     nb = ops.next_in_set(tgt, (2, 3))
     for o in (2, 4, 8, 16):
-        sums, _ = ops.ce_fwd(logits.view(-1, V), tgt, B, T, shift=o - 1, next_boundary=nb, smoothing=0.05)
+        sums, _, mean = ops.ce_fwd(logits.view(-1, V), tgt, B, T, shift=o - 1, next_boundary=nb, smoothing=0.05,
+                                   zero_if_empty=True)
         total, losses = O.multi_offset_lm_loss({o: logits.cpu()}, tgt.cpu(), {o: 1.0}, label_smoothing=0.05)
         if o in losses:
             assert (sums[0] / sums[1]).item() == pytest.approx(losses[o].item(), rel=3e-6)
         else:
-            assert sums[1].item() == 0.0
+            assert sums[1].item() == 0.0 and mean.item() == 0.0
 
 
 # ------------------------------------------------------------------------------------------ attention
