@@ -1141,6 +1141,7 @@ attn_fwd_w3_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail; its results are read from here on
   const uint32_t tS = tmem_base + strm * 256, tO = tS + 128;  // S: 128 columns, O: HD columns (accumulated over an item)
 
   auto kv_lo_of = [&](int qb, int b) { return row_jlo(seg_start ? seg_start + (size_t)b * T : nullptr, qb * BQ, T, window) / BKV; };
@@ -1463,6 +1464,7 @@ __global__ void attn_delta_vec_kernel(const __nv_bfloat16* __restrict__ o, const
                                       float* __restrict__ delta, int B, int T, int H,
                                       const int32_t* __restrict__ seg_start, int window, int* __restrict__ qhi_tab,
                                       int ctr_init, float4* __restrict__ dq_zero) {
+  pdl_wait();
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte chunk index
   if (qhi_tab && e < (long long)B * ((T + BKV - 1) / BKV)) fill_qhi_tab((int)e, B, T, seg_start, window, qhi_tab, ctr_init);
   const long long total = (long long)B * T * H * G;
@@ -2046,6 +2048,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 256 + HD;
   const uint32_t tdQ0 = tmem_base + 256 + 2 * HD;  // + buf * HD
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail; its results are read from here on
 
   // Work distribution.  The first pair of a CTA is its block index; every further pair is claimed from a global
   // counter (initialised to the grid size by the delta kernel), so CTAs that drew short items (segment masks make
@@ -2537,6 +2540,7 @@ __global__ void __launch_bounds__(256)
 attn_dq_convert_kernel(const float* __restrict__ dq_ws, __nv_bfloat16* __restrict__ dqkv, int T, int H, int hd, int W,
                        float scale, float* __restrict__ colsum) {
   __shared__ float red[256][8];
+  pdl_wait();
   const int hd8 = hd >> 3;
   const int rpi = 256 / hd8;  // rows per iteration
   const int tid = threadIdx.x;
@@ -2678,7 +2682,11 @@ int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B
       }
       const int half_pairs = (n_pairs + 1) / 2;  // two item streams per CTA
       const int g2 = half_pairs < num_sms() ? half_pairs : num_sms();
-      k2<<<g2, 384, S2::kDynamic, st>>>(tm, to2, seg, lse, B, T, H, Hk, window, scale * kLog2e, drop, S2::kDynamic);
+      if (variant == 2)  // only the w3 kernels carry the pdl_wait() a programmatic launch needs
+        CGPT_CHECK(launch_pdl(k2, dim3(g2), dim3(384), S2::kDynamic, st, 1, tm, to2, seg, lse, B, T, H, Hk, window,
+                              scale * kLog2e, drop, (int)S2::kDynamic));
+      else
+        k2<<<g2, 384, S2::kDynamic, st>>>(tm, to2, seg, lse, B, T, H, Hk, window, scale * kLog2e, drop, S2::kDynamic);
       count_launch();
       CGPT_LAUNCH_CHECK();
       return 0;
@@ -2751,9 +2759,8 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     constexpr int G = HD / 8;
     if constexpr (G == 2 || G == 4 || G == 8 || G == 16) {
       const long long chunks = (long long)B * T * H * G;  // >= B * kv tiles, so the table job fits too
-      attn_delta_vec_kernel<G><<<(unsigned)((chunks + 255) / 256), 256, 0, st>>>(po, pd, delta, B, T, H, seg, window,
-                                                                               qhi_tab, ws_grid,
-                                                                               reinterpret_cast<float4*>(dq_ws));
+      CGPT_CHECK(launch_pdl(attn_delta_vec_kernel<G>, dim3((unsigned)((chunks + 255) / 256)), dim3(256), 0, st, 1, po, pd,
+                            delta, B, T, H, seg, window, qhi_tab, ws_grid, reinterpret_cast<float4*>(dq_ws)));
     } else {
       const long long warps = (long long)B * T * H;
       attn_delta_kernel<<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(po, pd, delta, B, T, H, HD, seg, window, qhi_tab,
@@ -2773,8 +2780,9 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
       CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SW::kDynamic));
       configured = true;
     }
-    kern<<<grid, 288, SW::kDynamic, st>>>(tq, td, tdq, tdkv, seg, qhi_tab, lse, delta, reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws,
-                                          colsum, B, T, H, Hk, window, scale, drop, SW::kDynamic);
+    CGPT_CHECK(launch_pdl(kern, dim3(grid), dim3(288), SW::kDynamic, st, 1, tq, td, tdq, tdkv, seg, qhi_tab, lse, delta,
+                          reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, colsum, B, T, H, Hk, window, scale, drop,
+                          (int)SW::kDynamic));
   } else {
     auto kern = attn_bwd_kernel<HD>;
     static bool configured = false;
@@ -2790,8 +2798,8 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   {
     // hd <= 64: the k / v column sums came out of the main kernel's epilogue, the q part comes out of this one
     float* qsum = (HD <= 64) ? colsum : nullptr;
-    attn_dq_convert_kernel<<<dim3((T + 255) / 256, B * H), 256, 0, st>>>(dq_ws, reinterpret_cast<__nv_bfloat16*>(dqkv), T, H,
-                                                                        HD, W, scale, qsum);
+    CGPT_CHECK(launch_pdl(attn_dq_convert_kernel, dim3((T + 255) / 256, B * H), dim3(256), 0, st, 1, dq_ws,
+                          reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, HD, W, scale, qsum));
     count_launch();
     CGPT_LAUNCH_CHECK();
   }

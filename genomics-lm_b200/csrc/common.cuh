@@ -6,6 +6,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <string.h>
+
+#include <utility>
 
 #include "../../include/cgpt.h"
 
@@ -30,6 +33,10 @@ int check_cuda(cudaError_t e, const char* what);
 
 int num_sms();
 void count_launch(int n = 1);
+// CGPT_PDL=1 turns programmatic dependent launch on for the kernels that carry pdl_wait().  Off by default: under the
+// captured step at the headline shape it measured 27.69 / 27.81 ms against 27.56 / 27.58 ms without (same box, A/B);
+// read once
+bool pdl_enabled();
 
 // TMA descriptor for a row-major bf16 tensor viewed as rank-`rank` (dims innermost first).
 // box = tile extents (innermost first); swizzle_bytes in {0,32,64,128}.
@@ -42,6 +49,46 @@ int make_tmap_f32(CUtensorMap* map, const void* base, int rank, const uint64_t* 
 
 // ---------------------------------------------------------------- device helpers
 #ifdef __CUDACC__
+
+// ---- programmatic dependent launch.  A kernel launched with launch_pdl() may have its CTAs placed (as SMs drain) and
+// run its prologue — barrier init, TMEM allocation, descriptor prefetch, parameter staging — while the PREVIOUS kernel
+// in the stream is still finishing; pdl_wait() then blocks until that kernel has completed and its writes are
+// visible, so it must precede the first access to any global memory another kernel produces or still reads.
+// Every thread of a kernel launched this way calls pdl_wait() exactly once, on every path: the completion of this
+// grid is what the NEXT kernel's pdl_wait() observes, so the chain of dependencies stays transitive.  The trigger
+// sits right behind the wait: at most one kernel runs ahead.  Both are no-ops under a plain launch.
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              int cluster_x, Args&&... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

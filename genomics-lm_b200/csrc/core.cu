@@ -1,5 +1,6 @@
 // Library plumbing: error text, device check, TMA descriptor encoding, launch counter.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -29,6 +30,14 @@ int check_cuda(cudaError_t e, const char* what) {
 }
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("CGPT_PDL");
+    return e && e[0] == '1';
+  }();
+  return on;
+}
 
 int num_sms() {
   static int sms = 0;

@@ -217,6 +217,7 @@ __global__ void __launch_bounds__(256)
 layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                      __nv_bfloat16* __restrict__ yb, float* __restrict__ yf, float* __restrict__ mean,
                      float* __restrict__ rstd, int M, int d, float eps, int rev) {
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int wpb = blockDim.x >> 5;
   const int nvec = d >> 2;
@@ -276,6 +277,7 @@ layernorm_bwd_kernel(const void* __restrict__ dy_, const float* __restrict__ x, 
                      float* __restrict__ dx, __nv_bfloat16* __restrict__ dxb, float* __restrict__ dgamma,
                      float* __restrict__ dbeta, float* __restrict__ dxsum, int M, int d, int rev) {
   __shared__ float red[8][VPT * 128];
+  pdl_wait();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   const int wpb = blockDim.x >> 5;
@@ -411,6 +413,7 @@ layernorm_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict
     fence_proxy_async_smem();
   }
   __syncwarp();
+  pdl_wait();
   const int stride = gridDim.x * kLnWarps;
   const int row0 = blockIdx.x * kLnWarps + warp;
   if (lane == 0) {
@@ -509,6 +512,7 @@ layernorm_bwd_stream_kernel(const __nv_bfloat16* __restrict__ dy, const float* _
     fence_proxy_async_smem();
   }
   __syncwarp();
+  pdl_wait();
   const int stride = gridDim.x * kLnWarps;
   const int row0 = blockIdx.x * kLnWarps + warp;
   const uint32_t row_tx = dres ? L::kRowBytes : D * 6;
@@ -1260,13 +1264,14 @@ int cgpt_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
       attr_set = true;
     }
     const int grid = grid_for((long long)M * 32, kLnWarps * 32, 3);
-    layernorm_fwd_stream_kernel<4, 4><<<grid, kLnWarps * 32, L::kSmem, ST(stream)>>>(x, gamma, beta, yb, y_f32, mean, rstd, M, eps, rev);
+    CGPT_CHECK(launch_pdl(layernorm_fwd_stream_kernel<4, 4>, dim3(grid), dim3(kLnWarps * 32), L::kSmem, ST(stream), 1, x, gamma,
+                          beta, yb, y_f32, mean, rstd, M, eps, rev));
     count_launch();
     CGPT_LAUNCH_CHECK();
     return 0;
   }
   const int grid = grid_for((long long)M * 32, 256, 4);
-#define LN_FWD(V) layernorm_fwd_kernel<V><<<grid, 256, 0, ST(stream)>>>(x, gamma, beta, yb, y_f32, mean, rstd, M, d, eps, rev)
+#define LN_FWD(V) CGPT_CHECK(launch_pdl(layernorm_fwd_kernel<V>, dim3(grid), dim3(256), 0, ST(stream), 1, x, gamma, beta, yb, y_f32, mean, rstd, M, d, eps, rev))
   if (vpt <= 1) LN_FWD(1); else if (vpt <= 2) LN_FWD(2); else if (vpt <= 4) LN_FWD(4); else LN_FWD(8);
 #undef LN_FWD
   count_launch();
@@ -1292,14 +1297,15 @@ int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const floa
       attr_set = true;
     }
     const int grid = grid_for((long long)M * 32, kLnWarps * 32, 2);
-    layernorm_bwd_stream_kernel<4, 2><<<grid, kLnWarps * 32, L::kSmem, ST(stream)>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, rev);
+    CGPT_CHECK(launch_pdl(layernorm_bwd_stream_kernel<4, 2>, dim3(grid), dim3(kLnWarps * 32), L::kSmem, ST(stream), 1,
+                          reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta,
+                          dx_colsum, M, rev));
     count_launch();
     CGPT_LAUNCH_CHECK();
     return 0;
   }
   const int grid = grid_for((long long)M * 32, 256, vpt <= 4 ? 2 : 1);
-#define LN_BWD(V, F) layernorm_bwd_kernel<V, F><<<grid, 256, 0, ST(stream)>>>(dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, d, rev)
+#define LN_BWD(V, F) CGPT_CHECK(launch_pdl(layernorm_bwd_kernel<V, F>, dim3(grid), dim3(256), 0, ST(stream), 1, dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, d, rev))
   if (dy_is_f32) {
     if (vpt <= 1) LN_BWD(1, true); else if (vpt <= 2) LN_BWD(2, true); else if (vpt <= 4) LN_BWD(4, true); else LN_BWD(8, true);
   } else {

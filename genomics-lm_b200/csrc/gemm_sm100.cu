@@ -634,6 +634,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if constexpr (TWO) cluster_sync_all();  // the peer's barriers are initialised before anything arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // everything above ran while the previous kernel of the stream was still draining (programmatic dependent launch);
+  // from here on its results are read
+  pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -921,23 +924,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   if constexpr (TWO) {
     const int pairs = num_sms() / 2;
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof(cfg));
-    cfg.gridDim = dim3(2 * (total < pairs ? total : pairs));
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = L::kDynamic;
-    cfg.stream = st;
-    cudaLaunchAttribute attr;
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 2;
-    attr.val.clusterDim.y = 1;
-    attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    CGPT_CHECK(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc, tx, p));
+    CGPT_CHECK(launch_pdl(kern, dim3(2 * (total < pairs ? total : pairs)), dim3(kThreads), L::kDynamic, st, 2, ta, tb, tc,
+                          tx, p));
   } else {
     const int grid = total < num_sms() ? total : num_sms();
-    kern<<<grid, kThreads, L::kDynamic, st>>>(ta, tb, tc, tx, p);
+    CGPT_CHECK(launch_pdl(kern, dim3(grid), dim3(kThreads), L::kDynamic, st, 1, ta, tb, tc, tx, p));
   }
   count_launch();
   CGPT_LAUNCH_CHECK();
