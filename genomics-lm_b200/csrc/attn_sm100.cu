@@ -2683,7 +2683,7 @@ int launch_fwd(const void* qkv, const int32_t* seg, void* out, float* lse, int B
       const int half_pairs = (n_pairs + 1) / 2;  // two item streams per CTA
       const int g2 = half_pairs < num_sms() ? half_pairs : num_sms();
       if (variant == 2)  // only the w3 kernels carry the pdl_wait() a programmatic launch needs
-        CGPT_CHECK(launch_pdl(k2, dim3(g2), dim3(384), S2::kDynamic, st, 1, tm, to2, seg, lse, B, T, H, Hk, window,
+        CGPT_CHECK(launch_pdl(k2, dim3(g2), dim3(384), S2::kDynamic, st, 1, (long long)B * T, tm, to2, seg, lse, B, T, H, Hk, window,
                               scale * kLog2e, drop, (int)S2::kDynamic));
       else
         k2<<<g2, 384, S2::kDynamic, st>>>(tm, to2, seg, lse, B, T, H, Hk, window, scale * kLog2e, drop, S2::kDynamic);
@@ -2759,7 +2759,7 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
     constexpr int G = HD / 8;
     if constexpr (G == 2 || G == 4 || G == 8 || G == 16) {
       const long long chunks = (long long)B * T * H * G;  // >= B * kv tiles, so the table job fits too
-      CGPT_CHECK(launch_pdl(attn_delta_vec_kernel<G>, dim3((unsigned)((chunks + 255) / 256)), dim3(256), 0, st, 1, po, pd,
+      CGPT_CHECK(launch_pdl(attn_delta_vec_kernel<G>, dim3((unsigned)((chunks + 255) / 256)), dim3(256), 0, st, 1, (long long)B * T, po, pd,
                             delta, B, T, H, seg, window, qhi_tab, ws_grid, reinterpret_cast<float4*>(dq_ws)));
     } else {
       const long long warps = (long long)B * T * H;
@@ -2780,7 +2780,7 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
       CGPT_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SW::kDynamic));
       configured = true;
     }
-    CGPT_CHECK(launch_pdl(kern, dim3(grid), dim3(288), SW::kDynamic, st, 1, tq, td, tdq, tdkv, seg, qhi_tab, lse, delta,
+    CGPT_CHECK(launch_pdl(kern, dim3(grid), dim3(288), SW::kDynamic, st, 1, (long long)B * T, tq, td, tdq, tdkv, seg, qhi_tab, lse, delta,
                           reinterpret_cast<__nv_bfloat16*>(dqkv), dq_ws, colsum, B, T, H, Hk, window, scale, drop,
                           (int)SW::kDynamic));
   } else {
@@ -2798,7 +2798,7 @@ int launch_bwd(const void* qkv, const int32_t* seg, const void* out, const void*
   {
     // hd <= 64: the k / v column sums came out of the main kernel's epilogue, the q part comes out of this one
     float* qsum = (HD <= 64) ? colsum : nullptr;
-    CGPT_CHECK(launch_pdl(attn_dq_convert_kernel, dim3((T + 255) / 256, B * H), dim3(256), 0, st, 1, dq_ws,
+    CGPT_CHECK(launch_pdl(attn_dq_convert_kernel, dim3((T + 255) / 256, B * H), dim3(256), 0, st, 1, (long long)B * T, dq_ws,
                           reinterpret_cast<__nv_bfloat16*>(dqkv), T, H, HD, W, scale, qsum));
     count_launch();
     CGPT_LAUNCH_CHECK();

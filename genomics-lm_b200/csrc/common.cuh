@@ -33,10 +33,10 @@ int check_cuda(cudaError_t e, const char* what);
 
 int num_sms();
 void count_launch(int n = 1);
-// CGPT_PDL=1 turns programmatic dependent launch on for the kernels that carry pdl_wait().  Off by default: under the
-// captured step at the headline shape it measured 27.69 / 27.81 ms against 27.56 / 27.58 ms without (same box, A/B);
-// read once
-bool pdl_enabled();
+// Programmatic dependent launch for the kernels that carry pdl_wait(): CGPT_PDL=1 always, =0 never, unset: only for
+// launches over at most 16384 token rows.  Measured under the captured step (same box, A/B): C4 training at B = 8
+// (4096 rows) 2.52 -> 2.40 ms, C2 4.00 -> 3.92 ms; the headline shape (65536 rows) 27.57 -> 27.75 ms, hence the limit.
+bool pdl_enabled(long long token_rows);
 
 // TMA descriptor for a row-major bf16 tensor viewed as rank-`rank` (dims innermost first).
 // box = tile extents (innermost first); swizzle_bytes in {0,32,64,128}.
@@ -64,7 +64,7 @@ __device__ __forceinline__ void pdl_wait() {
 
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
-                              int cluster_x, Args&&... args) {
+                              int cluster_x, long long token_rows, Args&&... args) {
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = grid;
@@ -80,7 +80,7 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
     attr[n].val.clusterDim.z = 1;
     ++n;
   }
-  if (pdl_enabled()) {
+  if (pdl_enabled(token_rows)) {
     attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[n].val.programmaticStreamSerializationAllowed = 1;
     ++n;

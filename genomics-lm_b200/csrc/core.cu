@@ -31,12 +31,12 @@ int check_cuda(cudaError_t e, const char* what) {
 
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
-bool pdl_enabled() {
-  static const bool on = [] {
+bool pdl_enabled(long long token_rows) {
+  static const int mode = [] {
     const char* e = getenv("CGPT_PDL");
-    return e && e[0] == '1';
+    return e ? (e[0] == '1' ? 1 : 0) : -1;
   }();
-  return on;
+  return mode < 0 ? token_rows <= 16384 : mode == 1;
 }
 
 int num_sms() {

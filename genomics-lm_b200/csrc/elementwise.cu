@@ -1264,14 +1264,14 @@ int cgpt_layernorm_fwd(const float* x, const float* gamma, const float* beta, vo
       attr_set = true;
     }
     const int grid = grid_for((long long)M * 32, kLnWarps * 32, 3);
-    CGPT_CHECK(launch_pdl(layernorm_fwd_stream_kernel<4, 4>, dim3(grid), dim3(kLnWarps * 32), L::kSmem, ST(stream), 1, x, gamma,
+    CGPT_CHECK(launch_pdl(layernorm_fwd_stream_kernel<4, 4>, dim3(grid), dim3(kLnWarps * 32), L::kSmem, ST(stream), 1, M, x, gamma,
                           beta, yb, y_f32, mean, rstd, M, eps, rev));
     count_launch();
     CGPT_LAUNCH_CHECK();
     return 0;
   }
   const int grid = grid_for((long long)M * 32, 256, 4);
-#define LN_FWD(V) CGPT_CHECK(launch_pdl(layernorm_fwd_kernel<V>, dim3(grid), dim3(256), 0, ST(stream), 1, x, gamma, beta, yb, y_f32, mean, rstd, M, d, eps, rev))
+#define LN_FWD(V) CGPT_CHECK(launch_pdl(layernorm_fwd_kernel<V>, dim3(grid), dim3(256), 0, ST(stream), 1, M, x, gamma, beta, yb, y_f32, mean, rstd, M, d, eps, rev))
   if (vpt <= 1) LN_FWD(1); else if (vpt <= 2) LN_FWD(2); else if (vpt <= 4) LN_FWD(4); else LN_FWD(8);
 #undef LN_FWD
   count_launch();
@@ -1297,7 +1297,7 @@ int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const floa
       attr_set = true;
     }
     const int grid = grid_for((long long)M * 32, kLnWarps * 32, 2);
-    CGPT_CHECK(launch_pdl(layernorm_bwd_stream_kernel<4, 2>, dim3(grid), dim3(kLnWarps * 32), L::kSmem, ST(stream), 1,
+    CGPT_CHECK(launch_pdl(layernorm_bwd_stream_kernel<4, 2>, dim3(grid), dim3(kLnWarps * 32), L::kSmem, ST(stream), 1, M,
                           reinterpret_cast<const __nv_bfloat16*>(dy), x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta,
                           dx_colsum, M, rev));
     count_launch();
@@ -1305,7 +1305,7 @@ int cgpt_layernorm_bwd(const void* dy, int dy_is_f32, const float* x, const floa
     return 0;
   }
   const int grid = grid_for((long long)M * 32, 256, vpt <= 4 ? 2 : 1);
-#define LN_BWD(V, F) CGPT_CHECK(launch_pdl(layernorm_bwd_kernel<V, F>, dim3(grid), dim3(256), 0, ST(stream), 1, dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, d, rev))
+#define LN_BWD(V, F) CGPT_CHECK(launch_pdl(layernorm_bwd_kernel<V, F>, dim3(grid), dim3(256), 0, ST(stream), 1, M, dy, x, gamma, mean, rstd, dres, dx, dxb, dgamma, dbeta, dx_colsum, M, d, rev))
   if (dy_is_f32) {
     if (vpt <= 1) LN_BWD(1, true); else if (vpt <= 2) LN_BWD(2, true); else if (vpt <= 4) LN_BWD(4, true); else LN_BWD(8, true);
   } else {

@@ -924,11 +924,11 @@ int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc, 
   const int total = p.tiles_m * p.tiles_n * p.split_k;
   if constexpr (TWO) {
     const int pairs = num_sms() / 2;
-    CGPT_CHECK(launch_pdl(kern, dim3(2 * (total < pairs ? total : pairs)), dim3(kThreads), L::kDynamic, st, 2, ta, tb, tc,
-                          tx, p));
+    CGPT_CHECK(launch_pdl(kern, dim3(2 * (total < pairs ? total : pairs)), dim3(kThreads), L::kDynamic, st, 2,
+                          p.M > p.K ? p.M : p.K, ta, tb, tc, tx, p));
   } else {
     const int grid = total < num_sms() ? total : num_sms();
-    CGPT_CHECK(launch_pdl(kern, dim3(grid), dim3(kThreads), L::kDynamic, st, 1, ta, tb, tc, tx, p));
+    CGPT_CHECK(launch_pdl(kern, dim3(grid), dim3(kThreads), L::kDynamic, st, 1, p.M > p.K ? p.M : p.K, ta, tb, tc, tx, p));
   }
   count_launch();
   CGPT_LAUNCH_CHECK();
