@@ -233,6 +233,9 @@ class ResidualLayerNormFn(Function):
         is the column sum of this node's dx), or None.  With a flat gradient buffer the backward kernel adds straight
         into its slot."""
         M, d = x.shape
+        # outputs nobody differentiates through (the residual alias and the bf16 copy of ln_f, whose fp32 output feeds
+        # the heads) must reach backward as None, not as zero tensors autograd would have to fill, convert and add
+        ctx.set_materialize_grads(False)
         yb, yf, mean, rstd = ops.layernorm_fwd(x, gamma, beta, want_bf16=True, want_f32=want_f32)
         ctx.save_for_backward(x, gamma, mean, rstd)
         ctx.masters = (gamma, beta)
@@ -687,6 +690,7 @@ class HeadsFn(Function):
         M, d = x.shape
         n_off = len(off) // 6
         need_bwd = any(ctx.needs_input_grad)
+        ctx.set_materialize_grads(False)  # an unused branch arrives as None in backward (handled there), not as zeros
         x3 = ops.split3(x)
         logits, _, w3, wk = _split_head_fwd(x, head_w, None, x3=x3)
         outs = [logits]
@@ -858,6 +862,7 @@ class CrossEntropyFn(Function):
                 grad_form=0):
         # the kernel's last CTA also forms the mean (0 instead of NaN for an empty selection when asked): no torch
         # arithmetic on the sums
+        ctx.set_materialize_grads(False)  # no zero tensor for the gradient of `sums`
         sums, row_lse, loss = ops.ce_fwd(logits2d, targets, B, T, shift=shift, next_boundary=next_boundary,
                                          class_w=class_w, smoothing=smoothing, ignore_index=ignore_index,
                                          zero_if_empty=zero_if_empty)
@@ -868,6 +873,8 @@ class CrossEntropyFn(Function):
 
     @staticmethod
     def backward(ctx, g, _gs):
+        if g is None:
+            return (None,) * 11
         logits2d, row_lse, targets, sums = ctx.saved_tensors
         next_boundary, class_w, B, T, shift, smoothing, ignore_index, grad_form = ctx.aux
         gs = g.reshape(1).to(f32).contiguous()

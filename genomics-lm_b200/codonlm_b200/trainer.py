@@ -103,6 +103,20 @@ class FlatGroup:
             self.shadow.copy_(self.flat)
 
 
+_PROBE_NO_ALLREDUCE = os.environ.get("CGPT_PROBE_NO_ALLREDUCE", "0") == "1"
+
+
+class _NoWork:
+    """Stand-in for a collective's work handle (CGPT_PROBE_NO_ALLREDUCE=1): wait() orders the streams, nothing more."""
+
+    def __init__(self, stream):
+        self.ev = torch.cuda.Event()
+        self.ev.record(stream)
+
+    def wait(self):
+        torch.cuda.current_stream().wait_event(self.ev)
+
+
 class GradBuckets:
     """Bucketed bf16 all-reduce of a flat gradient buffer, launched on a side stream as soon as every
     parameter of a bucket has received its gradient."""
@@ -177,7 +191,10 @@ class GradBuckets:
             self.comm_stream.wait_event(ready)
             stg = self.staging[b]
             ops.cast_bf16(self.g.grad[s:e].view(1, -1), out=stg.view(1, -1))
-            work = dist.all_reduce(stg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
+            if _PROBE_NO_ALLREDUCE:  # measurement only: what the step costs on N ranks without the collective
+                work = _NoWork(self.comm_stream)
+            else:
+                work = dist.all_reduce(stg, op=dist.ReduceOp.SUM, group=self.pg, async_op=True)
             self.pending.append((b, work))
 
     def join_without_backward(self):

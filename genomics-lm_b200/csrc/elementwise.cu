@@ -1101,13 +1101,14 @@ inline int ln_stream_enabled() {
   }();
   return on;
 }
-// CGPT_LN_REVERSE=0: rows in ascending order.  Default: LAST rows first — the GEMM in front of a LayerNorm produces its
-// rows in ascending order, so its newest lines are still in L2 when the LayerNorm starts, and the LayerNorm ends on
-// the rows the next GEMM reads first.
+// CGPT_LN_REVERSE=1: LAST rows first (the GEMM in front of a LayerNorm produces its rows in ascending order, so its
+// newest lines could still be in L2, and the LayerNorm would end on the rows the next GEMM reads first).  Measured on
+// the captured step: 29.33 ms against 29.37 / 29.40 ms in ascending order on the same box — within the noise, so the
+// default stays ascending.
 inline bool ln_reverse_enabled() {
   static const bool on = [] {
     const char* e = getenv("CGPT_LN_REVERSE");
-    return !(e && e[0] == '0');
+    return e && e[0] == '1';
   }();
   return on;
 }
