@@ -1230,6 +1230,7 @@ attn_fwd_w3_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
   } else {
     // ================================================================= softmax warps: thread = query row
     const int row = tid & 127;
+    const bool sleader = elect_one();  // issues this warp's output stores (uniform-register UTMASTG, no R2UR loop)
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     PairCursor cur;
     cur.begin(vcta, vgrid, nqb, H, Bsz, true);
@@ -1424,7 +1425,7 @@ attn_fwd_w3_kernel(const __grid_constant__ CUtensorMap tm, const __grid_constant
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (sleader) {
           tma_store_3d(&tm_out, smem_u32(stg), h * HD, q0 + (warp & 3) * 32, b);
           bulk_commit();
         }
@@ -2251,6 +2252,9 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
   } else {
     // ================================================================= math warps
     const int row = tid & 127, half = tid >> 7;
+    // the lane that issues (and commits) this warp's bulk tensor copies: behind an elected predicate ptxas issues
+    // UTMAREDG / UTMASTG straight from uniform registers instead of an R2UR ... BRA.U.ANY loop per instruction
+    const bool mleader = elect_one();
     const uint32_t lane_base = static_cast<uint32_t>((warp & 3) * 32) << 16;
     const float scale_log2 = scale * kLog2e;
     int g = 0, n_it = 0;
@@ -2282,7 +2286,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
                        : "memory");
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {
+        if (mleader) {
           asm volatile(
               "cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
                   reinterpret_cast<uint64_t>(&tm_dq)),
@@ -2497,7 +2501,7 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
         }
         fence_proxy_async_smem();
         __syncwarp();
-        if (lane == 0) {  // read completion is awaited (by this lane) before the warp next writes its dS rows
+        if (mleader) {  // read completion is awaited (by this lane) before the warp next writes its dS rows
           tma_store_3d(&tm_dkv, smem_u32(stg), kcol + half * HH, kv0 + (warp & 3) * 32, b);
           tma_store_3d(&tm_dkv, smem_u32(stg) + 32 * ROWB, vcol + half * HH, kv0 + (warp & 3) * 32, b);
           bulk_commit();

@@ -403,7 +403,10 @@ layernorm_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict
   constexpr int D = VPT * 128;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle (the compiler then keeps row indices and ring addresses in uniform registers) and an
+  // elected issuing lane: the bulk copies are issued without an R2UR ... BRA.U.ANY loop around each of them
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const bool leader = elect_one();
   uint8_t* ring = ln_smem + warp * SLOTS * L::kRowBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + L::kBarOff) + warp * SLOTS;
   if (lane == 0) {
@@ -416,7 +419,7 @@ layernorm_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict
   pdl_wait();
   const int stride = gridDim.x * kLnWarps;
   const int row0 = blockIdx.x * kLnWarps + warp;
-  if (lane == 0) {
+  if (leader) {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
       const long long r = row0 + (long long)s * stride;
@@ -447,7 +450,7 @@ layernorm_fwd_stream_kernel(const float* __restrict__ x, const float* __restrict
       s += (v[k].x + v[k].y) + (v[k].z + v[k].w);
     }
     __syncwarp();  // every lane has its part of the row in registers: the slot can be refilled
-    if (lane == 0) {
+    if (leader) {
       const long long rn = rowi + (long long)SLOTS * stride;
       if (rn < M) {
         mbar_expect_tx(&bars[slot], L::kRowBytes);
@@ -502,7 +505,10 @@ layernorm_bwd_stream_kernel(const __nv_bfloat16* __restrict__ dy, const float* _
   constexpr int D = L::D;
   extern __shared__ __align__(128) uint8_t ln_smem[];
   const int lane = threadIdx.x & 31;
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle (the compiler then keeps row indices and ring addresses in uniform registers) and an
+  // elected issuing lane: the bulk copies are issued without an R2UR ... BRA.U.ANY loop around each of them
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
+  const bool leader = elect_one();
   uint8_t* ring = ln_smem + warp * SLOTS * L::kRowBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ln_smem + L::kBarOff) + warp * SLOTS;
   if (lane == 0) {
@@ -524,7 +530,7 @@ layernorm_bwd_stream_kernel(const __nv_bfloat16* __restrict__ dy, const float* _
     bulk_load_1d(smem_u32(sb + L::kDyOff), dy + (size_t)r * D, D * 2, &bars[slot]);
     if (dres) bulk_load_1d(smem_u32(sb + L::kResOff), dres + (size_t)r * D, D * 4, &bars[slot]);
   };
-  if (lane == 0) {
+  if (leader) {
 #pragma unroll
     for (int s = 0; s < SLOTS; ++s) {
       const long long r = row0 + (long long)s * stride;
@@ -608,7 +614,7 @@ layernorm_bwd_stream_kernel(const __nv_bfloat16* __restrict__ dy, const float* _
       }
     }
     __syncwarp();  // every lane is done with the slot: refill it with the row SLOTS iterations ahead
-    if (lane == 0) {
+    if (leader) {
       const long long rn = rowi + (long long)SLOTS * stride;
       if (rn < M) issue(slot, rn);
     }

@@ -135,7 +135,7 @@ __device__ __forceinline__ uint32_t stg_cell(uint32_t base, int row, int cell) {
 // pack to bf16, transpose 32 x 32 through 2 KB of smem, 16-byte coalesced stores (4 lanes per 64-byte segment).
 template <bool GELU>
 __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
-                                               uint32_t taddr, uint32_t stg, int lane, int row0, int n0,
+                                               uint32_t taddr, uint32_t stg, int lane, bool leader, int row0, int n0,
                                                uint32_t bias_s /* smem address of this chunk's 32 bias floats */) {
   uint32_t r[32];
   if (!(p.debug & 2)) {
@@ -183,7 +183,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const CUtens
     const long long ld = (GELU && pass == 1) ? p.ldaux : p.ldc;
     if (dst == nullptr) break;
     if (p.tma_out & 1) {  // the staging buffer may still be feeding the previous bulk store
-      if (lane == 0) bulk_wait_read0();
+      if (leader) bulk_wait_read0();
       __syncwarp();
     }
 #pragma unroll
@@ -194,7 +194,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const CUtens
       // clipped by the hardware at the M / N edges; the warp moves on immediately
       fence_proxy_async_smem();
       __syncwarp();
-      if (lane == 0 && !(p.debug & 1)) {
+      if (leader && !(p.debug & 1)) {
         tma_store_2d((GELU && pass == 1) ? tmX : tmC, stg, n0, row0);
         bulk_commit();
       }
@@ -231,7 +231,7 @@ __device__ __forceinline__ void epi_chunk_bf16(const GemmParams& p, const CUtens
 // fp32 outputs (residual add, plain store, split-K atomics) and the multiply-by-aux epilogue: 16 accumulator
 // columns per step staged as fp32; afterwards lane l owns 4 consecutive columns of rows (l>>2) + 8g, and the
 // per-element global loads (residual / aux) of all 4 row groups are issued before the accumulator is read.
-__device__ __forceinline__ void epi_chunk_f32(const GemmParams& p, uint32_t taddr, uint32_t stg, int lane, int row0,
+__device__ __forceinline__ void epi_chunk_f32(const GemmParams& p, uint32_t taddr, uint32_t stg, int lane, bool leader, int row0,
                                               int n0, uint32_t bias_s /* smem address of this chunk's 16 bias floats */) {
   uint32_t r[16];
   tmem_ld16(taddr, r);
@@ -332,7 +332,7 @@ __device__ __forceinline__ void epi_chunk_f32(const GemmParams& p, uint32_t tadd
 // this chunk's own staging buffer; the product is written in place and leaves as one TMA bulk store.  `bar` is the
 // warp's mbarrier for the first chunk of a tile (it covers the loads of both chunks), nullptr for the second.
 __device__ __forceinline__ void epi_chunk_mulaux_pf(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr,
-                                                    uint32_t stg, int lane, int row0, int n0, uint32_t bias_s,
+                                                    uint32_t stg, int lane, bool leader, int row0, int n0, uint32_t bias_s,
                                                     uint64_t* bar, uint32_t& phase) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
@@ -362,7 +362,7 @@ __device__ __forceinline__ void epi_chunk_mulaux_pf(const GemmParams& p, const C
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (leader) {
     tma_store_2d(tmC, stg, n0, row0);
     bulk_commit();
   }
@@ -385,11 +385,11 @@ __device__ __forceinline__ void epi_chunk_mulaux_pf(const GemmParams& p, const C
 // bulk tensor load, is combined with the accumulator in the row layout (thread = row), written back to the same
 // swizzled cells and leaves through a bulk tensor store (or reduce-add for split-K).  No per-thread global access.
 __device__ __forceinline__ void epi_chunk_mulaux_tma(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
-                                                     uint32_t taddr, uint32_t stg, int lane, int row0, int n0,
+                                                     uint32_t taddr, uint32_t stg, int lane, bool leader, int row0, int n0,
                                                      uint32_t bias_s, uint64_t* bar, uint32_t& phase) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
-  if (lane == 0) {
+  if (leader) {
     bulk_wait_read0();  // the previous store has finished reading the staging buffer
     mbar_expect_tx(bar, 32 * 64);
     tma_load_2d_s(stg, tmX, bar, n0, row0);
@@ -416,7 +416,7 @@ __device__ __forceinline__ void epi_chunk_mulaux_tma(const GemmParams& p, const 
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (leader) {
     tma_store_2d(tmC, stg, n0, row0);
     bulk_commit();
   }
@@ -437,12 +437,12 @@ __device__ __forceinline__ void epi_chunk_mulaux_tma(const GemmParams& p, const 
 }
 
 __device__ __forceinline__ void epi_chunk_f32_tma(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
-                                                  uint32_t taddr, uint32_t stg, int lane, int row0, int n0,
+                                                  uint32_t taddr, uint32_t stg, int lane, bool leader, int row0, int n0,
                                                   uint32_t bias_s, uint64_t* bar, uint32_t& phase) {
   uint32_t r[16];
   tmem_ld16(taddr, r);
   const bool has_res = p.residual != nullptr;
-  if (lane == 0) {
+  if (leader) {
     bulk_wait_read0();
     if (has_res) {
       mbar_expect_tx(bar, 32 * 64);
@@ -473,7 +473,7 @@ __device__ __forceinline__ void epi_chunk_f32_tma(const GemmParams& p, const CUt
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (leader) {
     if (p.accumulate)
       tma_reduce_add_2d(tmC, stg, n0, row0);
     else
@@ -487,11 +487,11 @@ __device__ __forceinline__ void epi_chunk_f32_tma(const GemmParams& p, const CUt
 // and one group's temporaries are live — the register budget that made ptxas serialise the chains — and the two
 // bulk stores leave together without a read-completion wait between them.
 __device__ __forceinline__ void epi_chunk_gelu_2buf(const GemmParams& p, const CUtensorMap* tmC, const CUtensorMap* tmX,
-                                                    uint32_t taddr, uint32_t stg, int lane, int row0, int n0,
+                                                    uint32_t taddr, uint32_t stg, int lane, bool leader, int row0, int n0,
                                                     uint32_t bias_s) {
   uint32_t r[32];
   tmem_ld32(taddr, r);
-  if (lane == 0) bulk_wait_read0();  // the previous chunk's stores have read both buffers
+  if (leader) bulk_wait_read0();  // the previous chunk's stores have read both buffers
   __syncwarp();
   tmem_ld_wait();
 #pragma unroll
@@ -510,7 +510,7 @@ __device__ __forceinline__ void epi_chunk_gelu_2buf(const GemmParams& p, const C
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (leader) {
     tma_store_2d(tmC, stg, n0, row0);
     if (p.aux_out != nullptr) tma_store_2d(tmX, stg + kStgBytesPerWarp, n0, row0);
     bulk_commit();
@@ -521,7 +521,7 @@ __device__ __forceinline__ void epi_chunk_gelu_2buf(const GemmParams& p, const C
 // sits (or is about to land) in this chunk's own staging buffer; the sum is written in place and leaves as one TMA
 // bulk store.  `bar` is the warp's mbarrier for the first chunk of a tile (it covers all four loads), else nullptr.
 __device__ __forceinline__ void epi_chunk_f32_res_pf(const GemmParams& p, const CUtensorMap* tmC, uint32_t taddr,
-                                                     uint32_t stg, int lane, int row0, int n0, uint32_t bias_s,
+                                                     uint32_t stg, int lane, bool leader, int row0, int n0, uint32_t bias_s,
                                                      uint64_t* bar, uint32_t& phase) {
   uint32_t r[16];
   tmem_ld16(taddr, r);
@@ -544,7 +544,7 @@ __device__ __forceinline__ void epi_chunk_f32_res_pf(const GemmParams& p, const 
   }
   fence_proxy_async_smem();
   __syncwarp();
-  if (lane == 0) {
+  if (leader) {
     tma_store_2d(tmC, stg, n0, row0);
     bulk_commit();
   }
@@ -596,7 +596,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
   uint64_t* epi_bar = tempty_bar + 4;  // [kEpiWarps]: completion of the epilogue's own TMA loads
 
-  const int warp = threadIdx.x >> 5;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, so everything derived from it (staging
+  // addresses, tile coordinates) lives in uniform registers and the elected lane's TMA instructions are issued from
+  // them directly — behind a divergent `lane == 0` test ptxas wraps every UTMASTG / UTMALDG in an
+  // R2UR ... BRA.U.ANY loop
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0);
   const int lane = threadIdx.x & 31;
   const int total_work = p.tiles_m * p.tiles_n * p.split_k;
 
@@ -743,6 +747,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // TMEM lane = output row, so a thread first holds one row of the accumulator.  Every chunk goes through a
     // swizzled 4 KB smem transpose (explicit st/ld.shared) so that global traffic is coalesced 16-byte accesses.
     const int ew = warp - 2;
+    const bool leader = elect_one();  // the one lane that issues (and waits for) this warp's bulk copies
     const int q = warp & 3;   // TMEM lane quadrant this warp may access
     const int grp = ew >> 2;  // 0..3: which quarter of the column chunks
     const uint32_t stg = smem_u32(smem + L::kStgOff + ew * L::kStgPerWarp);
@@ -789,7 +794,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // MUL_AUX: the aux pieces of this warp's two column chunks start their trip from HBM now, while the
         // mainloop of the tile is still running (one mbarrier, armed with the bytes of both)
         if (tma_io && !p.out_f32) {
-          if (lane == 0) {
+          if (leader) {
             bulk_wait_read0();  // the previous tile's stores have read both staging halves
             int nvalid = 0;
 #pragma unroll
@@ -809,7 +814,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if constexpr (L::kResPrefetch) {
         // fp32 + residual: the residual pieces of this warp's four column chunks start their trip now
         if (tma_io && p.out_f32 && p.residual != nullptr) {
-          if (lane == 0) {
+          if (leader) {
             bulk_wait_read0();  // the previous tile's stores have read all four staging buffers
             int nvalid = 0;
 #pragma unroll
@@ -845,7 +850,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int c = grp + 4 * ci;
           const int n0 = n_blk * BN + c * 16;
           if (n0 < p.N)  // warp-uniform
-            epi_chunk_f32_res_pf(p, &tmC, tbase + c * 16, stg + ci * kStgBytesPerWarp, lane, row0, n0, bias_tile + c * 64,
+            epi_chunk_f32_res_pf(p, &tmC, tbase + c * 16, stg + ci * kStgBytesPerWarp, lane, leader, row0, n0, bias_tile + c * 64,
                                  ci == 0 ? &epi_bar[ew] : nullptr, epi_phase);
         }
       } else if (L::kAuxPrefetch && tma_io && !p.out_f32) {
@@ -854,7 +859,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int c = grp + 4 * ci;
           const int n0 = n_blk * BN + c * 32;
           if (n0 < p.N)  // warp-uniform
-            epi_chunk_mulaux_pf(p, &tmC, tbase + c * 32, stg + ci * kStgBytesPerWarp, lane, row0, n0, bias_tile + c * 128,
+            epi_chunk_mulaux_pf(p, &tmC, tbase + c * 32, stg + ci * kStgBytesPerWarp, lane, leader, row0, n0, bias_tile + c * 128,
                                 ci == 0 ? &epi_bar[ew] : nullptr, epi_phase);
         }
       } else if (tma_io && !p.out_f32) {
@@ -862,7 +867,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = grp; c < BN / 32; c += 4) {
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= p.N) break;  // warp-uniform
-          epi_chunk_mulaux_tma(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128, &epi_bar[ew],
+          epi_chunk_mulaux_tma(p, &tmC, &tmX, tbase + c * 32, stg, lane, leader, row0, n0, bias_tile + c * 128, &epi_bar[ew],
                                epi_phase);
         }
       } else if (tma_io) {
@@ -870,7 +875,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = grp; c < BN / 16; c += 4) {
           const int n0 = n_blk * BN + c * 16;
           if (n0 >= p.N) break;  // warp-uniform
-          epi_chunk_f32_tma(p, &tmC, &tmX, tbase + c * 16, stg, lane, row0, n0, bias_tile + c * 64, &epi_bar[ew],
+          epi_chunk_f32_tma(p, &tmC, &tmX, tbase + c * 16, stg, lane, leader, row0, n0, bias_tile + c * 64, &epi_bar[ew],
                             epi_phase);
         }
       } else if (bf16_rowmath) {
@@ -879,18 +884,18 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int n0 = n_blk * BN + c * 32;
           if (n0 >= p.N) break;  // warp-uniform
           if (L::kAuxPrefetch && p.epilogue == CGPT_EPI_GELU && (p.tma_out & 1) && (p.aux_out == nullptr || (p.tma_out & 2)))
-            epi_chunk_gelu_2buf(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128);
+            epi_chunk_gelu_2buf(p, &tmC, &tmX, tbase + c * 32, stg, lane, leader, row0, n0, bias_tile + c * 128);
           else if (p.epilogue == CGPT_EPI_GELU)
-            epi_chunk_bf16<true>(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128);
+            epi_chunk_bf16<true>(p, &tmC, &tmX, tbase + c * 32, stg, lane, leader, row0, n0, bias_tile + c * 128);
           else
-            epi_chunk_bf16<false>(p, &tmC, &tmX, tbase + c * 32, stg, lane, row0, n0, bias_tile + c * 128);
+            epi_chunk_bf16<false>(p, &tmC, &tmX, tbase + c * 32, stg, lane, leader, row0, n0, bias_tile + c * 128);
         }
       } else {
 #pragma unroll 1
         for (int c = grp; c < BN / 16; c += 4) {
           const int n0 = n_blk * BN + c * 16;
           if (n0 >= p.N) break;  // warp-uniform
-          epi_chunk_f32(p, tbase + c * 16, stg, lane, row0, n0, bias_tile + c * 64);
+          epi_chunk_f32(p, tbase + c * 16, stg, lane, leader, row0, n0, bias_tile + c * 64);
         }
       }
       tc_fence_before();
@@ -899,7 +904,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if constexpr (TWO) mbar_arrive_cluster(tempty_leader[acc]); else mbar_arrive(&tempty_bar[acc]);
       }
     }
-    if ((p.tma_out & 1) && lane == 0) bulk_wait0();  // smem must outlive the bulk stores that read it
+    if ((p.tma_out & 1) && leader) bulk_wait0();  // smem must outlive the bulk stores that read it
   }
 
   tc_fence_before();
