@@ -650,8 +650,13 @@ int cgpt_ce_fwd(const float* logits, const int64_t* targets, const int32_t* next
   // one ticket counter per launch in flight: launches on one stream are ordered anyway; launches on different streams
   // get different counters unless 64 other CE launches were issued in between
   static unsigned int next_ticket = 0;
-  static unsigned int* tickets = nullptr;  // one process per GPU: the symbol's address is looked up once
-  if (tickets == nullptr) CGPT_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&tickets), g_ce_tickets));
+  static unsigned int* ticket_base[64] = {nullptr};  // the symbol's address, looked up once per device
+  int dev = 0;
+  CGPT_CHECK(cudaGetDevice(&dev));
+  CGPT_REQUIRE(dev >= 0 && dev < 64, "ce_fwd: device index %d out of range", dev);
+  if (ticket_base[dev] == nullptr)
+    CGPT_CHECK(cudaGetSymbolAddress(reinterpret_cast<void**>(&ticket_base[dev]), g_ce_tickets));
+  unsigned int* tickets = ticket_base[dev];
   unsigned int* ticket = tickets + (next_ticket++ % kCeCounters);
   if (vec)
     ce_fwd_kernel<true><<<n_part, kCeThreads, smem, ST(stream)>>>(logits, targets, next_boundary, class_w, row_ws, row_lse,
