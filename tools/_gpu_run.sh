@@ -1,17 +1,21 @@
-mkdir -p gpurun_out/r2ag
+mkdir -p gpurun_out/r2aj
 cd /root/repo
-LIB=genomics-lm_b200/codonlm_b200/libcgpt_b200.so
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/r2ag/pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -3 gpurun_out/r2ag/pytest_gpu.log
-B="python bench.py --no-cpu-baseline --no-gpu-baseline --steps 20 --warmup 3"
-run() { name=$1; shift; env "$@" timeout 200 $B > gpurun_out/r2ag/bench_$name.json 2> gpurun_out/r2ag/bench_$name.err; python - <<PY
-import json
-try:
-    d=json.loads(open("gpurun_out/r2ag/bench_$name.json").read().strip().splitlines()[-1])
-    print("$name", d["ms_per_step"], d["value"], d["clocks"]["sm_mhz"], d["step_flops"]["frac_of_bf16_burst_peak"])
-except Exception as e:
-    print("$name", "failed", e)
+O=gpurun_out/r2aj
+timeout 600 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc $?"; tail -3 $O/pytest_gpu.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+( time timeout 600 python bench.py > $O/bench_c3.json 2> $O/bench_c3.err ) 2>&1 | grep real
+timeout 300 python bench.py --impl reference --steps 4 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err; tail -c 300 $O/bench_ref.json
+for w in c2 c4_train c4_infer c5_attn; do timeout 300 python bench.py --workload $w --no-cpu-baseline --no-gpu-baseline --steps 30 --warmup 3 > $O/bench_$w.json 2> $O/bench_$w.err; done
+timeout 300 python bench.py --dropout 0.1 --no-cpu-baseline --no-gpu-baseline --steps 12 --warmup 3 > $O/bench_c3_dropout.json 2> $O/bench_c3_dropout.err
+timeout 300 python bench.py --tokens realistic --no-cpu-baseline --no-gpu-baseline --steps 12 --warmup 3 > $O/bench_c3_realistic.json 2> $O/bench_c3_realistic.err
+timeout 300 python bench.py --no-graph --no-cpu-baseline --no-gpu-baseline --steps 8 --warmup 3 > $O/bench_c3_eager.json 2> $O/bench_c3_eager.err
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob("gpurun_out/r2aj/bench_*.json")):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split('/')[-1], d.get("ms_per_step"), d.get("value"), (d.get("clocks") or {}).get("sm_mhz"), (d.get("step_flops") or {}).get("frac_of_bf16_burst_peak"), (d.get("e2e") or {}).get("value"))
+    except Exception as e:
+        print(f, "failed", e)
 PY
-}
-for v in new prev new prev; do cp tools/_prev/libcgpt_$v.so $LIB; run $v$RANDOM X=1; done
-for v in new prev; do cp tools/_prev/libcgpt_$v.so $LIB; echo "== $v"; timeout 200 python tools/gemm_probe.py qkv_fwd fc1_fwd_gelu fc2_dgrad_mulaux_colsum proj_fwd_res fc1_wgrad 2>&1 | tail -5; timeout 100 python tools/attn_probe.py attn_bwd 2>&1 | tail -1; timeout 100 python tools/attn_probe.py attn_fwd 2>&1 | tail -1; timeout 60 python tools/ln_probe.py 2>&1 | tail -1; done
-cp tools/_prev/libcgpt_new.so $LIB
+CUDA_VISIBLE_DEVICES=0 timeout 400 python tools/train_cli_check.py /tmp/cli_check > $O/train_cli.log 2>&1; echo "cli rc $?"; tail -4 $O/train_cli.log
