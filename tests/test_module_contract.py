@@ -108,3 +108,33 @@ def test_boolean_masks_convert_to_interval_starts():
     for bad in (holed, full, tri[None, None].expand(3, 2, 50, 50)):
         with pytest.raises(NotImplementedError):
             mask_spec_from_bool(bad, 3, 50)
+
+
+def test_gradient_by_products_travel_on_the_tensor_and_through_views():
+    """The bf16 form of a logit gradient that the cross-entropy backward writes (functional.CrossEntropyFn) reaches the
+    head's backward ON the gradient tensor — also through the (B*T,V) <-> (B,T,V) views autograd puts in between —
+    is consumed once, and is ignored when its shape is not the one the consumer wants (it then recomputes)."""
+    from codonlm_b200 import functional as Fn
+    g = torch.zeros(12, 68)
+    side = torch.zeros(12, 72, dtype=torch.bfloat16)
+    Fn._attach(g, side, None)
+    via_view = g.view(3, 4, 68).view(12, 68)  # what ViewBackward hands on
+    assert Fn._grad_form_of(via_view, (12, 3 * 72)) is None  # not the form this consumer reads: it will recompute
+    assert Fn._grad_form_of(via_view, (12, 72)) is None      # ... and the by-product is gone: it is looked up once
+    Fn._attach(g, side, None)
+    assert Fn._grad_form_of(g.view(3, 4, 68).view(12, 68), (12, 72)) is side
+    assert Fn._grad_form_of(g, (12, 72)) is None
+    # a tensor that is not a full view of the producer's (a slice, a sum) never sees it
+    Fn._attach(g, side, None)
+    assert Fn._grad_form_of(g[:6], (6, 72)) is None
+    assert Fn._grad_form_of(g + 0, (12, 72)) is None
+    assert Fn._grad_form_of(g, (12, 72)) is side
+
+
+def test_multi_output_nodes_take_undefined_gradients_as_none():
+    """ResidualLayerNormFn / HeadsFn / CrossEntropyFn switch gradient materialisation off (an unused output must not cost
+    a zero fill, a conversion and an add in backward): checked on the autograd metadata, no kernel is launched."""
+    import inspect
+    from codonlm_b200 import functional as Fn
+    for cls in (Fn.ResidualLayerNormFn, Fn.HeadsFn, Fn.CrossEntropyFn):
+        assert "set_materialize_grads(False)" in inspect.getsource(cls.forward), cls.__name__
