@@ -449,11 +449,28 @@ __device__ __forceinline__ DropoutCfg resolve_dropout(DropoutCfg d) {
   return d;
 }
 // Attention-probability dropout: keep-mask of the 32 consecutive key positions jb .. jb+31 (jb % 32 == 0) of query
-// row i, head bh; bit e set = keep position jb+e.  Four Philox4x32-7 calls (7 rounds pass BigCrush; cuRAND's 10 are a
-// safety margin that costs 40 % more integer multiplies here), 16 bits per position.  Forward, backward and the dense
-// probability kernel all go through these two functions, so they see the same mask.
-__device__ __forceinline__ uint4 attn_dropout_octet(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t j8) {
-  return philox4x32<7>(make_uint2(d.key.x ^ d.off_lo, d.key.y ^ d.off_hi), make_uint4(j8, i, bh, 0x61747400u));
+// row i, head bh; bit e set = keep position jb+e; 16 random bits per position.  ONE Philox4x32-7 call per (row, 32-key
+// chunk) — 7 rounds pass BigCrush; cuRAND's 10 are a safety margin — gives 128 bits: the first 8 positions use them
+// directly, the other 24 use twelve more words expanded from them by a bijective 32-bit finaliser (xor-shift /
+// multiply, full avalanche) under three different whitening constants.  Four Philox calls per chunk cost more integer
+// work than the whole softmax of the chunk (~10 against ~4 instructions per score); this is ~5.  Forward, backward and
+// the dense probability kernel all go through these functions, so they see the same mask.
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {
+  x ^= x >> 16;
+  x *= 0x7feb352du;
+  x ^= x >> 15;
+  x *= 0x846ca68bu;
+  x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ uint4 attn_dropout_seed(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t j32) {
+  return philox4x32<7>(make_uint2(d.key.x ^ d.off_lo, d.key.y ^ d.off_hi), make_uint4(j32, i, bh, 0x61747400u));
+}
+// the 4 words (8 positions) of octet q = 0..3 of a chunk
+__device__ __forceinline__ uint4 attn_dropout_octet(const uint4 s, uint32_t q) {
+  if (q == 0) return s;
+  const uint32_t w = 0x9E3779B9u * q;
+  return make_uint4(mix32(s.x ^ w), mix32(s.y ^ w), mix32(s.z ^ w), mix32(s.w ^ w));
 }
 __device__ __forceinline__ uint32_t keep_bits8(const uint4 r, uint32_t t) {
   return (uint32_t)((r.x & 0xffffu) >= t) | ((uint32_t)((r.x >> 16) >= t) << 1) | ((uint32_t)((r.y & 0xffffu) >= t) << 2) |
@@ -461,13 +478,15 @@ __device__ __forceinline__ uint32_t keep_bits8(const uint4 r, uint32_t t) {
          ((uint32_t)((r.w & 0xffffu) >= t) << 6) | ((uint32_t)((r.w >> 16) >= t) << 7);
 }
 __device__ __forceinline__ uint32_t attn_keep_mask32(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t jb) {
+  const uint4 s = attn_dropout_seed(d, bh, i, jb >> 5);
   uint32_t m = 0;
 #pragma unroll
-  for (uint32_t q = 0; q < 4; ++q) m |= keep_bits8(attn_dropout_octet(d, bh, i, (jb >> 3) + q), d.thresh16) << (8 * q);
+  for (uint32_t q = 0; q < 4; ++q) m |= keep_bits8(attn_dropout_octet(s, q), d.thresh16) << (8 * q);
   return m;
 }
 __device__ __forceinline__ bool attn_keep(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t j) {
-  return (keep_bits8(attn_dropout_octet(d, bh, i, j >> 3), d.thresh16) >> (j & 7u)) & 1u;
+  const uint4 s = attn_dropout_seed(d, bh, i, j >> 5);
+  return (keep_bits8(attn_dropout_octet(s, (j >> 3) & 3u), d.thresh16) >> (j & 7u)) & 1u;
 }
 
 // ---- small math
