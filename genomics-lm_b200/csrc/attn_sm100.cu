@@ -2421,13 +2421,18 @@ attn_bwd_ws_kernel(const __grid_constant__ CUtensorMap tm_qkv, const __grid_cons
             }
           }
           if (drop.thresh) {
-            const uint32_t keep = attn_keep_mask32(drop, b * H + hq, i, kv0 + c4 * 32);
+            const uint4 sd = attn_dropout_seed(drop, b * H + hq, i, (kv0 + c4 * 32) >> 5);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float mk = ((keep >> j) & 1u) ? drop.inv_keep16 : 0.f;
+            for (int q = 0; q < 4; ++q) {
+              float mk[8];
+              attn_keep_scale8(attn_dropout_octet(sd, q), drop.thresh16, drop.inv_keep16, mk);
+#pragma unroll
+              for (int e = 0; e < 8; ++e) {
+                const int j = q * 8 + e;
                 const float pj = p[j];
-                ds[j] = pj * (__uint_as_float(rp[j]) * mk - dl);
-                p[j] = pj * mk;
+                ds[j] = pj * (__uint_as_float(rp[j]) * mk[e] - dl);
+                p[j] = pj * mk[e];
+              }
             }
           }
           // the single P buffer: the dV MMAs of the previous tile must have retired (they were issued right behind

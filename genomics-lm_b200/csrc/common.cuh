@@ -484,6 +484,16 @@ __device__ __forceinline__ uint32_t attn_keep_mask32(const DropoutCfg& d, uint32
   for (uint32_t q = 0; q < 4; ++q) m |= keep_bits8(attn_dropout_octet(s, q), d.thresh16) << (8 * q);
   return m;
 }
+// the same mask as 32 multipliers (1 / (1 - p) or 0), octet by octet: a 16-bit field goes straight to a compare and a
+// select — no keep-mask word is assembled and no bit of it is tested again
+__device__ __forceinline__ void attn_keep_scale8(const uint4 r, uint32_t t, float inv, float (&mk)[8]) {
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    mk[2 * k] = (w[k] & 0xffffu) >= t ? inv : 0.f;
+    mk[2 * k + 1] = (w[k] >> 16) >= t ? inv : 0.f;
+  }
+}
 __device__ __forceinline__ bool attn_keep(const DropoutCfg& d, uint32_t bh, uint32_t i, uint32_t j) {
   const uint4 s = attn_dropout_seed(d, bh, i, j >> 5);
   return (keep_bits8(attn_dropout_octet(s, (j >> 3) & 3u), d.thresh16) >> (j & 7u)) & 1u;
